@@ -1,0 +1,498 @@
+"""Static, level-ordered message schedule ("plan") for the sm_100a propagation kernels.
+
+The plan is everything the device needs that does not depend on the numbers: for every
+junction-tree edge the axis maps between clique and separator index spaces, the order in which
+messages are computed (collect bottom-up by level, distribute top-down by level, independent
+subtrees of one level fused into one launch), the evidence maps for clique initialisation and
+the maps that marginalise clique beliefs back to factor scopes.
+
+What it replaces in the reference (all recomputed there on every call, in Python):
+
+* ``junctiontree.py:203-226``  clique <- factors map and the per-clique einsum subscripts (E0)
+* ``computation.py:47-96``     collect recursion, per-edge einsum subscripts (E1, E2)
+* ``computation.py:140-224``   distribute recursion, exclude-one product, subscripts (E3-E5, D1, M1)
+* ``junctiontree.py:229-274``  marginalisation subscripts (E6)
+* ``computation.py:11-34``     evidence slicing (V1) -> integer strides per (factor, observed variable)
+
+Everything is expressed through one primitive, the *projection task*::
+
+    term(s, r) = src[ S(s) + R(r) ] * prod_j msg_j[ A_j(s) + B_j(r) ]
+    acc(s)     = sum_r term(s, r)
+    sm(s)      = prod_j smsg_j[ A_j(s) ]                (messages that do not depend on r)
+    out[s]     = acc(s) * sm(s)                         (optional)
+    bel[s]     = out[s] * own[s]                        (optional: separator belief = up * down)
+    beta[S(s)+R(r)] = term(s, r) * sm(s) * own[s]       (optional: clique belief, in place)
+
+``s`` enumerates the output (separator / factor scope) index space in row-major order, ``r``
+the remaining clique axes.  Every map is additive over axes, so it is stored as two small int32
+tables (leading axes / trailing axes of the index space): ``S(s) = hi[s // n_lo] + lo[s % n_lo]``.
+Identical tables are stored once.
+
+All device buffers use the batch-innermost layout ``[entry, B]``: the entry offsets in the plan
+are multiplied by the batch size on the device.
+"""
+
+import numpy as np
+
+from . import construction as cons
+
+MAGIC = 0x324E4C5042544A  # "JTBPLN2"
+VERSION = 3
+
+# header word indices (int64 words); mirrored in include/jt_b200.h
+H_MAGIC, H_VERSION, H_NCLIQUES, H_NSEPS, H_NFACTORS, H_NEVID, H_CLIQUE_ENTRIES, H_SEP_ENTRIES, \
+    H_FIN_ENTRIES, H_FOUT_ENTRIES, H_NTAB, H_NTASKS, H_NMSGS, H_NLAUNCHES, H_MAXDEPTH, \
+    H_NEVF, H_ROOT_ENTRIES, H_WORDS = range(18)
+
+TASK_WORDS = 24
+(T_KIND, T_SRC, T_OUT, T_BETA, T_BEL, T_OWN, T_NS, T_NR, T_NSLO, T_NRLO, T_SRC_SHI, T_SRC_SLO,
+ T_SRC_RHI, T_SRC_RLO, T_RMSG_BEGIN, T_RMSG_END, T_SMSG_BEGIN, T_SMSG_END, T_OUT_SPACE, T_NODE,
+ T_AUX) = range(21)
+
+MSG_WORDS = 6
+M_OFF, M_AHI, M_ALO, M_BHI, M_BLO, M_FID = range(6)
+
+LAUNCH_WORDS = 4
+L_PHASE, L_BEGIN, L_END, L_LEVEL = range(4)
+
+KIND_PROJECT, KIND_INIT = 0, 1
+PHASE_INIT, PHASE_COLLECT, PHASE_DIST_PRE, PHASE_DIST_MAIN, PHASE_MARGINAL = range(5)
+SPACE_WORK, SPACE_FOUT = 0, 1
+
+#: trailing-axes table is grown while its length stays within this bound
+LO_TABLE_MAX = 1024
+
+
+def _prod(xs):
+    p = 1
+    for x in xs:
+        p *= int(x)
+    return p
+
+
+def _row_major_strides(shape):
+    strides = [0] * len(shape)
+    acc = 1
+    for i in range(len(shape) - 1, -1, -1):
+        strides[i] = acc
+        acc *= int(shape[i])
+    return strides
+
+
+def _split_point(shape):
+    """Number of trailing axes that go into the ``lo`` table."""
+    k, acc = 0, 1
+    for n in reversed(shape):
+        if k > 0 and acc * int(n) > LO_TABLE_MAX:
+            break
+        acc *= int(n)
+        k += 1
+    return k
+
+
+class _TableArena:
+    """int32 tables, stored once per distinct content."""
+
+    def __init__(self):
+        self.chunks = []
+        self.size = 0
+        self.index = {}
+
+    def add(self, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.int64)
+        if arr.size and (arr.min() < 0 or arr.max() >= 2 ** 31):
+            raise OverflowError("index table entry does not fit int32")
+        arr = arr.astype(np.int32)
+        key = arr.tobytes()
+        hit = self.index.get(key)
+        if hit is not None:
+            return hit
+        off = self.size
+        self.index[key] = off
+        self.chunks.append(arr)
+        self.size += arr.size
+        return off
+
+    def array(self):
+        if not self.chunks:
+            return np.zeros(0, np.int32)
+        return np.concatenate(self.chunks)
+
+
+class _Space:
+    """An index space: ordered variables with sizes, split into leading / trailing axes."""
+
+    def __init__(self, variables, sizes):
+        self.vars = list(variables)
+        self.shape = [int(sizes[v]) for v in self.vars]
+        self.n = _prod(self.shape)
+        k = _split_point(self.shape)
+        self.hi_vars, self.lo_vars = self.vars[:len(self.vars) - k], self.vars[len(self.vars) - k:]
+        self.hi_shape, self.lo_shape = self.shape[:len(self.vars) - k], self.shape[len(self.vars) - k:]
+        self.n_lo = _prod(self.lo_shape)
+        self.n_hi = _prod(self.hi_shape)
+
+    @staticmethod
+    def _table(variables, shape, stride_of):
+        n = _prod(shape)
+        if not variables:
+            return np.zeros(1, np.int64)
+        tab = np.zeros(shape, np.int64)
+        for ax, (v, sz) in enumerate(zip(variables, shape)):
+            st = stride_of.get(v, 0)
+            if st:
+                idx = np.arange(sz, dtype=np.int64) * st
+                view = [1] * len(shape)
+                view[ax] = sz
+                tab = tab + idx.reshape(view)
+        return np.broadcast_to(tab, shape).reshape(n)
+
+    def tables(self, stride_of):
+        """(hi, lo) tables of the additive map x -> sum_v digit_v(x) * stride_of[v]."""
+        return (self._table(self.hi_vars, self.hi_shape, stride_of),
+                self._table(self.lo_vars, self.lo_shape, stride_of))
+
+    def touches(self, variables):
+        return any(v in variables for v in self.vars)
+
+
+class Plan:
+    """Compiled schedule.  See the module docstring for the task semantics.
+
+    :param tree: nested tree ``[clique, (sep, subtree), ...]`` (reference ``README.md:52-70``)
+    :param node_vars: ``maxcliques + separators`` variable lists (reference
+                      ``junctiontree.py:317-323``); axis order of every node is taken from here
+    :param sizes: ``{var: size}`` effective sizes (1 for observed variables)
+    :param factors: optional list of factor variable lists (enables init / marginal stages)
+    :param factor_to_clique: clique index per factor
+    :param evidence_vars: ordered list of variables observed per instance; their effective
+                          size must be 1 and ``full_sizes`` gives the size of the factor axis
+    :param full_sizes: ``{var: size}`` of the factor tables as stored (defaults to ``sizes``)
+    """
+
+    def __init__(self, tree, node_vars, sizes, factors=None, factor_to_clique=None,
+                 evidence_vars=(), full_sizes=None):
+        self.tree = tree
+        self.node_vars = [list(v) for v in node_vars]
+        self.sizes = dict(sizes)
+        self.factors = None if factors is None else [list(f) for f in factors]
+        self.factor_to_clique = None if factor_to_clique is None else list(factor_to_clique)
+        self.evidence_vars = list(evidence_vars)
+        self.full_sizes = dict(full_sizes) if full_sizes is not None else dict(sizes)
+        for v in self.evidence_vars:
+            if int(self.sizes[v]) != 1:
+                raise ValueError("observed variable %r must have effective size 1" % (v,))
+        self._compile()
+
+    # -----------------------------------------------------------------------------------------
+
+    def _compile(self):
+        order, parent, parent_sep, depth, children = cons.tree_edges(self.tree)
+        cliques = sorted(order)
+        n_nodes = len(self.node_vars)
+        self.n_cliques = len(cliques)
+        if cliques != list(range(self.n_cliques)):
+            raise ValueError("clique ids in the tree must be 0..N-1 (node_list = cliques + separators)")
+        self.n_seps = n_nodes - self.n_cliques
+        sep_ids = sorted(s for c in order for s, _ in children[c])
+        if sep_ids != list(range(self.n_cliques, n_nodes)):
+            raise ValueError("separator ids in the tree must be N..N+S-1, each used once")
+        self.order, self.parent, self.parent_sep, self.depth, self.children = \
+            order, parent, parent_sep, depth, children
+        self.root = order[0]
+        self.max_depth = max(depth.values()) if depth else 0
+
+        for c in order:
+            cv = set(self.node_vars[c])
+            if len(cv) != len(self.node_vars[c]):
+                raise ValueError("duplicate variable in clique %d" % c)
+            for s, ch in children[c]:
+                sv = self.node_vars[s]
+                if len(set(sv)) != len(sv):
+                    raise ValueError("duplicate variable in separator %d" % s)
+                if not set(sv) <= cv or not set(sv) <= set(self.node_vars[ch]):
+                    raise ValueError("separator %d is not contained in both of its cliques" % s)
+
+        self.node_shape = [[int(self.sizes[v]) for v in vs] for vs in self.node_vars]
+        self.node_size = [_prod(sh) for sh in self.node_shape]
+        self.node_off = [0] * n_nodes
+        acc = 0
+        for k in range(n_nodes):
+            self.node_off[k] = acc
+            acc += self.node_size[k]
+        self.clique_entries = sum(self.node_size[:self.n_cliques])
+        self.sep_entries = sum(self.node_size[self.n_cliques:])
+        # workspace regions (entries): [cliques | separator beliefs | up messages | down messages]
+        self.up_base = self.clique_entries + self.sep_entries
+        self.down_base = self.up_base + self.sep_entries
+        self.work_entries = self.down_base + self.sep_entries
+
+        self.tab = _TableArena()
+        self.tasks, self.msgs, self.launches = [], [], []
+
+        self._build_factor_tables()
+        self._build_init()
+        self._build_collect()
+        self._build_distribute()
+        self._build_marginal()
+
+        self.tables = self.tab.array()
+        self.tasks_arr = np.asarray(self.tasks, np.int64).reshape(-1, TASK_WORDS)
+        self.msgs_arr = np.asarray(self.msgs, np.int64).reshape(-1, MSG_WORDS)
+        self.launches_arr = np.asarray(self.launches, np.int64).reshape(-1, LAUNCH_WORDS)
+
+    # offsets of the three per-separator buffers
+    def bel_off(self, sep):
+        return self.node_off[sep]
+
+    def up_off(self, sep):
+        return self.up_base + self.node_off[sep] - self.clique_entries
+
+    def down_off(self, sep):
+        return self.down_base + self.node_off[sep] - self.clique_entries
+
+    def _strides(self, node):
+        return dict(zip(self.node_vars[node], _row_major_strides(self.node_shape[node])))
+
+    # -----------------------------------------------------------------------------------------
+
+    def _build_factor_tables(self):
+        self.fin_off, self.fin_size, self.fin_shape = [], [], []
+        self.fout_off, self.fout_size, self.fout_shape = [], [], []
+        self.evf_ptr, self.evf_var, self.evf_stride = [0], [], []
+        self.ev_card = [int(self.full_sizes[v]) for v in self.evidence_vars]
+        self.fin_entries = self.fout_entries = 0
+        if self.factors is None:
+            return
+        ev_index = {v: i for i, v in enumerate(self.evidence_vars)}
+        for f, fv in enumerate(self.factors):
+            if len(set(fv)) != len(fv):
+                raise ValueError("duplicate variable in factor %d" % f)
+            home = self.factor_to_clique[f]
+            if not set(fv) <= set(self.node_vars[home]):
+                raise ValueError("factor %d is not contained in its clique %d" % (f, home))
+            full = [int(self.full_sizes[v]) if v in ev_index else int(self.sizes[v]) for v in fv]
+            eff = [int(self.sizes[v]) for v in fv]
+            self.fin_shape.append(full)
+            self.fout_shape.append(eff)
+            self.fin_off.append(self.fin_entries)
+            self.fin_size.append(_prod(full))
+            self.fin_entries += _prod(full)
+            self.fout_off.append(self.fout_entries)
+            self.fout_size.append(_prod(eff))
+            self.fout_entries += _prod(eff)
+            for v, st in zip(fv, _row_major_strides(full)):
+                if v in ev_index:
+                    self.evf_var.append(ev_index[v])
+                    self.evf_stride.append(st)
+            self.evf_ptr.append(len(self.evf_var))
+
+    def _add_msg(self, off, s_space, r_space, stride_of, fid=-1):
+        a_hi, a_lo = s_space.tables(stride_of)
+        row = [0] * MSG_WORDS
+        row[M_OFF] = off
+        row[M_AHI], row[M_ALO] = self.tab.add(a_hi), self.tab.add(a_lo)
+        if r_space is not None:
+            b_hi, b_lo = r_space.tables(stride_of)
+            row[M_BHI], row[M_BLO] = self.tab.add(b_hi), self.tab.add(b_lo)
+        row[M_FID] = fid
+        self.msgs.append(row)
+
+    def _new_task(self, kind, s_space, r_space, node, src_node=None):
+        row = [0] * TASK_WORDS
+        row[T_KIND] = kind
+        for w in (T_SRC, T_OUT, T_BETA, T_BEL, T_OWN):
+            row[w] = -1
+        row[T_NS], row[T_NSLO] = s_space.n, s_space.n_lo
+        row[T_NR], row[T_NRLO] = (r_space.n, r_space.n_lo) if r_space is not None else (1, 1)
+        row[T_NODE] = node
+        if src_node is not None:
+            st = self._strides(src_node)
+            row[T_SRC] = self.node_off[src_node]
+            hi, lo = s_space.tables(st)
+            row[T_SRC_SHI], row[T_SRC_SLO] = self.tab.add(hi), self.tab.add(lo)
+            hi, lo = r_space.tables(st)
+            row[T_SRC_RHI], row[T_SRC_RLO] = self.tab.add(hi), self.tab.add(lo)
+        return row
+
+    def _attach_msgs(self, row, msgs, s_space, r_space):
+        """msgs: list of (workspace offset, separator node).  r-dependent ones first."""
+        rdep = [(off, sep) for off, sep in msgs if r_space.touches(set(self.node_vars[sep]))]
+        sonly = [(off, sep) for off, sep in msgs if not r_space.touches(set(self.node_vars[sep]))]
+        row[T_RMSG_BEGIN] = len(self.msgs)
+        for off, sep in rdep:
+            self._add_msg(off, s_space, r_space, self._strides(sep))
+        row[T_RMSG_END] = row[T_SMSG_BEGIN] = len(self.msgs)
+        for off, sep in sonly:
+            self._add_msg(off, s_space, None, self._strides(sep))
+        row[T_SMSG_END] = len(self.msgs)
+
+    def _launch(self, phase, begin, level):
+        if len(self.tasks) > begin:
+            self.launches.append([phase, begin, len(self.tasks), level])
+
+    # -----------------------------------------------------------------------------------------
+
+    def _build_init(self):
+        """E0 + V1: psi_C = prod of assigned factors, observed axes gathered per instance."""
+        if self.factors is None:
+            return
+        begin = len(self.tasks)
+        by_clique = [[] for _ in range(self.n_cliques)]
+        for f, home in enumerate(self.factor_to_clique):
+            by_clique[home].append(f)
+        self.clique_factors = by_clique
+        for c in range(self.n_cliques):
+            s_space = _Space(self.node_vars[c], self.sizes)
+            row = self._new_task(KIND_INIT, s_space, None, c)
+            row[T_OUT] = self.node_off[c]
+            row[T_SMSG_BEGIN] = row[T_RMSG_BEGIN] = row[T_RMSG_END] = len(self.msgs)
+            for f in by_clique[c]:
+                st = dict(zip(self.factors[f], _row_major_strides(self.fin_shape[f])))
+                # observed axes contribute through the per-instance base offset only
+                for v in self.evidence_vars:
+                    st.pop(v, None)
+                self._add_msg(self.fin_off[f], s_space, None, st, fid=f)
+            row[T_SMSG_END] = len(self.msgs)
+            self.tasks.append(row)
+        self._launch(PHASE_INIT, begin, 0)
+
+    def _build_collect(self):
+        """E1 + E2: up-messages, deepest level first."""
+        by_depth = {}
+        for c in self.order:
+            by_depth.setdefault(self.depth[c], []).append(c)
+        self.by_depth = by_depth
+        for d in range(self.max_depth, 0, -1):
+            begin = len(self.tasks)
+            for c in by_depth[d]:
+                psep = self.parent_sep[c]
+                s_space = _Space(self.node_vars[psep], self.sizes)
+                in_sep = set(self.node_vars[psep])
+                r_space = _Space([v for v in self.node_vars[c] if v not in in_sep], self.sizes)
+                row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c)
+                row[T_OUT] = self.up_off(psep)
+                self._attach_msgs(row, [(self.up_off(s), s) for s, _ in self.children[c]],
+                                  s_space, r_space)
+                self.tasks.append(row)
+            self._launch(PHASE_COLLECT, begin, d)
+
+    def _build_distribute(self):
+        """E3 + E4 + M1 + E5 with a division-free exclude-one product, top level first.
+
+        For a clique with k children there are k projection tasks (one per child separator);
+        the last one also writes the clique belief in place, so it runs in a second launch
+        after the others of its level have read psi_C.  A non-root leaf gets one elementwise
+        task.  psi_C is read max(k, 1) times and written once (the reference reads it k+2
+        times, ``computation.py:169-224``).
+        """
+        for d in range(0, self.max_depth + 1):
+            pre, main = [], []
+            for c in self.by_depth.get(d, []):
+                kids = self.children[c]
+                incoming = []
+                if self.parent[c] >= 0:
+                    incoming.append((self.down_off(self.parent_sep[c]), self.parent_sep[c]))
+                incoming += [(self.up_off(s), s) for s, _ in kids]
+                if not kids:
+                    if self.parent[c] < 0:
+                        continue  # single-clique tree: belief = potential
+                    s_space = _Space(self.node_vars[c], self.sizes)
+                    r_space = _Space([], self.sizes)
+                    row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c)
+                    row[T_BETA] = self.node_off[c]
+                    self._attach_msgs(row, incoming, s_space, r_space)
+                    main.append(row)
+                    continue
+                for i, (sep, _) in enumerate(kids):
+                    s_space = _Space(self.node_vars[sep], self.sizes)
+                    in_sep = set(self.node_vars[sep])
+                    r_space = _Space([v for v in self.node_vars[c] if v not in in_sep], self.sizes)
+                    row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c)
+                    row[T_OUT] = self.down_off(sep)
+                    row[T_BEL] = self.bel_off(sep)
+                    row[T_OWN] = self.up_off(sep)
+                    others = [m for m in incoming if m[1] != sep]
+                    writer = i == len(kids) - 1
+                    if writer:
+                        row[T_BETA] = self.node_off[c]
+                    # messages are appended when the task is placed (keeps ranges contiguous)
+                    (main if writer else pre).append((row, others, s_space, r_space))
+            for phase, group in ((PHASE_DIST_PRE, pre), (PHASE_DIST_MAIN, main)):
+                begin = len(self.tasks)
+                for item in group:
+                    if isinstance(item, tuple):
+                        row, others, s_space, r_space = item
+                        self._attach_msgs(row, others, s_space, r_space)
+                        self.tasks.append(row)
+                    else:
+                        self.tasks.append(item)
+                self._launch(phase, begin, d)
+
+    def _build_marginal(self):
+        """E6: per-factor output = clique belief summed down to the factor scope."""
+        if self.factors is None:
+            return
+        begin = len(self.tasks)
+        for f, fv in enumerate(self.factors):
+            c = self.factor_to_clique[f]
+            s_space = _Space(fv, self.sizes)
+            in_f = set(fv)
+            r_space = _Space([v for v in self.node_vars[c] if v not in in_f], self.sizes)
+            row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c)
+            row[T_OUT] = self.fout_off[f]
+            row[T_OUT_SPACE] = SPACE_FOUT
+            row[T_AUX] = f
+            row[T_RMSG_BEGIN] = row[T_RMSG_END] = row[T_SMSG_BEGIN] = row[T_SMSG_END] = len(self.msgs)
+            self.tasks.append(row)
+        self._launch(PHASE_MARGINAL, begin, 0)
+
+    # -----------------------------------------------------------------------------------------
+
+    def algorithmic_entries(self, with_init=True):
+        """Entries moved per instance by the minimal two-pass schedule:
+        4*sum(n_C) - n_root + 6*sum(n_S)  (3*sum(n_C) without the init write)."""
+        n_root = self.node_size[self.root] if self.n_cliques else 0
+        return (4 if with_init else 3) * self.clique_entries - n_root + 6 * self.sep_entries
+
+    def header(self):
+        h = np.zeros(H_WORDS, np.int64)
+        h[H_MAGIC], h[H_VERSION] = MAGIC, VERSION
+        h[H_NCLIQUES], h[H_NSEPS] = self.n_cliques, self.n_seps
+        h[H_NFACTORS] = 0 if self.factors is None else len(self.factors)
+        h[H_NEVID] = len(self.evidence_vars)
+        h[H_CLIQUE_ENTRIES], h[H_SEP_ENTRIES] = self.clique_entries, self.sep_entries
+        h[H_FIN_ENTRIES], h[H_FOUT_ENTRIES] = self.fin_entries, self.fout_entries
+        h[H_NTAB] = self.tables.size
+        h[H_NTASKS], h[H_NMSGS], h[H_NLAUNCHES] = len(self.tasks_arr), len(self.msgs_arr), len(self.launches_arr)
+        h[H_MAXDEPTH] = self.max_depth
+        h[H_NEVF] = len(self.evf_var)
+        h[H_ROOT_ENTRIES] = self.node_size[self.root] if self.n_cliques else 0
+        return h
+
+    def to_blob(self):
+        """Serialise to the byte blob ``jt_plan_create`` parses (layout: include/jt_b200.h)."""
+        i64 = lambda xs: np.asarray(xs, np.int64).reshape(-1)
+        tables = self.tables
+        if tables.size % 2:
+            tables = np.concatenate([tables, np.zeros(1, np.int32)])
+        parts = [
+            self.header(),
+            i64(self.node_off), i64(self.node_size),
+            i64(self.fin_off), i64(self.fin_size), i64(self.fout_off), i64(self.fout_size),
+            i64(self.ev_card), i64(self.evf_ptr if self.factors is not None else []),
+            i64(self.evf_var), i64(self.evf_stride),
+            i64(self.tasks_arr), i64(self.msgs_arr), i64(self.launches_arr),
+        ]
+        return b"".join(p.tobytes() for p in parts) + tables.tobytes()
+
+    def summary(self):
+        return {
+            "cliques": self.n_cliques, "separators": self.n_seps,
+            "clique_entries": self.clique_entries, "sep_entries": self.sep_entries,
+            "max_clique": max(self.node_size[:self.n_cliques]) if self.n_cliques else 0,
+            "root_entries": int(self.node_size[self.root]) if self.n_cliques else 0,
+            "depth": self.max_depth, "tasks": len(self.tasks_arr), "launches": len(self.launches_arr),
+            "table_entries": int(self.tables.size),
+            "algorithmic_entries": self.algorithmic_entries(),
+        }

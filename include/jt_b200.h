@@ -1,0 +1,154 @@
+/*
+ * jt_b200.h -- C ABI of the B200 (sm_100a) sum-product propagation library, libjt_b200.so.
+ *
+ * The reference (jluttine/junction-tree, pure Python + NumPy) has no native boundary; its
+ * boundary for this path is the Python call surface.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference checkout):
+ *
+ *   jt_init        CliqueGraph.evaluate                junctiontree/junctiontree.py:203-226
+ *                  + evidence slicing apply_evidence   junctiontree/computation.py:11-34
+ *   jt_collect     compute_beliefs / get_message       junctiontree/computation.py:47-96
+ *   jt_distribute  compute_beliefs / send_message      junctiontree/computation.py:140-224
+ *                  (remove_message :99-136 is replaced by a division-free exclude-one product)
+ *   jt_marginal    CliqueGraph.marginalize             junctiontree/junctiontree.py:229-274
+ *   jt_propagate   JunctionTree.propagate              junctiontree/junctiontree.py:297-331
+ *   jt_contract    SumProduct.einsum                   junctiontree/sum_product.py:14-35
+ *
+ * Conventions: plain C types only; every function returns JT_OK or an error code and never
+ * throws; jt_last_error_string() describes the last error of the calling thread.  The caller
+ * owns every device buffer.  All device work is enqueued on the caller's stream and the library
+ * never synchronises (so calls can be captured into a CUDA graph after jt_plan_upload).  A plan
+ * is immutable after jt_plan_upload and may be shared; a workspace belongs to one stream at a
+ * time.  There is no CPU fallback: without a CUDA device the compute entry points fail.
+ *
+ * Device memory layout: batch-innermost.  A node (clique or separator) with n entries and a
+ * batch of B independent propagations is stored as [n][B]; element (entry e, instance b) of the
+ * node at entry offset `off` lives at workspace[(off + e) * B + b].  Workspace regions, in
+ * entries: [ cliques | separator beliefs | up-messages | down-messages ], i.e. the first
+ * (clique_entries + sep_entries) rows are the reference's node order `maxcliques + separators`
+ * (junctiontree.py:317-323).  Entry offsets of nodes come from jt_plan_node_range().
+ *
+ * Plan blob (produced by junctiontree/schedule.py, Plan.to_blob): little-endian int64 words
+ *   header[JT_H_WORDS], node_off[n_nodes], node_size[n_nodes], fin_off[F], fin_size[F],
+ *   fout_off[F], fout_size[F], ev_card[n_evid], evf_ptr[F+1 or 0], evf_var[n_evf],
+ *   evf_stride[n_evf], tasks[n_tasks][JT_TASK_WORDS], msgs[n_msgs][JT_MSG_WORDS],
+ *   launches[n_launches][JT_LAUNCH_WORDS], then int32 tables[n_tab (padded to even)].
+ *
+ * Projection task semantics (s = output index, r = index over the remaining clique axes):
+ *   term(s,r) = src[S(s)+R(r)] * prod_j rmsg_j[A_j(s)+B_j(r)]      acc(s) = sum_r term(s,r)
+ *   sm(s)     = prod_j smsg_j[A_j(s)]
+ *   out[s]    = acc(s)*sm(s);   bel[s] = out[s]*own[s];   beta[S(s)+R(r)] = term*sm(s)*own[s]
+ * where every index map X(i) = tab[hi + i / n_lo] + tab[lo + i % n_lo].
+ */
+#ifndef JT_B200_H
+#define JT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JT_ABI_VERSION 3
+
+/* status codes */
+#define JT_OK 0
+#define JT_ERR_INVALID 1   /* bad argument or malformed plan blob */
+#define JT_ERR_CUDA 2      /* CUDA runtime error (no device, launch failure, ...) */
+#define JT_ERR_NOMEM 3
+
+/* dtype */
+#define JT_F32 0
+#define JT_F64 1
+
+/* flags of jt_distribute / jt_propagate */
+#define JT_SEP_BELIEFS 1   /* also write separator beliefs (up*down), computation.py:210 */
+#define JT_SKIP_MARGINAL 2 /* jt_propagate: stop after distribute */
+
+/* plan blob header words */
+#define JT_MAGIC 0x324E4C5042544ALL
+enum {
+    JT_H_MAGIC, JT_H_VERSION, JT_H_NCLIQUES, JT_H_NSEPS, JT_H_NFACTORS, JT_H_NEVID,
+    JT_H_CLIQUE_ENTRIES, JT_H_SEP_ENTRIES, JT_H_FIN_ENTRIES, JT_H_FOUT_ENTRIES, JT_H_NTAB,
+    JT_H_NTASKS, JT_H_NMSGS, JT_H_NLAUNCHES, JT_H_MAXDEPTH, JT_H_NEVF, JT_H_ROOT_ENTRIES,
+    JT_H_WORDS
+};
+#define JT_TASK_WORDS 24
+enum {
+    JT_T_KIND, JT_T_SRC, JT_T_OUT, JT_T_BETA, JT_T_BEL, JT_T_OWN, JT_T_NS, JT_T_NR, JT_T_NSLO,
+    JT_T_NRLO, JT_T_SRC_SHI, JT_T_SRC_SLO, JT_T_SRC_RHI, JT_T_SRC_RLO, JT_T_RMSG_BEGIN,
+    JT_T_RMSG_END, JT_T_SMSG_BEGIN, JT_T_SMSG_END, JT_T_OUT_SPACE, JT_T_NODE, JT_T_AUX
+};
+#define JT_MSG_WORDS 6
+enum { JT_M_OFF, JT_M_AHI, JT_M_ALO, JT_M_BHI, JT_M_BLO, JT_M_FID };
+#define JT_LAUNCH_WORDS 4
+enum { JT_L_PHASE, JT_L_BEGIN, JT_L_END, JT_L_LEVEL };
+enum { JT_KIND_PROJECT = 0, JT_KIND_INIT = 1 };
+enum { JT_PHASE_INIT, JT_PHASE_COLLECT, JT_PHASE_DIST_PRE, JT_PHASE_DIST_MAIN, JT_PHASE_MARGINAL };
+
+typedef struct jt_plan jt_plan;
+
+/* ---- library ---- */
+int jt_abi_version(void);
+const char* jt_last_error_string(void);
+/* number of kernel launches issued by this library in this process (all threads) */
+int64_t jt_launch_count(void);
+
+/* ---- plan (host only until jt_plan_upload; no CUDA call is made by create/query/destroy) ---- */
+int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out);
+void jt_plan_destroy(jt_plan* plan);
+/* `what` is a JT_H_* header index */
+int jt_plan_query(const jt_plan* plan, int what, int64_t* out);
+/* entry offset and entry count of node k (cliques 0..N-1 then separators) in the workspace */
+int jt_plan_node_range(const jt_plan* plan, int node, int64_t* offset, int64_t* count);
+/* entry offset of separator node k's up / down message buffers */
+int jt_plan_message_offsets(const jt_plan* plan, int sep_node, int64_t* up, int64_t* down);
+/* bytes of workspace for a batch of B (includes the evidence-offset scratch) */
+int jt_workspace_bytes(const jt_plan* plan, int64_t B, int dtype, size_t* out);
+/* copy the schedule tables to the current CUDA device (idempotent) */
+int jt_plan_upload(jt_plan* plan);
+
+/*
+ * ---- stages; all pointers are device pointers, stream is a cudaStream_t ----
+ *
+ * factor_tables : concatenated factor tables in plan order, fin_entries values of `dtype`
+ *                 (factors_batched = 0, shared by the batch), or [fin_entries][B] per-instance
+ *                 tables (factors_batched = 1).
+ * evidence      : int32 [B][n_evid] observed states (row-major), or NULL when the plan has no
+ *                 per-instance evidence variables.  States outside [0, card) are clamped and
+ *                 counted; see jt_evidence_errors.
+ */
+int jt_init(jt_plan* plan, const void* factor_tables, int factors_batched, const int32_t* evidence,
+            int64_t B, int dtype, void* workspace, void* stream);
+int jt_collect(jt_plan* plan, int64_t B, int dtype, void* workspace, void* stream);
+int jt_distribute(jt_plan* plan, int64_t B, int dtype, void* workspace, int flags, void* stream);
+/* factor_out: [fout_entries][B] values of `dtype` */
+int jt_marginal(jt_plan* plan, int64_t B, int dtype, void* workspace, void* factor_out, void* stream);
+/* init + collect + distribute (+ marginal unless JT_SKIP_MARGINAL) */
+int jt_propagate(jt_plan* plan, const void* factor_tables, int factors_batched,
+                 const int32_t* evidence, int64_t B, int dtype, void* workspace, void* factor_out,
+                 int flags, void* stream);
+/* number of out-of-range evidence states seen by jt_init calls on this workspace since it was
+ * last zeroed (synchronises the stream) */
+int jt_evidence_errors(jt_plan* plan, int64_t B, int dtype, void* workspace, void* stream, int64_t* out);
+
+/*
+ * ---- single operator: the SumProduct surface (sum_product.py:14-35) ----
+ * out[s] = sum_r prod_j op_j[ A_j(s) + B_j(r) ], every operand and the output batch-innermost
+ * ([n][B]).  `tables` (host, int32) holds all index tables; per operand j the four table
+ * offsets are maps[4*j .. 4*j+3] = (a_hi, a_lo, b_hi, b_lo).  ops[j] are device pointers.
+ * "project" is the case of one operand, "absorb" the case n_r = 1.
+ */
+int jt_contract(const void* const* ops, int n_ops, const int32_t* tables, int64_t n_tab,
+                const int32_t* maps, int64_t n_s, int64_t n_r, int64_t n_slo, int64_t n_rlo,
+                int64_t B, int dtype, void* out, void* stream);
+
+/* Hugin separator ratio: out[i] = old[i] != 0 ? new[i] / old[i] : 0, n contiguous elements.
+ * (The propagation schedule itself is division-free; this serves SumProduct.absorb(old=...).) */
+int jt_ratio(const void* new_values, const void* old_values, void* out, int64_t n, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JT_B200_H */

@@ -1,0 +1,903 @@
+// libjt_b200: sm_100a kernels + C ABI for batched junction-tree sum-product propagation.
+// ABI and task semantics: include/jt_b200.h.  Schedule producer: junctiontree/schedule.py.
+//
+// Everything on this path is HBM-bound (2 flops per 8..16 bytes), so the kernels are built
+// around coalesced 16-byte accesses on the batch-innermost layout [entry][B]: a thread owns
+// VEC consecutive instances of one output index s and walks the remaining clique axes r;
+// all index arithmetic is table-driven, warp-uniform whenever the batch tile is >= 32 wide.
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/jt_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// error handling
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define JT_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(JT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// device-side descriptors
+
+struct DTask {
+    long long src, out, beta, bel, own;  // entry offsets, -1 = absent
+    int n_s, n_r, n_slo, n_rlo;
+    int src_shi, src_slo, src_rhi, src_rlo;
+    int rmsg_begin, rmsg_end, smsg_begin, smsg_end;
+    int kind, out_space;
+};
+
+struct DMsg {
+    long long off;    // entry offset (multiplied by B on the device)
+    long long eoff;   // element offset added as is (jt_contract operands; 0 inside a plan)
+    int a_hi, a_lo, b_hi, b_lo;
+    int fid, pad;
+};
+
+struct KArgs {
+    const DTask* tasks;   // first task of this launch
+    const DMsg* msgs;     // all messages of the plan
+    const int* tab;       // all index tables
+    const int* prefix;    // [n_tasks + 1] first block of each task for this launch / tile shape
+    void* work;
+    void* fout;
+    const void* fin;
+    const int* fbase;     // [F][B] per-instance factor base offsets, or null
+    long long B;          // instances (row pitch in elements)
+    long long Bv;         // B / VEC
+    int n_tasks;
+    int bx_log2;          // batch-tile width in vectors (log2)
+    int sy_log2;          // rows of s per block (log2)
+    int flags;
+    int fin_batched;
+};
+
+constexpr int kThreads = 256;
+constexpr int kMaxSyLog2 = 8;
+constexpr int kRegMsgs = 4;   // r-dependent messages kept in registers
+constexpr int kUnroll = 4;    // independent row loads in flight per thread
+
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) Pack {
+    T v[VEC];
+};
+
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> pack_fill(T x) {
+    Pack<T, VEC> p;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) p.v[i] = x;
+    return p;
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> ld(const T* p) {
+    return *reinterpret_cast<const Pack<T, VEC>*>(p);
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void st(T* p, const Pack<T, VEC>& x) {
+    *reinterpret_cast<Pack<T, VEC>*>(p) = x;
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void mul(Pack<T, VEC>& a, const Pack<T, VEC>& b) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) a.v[i] *= b.v[i];
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void add(Pack<T, VEC>& a, const Pack<T, VEC>& b) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) a.v[i] += b.v[i];
+}
+
+// Locate the task of this block and the output index s of this thread.
+__device__ __forceinline__ const DTask* locate(const KArgs& a, long long& s, long long& bv) {
+    const int tx = threadIdx.x & ((1 << a.bx_log2) - 1);
+    const int ty = threadIdx.x >> a.bx_log2;
+    bv = ((long long)blockIdx.y << a.bx_log2) + tx;
+    const int bid = blockIdx.x;
+    int lo = 0, hi = a.n_tasks;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a.prefix + mid) <= bid) lo = mid; else hi = mid;
+    }
+    s = ((long long)(bid - __ldg(a.prefix + lo)) << a.sy_log2) + ty;
+    return a.tasks + lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// evidence slicing (V1): per-instance base offset of every factor table
+//   fbase[f][b] = sum over observed axes k of factor f:  state[b][var_k] * stride_k
+// Pure integer arithmetic; out-of-range states are clamped and counted.
+
+__global__ void __launch_bounds__(kThreads)
+jt_evidence_kernel(const int* __restrict__ evidence, int n_evid, const int* __restrict__ ev_card,
+                   const int* __restrict__ evf_ptr, const int* __restrict__ evf_var,
+                   const int* __restrict__ evf_stride, int n_factors, long long B,
+                   int* __restrict__ fbase, unsigned long long* __restrict__ errors) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int* row = evidence + b * n_evid;
+    unsigned bad = 0;
+    for (int f = 0; f < n_factors; ++f) {
+        int acc = 0;
+        for (int k = evf_ptr[f]; k < evf_ptr[f + 1]; ++k) {
+            const int var = evf_var[k];
+            int state = row[var];
+            const int card = ev_card[var];
+            if (state < 0 || state >= card) {
+                ++bad;
+                state = state < 0 ? 0 : card - 1;
+            }
+            acc += state * evf_stride[k];
+        }
+        fbase[(long long)f * B + b] = acc;
+    }
+    if (bad) atomicAdd(errors, (unsigned long long)bad);
+}
+
+// ------------------------------------------------------------------------------------------
+// clique initialisation (E0 + V1): psi_C[s][b] = prod_f phi_f[ A_f(s) + fbase[f][b] ]
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
+    typedef Pack<T, VEC> P;
+    long long s, bv;
+    const DTask* tk = locate(a, s, bv);
+    if (s >= tk->n_s || bv >= a.Bv) return;
+    const int* __restrict__ tab = a.tab;
+    const long long B = a.B, col = bv * VEC;
+    const int n_slo = tk->n_slo;
+    int s_hi = 0, s_lo = (int)s;
+    if (n_slo < tk->n_s) {
+        s_hi = (int)(s / n_slo);
+        s_lo = (int)(s - (long long)s_hi * n_slo);
+    }
+    const T* __restrict__ fin = static_cast<const T*>(a.fin);
+    P val = pack_fill<T, VEC>(T(1));
+    for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
+        const DMsg* m = a.msgs + j;
+        const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+        if (a.fin_batched) {
+            mul(val, ld<T, VEC>(fin + idx * B + col));
+        } else if (a.fbase) {
+            const int* fb = a.fbase + (long long)m->fid * B + col;
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) val.v[u] *= __ldg(fin + idx + fb[u]);
+        } else {
+            const T x = __ldg(fin + idx);
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) val.v[u] *= x;
+        }
+    }
+    st<T, VEC>(static_cast<T*>(a.work) + (tk->out + s) * B + col, val);
+}
+
+// ------------------------------------------------------------------------------------------
+// projection task (collect E1+E2, distribute E3+E4+M1+E5, marginal E6, contract)
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
+    typedef Pack<T, VEC> P;
+    long long s, bv;
+    const DTask* tk = locate(a, s, bv);
+    const int n_s = tk->n_s;
+    if (s >= n_s || bv >= a.Bv) return;
+
+    const int* __restrict__ tab = a.tab;
+    const DMsg* __restrict__ msgs = a.msgs;
+    const long long B = a.B, col = bv * VEC;
+    T* work = static_cast<T*>(a.work);
+
+    const int n_slo = tk->n_slo;
+    int s_hi = 0, s_lo = (int)s;
+    if (n_slo < n_s) {
+        s_hi = (int)(s / n_slo);
+        s_lo = (int)(s - (long long)s_hi * n_slo);
+    }
+
+    // messages that do not depend on r, and the task's own up-message
+    P sm = pack_fill<T, VEC>(T(1));
+    for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
+        const DMsg* m = msgs + j;
+        const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+        mul(sm, ld<T, VEC>(work + m->eoff + idx * B + col));
+    }
+    const bool has_own = tk->own >= 0;
+    P own = pack_fill<T, VEC>(T(1));
+    if (has_own) own = ld<T, VEC>(work + (tk->own + s) * B + col);
+
+    // r-dependent messages: the first kRegMsgs are tracked in registers
+    const int rm0 = tk->rmsg_begin;
+    const int nr = tk->rmsg_end - rm0;
+    const T* mptr[kRegMsgs];
+    int mbhi[kRegMsgs], mblo[kRegMsgs];
+#pragma unroll
+    for (int j = 0; j < kRegMsgs; ++j) {
+        mptr[j] = work;
+        mbhi[j] = mblo[j] = 0;
+        if (j < nr) {
+            const DMsg* m = msgs + rm0 + j;
+            const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+            mptr[j] = work + m->eoff + idx * B + col;
+            mbhi[j] = m->b_hi;
+            mblo[j] = m->b_lo;
+        }
+    }
+
+    const bool has_src = tk->src >= 0;
+    const long long s_off = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo);
+    const T* sptr = work + ((has_src ? tk->src : 0) + s_off) * B + col;
+    const bool wbeta = tk->beta >= 0;
+    T* bptr = work + ((wbeta ? tk->beta : 0) + s_off) * B + col;
+    P scale = sm;
+    mul(scale, own);
+
+    const int n_rlo = tk->n_rlo;
+    const int n_rhi = tk->n_r / n_rlo;
+    const int* __restrict__ t_rhi = tab + tk->src_rhi;
+    const int* __restrict__ t_rlo = tab + tk->src_rlo;
+
+    P acc[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) acc[u] = pack_fill<T, VEC>(T(0));
+
+    for (int rh = 0; rh < n_rhi; ++rh) {
+        const long long e_hi = __ldg(t_rhi + rh);
+        long long mh[kRegMsgs];
+#pragma unroll
+        for (int j = 0; j < kRegMsgs; ++j) mh[j] = (j < nr) ? (long long)__ldg(tab + mbhi[j] + rh) : 0;
+
+        int rl = 0;
+        for (; rl + kUnroll <= n_rlo; rl += kUnroll) {
+            long long e[kUnroll];
+            P v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) e[u] = (e_hi + __ldg(t_rlo + rl + u)) * B;
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                v[u] = has_src ? ld<T, VEC>(sptr + e[u]) : pack_fill<T, VEC>(T(1));
+#pragma unroll
+            for (int j = 0; j < kRegMsgs; ++j) {
+                if (j < nr) {
+                    P w[kUnroll];
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u)
+                        w[u] = ld<T, VEC>(mptr[j] + (mh[j] + __ldg(tab + mblo[j] + rl + u)) * B);
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) mul(v[u], w[u]);
+                }
+            }
+            for (int j = kRegMsgs; j < nr; ++j) {   // rare: more than kRegMsgs r-dependent messages
+                const DMsg* m = msgs + rm0 + j;
+                const long long base = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo) +
+                                       __ldg(tab + m->b_hi + rh);
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u)
+                    mul(v[u], ld<T, VEC>(work + m->eoff + (base + __ldg(tab + m->b_lo + rl + u)) * B + col));
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) add(acc[u], v[u]);
+            if (wbeta) {
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    mul(v[u], scale);
+                    st<T, VEC>(bptr + e[u], v[u]);
+                }
+            }
+        }
+        for (; rl < n_rlo; ++rl) {
+            const long long e = (e_hi + __ldg(t_rlo + rl)) * B;
+            P v = has_src ? ld<T, VEC>(sptr + e) : pack_fill<T, VEC>(T(1));
+#pragma unroll
+            for (int j = 0; j < kRegMsgs; ++j)
+                if (j < nr) mul(v, ld<T, VEC>(mptr[j] + (mh[j] + __ldg(tab + mblo[j] + rl)) * B));
+            for (int j = kRegMsgs; j < nr; ++j) {
+                const DMsg* m = msgs + rm0 + j;
+                const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo) +
+                                      __ldg(tab + m->b_hi + rh) + __ldg(tab + m->b_lo + rl);
+                mul(v, ld<T, VEC>(work + m->eoff + idx * B + col));
+            }
+            add(acc[0], v);
+            if (wbeta) {
+                mul(v, scale);
+                st<T, VEC>(bptr + e, v);
+            }
+        }
+    }
+
+    if (tk->out >= 0) {
+        // pairwise combination of the partial sums
+        add(acc[0], acc[1]);
+        add(acc[2], acc[3]);
+        add(acc[0], acc[2]);
+        P o = acc[0];
+        mul(o, sm);
+        T* obase = tk->out_space ? static_cast<T*>(a.fout) : work;
+        st<T, VEC>(obase + (tk->out + s) * B + col, o);
+        if (tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS)) {
+            mul(o, own);
+            st<T, VEC>(work + (tk->bel + s) * B + col, o);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+jt_ratio_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T d = b[i];
+        out[i] = d != T(0) ? a[i] / d : T(0);
+    }
+}
+
+static_assert(kUnroll == 4, "the pairwise combination above assumes four partial sums");
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side
+
+struct jt_plan {
+    std::vector<int64_t> hdr, node_off, node_size, fin_off, fin_size, fout_off, fout_size;
+    std::vector<int> ev_card, evf_ptr, evf_var, evf_stride;
+    std::vector<DTask> tasks;
+    std::vector<DMsg> msgs;
+    std::vector<int> tab;
+    struct Launch {
+        int phase, begin, end, level;
+        size_t prefix_off[kMaxSyLog2 + 1];
+        long long blocks[kMaxSyLog2 + 1];
+    };
+    std::vector<Launch> launches;
+    std::vector<int> prefix;
+
+    int device = -1;
+    DTask* d_tasks = nullptr;
+    DMsg* d_msgs = nullptr;
+    int* d_tab = nullptr;
+    int* d_prefix = nullptr;
+    int* d_ev = nullptr;   // ev_card | evf_ptr | evf_var | evf_stride
+};
+
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t dtype_size(int dtype) { return dtype == JT_F64 ? 8 : 4; }
+
+struct WorkspaceLayout {
+    size_t work_bytes, fbase_off, err_off, total;
+};
+
+WorkspaceLayout workspace_layout(const jt_plan* p, int64_t B, int dtype) {
+    WorkspaceLayout w;
+    const int64_t entries = p->hdr[JT_H_CLIQUE_ENTRIES] + 3 * p->hdr[JT_H_SEP_ENTRIES];
+    w.work_bytes = align_up((size_t)entries * (size_t)B * dtype_size(dtype), 256);
+    w.fbase_off = w.work_bytes;
+    const size_t fbase = p->hdr[JT_H_NEVID] > 0 ? (size_t)p->hdr[JT_H_NFACTORS] * (size_t)B * 4 : 0;
+    w.err_off = w.fbase_off + align_up(fbase, 256);
+    w.total = w.err_off + 256;
+    return w;
+}
+
+int pick_vec(int64_t B, int dtype) {
+    const int maxv = dtype == JT_F64 ? 2 : 4;
+    for (int v = maxv; v > 1; v >>= 1)
+        if (B % v == 0) return v;
+    return 1;
+}
+
+// tile shape for a batch of Bv vectors: bx = min(256, pow2ceil(Bv)), sy = 256 / bx
+void pick_tile(long long Bv, int& bx_log2, int& sy_log2) {
+    bx_log2 = 0;
+    while ((1LL << bx_log2) < Bv && bx_log2 < 8) ++bx_log2;
+    sy_log2 = 8 - bx_log2;
+}
+
+template <typename T, int VEC>
+int launch_tasks(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
+    int bx_log2, sy_log2;
+    pick_tile(a.Bv, bx_log2, sy_log2);
+    a.bx_log2 = bx_log2;
+    a.sy_log2 = sy_log2;
+    a.tasks = p->d_tasks + L.begin;
+    a.n_tasks = L.end - L.begin;
+    a.prefix = p->d_prefix + L.prefix_off[sy_log2];
+    const long long gx = L.blocks[sy_log2];
+    const long long gy = (a.Bv + (1LL << bx_log2) - 1) >> bx_log2;
+    if (gx <= 0) return JT_OK;
+    if (gx > 2147483647LL || gy > 65535)
+        return fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
+    dim3 grid((unsigned)gx, (unsigned)gy, 1);
+    if (L.phase == JT_PHASE_INIT)
+        jt_init_kernel<T, VEC><<<grid, kThreads, 0, stream>>>(a);
+    else
+        jt_project_kernel<T, VEC><<<grid, kThreads, 0, stream>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    JT_CUDA(cudaGetLastError());
+    return JT_OK;
+}
+
+int dispatch(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec,
+             cudaStream_t stream) {
+    if (dtype == JT_F64) {
+        if (vec == 2) return launch_tasks<double, 2>(p, L, a, stream);
+        return launch_tasks<double, 1>(p, L, a, stream);
+    }
+    if (vec == 4) return launch_tasks<float, 4>(p, L, a, stream);
+    if (vec == 2) return launch_tasks<float, 2>(p, L, a, stream);
+    return launch_tasks<float, 1>(p, L, a, stream);
+}
+
+int check_common(const jt_plan* p, int64_t B, int dtype, const void* workspace) {
+    if (!p) return fail(JT_ERR_INVALID, "plan is null");
+    if (B <= 0) return fail(JT_ERR_INVALID, "batch size must be positive");
+    if (dtype != JT_F32 && dtype != JT_F64) return fail(JT_ERR_INVALID, "dtype must be JT_F32 or JT_F64");
+    if (!workspace) return fail(JT_ERR_INVALID, "workspace is null");
+    if (p->device < 0) return fail(JT_ERR_INVALID, "plan not uploaded: call jt_plan_upload first");
+    return JT_OK;
+}
+
+KArgs base_args(const jt_plan* p, int64_t B, int dtype, void* workspace, int vec) {
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.msgs = p->d_msgs;
+    a.tab = p->d_tab;
+    a.work = workspace;
+    a.B = B;
+    a.Bv = B / vec;
+    return a;
+}
+
+int run_phases(jt_plan* p, int64_t B, int dtype, void* workspace, int phase_lo, int phase_hi,
+               KArgs a, int vec, cudaStream_t stream) {
+    for (const auto& L : p->launches) {
+        if (L.phase < phase_lo || L.phase > phase_hi) continue;
+        int rc = dispatch(p, L, a, dtype, vec, stream);
+        if (rc != JT_OK) return rc;
+    }
+    return JT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jt_abi_version(void) { return JT_ABI_VERSION; }
+
+const char* jt_last_error_string(void) { return g_err; }
+
+int64_t jt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
+    if (!blob || !out) return fail(JT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (nbytes < JT_H_WORDS * 8 || nbytes % 8) return fail(JT_ERR_INVALID, "plan blob too short or misaligned");
+    const int64_t* w = static_cast<const int64_t*>(blob);
+    std::vector<int64_t> copy;
+    if (reinterpret_cast<uintptr_t>(blob) % 8) {   // tolerate unaligned input
+        copy.resize(nbytes / 8);
+        memcpy(copy.data(), blob, nbytes);
+        w = copy.data();
+    }
+    if (w[JT_H_MAGIC] != JT_MAGIC) return fail(JT_ERR_INVALID, "bad plan magic");
+    if (w[JT_H_VERSION] != JT_ABI_VERSION)
+        return fail(JT_ERR_INVALID, "plan version %lld, library expects %d", (long long)w[JT_H_VERSION], JT_ABI_VERSION);
+    for (int i = 2; i < JT_H_WORDS; ++i)
+        if (w[i] < 0) return fail(JT_ERR_INVALID, "negative header word %d", i);
+    jt_plan* p = new (std::nothrow) jt_plan;
+    if (!p) return fail(JT_ERR_NOMEM, "out of host memory");
+    p->hdr.assign(w, w + JT_H_WORDS);
+    const int64_t n_nodes = w[JT_H_NCLIQUES] + w[JT_H_NSEPS];
+    const int64_t F = w[JT_H_NFACTORS], n_evid = w[JT_H_NEVID], n_evf = w[JT_H_NEVF];
+    const int64_t n_tasks = w[JT_H_NTASKS], n_msgs = w[JT_H_NMSGS], n_launch = w[JT_H_NLAUNCHES];
+    const int64_t n_tab = w[JT_H_NTAB];
+    const int64_t evf_ptr_n = F > 0 ? F + 1 : 0;
+    const int64_t words = JT_H_WORDS + 2 * n_nodes + 4 * F + n_evid + evf_ptr_n + 2 * n_evf +
+                          n_tasks * JT_TASK_WORDS + n_msgs * JT_MSG_WORDS + n_launch * JT_LAUNCH_WORDS;
+    const int64_t tab_words = (n_tab + 1) / 2;
+    if ((int64_t)(nbytes / 8) != words + tab_words) {
+        delete p;
+        return fail(JT_ERR_INVALID, "plan blob size mismatch: %zu bytes, expected %lld", nbytes,
+                    (long long)(words + tab_words) * 8);
+    }
+    const int64_t* q = w + JT_H_WORDS;
+    auto take64 = [&](std::vector<int64_t>& v, int64_t n) { v.assign(q, q + n); q += n; };
+    auto take32 = [&](std::vector<int>& v, int64_t n) {
+        v.resize(n);
+        for (int64_t i = 0; i < n; ++i) v[i] = (int)q[i];
+        q += n;
+    };
+    take64(p->node_off, n_nodes);
+    take64(p->node_size, n_nodes);
+    take64(p->fin_off, F);
+    take64(p->fin_size, F);
+    take64(p->fout_off, F);
+    take64(p->fout_size, F);
+    take32(p->ev_card, n_evid);
+    take32(p->evf_ptr, evf_ptr_n);
+    take32(p->evf_var, n_evf);
+    take32(p->evf_stride, n_evf);
+
+    const int64_t work_entries = w[JT_H_CLIQUE_ENTRIES] + 3 * w[JT_H_SEP_ENTRIES];
+    auto bad = [&](const char* what, int64_t i) {
+        delete p;
+        return fail(JT_ERR_INVALID, "malformed plan: %s (item %lld)", what, (long long)i);
+    };
+    for (int64_t k = 0; k < n_evf; ++k)
+        if (p->evf_var[k] < 0 || p->evf_var[k] >= n_evid) return bad("evidence variable index", k);
+    for (int64_t f = 0; f + 1 < evf_ptr_n; ++f)
+        if (p->evf_ptr[f] > p->evf_ptr[f + 1] || p->evf_ptr[f + 1] > n_evf) return bad("evidence pointer", f);
+
+    p->tasks.resize(n_tasks);
+    for (int64_t i = 0; i < n_tasks; ++i, q += JT_TASK_WORDS) {
+        DTask& t = p->tasks[i];
+        t.src = q[JT_T_SRC]; t.out = q[JT_T_OUT]; t.beta = q[JT_T_BETA]; t.bel = q[JT_T_BEL]; t.own = q[JT_T_OWN];
+        if (q[JT_T_NS] <= 0 || q[JT_T_NS] > 2147483647LL || q[JT_T_NR] <= 0 || q[JT_T_NR] > 2147483647LL)
+            return bad("task index-space size", i);
+        t.n_s = (int)q[JT_T_NS]; t.n_r = (int)q[JT_T_NR]; t.n_slo = (int)q[JT_T_NSLO]; t.n_rlo = (int)q[JT_T_NRLO];
+        if (t.n_slo <= 0 || t.n_rlo <= 0 || t.n_s % t.n_slo || t.n_r % t.n_rlo) return bad("task table split", i);
+        t.src_shi = (int)q[JT_T_SRC_SHI]; t.src_slo = (int)q[JT_T_SRC_SLO];
+        t.src_rhi = (int)q[JT_T_SRC_RHI]; t.src_rlo = (int)q[JT_T_SRC_RLO];
+        t.rmsg_begin = (int)q[JT_T_RMSG_BEGIN]; t.rmsg_end = (int)q[JT_T_RMSG_END];
+        t.smsg_begin = (int)q[JT_T_SMSG_BEGIN]; t.smsg_end = (int)q[JT_T_SMSG_END];
+        t.kind = (int)q[JT_T_KIND]; t.out_space = (int)q[JT_T_OUT_SPACE];
+        if (t.rmsg_begin < 0 || t.rmsg_begin > t.rmsg_end || t.rmsg_end > n_msgs || t.smsg_begin < 0 ||
+            t.smsg_begin > t.smsg_end || t.smsg_end > n_msgs)
+            return bad("task message range", i);
+        const int n_shi = t.n_s / t.n_slo, n_rhi = t.n_r / t.n_rlo;
+        if (t.kind == JT_KIND_PROJECT) {
+            if (t.src_shi < 0 || t.src_shi + n_shi > n_tab || t.src_slo < 0 || t.src_slo + t.n_slo > n_tab ||
+                t.src_rhi < 0 || t.src_rhi + n_rhi > n_tab || t.src_rlo < 0 || t.src_rlo + t.n_rlo > n_tab)
+                return bad("task table range", i);
+        } else if (t.kind != JT_KIND_INIT) {
+            return bad("task kind", i);
+        }
+        for (long long off : {t.src, t.beta, t.bel, t.own})
+            if (off < -1 || off >= work_entries) return bad("task buffer offset", i);
+        if (t.out < -1) return bad("task output offset", i);
+        if (t.out_space == 0 && t.out >= work_entries) return bad("task output offset", i);
+        if (t.out_space == 1 && t.out + t.n_s > w[JT_H_FOUT_ENTRIES]) return bad("factor output range", i);
+    }
+    p->msgs.resize(n_msgs);
+    for (int64_t i = 0; i < n_msgs; ++i, q += JT_MSG_WORDS) {
+        DMsg& m = p->msgs[i];
+        m.off = q[JT_M_OFF];
+        m.a_hi = (int)q[JT_M_AHI]; m.a_lo = (int)q[JT_M_ALO]; m.b_hi = (int)q[JT_M_BHI]; m.b_lo = (int)q[JT_M_BLO];
+        m.fid = (int)q[JT_M_FID]; m.pad = 0; m.eoff = 0;
+        if (m.off < 0 || m.a_hi < 0 || m.a_lo < 0 || m.b_hi < 0 || m.b_lo < 0 || m.a_hi >= n_tab + 1 ||
+            m.a_lo >= n_tab + 1 || m.b_hi >= n_tab + 1 || m.b_lo >= n_tab + 1 || m.fid >= F)
+            return bad("message descriptor", i);
+    }
+    p->launches.resize(n_launch);
+    for (int64_t i = 0; i < n_launch; ++i, q += JT_LAUNCH_WORDS) {
+        jt_plan::Launch& L = p->launches[i];
+        L.phase = (int)q[JT_L_PHASE]; L.begin = (int)q[JT_L_BEGIN]; L.end = (int)q[JT_L_END]; L.level = (int)q[JT_L_LEVEL];
+        if (L.phase < JT_PHASE_INIT || L.phase > JT_PHASE_MARGINAL || L.begin < 0 || L.begin >= L.end || L.end > n_tasks)
+            return bad("launch descriptor", i);
+        for (int t = L.begin; t < L.end; ++t)
+            if ((p->tasks[t].kind == JT_KIND_INIT) != (L.phase == JT_PHASE_INIT)) return bad("task kind vs phase", i);
+        // block prefix per tile shape: a block covers 2^sy consecutive values of s of one task
+        for (int sy = 0; sy <= kMaxSyLog2; ++sy) {
+            L.prefix_off[sy] = p->prefix.size();
+            long long acc = 0;
+            for (int t = L.begin; t < L.end; ++t) {
+                p->prefix.push_back((int)acc);
+                acc += ((long long)p->tasks[t].n_s + (1 << sy) - 1) >> sy;
+                if (acc > 2147483647LL) return bad("launch too large", i);
+            }
+            p->prefix.push_back((int)acc);
+            L.blocks[sy] = acc;
+        }
+    }
+    const int32_t* tabp = reinterpret_cast<const int32_t*>(q);
+    p->tab.assign(tabp, tabp + n_tab);
+    *out = p;
+    return JT_OK;
+}
+
+void jt_plan_destroy(jt_plan* p) {
+    if (!p) return;
+    if (p->device >= 0) {
+        cudaFree(p->d_tasks);
+        cudaFree(p->d_msgs);
+        cudaFree(p->d_tab);
+        cudaFree(p->d_prefix);
+        cudaFree(p->d_ev);
+    }
+    delete p;
+}
+
+int jt_plan_query(const jt_plan* p, int what, int64_t* out) {
+    if (!p || !out || what < 0 || what >= JT_H_WORDS) return fail(JT_ERR_INVALID, "bad query");
+    *out = p->hdr[what];
+    return JT_OK;
+}
+
+int jt_plan_node_range(const jt_plan* p, int node, int64_t* offset, int64_t* count) {
+    if (!p || node < 0 || node >= (int)p->node_off.size()) return fail(JT_ERR_INVALID, "bad node index");
+    if (offset) *offset = p->node_off[node];
+    if (count) *count = p->node_size[node];
+    return JT_OK;
+}
+
+int jt_plan_message_offsets(const jt_plan* p, int node, int64_t* up, int64_t* down) {
+    if (!p) return fail(JT_ERR_INVALID, "plan is null");
+    const int64_t n_c = p->hdr[JT_H_NCLIQUES];
+    if (node < n_c || node >= (int64_t)p->node_off.size()) return fail(JT_ERR_INVALID, "not a separator node");
+    const int64_t rel = p->node_off[node] - p->hdr[JT_H_CLIQUE_ENTRIES];
+    const int64_t up_base = p->hdr[JT_H_CLIQUE_ENTRIES] + p->hdr[JT_H_SEP_ENTRIES];
+    if (up) *up = up_base + rel;
+    if (down) *down = up_base + p->hdr[JT_H_SEP_ENTRIES] + rel;
+    return JT_OK;
+}
+
+int jt_workspace_bytes(const jt_plan* p, int64_t B, int dtype, size_t* out) {
+    if (!p || !out || B <= 0 || (dtype != JT_F32 && dtype != JT_F64)) return fail(JT_ERR_INVALID, "bad argument");
+    *out = workspace_layout(p, B, dtype).total;
+    return JT_OK;
+}
+
+int jt_plan_upload(jt_plan* p) {
+    if (!p) return fail(JT_ERR_INVALID, "plan is null");
+    int dev = -1;
+    JT_CUDA(cudaGetDevice(&dev));
+    if (p->device == dev) return JT_OK;
+    if (p->device >= 0) return fail(JT_ERR_INVALID, "plan already uploaded to device %d", p->device);
+    auto up = [](auto** dst, const auto& v) -> cudaError_t {
+        const size_t bytes = v.size() * sizeof(v[0]);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), bytes ? bytes : 16);
+        if (e != cudaSuccess || !bytes) return e;
+        return cudaMemcpy(*dst, v.data(), bytes, cudaMemcpyHostToDevice);
+    };
+    JT_CUDA(up(&p->d_tasks, p->tasks));
+    JT_CUDA(up(&p->d_msgs, p->msgs));
+    JT_CUDA(up(&p->d_tab, p->tab));
+    JT_CUDA(up(&p->d_prefix, p->prefix));
+    std::vector<int> ev;
+    ev.insert(ev.end(), p->ev_card.begin(), p->ev_card.end());
+    ev.insert(ev.end(), p->evf_ptr.begin(), p->evf_ptr.end());
+    ev.insert(ev.end(), p->evf_var.begin(), p->evf_var.end());
+    ev.insert(ev.end(), p->evf_stride.begin(), p->evf_stride.end());
+    JT_CUDA(up(&p->d_ev, ev));
+    p->device = dev;
+    return JT_OK;
+}
+
+int jt_init(jt_plan* p, const void* factor_tables, int factors_batched, const int32_t* evidence, int64_t B,
+            int dtype, void* workspace, void* stream_) {
+    int rc = check_common(p, B, dtype, workspace);
+    if (rc != JT_OK) return rc;
+    if (p->hdr[JT_H_NFACTORS] == 0) return fail(JT_ERR_INVALID, "plan has no factors: nothing to initialise");
+    if (!factor_tables) return fail(JT_ERR_INVALID, "factor_tables is null");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const WorkspaceLayout wl = workspace_layout(p, B, dtype);
+    const int n_evid = (int)p->hdr[JT_H_NEVID];
+    const int vec = pick_vec(B, dtype);
+    KArgs a = base_args(p, B, dtype, workspace, vec);
+    a.fin = factor_tables;
+    a.fin_batched = factors_batched ? 1 : 0;
+    if (n_evid > 0) {
+        if (!evidence) return fail(JT_ERR_INVALID, "plan has %d evidence variables but evidence is null", n_evid);
+        if (factors_batched) return fail(JT_ERR_INVALID, "per-instance factor tables cannot be combined with evidence indices");
+        int* fbase = reinterpret_cast<int*>(static_cast<char*>(workspace) + wl.fbase_off);
+        unsigned long long* err = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + wl.err_off);
+        const int F = (int)p->hdr[JT_H_NFACTORS];
+        const int* d_card = p->d_ev;
+        const int* d_ptr = d_card + p->ev_card.size();
+        const int* d_var = d_ptr + p->evf_ptr.size();
+        const int* d_stride = d_var + p->evf_var.size();
+        const long long blocks = (B + kThreads - 1) / kThreads;
+        jt_evidence_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(evidence, n_evid, d_card, d_ptr, d_var,
+                                                                      d_stride, F, B, fbase, err);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        JT_CUDA(cudaGetLastError());
+        a.fbase = fbase;
+    }
+    return run_phases(p, B, dtype, workspace, JT_PHASE_INIT, JT_PHASE_INIT, a, vec, stream);
+}
+
+int jt_collect(jt_plan* p, int64_t B, int dtype, void* workspace, void* stream) {
+    int rc = check_common(p, B, dtype, workspace);
+    if (rc != JT_OK) return rc;
+    const int vec = pick_vec(B, dtype);
+    return run_phases(p, B, dtype, workspace, JT_PHASE_COLLECT, JT_PHASE_COLLECT,
+                      base_args(p, B, dtype, workspace, vec), vec, static_cast<cudaStream_t>(stream));
+}
+
+int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, void* stream) {
+    int rc = check_common(p, B, dtype, workspace);
+    if (rc != JT_OK) return rc;
+    const int vec = pick_vec(B, dtype);
+    KArgs a = base_args(p, B, dtype, workspace, vec);
+    a.flags = flags;
+    return run_phases(p, B, dtype, workspace, JT_PHASE_DIST_PRE, JT_PHASE_DIST_MAIN, a, vec,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int jt_marginal(jt_plan* p, int64_t B, int dtype, void* workspace, void* factor_out, void* stream) {
+    int rc = check_common(p, B, dtype, workspace);
+    if (rc != JT_OK) return rc;
+    if (!factor_out) return fail(JT_ERR_INVALID, "factor_out is null");
+    const int vec = pick_vec(B, dtype);
+    KArgs a = base_args(p, B, dtype, workspace, vec);
+    a.fout = factor_out;
+    return run_phases(p, B, dtype, workspace, JT_PHASE_MARGINAL, JT_PHASE_MARGINAL, a, vec,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int jt_propagate(jt_plan* p, const void* factor_tables, int factors_batched, const int32_t* evidence, int64_t B,
+                 int dtype, void* workspace, void* factor_out, int flags, void* stream) {
+    int rc = jt_init(p, factor_tables, factors_batched, evidence, B, dtype, workspace, stream);
+    if (rc != JT_OK) return rc;
+    rc = jt_collect(p, B, dtype, workspace, stream);
+    if (rc != JT_OK) return rc;
+    rc = jt_distribute(p, B, dtype, workspace, flags, stream);
+    if (rc != JT_OK) return rc;
+    if (flags & JT_SKIP_MARGINAL) return JT_OK;
+    return jt_marginal(p, B, dtype, workspace, factor_out, stream);
+}
+
+int jt_evidence_errors(jt_plan* p, int64_t B, int dtype, void* workspace, void* stream, int64_t* out) {
+    int rc = check_common(p, B, dtype, workspace);
+    if (rc != JT_OK) return rc;
+    if (!out) return fail(JT_ERR_INVALID, "out is null");
+    const WorkspaceLayout wl = workspace_layout(p, B, dtype);
+    unsigned long long v = 0;
+    JT_CUDA(cudaMemcpyAsync(&v, static_cast<char*>(workspace) + wl.err_off, sizeof(v), cudaMemcpyDeviceToHost,
+                            static_cast<cudaStream_t>(stream)));
+    JT_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    *out = (int64_t)v;
+    return JT_OK;
+}
+
+int jt_ratio(const void* new_values, const void* old_values, void* out, int64_t n, int dtype, void* stream_) {
+    if (!new_values || !old_values || !out || n < 0) return fail(JT_ERR_INVALID, "bad argument");
+    if (dtype != JT_F32 && dtype != JT_F64) return fail(JT_ERR_INVALID, "dtype must be JT_F32 or JT_F64");
+    if (n == 0) return JT_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    long long blocks = (n + kThreads - 1) / kThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (dtype == JT_F64)
+        jt_ratio_kernel<double><<<(unsigned)blocks, kThreads, 0, stream>>>(
+            static_cast<const double*>(new_values), static_cast<const double*>(old_values),
+            static_cast<double*>(out), n);
+    else
+        jt_ratio_kernel<float><<<(unsigned)blocks, kThreads, 0, stream>>>(
+            static_cast<const float*>(new_values), static_cast<const float*>(old_values),
+            static_cast<float*>(out), n);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    JT_CUDA(cudaGetLastError());
+    return JT_OK;
+}
+
+int jt_contract(const void* const* ops, int n_ops, const int32_t* tables, int64_t n_tab, const int32_t* maps,
+                int64_t n_s, int64_t n_r, int64_t n_slo, int64_t n_rlo, int64_t B, int dtype, void* out,
+                void* stream_) {
+    if (!ops || n_ops <= 0 || !tables || !maps || !out) return fail(JT_ERR_INVALID, "null argument");
+    if (n_s <= 0 || n_r <= 0 || n_slo <= 0 || n_rlo <= 0 || n_s % n_slo || n_r % n_rlo || n_s > 2147483647LL ||
+        n_r > 2147483647LL || B <= 0 || n_tab <= 0)
+        return fail(JT_ERR_INVALID, "bad index-space sizes");
+    if (dtype != JT_F32 && dtype != JT_F64) return fail(JT_ERR_INVALID, "dtype must be JT_F32 or JT_F64");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t w = dtype_size(dtype);
+    const int n_shi = (int)(n_s / n_slo), n_rhi = (int)(n_r / n_rlo);
+    for (int j = 0; j < n_ops; ++j) {
+        const int32_t* m = maps + 4 * j;
+        if (m[0] < 0 || m[0] + n_shi > n_tab || m[1] < 0 || m[1] + n_slo > n_tab || m[2] < 0 ||
+            m[2] + n_rhi > n_tab || m[3] < 0 || m[3] + n_rlo > n_tab)
+            return fail(JT_ERR_INVALID, "operand %d: table range", j);
+    }
+    int vec = pick_vec(B, dtype);
+    auto misaligned = [&](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % (w * vec) != 0; };
+    while (vec > 1) {
+        bool bad = misaligned(out);
+        for (int j = 0; j < n_ops; ++j) bad = bad || misaligned(ops[j]);
+        if (!bad) break;
+        vec >>= 1;
+    }
+    // device scratch: [DTask | DMsg x n_ops | prefix(2) | tables]
+    const size_t msg_off = align_up(sizeof(DTask), 16);
+    const size_t prefix_off = align_up(msg_off + sizeof(DMsg) * n_ops, 16);
+    const size_t tab_off = align_up(prefix_off + 2 * sizeof(int), 16);
+    const size_t total = tab_off + (size_t)n_tab * 4;
+    std::vector<char> host(total, 0);
+    int bx_log2, sy_log2;
+    pick_tile(B / vec, bx_log2, sy_log2);
+    DTask t;
+    memset(&t, 0, sizeof(t));
+    t.src = t.beta = t.bel = t.own = -1;
+    t.out = 0;
+    t.n_s = (int)n_s; t.n_r = (int)n_r; t.n_slo = (int)n_slo; t.n_rlo = (int)n_rlo;
+    // no src operand: point the (unused) src maps at operand 0's tables so every read is in range
+    t.src_shi = maps[0]; t.src_slo = maps[1]; t.src_rhi = maps[2]; t.src_rlo = maps[3];
+    t.rmsg_begin = 0; t.rmsg_end = n_ops; t.smsg_begin = t.smsg_end = n_ops;
+    t.kind = JT_KIND_PROJECT; t.out_space = 1;
+    memcpy(host.data(), &t, sizeof(t));
+    const char* out_c = static_cast<const char*>(out);
+    for (int j = 0; j < n_ops; ++j) {
+        DMsg m;
+        memset(&m, 0, sizeof(m));
+        const ptrdiff_t delta = static_cast<const char*>(ops[j]) - out_c;
+        if (delta % (ptrdiff_t)w) return fail(JT_ERR_INVALID, "operand %d misaligned relative to out", j);
+        m.eoff = delta / (ptrdiff_t)w;
+        m.a_hi = maps[4 * j]; m.a_lo = maps[4 * j + 1]; m.b_hi = maps[4 * j + 2]; m.b_lo = maps[4 * j + 3];
+        m.fid = -1;
+        memcpy(host.data() + msg_off + sizeof(DMsg) * j, &m, sizeof(m));
+    }
+    const long long blocks = ((long long)n_s + (1 << sy_log2) - 1) >> sy_log2;
+    int prefix[2] = {0, (int)blocks};
+    memcpy(host.data() + prefix_off, prefix, sizeof(prefix));
+    memcpy(host.data() + tab_off, tables, (size_t)n_tab * 4);
+    char* dev = nullptr;
+    JT_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dev), total, stream));
+    cudaError_t e = cudaMemcpyAsync(dev, host.data(), total, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(dev, stream);
+        return fail(JT_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+    }
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tasks = reinterpret_cast<const DTask*>(dev);
+    a.msgs = reinterpret_cast<const DMsg*>(dev + msg_off);
+    a.prefix = reinterpret_cast<const int*>(dev + prefix_off);
+    a.tab = reinterpret_cast<const int*>(dev + tab_off);
+    a.work = out;   // operands are addressed relative to `out` (DMsg::eoff)
+    a.fout = out;
+    a.B = B;
+    a.Bv = B / vec;
+    a.n_tasks = 1;
+    a.bx_log2 = bx_log2;
+    a.sy_log2 = sy_log2;
+    const long long gy = (a.Bv + (1LL << bx_log2) - 1) >> bx_log2;
+    int rc = JT_OK;
+    if (blocks > 2147483647LL || gy > 65535) {
+        rc = fail(JT_ERR_INVALID, "launch grid exceeds CUDA limits; split the batch");
+    } else {
+        dim3 grid((unsigned)blocks, (unsigned)gy, 1);
+        if (dtype == JT_F64) {
+            if (vec == 2) jt_project_kernel<double, 2><<<grid, kThreads, 0, stream>>>(a);
+            else jt_project_kernel<double, 1><<<grid, kThreads, 0, stream>>>(a);
+        } else {
+            if (vec == 4) jt_project_kernel<float, 4><<<grid, kThreads, 0, stream>>>(a);
+            else if (vec == 2) jt_project_kernel<float, 2><<<grid, kThreads, 0, stream>>>(a);
+            else jt_project_kernel<float, 1><<<grid, kThreads, 0, stream>>>(a);
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(JT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    cudaFreeAsync(dev, stream);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+"""Device execution of a compiled schedule: memory, streams and stage calls.
+
+PyTorch is used for device memory, streams and (optionally) ``torch.distributed``; all compute
+goes through the C ABI of ``libjt_b200.so`` (``_native.py``).  Buffers use the batch-innermost
+layout ``[entry, B]`` (see ``include/jt_b200.h``).
+"""
+
+import numpy as np
+
+from . import _native
+from . import schedule as sch
+
+_torch = None
+
+
+def torch():
+    """Import torch lazily (the host-side compile must work without it being initialised)."""
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+def require_cuda():
+    t = torch()
+    if not t.cuda.is_available():
+        raise _native.NativeError(
+            "no CUDA device: junctiontree (B200 build) has no CPU execution path")
+    return t
+
+
+def torch_dtype(dtype):
+    t = torch()
+    return {np.dtype(np.float64): t.float64, np.dtype(np.float32): t.float32}[np.dtype(dtype)]
+
+
+class Engine:
+    """Runs one :class:`schedule.Plan` on the current CUDA device."""
+
+    def __init__(self, plan):
+        self.plan = plan
+        self.dev = _native.DevicePlan(plan.to_blob())
+        self._workspaces = {}
+
+    # -----------------------------------------------------------------------------------------
+    # memory
+
+    def workspace(self, B, dtype):
+        """uint8 tensor holding ``[work_entries, B]`` values plus the evidence scratch.
+
+        One workspace per (B, dtype) is cached; callers running several streams allocate their
+        own with :meth:`new_workspace`."""
+        key = (int(B), np.dtype(dtype).str)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            ws = self.new_workspace(B, dtype)
+            self._workspaces[key] = ws
+        return ws
+
+    def new_workspace(self, B, dtype):
+        t = require_cuda()
+        self.dev.upload()
+        nbytes = self.dev.workspace_bytes(B, dtype)
+        ws = t.empty(nbytes, dtype=t.uint8, device="cuda")
+        ws[-256:].zero_()   # evidence error counter
+        return ws
+
+    def release(self):
+        self._workspaces.clear()
+
+    def work_view(self, ws, B, dtype):
+        """``[work_entries, B]`` typed view of a workspace."""
+        n = self.plan.work_entries
+        itemsize = np.dtype(dtype).itemsize
+        return ws[: n * B * itemsize].view(torch_dtype(dtype)).view(n, B)
+
+    def evidence_offsets_view(self, ws, B, dtype):
+        """int32 ``[n_factors, B]`` per-instance factor base offsets written by ``jt_init``
+        (workspace layout: include/jt_b200.h)."""
+        t = torch()
+        work_bytes = self.plan.work_entries * B * np.dtype(dtype).itemsize
+        start = (work_bytes + 255) // 256 * 256
+        F = len(self.plan.factors)
+        return ws[start:start + F * B * 4].view(t.int32).view(F, B)
+
+    def factors_to_device(self, values, dtype, B=None):
+        """Concatenate factor tables in plan order.
+
+        ``values[f]`` has the factor's stored shape (shared by the batch) or ``[B, *shape]``
+        (per-instance tables; all factors must then be per-instance).
+        Returns ``(tensor, batched)``.
+        """
+        t = require_cuda()
+        plan = self.plan
+        tdt = torch_dtype(dtype)
+        arrays = [np.asarray(v) if not t.is_tensor(v) else v for v in values]
+        if len(arrays) != len(plan.factors):
+            raise ValueError("expected %d factor arrays, got %d" % (len(plan.factors), len(arrays)))
+        batched = [a.ndim == len(shape) + 1 for a, shape in zip(arrays, plan.fin_shape)]
+        if any(batched) and not all(batched):
+            raise ValueError("either all factor arrays carry a leading batch axis or none does")
+        if all(batched) and arrays:
+            if B is None:
+                B = arrays[0].shape[0]
+            flat = t.empty((plan.fin_entries, B), dtype=tdt, device="cuda")
+            for f, a in enumerate(arrays):
+                if list(a.shape) != [B] + plan.fin_shape[f]:
+                    raise ValueError("factor %d: expected shape %s, got %s"
+                                     % (f, [B] + plan.fin_shape[f], list(a.shape)))
+                dev = t.as_tensor(a).to(device="cuda", dtype=tdt, non_blocking=True)
+                flat[plan.fin_off[f]:plan.fin_off[f] + plan.fin_size[f]] = dev.reshape(B, -1).t()
+            return flat, True
+        host = np.empty(plan.fin_entries, dtype=np.dtype(dtype))
+        for f, a in enumerate(arrays):
+            if t.is_tensor(a):
+                a = a.detach().cpu().numpy()
+            if list(a.shape) != plan.fin_shape[f]:
+                raise ValueError("factor %d: expected shape %s, got %s"
+                                 % (f, plan.fin_shape[f], list(a.shape)))
+            host[plan.fin_off[f]:plan.fin_off[f] + plan.fin_size[f]] = a.reshape(-1)
+        return t.from_numpy(host).to("cuda"), False
+
+    def evidence_to_device(self, evidence, B):
+        t = require_cuda()
+        n_ev = len(self.plan.evidence_vars)
+        if n_ev == 0:
+            return None
+        if evidence is None:
+            raise ValueError("the plan has evidence variables %r but no evidence was given"
+                             % (self.plan.evidence_vars,))
+        if t.is_tensor(evidence):
+            ev = evidence.to(device="cuda", dtype=t.int32).contiguous()
+        else:
+            ev = t.from_numpy(np.ascontiguousarray(evidence, dtype=np.int32)).to("cuda")
+        if tuple(ev.shape) != (B, n_ev):
+            raise ValueError("evidence must have shape [%d, %d], got %s" % (B, n_ev, tuple(ev.shape)))
+        return ev
+
+    # -----------------------------------------------------------------------------------------
+    # stages
+
+    @staticmethod
+    def _stream():
+        return torch().cuda.current_stream().cuda_stream
+
+    def propagate(self, factor_dev, batched, evidence_dev, B, dtype, ws=None, sep_beliefs=False,
+                  marginal=True):
+        """init + collect + distribute (+ marginal).  Returns ``(ws, factor_out)``; ``factor_out``
+        is a ``[fout_entries, B]`` tensor (``None`` when ``marginal`` is False)."""
+        t = require_cuda()
+        self.dev.upload()
+        if ws is None:
+            ws = self.workspace(B, dtype)
+        fout = None
+        flags = (_native.JT_SEP_BELIEFS if sep_beliefs else 0)
+        if marginal:
+            fout = t.empty((self.plan.fout_entries, B), dtype=torch_dtype(dtype), device="cuda")
+        else:
+            flags |= _native.JT_SKIP_MARGINAL
+        self.dev.propagate(factor_dev.data_ptr(), batched,
+                           evidence_dev.data_ptr() if evidence_dev is not None else None,
+                           B, dtype, ws.data_ptr(), fout.data_ptr() if fout is not None else None,
+                           flags, self._stream())
+        return ws, fout
+
+    def beliefs_from_potentials(self, work, B, dtype, ws, sep_beliefs=True):
+        """collect + distribute on clique potentials already stored in the workspace."""
+        self.dev.upload()
+        stream = self._stream()
+        self.dev.collect(B, dtype, ws.data_ptr(), stream)
+        self.dev.distribute(B, dtype, ws.data_ptr(), _native.JT_SEP_BELIEFS if sep_beliefs else 0, stream)
+
+    # -----------------------------------------------------------------------------------------
+    # views of results
+
+    def node_tensor(self, ws, node, B, dtype):
+        """Node ``node`` (clique or separator belief) as a ``[B, *shape]`` view."""
+        work = self.work_view(ws, B, dtype)
+        off, n = self.plan.node_off[node], self.plan.node_size[node]
+        shape = tuple(self.plan.node_shape[node])
+        return work[off:off + n].view(shape + (B,)).movedim(-1, 0)
+
+    def factor_tensor(self, fout, f, B):
+        off, n = self.plan.fout_off[f], self.plan.fout_size[f]
+        shape = tuple(self.plan.fout_shape[f])
+        return fout[off:off + n].view(shape + (B,)).movedim(-1, 0)
+
+
+def make_plan(tree, node_vars, sizes, factors=None, factor_to_clique=None, evidence_vars=(),
+              full_sizes=None):
+    return sch.Plan(tree, node_vars, sizes, factors, factor_to_clique, evidence_vars, full_sizes)

@@ -1,0 +1,306 @@
+"""
+User interface of the junction tree library (B200 build).
+
+Mirror of ``/root/reference/junctiontree/junctiontree.py``: ``create_junction_tree`` (``:12-16``),
+``FactorGraph`` (``:83-117``), ``CliqueGraph`` (``:120-274``) and ``JunctionTree`` (``:277-331``)
+keep their names, attributes and call signatures.  Compilation stays on the host
+(``construction.py``); ``evaluate`` / ``propagate`` / ``marginalize`` run on the GPU through the
+compiled schedule (``schedule.py`` -> ``libjt_b200.so``).  ``propagate_batch`` is new: many
+independent propagations over the same tree per launch, with per-instance evidence.
+"""
+
+import numpy as np
+import attr
+
+from . import computation as comp
+from . import construction as cons
+from . import engine as eng
+from . import schedule as sch
+
+
+def create_junction_tree(factors, sizes, order=None):
+    """Create a Junction tree for a given factor graph.
+
+    ``order`` (optional, new) is an elimination order over the variables; the default is
+    min-fill.  Grid-like models need a sweep order to reach their treewidth."""
+    assert all(type(l) == list for l in factors), "Provided factor is not a list"
+    fg = FactorGraph(factors=factors, sizes=sizes)
+    return fg.triangulate(order=order).create_junction_tree()
+
+
+def einsum(xs, xs_keys, y_keys):
+    """Product of ``xs`` (axes ``xs_keys``) summed to ``y_keys``, arbitrary keys; keys that only
+    occur in the output become size-1 axes (reference ``junctiontree.py:34-80``).  Runs on the
+    device through the sum-product plugin."""
+    xs = [np.asarray(x) for x in xs]
+    xs_keys = [list(k) for k in xs_keys]
+    present = set(k for keys in xs_keys for k in keys)
+    missing = [k for k in y_keys if k not in present]
+    if xs:
+        xs[0] = np.reshape(xs[0], len(missing) * (1,) + np.shape(xs[0]))
+        xs_keys[0] = missing + xs_keys[0]
+    args = [arg for pair in zip(xs, xs_keys) for arg in pair] + [list(y_keys)]
+    return comp.sum_product.einsum(*args)
+
+
+@attr.s(frozen=True)
+class FactorGraph():
+    """A graph containing a set of nodes that each contain a set of variables.
+
+    Each variable has a corresponding size associated to it.
+    """
+
+    # Axis variables in each factor
+    factors = attr.ib()
+
+    # Size of each axis
+    sizes = attr.ib()
+
+    def triangulate(self, order=None):
+        """Create a triangulated clique tree from a factor graph."""
+        (_, maxcliques, factor_to_maxclique) = cons.find_triangulation(
+            self.factors,
+            self.sizes,
+            order
+        )
+        return CliqueGraph(
+            maxcliques=maxcliques,
+            factor_to_maxclique=factor_to_maxclique,
+            factor_graph=self,
+        )
+
+
+def _effective_sizes(factors, xs, batched=False):
+    """Variable sizes as found in the factor arrays (the reference derives all clique shapes
+    from the arrays and only the throw-away separator ones from ``sizes``,
+    ``junctiontree.py:311-315``)."""
+    sizes = {}
+    for f, (fv, x) in enumerate(zip(factors, xs)):
+        shape = tuple(np.shape(x))[1:] if batched else tuple(np.shape(x))
+        if len(shape) != len(fv):
+            raise ValueError("factor %d has variables %r but its array has shape %s" % (f, fv, shape))
+        for var, n in zip(fv, shape):
+            if sizes.setdefault(var, int(n)) != int(n):
+                raise ValueError("variable %r has size %d in one factor array and %d in another"
+                                 % (var, sizes[var], n))
+    return sizes
+
+
+@attr.s(frozen=False)
+class CliqueGraph():
+    """
+    Clique graph for an underlying factor graph.
+    """
+
+    # Axis variables in each maximal clique
+    maxcliques = attr.ib()
+
+    # Maximal clique for each factor (multiple factors can belong to the same
+    # maximal clique)
+    factor_to_maxclique = attr.ib()
+
+    # The underlying factor graph
+    factor_graph = attr.ib()
+
+    _engines = attr.ib(factory=dict, init=False, repr=False, eq=False)
+
+    def create_junction_tree(self):
+        """Create a Junction tree from a triangulated clique tree."""
+        (tree, separators) = cons.construct_junction_tree(
+            self.maxcliques,
+            self.factor_graph.sizes
+        )
+        return JunctionTree(
+            tree=tree,
+            separators=separators,
+            clique_tree=self
+        )
+
+    def _f2c(self):
+        f2c = self.factor_to_maxclique
+        return [f2c[i] for i in range(len(self.factor_graph.factors))]   # list or dict (reference D13)
+
+    def _engine(self, sizes, tree=None, separators=(), evidence_vars=(), full_sizes=None):
+        key = (tuple(sizes.get(v) for c in self.maxcliques for v in c), tree is not None,
+               tuple(evidence_vars), tuple(tuple(c) for c in self.maxcliques), tuple(self._f2c()))
+        hit = self._engines.get(key)
+        if hit is None:
+            node_vars = list(self.maxcliques) + ([list(s) for s in separators] if tree is not None else [])
+            plan = sch.Plan(tree, node_vars, sizes, self.factor_graph.factors, self._f2c(),
+                            evidence_vars, full_sizes)
+            hit = eng.Engine(plan)
+            self._engines[key] = hit
+        return hit
+
+    def evaluate(self, xs):
+        """Compute maximum clique values based on factor values.
+
+        GPU stage ``jt_init``.  Unlike the reference (``junctiontree.py:52-61``) a clique
+        variable that none of the assigned factors covers keeps its full size instead of
+        becoming a size-1 axis; the values are the same under broadcasting."""
+        t = eng.require_cuda()
+        sizes = dict(self.factor_graph.sizes)
+        sizes.update(_effective_sizes(self.factor_graph.factors, xs))
+        engine = self._engine(sizes)
+        plan = engine.plan
+        dtype = _result_dtype(xs)
+        fdev, _ = engine.factors_to_device(xs, dtype)
+        ws = engine.workspace(1, dtype)
+        engine.dev.upload()
+        engine.dev.init(fdev.data_ptr(), False, None, 1, dtype, ws.data_ptr(), engine._stream())
+        flat = engine.work_view(ws, 1, dtype)[:plan.clique_entries, 0].cpu().numpy()
+        return [
+            flat[plan.node_off[c]:plan.node_off[c] + plan.node_size[c]].reshape(tuple(plan.node_shape[c])).copy()
+            for c in range(plan.n_cliques)
+        ]
+
+    def marginalize(self, ys):
+        """Marginalize results for maxcliques to results for factors
+
+        For each factor, take the maxclique it belongs to and sum out the axes that don't belong
+        to the factor; axes come out in the factor's own order (reference
+        ``junctiontree.py:229-274``).  GPU stage ``jt_marginal``.
+        """
+        t = eng.require_cuda()
+        ys = [np.asarray(y) for y in ys]
+        sizes = dict(self.factor_graph.sizes)
+        for cv, y in zip(self.maxcliques, ys):
+            for var, n in zip(cv, y.shape):
+                sizes[var] = int(n)
+        engine = self._engine(sizes)
+        plan = engine.plan
+        dtype = _result_dtype(ys)
+        ws = engine.workspace(1, dtype)
+        work = engine.work_view(ws, 1, dtype)
+        host = np.empty(plan.clique_entries, dtype)
+        for c, y in enumerate(ys):
+            host[plan.node_off[c]:plan.node_off[c] + plan.node_size[c]] = \
+                np.broadcast_to(y, tuple(plan.node_shape[c])).reshape(-1)
+        work[:plan.clique_entries, 0].copy_(t.from_numpy(host))
+        fout = t.empty((plan.fout_entries, 1), dtype=eng.torch_dtype(dtype), device="cuda")
+        engine.dev.upload()
+        engine.dev.marginal(1, dtype, ws.data_ptr(), fout.data_ptr(), engine._stream())
+        flat = fout[:, 0].cpu().numpy()
+        return [
+            flat[plan.fout_off[f]:plan.fout_off[f] + plan.fout_size[f]].reshape(tuple(plan.fout_shape[f])).copy()
+            for f in range(len(plan.factors))
+        ]
+
+
+def _result_dtype(arrays):
+    """float32 only when every input is float32; otherwise float64 (the reference's float64
+    separators promote everything, ``junctiontree.py:311-315``)."""
+    kinds = [np.asarray(a).dtype for a in arrays]
+    if kinds and all(k == np.float32 for k in kinds):
+        return np.dtype(np.float32)
+    return np.dtype(np.float64)
+
+
+@attr.s(frozen=True)
+class JunctionTree():
+    """
+    Junction tree for an underlying factor graph.
+    """
+
+    # Tree data structure
+    #
+    # (cliqueID, (separatorID, subtree), (separatorID, subtree), ...)
+    tree = attr.ib()
+
+    # Tuple of axis vars in each separator
+    #
+    # ( (var3, var1), (var2, var1), (var2) )
+    separators = attr.ib()
+
+    # The underlying triangulated clique graph
+    clique_tree = attr.ib()
+
+    def _engine(self, sizes, evidence_vars=(), full_sizes=None):
+        return self.clique_tree._engine(sizes, self.tree, self.separators, evidence_vars, full_sizes)
+
+    def plan(self, evidence_vars=(), sizes=None):
+        """The compiled schedule for the current variable sizes (``schedule.Plan``)."""
+        full = dict(self.clique_tree.factor_graph.sizes) if sizes is None else dict(sizes)
+        eff = dict(full)
+        for v in evidence_vars:
+            eff[v] = 1
+        return self._engine(eff, evidence_vars, full).plan
+
+    def propagate(self, xs, dtype=None):
+        """Run belief propagation on the Junction tree.
+
+        :param xs: one array per factor (shape = sizes of the factor's variables; an observed
+                   variable is conditioned on by slicing its axis to length 1, reference
+                   ``README.md:148-166``)
+        :return: one array per factor with the same shape: the consistent (unnormalised)
+                 clique belief summed down to the factor's variables (reference
+                 ``junctiontree.py:297-331``)
+        """
+        fg = self.clique_tree.factor_graph
+        sizes = dict(fg.sizes)
+        sizes.update(_effective_sizes(fg.factors, xs))
+        engine = self._engine(sizes)
+        dtype = np.dtype(dtype) if dtype is not None else _result_dtype(xs)
+        fdev, _ = engine.factors_to_device(xs, dtype)
+        _, fout = engine.propagate(fdev, False, None, 1, dtype)
+        plan = engine.plan
+        flat = fout[:, 0].cpu().numpy()
+        return [
+            flat[plan.fout_off[f]:plan.fout_off[f] + plan.fout_size[f]].reshape(tuple(plan.fout_shape[f])).copy()
+            for f in range(len(plan.factors))
+        ]
+
+    def propagate_batch(self, xs, evidence_vars=(), evidence=None, batch=None, dtype=None,
+                        nodes=False, device_output=False):
+        """Many independent propagations over this tree in one pass.
+
+        :param xs: factor tables shared by the whole batch (stored shapes, observed axes at full
+                   size), or per-instance tables with a leading batch axis ``[B, *shape]``
+        :param evidence_vars: variables observed in every instance
+        :param evidence: int array ``[B, len(evidence_vars)]`` of observed states; equivalent to
+                         ``apply_evidence`` / slicing ``e:e+1`` per instance
+        :param batch: batch size when neither ``evidence`` nor batched ``xs`` determine it
+        :param nodes: also return the clique and separator beliefs (node order
+                      ``maxcliques + separators``)
+        :param device_output: return CUDA tensors (views of the batch-innermost buffers) instead
+                              of NumPy arrays
+        :return: list of ``[B, *factor_shape]`` arrays (observed axes have length 1); with
+                 ``nodes=True`` a pair ``(factor_outputs, node_beliefs)``
+        """
+        t = eng.require_cuda()
+        fg = self.clique_tree.factor_graph
+        evidence_vars = list(evidence_vars)
+        per_instance = bool(xs) and np.ndim(xs[0]) == len(fg.factors[0]) + 1
+        full = dict(fg.sizes)
+        full.update(_effective_sizes(fg.factors, xs, batched=per_instance))
+        eff = dict(full)
+        for v in evidence_vars:
+            eff[v] = 1
+        engine = self._engine(eff, evidence_vars, full)
+        plan = engine.plan
+        dtype = np.dtype(dtype) if dtype is not None else _result_dtype(xs)
+        if evidence is not None:
+            B = int(evidence.shape[0])
+        elif per_instance:
+            B = int(np.shape(xs[0])[0])
+        elif batch is not None:
+            B = int(batch)
+        else:
+            raise ValueError("batch size unknown: give evidence, batched tables or batch=")
+        fdev, batched = engine.factors_to_device(xs, dtype, B)
+        edev = engine.evidence_to_device(evidence, B)
+        ws, fout = engine.propagate(fdev, batched, edev, B, dtype, sep_beliefs=nodes)
+        if edev is not None:
+            bad = engine.dev.evidence_errors(B, dtype, ws.data_ptr(), engine._stream())
+            if bad:
+                ws[-256:].zero_()
+                raise ValueError("%d evidence states are outside the range of their variable" % bad)
+        outs = [engine.factor_tensor(fout, f, B) for f in range(len(plan.factors))]
+        node_out = None
+        if nodes:
+            node_out = [engine.node_tensor(ws, k, B, dtype) for k in range(len(plan.node_vars))]
+        if not device_output:
+            outs = [o.cpu().numpy() for o in outs]
+            if nodes:
+                node_out = [o.cpu().numpy() for o in node_out]
+        return (outs, node_out) if nodes else outs

@@ -159,7 +159,8 @@ class _Space:
 class Plan:
     """Compiled schedule.  See the module docstring for the task semantics.
 
-    :param tree: nested tree ``[clique, (sep, subtree), ...]`` (reference ``README.md:52-70``)
+    :param tree: nested tree ``[clique, (sep, subtree), ...]`` (reference ``README.md:52-70``),
+                 or ``None`` for a bare clique graph (init and marginal stages only)
     :param node_vars: ``maxcliques + separators`` variable lists (reference
                       ``junctiontree.py:317-323``); axis order of every node is taken from here
     :param sizes: ``{var: size}`` effective sizes (1 for observed variables)
@@ -187,9 +188,17 @@ class Plan:
     # -----------------------------------------------------------------------------------------
 
     def _compile(self):
-        order, parent, parent_sep, depth, children = cons.tree_edges(self.tree)
-        cliques = sorted(order)
         n_nodes = len(self.node_vars)
+        if self.tree is None:
+            # clique graph without a tree: only the init and marginal stages are scheduled
+            order = list(range(n_nodes))
+            parent = {c: -1 for c in order}
+            parent_sep = {c: -1 for c in order}
+            depth = {c: 0 for c in order}
+            children = {c: [] for c in order}
+        else:
+            order, parent, parent_sep, depth, children = cons.tree_edges(self.tree)
+        cliques = sorted(order)
         self.n_cliques = len(cliques)
         if cliques != list(range(self.n_cliques)):
             raise ValueError("clique ids in the tree must be 0..N-1 (node_list = cliques + separators)")
@@ -199,7 +208,7 @@ class Plan:
             raise ValueError("separator ids in the tree must be N..N+S-1, each used once")
         self.order, self.parent, self.parent_sep, self.depth, self.children = \
             order, parent, parent_sep, depth, children
-        self.root = order[0]
+        self.root = order[0] if self.tree is not None else -1
         self.max_depth = max(depth.values()) if depth else 0
 
         for c in order:
@@ -452,7 +461,7 @@ class Plan:
     def algorithmic_entries(self, with_init=True):
         """Entries moved per instance by the minimal two-pass schedule:
         4*sum(n_C) - n_root + 6*sum(n_S)  (3*sum(n_C) without the init write)."""
-        n_root = self.node_size[self.root] if self.n_cliques else 0
+        n_root = self.node_size[self.root] if self.root >= 0 else 0
         return (4 if with_init else 3) * self.clique_entries - n_root + 6 * self.sep_entries
 
     def header(self):
@@ -467,7 +476,7 @@ class Plan:
         h[H_NTASKS], h[H_NMSGS], h[H_NLAUNCHES] = len(self.tasks_arr), len(self.msgs_arr), len(self.launches_arr)
         h[H_MAXDEPTH] = self.max_depth
         h[H_NEVF] = len(self.evf_var)
-        h[H_ROOT_ENTRIES] = self.node_size[self.root] if self.n_cliques else 0
+        h[H_ROOT_ENTRIES] = self.node_size[self.root] if self.root >= 0 else 0
         return h
 
     def to_blob(self):
@@ -491,7 +500,7 @@ class Plan:
             "cliques": self.n_cliques, "separators": self.n_seps,
             "clique_entries": self.clique_entries, "sep_entries": self.sep_entries,
             "max_clique": max(self.node_size[:self.n_cliques]) if self.n_cliques else 0,
-            "root_entries": int(self.node_size[self.root]) if self.n_cliques else 0,
+            "root_entries": int(self.node_size[self.root]) if self.root >= 0 else 0,
             "depth": self.max_depth, "tasks": len(self.tasks_arr), "launches": len(self.launches_arr),
             "table_entries": int(self.tables.size),
             "algorithmic_entries": self.algorithmic_entries(),

@@ -1,0 +1,47 @@
+"""Shared helpers for the test-suite (golden vectors, network compilation, comparisons)."""
+
+import json
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN_JSON = os.path.join(HERE, "golden", "reference_golden.json")
+GOLDEN_NPZ = os.path.join(HERE, "golden", "reference_golden.npz")
+
+# tolerances stated by BASELINE.json's north_star
+RTOL_F64 = 1e-12
+RTOL_F32 = 1e-5
+
+
+def load_golden():
+    with open(GOLDEN_JSON) as fh:
+        meta = json.load(fh)
+    arrays = np.load(GOLDEN_NPZ)
+    return meta["cases"], arrays
+
+
+def tuplify(tree):
+    """JSON nested lists -> the reference's tree format [clique, (sep, subtree), ...]."""
+    return [tree[0]] + [(s, tuplify(t)) for s, t in tree[1:]]
+
+
+def assert_close(got, want, rtol, what=""):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, "%s: shape %s vs %s" % (what, got.shape, want.shape)
+    scale = np.max(np.abs(want)) if want.size else 0.0
+    # relative error on every entry; entries that are tiny relative to the array (cancellation
+    # in signed test data) are compared against the array scale
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol * scale * 1e-3, err_msg=what)
+
+
+def compile_net(net, with_evidence=True):
+    """(tree, separators, maxcliques, factor_to_clique, effective sizes, evidence_vars)."""
+    from junctiontree import construction as cons
+    _, mc, f2c = cons.find_triangulation(net["factors"], net["sizes"], net.get("order"))
+    tree, seps = cons.construct_junction_tree(mc, net["sizes"])
+    evars = list(net.get("evidence_vars", [])) if with_evidence else []
+    eff = dict(net["sizes"])
+    for v in evars:
+        eff[v] = 1
+    return tree, seps, mc, f2c, eff, evars

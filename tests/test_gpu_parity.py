@@ -1,0 +1,309 @@
+"""GPU parity tests: the sm_100a path (through the C ABI) against the oracles.
+
+Tolerances are BASELINE.json's: relative 1e-12 (float64) / 1e-5 (float32) on every clique and
+separator potential and on every per-factor output; evidence slicing and index maps bit-exact.
+"""
+
+import numpy as np
+import pytest
+
+import jt_workloads as wl
+from helpers import RTOL_F32, RTOL_F64, assert_close, compile_net, load_golden, tuplify
+
+pytestmark = pytest.mark.gpu
+
+
+def _nets():
+    return [
+        wl.sprinkler(), wl.huang_darwiche(), wl.wisconsin(),
+        wl.random_dag(12, 3, 2, 3, 8, 5), wl.random_dag(16, 3, 2, 4, 6, 11),
+        wl.ising(4), wl.large_state_tree((4, 6, 8, 4, 6, 8)),
+    ]
+
+
+def _oracle(tree, net, evars, ev, B):
+    from oracle import ref_fixed
+    ct = tree.clique_tree
+    return ref_fixed.propagate_batch(tree.tree, tree.separators, ct.maxcliques, ct.factor_to_maxclique,
+                                     net["factors"], net["sizes"], net["values"], evars, ev, n=B)
+
+
+@pytest.mark.parametrize("net", _nets(), ids=lambda n: n["name"])
+@pytest.mark.parametrize("B", [1, 3, 8, 70])
+def test_batched_propagation_f64(net, B):
+    import junctiontree as jt
+    tree = jt.create_junction_tree(net["factors"], net["sizes"], order=net.get("order"))
+    evars = net.get("evidence_vars", [])
+    ev = wl.draw_evidence(net, B) if evars else None
+    outs, nodes = tree.propagate_batch(net["values"], evars, ev, batch=B, nodes=True)
+    want_f, want_n = _oracle(tree, net, evars, ev, B)
+    for k, (g, w) in enumerate(zip(nodes, want_n)):
+        assert_close(g, w, RTOL_F64, "node %d" % k)
+    for f, (g, w) in enumerate(zip(outs, want_f)):
+        assert_close(g, w, RTOL_F64, "factor %d" % f)
+
+
+@pytest.mark.parametrize("net", _nets(), ids=lambda n: n["name"])
+@pytest.mark.parametrize("B", [1, 6, 64])
+def test_batched_propagation_f32(net, B):
+    """float32 pipeline vs the float64 oracle on float32-rounded inputs."""
+    import junctiontree as jt
+    net = dict(net)
+    net["values"] = [np.asarray(v, np.float32) for v in net["values"]]
+    tree = jt.create_junction_tree(net["factors"], net["sizes"], order=net.get("order"))
+    evars = net.get("evidence_vars", [])
+    ev = wl.draw_evidence(net, B) if evars else None
+    outs, nodes = tree.propagate_batch(net["values"], evars, ev, batch=B, nodes=True)
+    assert all(o.dtype == np.float32 for o in outs)
+    net64 = dict(net)
+    net64["values"] = [np.asarray(v, np.float64) for v in net["values"]]
+    want_f, want_n = _oracle(tree, net64, evars, ev, B)
+    for k, (g, w) in enumerate(zip(nodes, want_n)):
+        assert_close(g, w, RTOL_F32, "node %d" % k)
+    for f, (g, w) in enumerate(zip(outs, want_f)):
+        assert_close(g, w, RTOL_F32, "factor %d" % f)
+
+
+def test_per_instance_factor_tables():
+    """Leading batch axis on the factor arrays: every instance has its own tables."""
+    import junctiontree as jt
+    from oracle import ref_fixed
+    net = wl.random_dag(10, 3, 2, 3, 8, 3)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    B = 10
+    rng = np.random.default_rng(7)
+    vals = [rng.random((B,) + v.shape) + 0.05 for v in net["values"]]
+    outs, nodes = tree.propagate_batch(vals, nodes=True)
+    ct = tree.clique_tree
+    for b in range(B):
+        fo, ys = ref_fixed.propagate(tree.tree, tree.separators, ct.maxcliques, ct.factor_to_maxclique,
+                                     net["factors"], net["sizes"], [v[b] for v in vals])
+        for k, y in enumerate(ys):
+            assert_close(nodes[k][b], y, RTOL_F64, "node %d instance %d" % (k, b))
+        for f, o in enumerate(fo):
+            assert_close(outs[f][b], o, RTOL_F64, "factor %d instance %d" % (f, b))
+
+
+def test_golden_end_to_end_vs_reference():
+    """propagate() through our own host compile against the unmodified reference's outputs."""
+    import junctiontree as jt
+    cases, arrays = load_golden()
+    n = 0
+    for case in cases:
+        if case["kind"] != "end_to_end":
+            continue
+        values = [arrays[k] for k in case["values"]]
+        tree = jt.create_junction_tree(case["factors"], dict(case["sizes"]))
+        outs = tree.propagate(values)      # sliced arrays carry the conditioning
+        for f, key in enumerate(case["outputs"]):
+            if case["outputs_valid"][f]:
+                assert_close(outs[f], arrays[key], RTOL_F64, "%s factor %d" % (case["name"], f))
+                n += 1
+    assert n >= 40
+
+
+def test_golden_compute_beliefs_on_reference_trees():
+    """compute_beliefs on the trees the reference built (its axis orders), vs its outputs."""
+    from junctiontree import computation as comp
+    cases, arrays = load_golden()
+    n = 0
+    for case in cases:
+        if "beliefs" not in case:
+            continue
+        if case["kind"] == "operator":
+            pots = [arrays[k] for k in case["potentials"]]
+            node_vars = case["variables"]
+        else:
+            node_vars = case["maxcliques"] + case["separators"]
+            sizes = dict(case["sizes"])
+            sizes.update({v: 1 for v in case["slices"]})
+            pots = [arrays[k] for k in case["psi"]] + \
+                   [np.ones(tuple(sizes[v] for v in s)) for s in case["separators"]]
+        got = comp.compute_beliefs(tuplify(case["tree"]), pots, node_vars)
+        for k, key in enumerate(case["beliefs"]):
+            if case["beliefs_valid"][k]:
+                want = arrays[key]
+                want = np.broadcast_to(want, got[k].shape) if want.shape != got[k].shape else want
+                assert_close(got[k], want, RTOL_F64, "%s node %d" % (case["name"], k))
+                n += 1
+    assert n >= 100
+
+
+def test_compute_beliefs_does_not_modify_inputs():
+    from junctiontree import computation as comp
+    rng = np.random.default_rng(0)
+    pots = [rng.standard_normal((2, 3)), rng.standard_normal((3, 4)), np.ones((3,))]
+    keep = [p.copy() for p in pots]
+    comp.compute_beliefs([0, (2, [1])], pots, [[3, 5], [5, 9], [5]])
+    for p, k in zip(pots, keep):
+        assert np.array_equal(p, k)
+
+
+def test_conditioned_readme_example():
+    """README conditioning flow (sizes mutated, arrays sliced; reference
+    tests/test_junctiontree.py:345-419) -- and the clique the reference gets wrong (D3)."""
+    import junctiontree as jt
+    from oracle import brute
+    net = wl.sprinkler()
+    tree = jt.create_junction_tree(net["factors"], dict(net["sizes"]))
+    tree.clique_tree.factor_graph.sizes["wet_grass"] = 1
+    vals = [v.copy() for v in net["values"]]
+    vals[3] = vals[3][:, :, 1:]
+    out = tree.propagate(vals)
+    marg = out[1].sum(axis=0)
+    np.testing.assert_allclose(marg / marg.sum(), [0.57024, 0.42976], atol=0.01)
+    truth = brute.joint_marginals(vals, net["factors"], net["factors"])
+    for f in range(4):
+        assert_close(out[f], truth[f], RTOL_F64, "factor %d" % f)
+    tree.clique_tree.factor_graph.sizes["rain"] = 1
+    vals[3] = vals[3][1:, :, :]
+    vals[2] = vals[2][:, 1:]
+    out = tree.propagate(vals)
+    marg = out[1].sum(axis=0)
+    np.testing.assert_allclose(marg / marg.sum(), [0.8055, 0.1945], atol=0.01)
+
+
+def test_evidence_slicing_is_bit_exact():
+    """Stage V1 + E0: per-instance factor offsets and the initial clique potentials equal NumPy
+    slicing exactly (integers and products of the same doubles in the same order)."""
+    import torch
+    import junctiontree as jt
+    from junctiontree import computation as comp
+    from oracle import plan_interp
+    net = wl.random_dag(14, 3, 2, 4, 8, 9)
+    B = 33
+    ev = wl.draw_evidence(net, B)
+    evars = net["evidence_vars"]
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    plan = tree.plan(evars)
+    engine = tree._engine(plan.sizes, evars, plan.full_sizes)
+    fdev, _ = engine.factors_to_device(net["values"], np.float64)
+    edev = engine.evidence_to_device(ev, B)
+    ws = engine.workspace(B, np.float64)
+    engine.dev.upload()
+    engine.dev.init(fdev.data_ptr(), False, edev.data_ptr(), B, np.float64, ws.data_ptr(), engine._stream())
+    torch.cuda.synchronize()
+    fbase = engine.evidence_offsets_view(ws, B, np.float64).cpu().numpy()
+    assert np.array_equal(fbase, plan_interp.evidence_offsets(plan, ev, B))
+    work = engine.work_view(ws, B, np.float64).cpu().numpy()
+    # reference semantics: apply_evidence slices, then evaluate multiplies the factors in order
+    for b in range(B):
+        sliced = [p[0] for p in comp.apply_evidence(net["values"], net["factors"],
+                                                    {v: int(ev[b, i]) for i, v in enumerate(evars)})]
+        for c in range(plan.n_cliques):
+            psi = np.ones(plan.node_shape[c])
+            for f in plan.clique_factors[c]:
+                axes = [plan.node_vars[c].index(v) for v in net["factors"][f]]
+                shape = [1] * len(plan.node_vars[c])
+                perm = np.argsort(axes)
+                arr = np.transpose(sliced[f], perm)
+                for ax, n in zip(sorted(axes), arr.shape):
+                    shape[ax] = n
+                psi = psi * arr.reshape(shape)
+            got = work[plan.node_off[c]:plan.node_off[c] + plan.node_size[c], b].reshape(plan.node_shape[c])
+            assert np.array_equal(got, psi), (b, c)
+
+
+def test_out_of_range_evidence_is_reported():
+    import junctiontree as jt
+    net = wl.random_dag(8, 2, 2, 3, 8, 1)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    ev = wl.draw_evidence(net, 4)
+    ev[2, 0] = 99
+    with pytest.raises(ValueError):
+        tree.propagate_batch(net["values"], net["evidence_vars"], ev)
+
+
+def test_evaluate_and_marginalize():
+    """CliqueGraph.evaluate / marginalize (reference tests/test_junctiontree.py:9-111)."""
+    import junctiontree as jt
+    rng = np.random.default_rng(3)
+    sizes = {"a": 2, "b": 3, "c": 4, "d": 5, "e": 6}
+    factors = [["a", "b"], ["b", "c"], ["c", "d"], ["a", "e"]]
+    g = jt.CliqueGraph(maxcliques=[["a", "b", "c"], ["a", "c", "d", "e"], ["a", "d", "e"]],
+                       factor_to_maxclique=[0, 0, 1, 2],
+                       factor_graph=jt.FactorGraph(factors=factors, sizes=sizes))
+    xs = [rng.standard_normal([sizes[v] for v in f]) for f in factors]
+    ys = g.evaluate(xs)
+    want = [np.einsum("ab,bc->abc", xs[0], xs[1]),
+            np.einsum("ae,cd->acde", [[1]], xs[2]),
+            np.einsum("d,ae->ade", [1], xs[3])]
+    for y, w in zip(ys, want):
+        np.testing.assert_allclose(y, np.broadcast_to(w, y.shape), rtol=RTOL_F64)
+    back = g.marginalize(ys)
+    assert_close(back[0], np.einsum("abc->ab", ys[0]), RTOL_F64)
+    assert_close(back[1], np.einsum("abc->bc", ys[0]), RTOL_F64)
+    assert_close(back[2], np.einsum("acde->cd", ys[1]), RTOL_F64)
+    assert_close(back[3], np.einsum("ade->ae", ys[2]), RTOL_F64)
+
+
+def test_sum_product_operator_surface():
+    """SumProduct.einsum / project / absorb on the device vs np.einsum."""
+    from junctiontree import computation as comp
+    rng = np.random.default_rng(5)
+    A, B_, C = rng.random((3, 4, 2)), rng.random((4, 2)), rng.random((3,))
+    sp = comp.sum_product
+    assert sp.on_device
+    assert_close(sp.einsum(A, ["a", "b", "c"], B_, ["b", "c"], ["b", "c"]),
+                 np.einsum("abc,bc->bc", A, B_), RTOL_F64)
+    assert_close(sp.einsum(A, [0, 1, 2], C, [0], []), np.einsum("abc,a->", A, C), RTOL_F64)
+    assert_close(sp.einsum(A, [0, 1, 2], C, [0], [2, 0]), np.einsum("abc,a->ca", A, C), RTOL_F64)
+    assert_close(sp.project(A, "abc", "ca"), np.einsum("abc->ca", A), RTOL_F64)
+    assert_close(sp.absorb(A, "abc", B_, "bc"), A * B_[None], RTOL_F64)
+    old = B_.copy()
+    old[1, 0] = 0.0
+    ratio = np.divide(B_, old, out=np.zeros_like(B_), where=old != 0)
+    assert_close(sp.absorb(A, "abc", B_, "bc", old=old), A * ratio[None], RTOL_F64)
+    # evidence shrinking equivalence, reference tests/test_computation.py:411-459
+    a = np.zeros(3)
+    a[2] = 1
+    upd = sp.einsum(A, [0, 1, 2], a, [0], [0, 1, 2])
+    assert_close(sp.einsum(upd, [0, 1, 2], B_, [1, 2], [1, 2]),
+                 sp.einsum(upd[2], [1, 2], B_, [1, 2], [1, 2]), RTOL_F64)
+    # diagonal and broadcast
+    M = rng.random((4, 4))
+    assert_close(sp.einsum(M, [0, 0], [0]), np.diagonal(M), RTOL_F64)
+    assert_close(sp.einsum(M, [0, 1], np.ones((1, 4)), [0, 1], [1]), M.sum(axis=0), RTOL_F64)
+
+
+def test_large_marginal_summation_accuracy():
+    """A 2^16-entry clique marginalised to one variable: long sums stay within 1e-12."""
+    import junctiontree as jt
+    from oracle import ref_fixed
+    net = wl.ising(4)
+    rng = np.random.default_rng(1)
+    factors = [["v%d" % i for i in range(16)], ["v0"]]
+    sizes = {"v%d" % i: 2 for i in range(16)}
+    values = [rng.random((2,) * 16) + 0.05, rng.random(2) + 0.05]
+    tree = jt.create_junction_tree(factors, sizes)
+    out = tree.propagate(values)
+    want = np.einsum(values[0], list(range(16)), values[1], [0], [0], dtype=np.longdouble)
+    assert_close(out[1], np.asarray(want, np.float64), RTOL_F64)
+
+
+def test_properties_at_scale_dag37():
+    """Config 2 shape at a reduced batch: size-independent invariants on every instance --
+    every node sums to the same Z, neighbouring nodes agree on separator marginals."""
+    import junctiontree as jt
+    net = wl.dag37()
+    B = 256
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    ev = wl.draw_evidence(net, B)
+    outs, nodes = tree.propagate_batch(net["values"], net["evidence_vars"], ev, nodes=True)
+    plan = tree.plan(net["evidence_vars"])
+    Z = nodes[0].reshape(B, -1).sum(axis=1)
+    for k, nd in enumerate(nodes):
+        np.testing.assert_allclose(nd.reshape(B, -1).sum(axis=1), Z, rtol=1e-11, err_msg="node %d" % k)
+    for c in plan.order:
+        for sep, child in plan.children[c]:
+            for clique in (c, child):
+                cv, sv = plan.node_vars[clique], plan.node_vars[sep]
+                axes = tuple(1 + i for i, v in enumerate(cv) if v not in sv)
+                marg = nodes[clique].sum(axis=axes)
+                kept = [v for v in cv if v in sv]
+                marg = np.transpose(marg, [0] + [1 + kept.index(v) for v in sv])
+                np.testing.assert_allclose(marg, nodes[sep], rtol=1e-11)
+    # and a sample of instances against the oracle
+    want_f, _ = _oracle(tree, net, net["evidence_vars"], ev[:4], 4)
+    for f, w in enumerate(want_f):
+        assert_close(outs[f][:4], w, RTOL_F64, "factor %d" % f)

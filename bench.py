@@ -1,0 +1,386 @@
+"""Benchmark: batched junction-tree propagations/sec on B200 (contract: see DESIGN.md section 6).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3              # our arm (sm_100a kernels)
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1   # CPU reference arm
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W        # N > 1, weak scaling
+
+A step is one pass of the hot path (evidence slicing + clique initialisation + collect +
+distribute, all clique and separator beliefs written) over one batch of synthetic evidence for
+BASELINE.json configs[1]: the 37-node random DAG, 65,536 instances per GPU, float64.  One JSON
+line is printed by rank 0.
+"""
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "junction-tree_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import jt_workloads as wl  # noqa: E402
+
+METRIC = "batched propagations/sec (collect+distribute)"
+UNIT = "propagations/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_net(name):
+    if name == "dag37":
+        return wl.dag37()
+    if name == "dag500":
+        return wl.dag500()
+    if name == "ising16":
+        return wl.ising(16)
+    if name == "large_state_tree":
+        return wl.large_state_tree()
+    if name == "sprinkler":
+        return wl.sprinkler()
+    raise SystemExit("unknown --config %s" % name)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        while self.ok and not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.handle, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.02)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (the oracle port of the reference's NumPy path; the reference itself cannot build the
+# valid trees these configs need -- SURVEY.md 0.4 -- and does not travel to the GPU box)
+
+_CPU = {}
+
+
+def _cpu_setup(name):
+    from junctiontree import construction as cons
+    net = make_net(name)
+    _, mc, f2c = cons.find_triangulation(net["factors"], net["sizes"], net.get("order"))
+    tree, seps = cons.construct_junction_tree(mc, net["sizes"])
+    _CPU.update(net=net, mc=mc, f2c=f2c, tree=tree, seps=seps)
+
+
+def _cpu_work(ev_rows):
+    from oracle import ref_fixed
+    net = _CPU["net"]
+    outs, _ = ref_fixed.propagate_batch(_CPU["tree"], _CPU["seps"], _CPU["mc"], _CPU["f2c"], net["factors"],
+                                        net["sizes"], net["values"], net.get("evidence_vars", []), ev_rows,
+                                        n=len(ev_rows))
+    return float(sum(o.sum() for o in outs))
+
+
+def cpu_throughput(name, per_core, repeats=1, pool=None):
+    """props/s of oracle/ref_fixed.py over all host cores on a bounded sample."""
+    import multiprocessing as mp
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    cores = os.cpu_count() or 1
+    net = make_net(name)
+    own_pool = pool is None
+    if own_pool:
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_setup, initargs=(name,))
+    try:
+        n = per_core * cores
+        ev = wl.draw_evidence(net, n) if net.get("evidence_vars") else np.zeros((n, 0), np.int32)
+        chunks = [ev[i::cores] for i in range(cores)]
+        pool.map(_cpu_work, [c[:1] for c in chunks])          # warm-up: imports, first einsum paths
+        best = None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_cpu_work, chunks)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    finally:
+        if own_pool:
+            pool.close()
+            pool.join()
+    return n / best, cores, n, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_setup, initargs=(args.config,))
+    try:
+        for _ in range(args.warmup):
+            cpu_throughput(args.config, 1, pool=pool)
+        times, n = [], 0
+        for _ in range(args.steps):
+            value, cores, n, dt = cpu_throughput(args.config, args.cpu_per_core, pool=pool)
+            times.append(dt)
+    finally:
+        pool.close()
+        pool.join()
+    ms = 1e3 * float(np.mean(times))
+    value = n / (ms / 1e3)
+    sample = "%d instances per step (%d per core) of %s through oracle/ref_fixed.py, %d processes" % (
+        n, args.cpu_per_core, args.config, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    return "configs[1]: random 37-node DAG (<=4 parents, 2-4 states, window 8, seed 0), evidence on the " \
+           "8 highest-numbered variables, %d instances per GPU" % args.batch if args.config == "dag37" \
+        else "%s, %d instances per GPU" % (args.config, args.batch)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+
+
+def run_gpu(args):
+    import torch
+    import junctiontree as jt
+    from junctiontree import _native, distributed as jdist
+
+    rank, world = jdist.init_from_env("nccl")
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    import torch.distributed as dist
+    dev = torch.cuda.current_device()
+    dtype = np.dtype(np.float64 if args.dtype == "f64" else np.float32)
+    w = dtype.itemsize
+
+    net = make_net(args.config)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"], order=net.get("order"))
+    evars = [] if args.no_evidence else list(net.get("evidence_vars", []))
+    plan = tree.plan(evars)
+    engine = tree._engine(plan.sizes, evars, plan.full_sizes)
+    B = args.batch                                   # per GPU (weak scaling)
+    ev_all = wl.draw_evidence(net, B * world) if evars else None
+    lo, hi = jdist.shard_bounds(B * world, world, rank)
+    ev_host = torch.from_numpy(ev_all[lo:hi].copy()).pin_memory() if evars else None
+
+    fdev, batched = engine.factors_to_device(net["values"], dtype)
+    ev_dev = ev_host.to("cuda") if evars else None
+    ws = engine.workspace(B, dtype)
+    engine.dev.upload()
+    fout = torch.empty((plan.fout_entries, B), dtype=engine_dtype(dtype), device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    ev_ptr = ev_dev.data_ptr() if evars else None
+    flags = _native.JT_SEP_BELIEFS
+
+    def hot_path(events=None):
+        if events is not None:
+            events[0].record()
+        engine.dev.init(fdev.data_ptr(), batched, ev_ptr, B, dtype, ws.data_ptr(), stream)
+        if events is not None:
+            events[1].record()
+        engine.dev.collect(B, dtype, ws.data_ptr(), stream)
+        engine.dev.distribute(B, dtype, ws.data_ptr(), flags, stream)
+        if events is not None:
+            events[2].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        hot_path()
+    barrier()
+
+    # ---- timed region: exactly K steps, device-timed, max over ranks ----
+    sampler = ClockSampler(dev)
+    sampler.start()
+    launches0 = _native.launch_count()
+    ev_pairs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for k in range(args.steps):
+        hot_path(ev_pairs[k])
+    t_end.record()
+    barrier()
+    launches = _native.launch_count() - launches0
+    clocks = sampler.finish()
+    total_ms = t_start.elapsed_time(t_end)
+    init_ms = sum(e[0].elapsed_time(e[1]) for e in ev_pairs)
+    msg_ms = sum(e[1].elapsed_time(e[2]) for e in ev_pairs)
+
+    # ---- end to end through the public API: pinned host evidence in, per-factor beliefs out ----
+    pipe = engine.pipeline(B, dtype, chunk=args.chunk)
+    out_host = pipe.host_output()
+    for _ in range(2):
+        pipe.run(fdev, batched, ev_host, out_host)
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l_e2e0 = _native.launch_count()
+    e0.record()
+    for _ in range(e2e_steps):
+        pipe.run(fdev, batched, ev_host, out_host)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    e2e_launches = _native.launch_count() - l_e2e0
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        tns = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    total_ms, init_ms, msg_ms, e2e_ms = (max_over_ranks(x) for x in (total_ms, init_ms, msg_ms, e2e_ms))
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+
+    ms_per_step = total_ms / args.steps
+    value = B * world / (ms_per_step / 1e3)
+    peak, peak_src = load_peaks()
+    # algorithmic bytes: A = w(4 sum n_C - n_root + 6 sum n_S) per instance;
+    # the message-passing kernel moves everything but the init write (w * sum n_C)
+    A = w * plan.algorithmic_entries(with_init=True)
+    A_msg = w * plan.algorithmic_entries(with_init=False)
+    msg_launches = sum(1 for L in plan.launches_arr if L[0] in (1, 2, 3))
+    msg_ms_per_launch = msg_ms / args.steps / max(msg_launches, 1)
+    achieved = A_msg * B / (msg_ms / args.steps / 1e3) / 1e9
+    step_gbs = A * B / (ms_per_step / 1e3) / 1e9
+
+    cpu = None
+    if not args.skip_cpu:
+        v, cores, n, dt = cpu_throughput(args.config, args.cpu_per_core)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d instances of the same workload (%d per core, %.1f s) through oracle/ref_fixed.py "
+                         "(NumPy restatement of the reference), %d processes" % (n, args.cpu_per_core, dt, cores)}
+
+    e2e_value = B * world / (e2e_ms / e2e_steps / 1e3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {
+            "workload": workload_name(args), "batch_per_gpu": B, "global_batch": B * world,
+            "parallelism": "batch-sharded x%d, no data-path collective" % world,
+            "cliques": plan.n_cliques, "clique_entries": plan.clique_entries, "sep_entries": plan.sep_entries,
+            "levels": plan.max_depth, "algorithmic_bytes_per_propagation": A,
+            "step": "evidence slicing + clique init + collect + distribute (clique and separator beliefs)",
+            "l2": "inputs larger than L2 (working set %.1f GB per GPU)" % (plan.work_entries * B * w / 1e9),
+            "step_gbs_algorithmic": step_gbs, "init_ms_per_step": init_ms / args.steps,
+            "message_passing_ms_per_step": msg_ms / args.steps,
+        },
+        "roofline": {
+            "bound": "hbm", "kernel": "jt_project_kernel<%s,%d>" % ("double" if w == 8 else "float",
+                                                                     pick_vec(B, w)),
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": peak_src, "traffic": None,
+            "launches_per_step": msg_launches, "avg_launch_ms": msg_ms_per_launch,
+            "algorithmic_bytes_per_launch": A_msg * B / max(msg_launches, 1),
+        },
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(ev_host.numel() * 4) if evars else 0,
+                "d2h_bytes_per_step": int(plan.fout_entries * B * w),
+                "ms_per_step": e2e_ms / e2e_steps, "chunk": pipe.chunk,
+                "what": "tree-level streaming API: pinned int32 evidence -> device, propagate incl. "
+                        "marginalisation to factor scopes, per-factor beliefs -> pinned host"},
+        "gpu_launches": int(launches),
+        "gpu_launches_e2e": int(e2e_launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+
+
+def pick_vec(B, w):
+    for v in ((2,) if w == 8 else (4, 2)):
+        if B % v == 0:
+            return v
+    return 1
+
+
+def engine_dtype(dtype):
+    from junctiontree import engine as eng
+    return eng.torch_dtype(dtype)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="dag37")
+    ap.add_argument("--batch", type=int, default=65536, help="instances per GPU")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--chunk", type=int, default=16384, help="instances per pipeline chunk (e2e)")
+    ap.add_argument("--no-evidence", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-per-core", type=int, default=256, help="CPU baseline: instances per core")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,12 @@ int jt_contract(const void* const* ops, int n_ops, const int32_t* tables, int64_
                 const int32_t* maps, int64_t n_s, int64_t n_r, int64_t n_slo, int64_t n_rlo,
                 int64_t B, int dtype, void* out, void* stream);
 
+/* Strided row copy between a device buffer and a (pinned) host buffer on `stream`
+ * (cudaMemcpy2DAsync): `rows` rows of `width_bytes`; to_host = 1 for device -> host.  Used to
+ * move a batch chunk [rows][chunk] into / out of a [rows][B] buffer without a host transpose. */
+int jt_copy_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                 size_t rows, int to_host, void* stream);
+
 /* Hugin separator ratio: out[i] = old[i] != 0 ? new[i] / old[i] : 0, n contiguous elements.
  * (The propagation schedule itself is division-free; this serves SumProduct.absorb(old=...).) */
 int jt_ratio(const void* new_values, const void* old_values, void* out, int64_t n, int dtype, void* stream);

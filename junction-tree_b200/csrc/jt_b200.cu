@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -78,7 +79,7 @@ struct KArgs {
 };
 
 constexpr int kThreads = 256;
-constexpr int kMaxSyLog2 = 8;
+constexpr int kMaxSyLog2 = 12;  // largest chunk of s per block: 4096
 constexpr int kRegMsgs = 4;   // r-dependent messages kept in registers
 constexpr int kUnroll = 4;    // independent row loads in flight per thread
 
@@ -117,19 +118,63 @@ __device__ __forceinline__ void add(Pack<T, VEC>& a, const Pack<T, VEC>& b) {
     for (int i = 0; i < VEC; ++i) a.v[i] += b.v[i];
 }
 
-// Locate the task of this block and the output index s of this thread.
-__device__ __forceinline__ const DTask* locate(const KArgs& a, long long& s, long long& bv) {
-    const int tx = threadIdx.x & ((1 << a.bx_log2) - 1);
-    const int ty = threadIdx.x >> a.bx_log2;
-    bv = ((long long)blockIdx.y << a.bx_log2) + tx;
+// Locate the task of this block; s0 = first output index of the block's chunk of 2^sy_log2.
+__device__ __forceinline__ const DTask* locate_chunk(const KArgs& a, int& s0) {
     const int bid = blockIdx.x;
     int lo = 0, hi = a.n_tasks;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (__ldg(a.prefix + mid) <= bid) lo = mid; else hi = mid;
     }
-    s = ((long long)(bid - __ldg(a.prefix + lo)) << a.sy_log2) + ty;
+    s0 = (bid - __ldg(a.prefix + lo)) << a.sy_log2;
     return a.tasks + lo;
+}
+
+// Locate the task of this block and the output index s of this thread (2^sy_log2 rows of s per
+// block, 2^bx_log2 batch vectors per row).
+__device__ __forceinline__ const DTask* locate(const KArgs& a, int& s, long long& bv) {
+    const int tx = threadIdx.x & ((1 << a.bx_log2) - 1);
+    const int ty = threadIdx.x >> a.bx_log2;
+    bv = ((long long)blockIdx.y << a.bx_log2) + tx;
+    int s0;
+    const DTask* tk = locate_chunk(a, s0);
+    s = s0 + ty;
+    return tk;
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy (TMA) primitives, inline PTX for sm_100a
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "JT_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra JT_DONE_%=;\n"
+        "bra JT_WAIT_%=;\n"
+        "JT_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -166,38 +211,80 @@ jt_evidence_kernel(const int* __restrict__ evidence, int n_evid, const int* __re
 // ------------------------------------------------------------------------------------------
 // clique initialisation (E0 + V1): psi_C[s][b] = prod_f phi_f[ A_f(s) + fbase[f][b] ]
 
+// A thread owns VEC batch columns and walks its rows of the block's chunk of s, so the
+// per-instance factor offsets (which do not depend on s) are read once and kept in registers.
+constexpr int kInitRegFactors = 6;
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
     typedef Pack<T, VEC> P;
-    long long s, bv;
+    int s;
+    long long bv;
     const DTask* tk = locate(a, s, bv);
-    if (s >= tk->n_s || bv >= a.Bv) return;
+    const int n_s = tk->n_s;
+    if (s >= n_s || bv >= a.Bv) return;
+    const int rows = kThreads >> a.bx_log2;                       // rows of s handled per step
+    const int s_end = min(n_s, (s - (int)(threadIdx.x >> a.bx_log2)) + (1 << a.sy_log2));
     const int* __restrict__ tab = a.tab;
+    const DMsg* __restrict__ msgs = a.msgs;
     const long long B = a.B, col = bv * VEC;
     const int n_slo = tk->n_slo;
-    int s_hi = 0, s_lo = (int)s;
-    if (n_slo < tk->n_s) {
-        s_hi = (int)(s / n_slo);
-        s_lo = (int)(s - (long long)s_hi * n_slo);
+    int s_hi = 0, s_lo = s;
+    if (n_slo < n_s) {
+        s_hi = s / n_slo;
+        s_lo = s - s_hi * n_slo;
     }
     const T* __restrict__ fin = static_cast<const T*>(a.fin);
-    P val = pack_fill<T, VEC>(T(1));
-    for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
-        const DMsg* m = a.msgs + j;
-        const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
-        if (a.fin_batched) {
-            mul(val, ld<T, VEC>(fin + idx * B + col));
-        } else if (a.fbase) {
-            const int* fb = a.fbase + (long long)m->fid * B + col;
+    const int f0 = tk->smsg_begin, nf = tk->smsg_end - f0;
+    const bool gather = !a.fin_batched && a.fbase != nullptr;
+
+    // per-factor, per-instance base offsets (evidence slicing), resident in registers
+    int fb[kInitRegFactors][VEC];
 #pragma unroll
-            for (int u = 0; u < VEC; ++u) val.v[u] *= __ldg(fin + idx + fb[u]);
-        } else {
-            const T x = __ldg(fin + idx);
+    for (int j = 0; j < kInitRegFactors; ++j) {
 #pragma unroll
-            for (int u = 0; u < VEC; ++u) val.v[u] *= x;
+        for (int u = 0; u < VEC; ++u) fb[j][u] = 0;
+        if (gather && j < nf) {
+            const int* p = a.fbase + (long long)msgs[f0 + j].fid * B + col;
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) fb[j][u] = p[u];
         }
     }
-    st<T, VEC>(static_cast<T*>(a.work) + (tk->out + s) * B + col, val);
+
+    T* out = static_cast<T*>(a.work) + tk->out * B + col;
+    for (; s < s_end; s += rows) {
+        P val = pack_fill<T, VEC>(T(1));
+#pragma unroll
+        for (int j = 0; j < kInitRegFactors; ++j) {
+            if (j < nf) {
+                const DMsg* m = msgs + f0 + j;
+                const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+                if (a.fin_batched) {
+                    mul(val, ld<T, VEC>(fin + idx * B + col));
+                } else {
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) val.v[u] *= __ldg(fin + idx + fb[j][u]);
+                }
+            }
+        }
+        for (int j = kInitRegFactors; j < nf; ++j) {   // rare: many factors in one clique
+            const DMsg* m = msgs + f0 + j;
+            const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+            if (a.fin_batched) {
+                mul(val, ld<T, VEC>(fin + idx * B + col));
+            } else {
+                const int* p = a.fbase ? a.fbase + (long long)m->fid * B + col : nullptr;
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) val.v[u] *= __ldg(fin + idx + (p ? p[u] : 0));
+            }
+        }
+        st<T, VEC>(out + (long long)s * B, val);
+        s_lo += rows;
+        while (s_lo >= n_slo) {
+            s_lo -= n_slo;
+            ++s_hi;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -206,7 +293,8 @@ __global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
     typedef Pack<T, VEC> P;
-    long long s, bv;
+    int s;
+    long long bv;
     const DTask* tk = locate(a, s, bv);
     const int n_s = tk->n_s;
     if (s >= n_s || bv >= a.Bv) return;
@@ -217,10 +305,10 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
     T* work = static_cast<T*>(a.work);
 
     const int n_slo = tk->n_slo;
-    int s_hi = 0, s_lo = (int)s;
+    int s_hi = 0, s_lo = s;
     if (n_slo < n_s) {
-        s_hi = (int)(s / n_slo);
-        s_lo = (int)(s - (long long)s_hi * n_slo);
+        s_hi = s / n_slo;
+        s_lo = s - s_hi * n_slo;
     }
 
     // messages that do not depend on r, and the task's own up-message
@@ -349,6 +437,202 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA-pipelined projection (same task semantics as jt_project_kernel).
+//
+// The LDG kernel above keeps every in-flight row in registers, so its memory-level parallelism
+// is capped by occupancy (ncu, round 1: 22 % warps active, DRAM 33-53 %).  Here one elected
+// producer thread walks the (s, r) index space and issues 1-D bulk async copies (cp.async.bulk,
+// SASS UBLKCP) of whole batch-tile rows -- the clique row and one row per message -- into a
+// shared-memory ring guarded by full/empty mbarriers; the consumer warps (one thread per 16-byte
+// batch vector) multiply/accumulate out of shared memory and store beliefs and messages with
+// coalesced 16-byte stores.  Bytes in flight = ring size (~96 KB per CTA, two CTAs per SM),
+// independent of register pressure.  A stage holds the rows of one (s, r) item; the rows that
+// depend on s only (s-only messages, the own up-message) ride along with the r = 0 item.
+
+constexpr int kTmaSlots = 24;     // ring size in rows (one row = 16 bytes x consumer threads)
+constexpr int kTmaMaxRows = 8;    // rows per stage supported (src + messages + own)
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads + 32, 2) jt_project_tma_kernel(const KArgs a) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    typedef Pack<T, VEC> P;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int ct = blockDim.x - 32;                      // consumer threads = batch vectors per tile
+    const int row_pitch = ct * 16;                       // bytes per ring row
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + kTmaSlots * row_pitch);
+    int* e_row = reinterpret_cast<int*>(bars + 2 * kTmaSlots);
+    const uint32_t slots_u32 = smem_u32(smem_raw);
+    const uint32_t full_u32 = smem_u32(bars), empty_u32 = smem_u32(bars + kTmaSlots);
+
+    int s0;
+    const DTask* tk = locate_chunk(a, s0);
+    const int n_s = tk->n_s;
+    const int s1 = min(n_s, s0 + (1 << a.sy_log2));
+    const long long col0v = (long long)blockIdx.y * ct;
+    const int ncols = (int)min((long long)ct, a.Bv - col0v);
+    const uint32_t row_bytes = (uint32_t)ncols * 16u;
+
+    const bool has_src = tk->src >= 0, has_own = tk->own >= 0;
+    const int m0 = tk->rmsg_begin;                       // r-dependent messages, then s-only ones
+    const int nr = tk->rmsg_end - m0;
+    const int nsm = tk->smsg_end - tk->smsg_begin;
+    const int rows_item = (has_src ? 1 : 0) + nr;
+    const int rows_extra = nsm + (has_own ? 1 : 0);
+    const int rows_stage = rows_item + rows_extra;
+    const int n_stage = kTmaSlots / rows_stage;
+    const int n_r = tk->n_r;
+    const long long B = a.B;
+
+    const int n_cwarps = ct >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < n_stage; ++i) {
+            mbar_init(full_u32 + 8 * i, 1);
+            mbar_init(empty_u32 + 8 * i, n_cwarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == n_cwarps) {
+        // ---------------- producer: one thread issues every copy of this CTA ----------------
+        if (lane != 0) return;
+        const int* __restrict__ tab = a.tab;
+        const DMsg* __restrict__ msgs = a.msgs + m0;
+        const T* work = static_cast<const T*>(a.work);
+        const long long colE = col0v * VEC;
+        const int n_slo = tk->n_slo, n_rlo = tk->n_rlo, n_rhi = n_r / n_rlo;
+        const int* __restrict__ t_rhi = tab + tk->src_rhi;
+        const int* __restrict__ t_rlo = tab + tk->src_rlo;
+        const long long src = tk->src, own = tk->own;
+        const int nm = nr + nsm;
+        int s_hi = 0, s_lo = s0;
+        if (n_slo < n_s) {
+            s_hi = s0 / n_slo;
+            s_lo = s0 - s_hi * n_slo;
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int s = s0; s < s1; ++s) {
+            const int s_off = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo);
+            const T* mrow[kTmaMaxRows];                  // message row pointers at r = 0
+#pragma unroll
+            for (int j = 0; j < kTmaMaxRows; ++j) {
+                mrow[j] = work;
+                if (j < nm) {
+                    const DMsg* m = msgs + j;
+                    const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+                    mrow[j] = work + m->eoff + idx * B + colE;
+                }
+            }
+            int r = 0;
+            for (int rh = 0; rh < n_rhi; ++rh) {
+                const int e_hi = s_off + __ldg(t_rhi + rh);
+                int mh[kTmaMaxRows];
+#pragma unroll
+                for (int j = 0; j < kTmaMaxRows; ++j) mh[j] = (j < nr) ? __ldg(tab + msgs[j].b_hi + rh) : 0;
+                for (int rl = 0; rl < n_rlo; ++rl, ++r) {
+                    const int e = e_hi + __ldg(t_rlo + rl);
+                    const uint32_t full = full_u32 + 8 * stage;
+                    mbar_wait(empty_u32 + 8 * stage, phase ^ 1);
+                    e_row[stage] = e;
+                    const int rows_now = rows_item + (r == 0 ? rows_extra : 0);
+                    mbar_arrive_expect_tx(full, (uint32_t)rows_now * row_bytes);
+                    uint32_t dst = slots_u32 + (uint32_t)(stage * rows_stage) * (uint32_t)row_pitch;
+                    if (has_src) {
+                        bulk_g2s(dst, work + (src + e) * B + colE, row_bytes, full);
+                        dst += row_pitch;
+                    }
+#pragma unroll
+                    for (int j = 0; j < kTmaMaxRows; ++j) {
+                        if (j < nr) {
+                            const long long off = (long long)(mh[j] + __ldg(tab + msgs[j].b_lo + rl)) * B;
+                            bulk_g2s(dst, mrow[j] + off, row_bytes, full);
+                            dst += row_pitch;
+                        }
+                    }
+                    if (r == 0) {
+#pragma unroll
+                        for (int j = 0; j < kTmaMaxRows; ++j) {
+                            if (j >= nr && j < nm) {
+                                bulk_g2s(dst, mrow[j], row_bytes, full);
+                                dst += row_pitch;
+                            }
+                        }
+                        if (has_own) bulk_g2s(dst, work + (own + s) * B + colE, row_bytes, full);
+                    }
+                    if (++stage == n_stage) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+            if (++s_lo == n_slo) {
+                s_lo = 0;
+                ++s_hi;
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: thread t owns batch vector col0v + t ----------------
+    const int t = threadIdx.x;
+    const bool active = t < ncols;
+    T* work = static_cast<T*>(a.work);
+    const long long col = (col0v + t) * VEC;
+    const bool wbeta = tk->beta >= 0, wout = tk->out >= 0;
+    const bool wbel = wout && tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS);
+    T* bptr = work + (wbeta ? tk->beta : 0) * B + col;
+    T* optr = (tk->out_space ? static_cast<T*>(a.fout) : work) + (wout ? tk->out : 0) * B + col;
+    T* lptr = work + (wbel ? tk->bel : 0) * B + col;
+    const unsigned char* my = smem_raw + t * 16;
+    const int stage_pitch = rows_stage * row_pitch;
+    const int src_rows = has_src ? 1 : 0;
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = s0; s < s1; ++s) {
+        P sm = pack_fill<T, VEC>(T(1)), own = sm, scale = sm;
+        P acc0 = pack_fill<T, VEC>(T(0)), acc1 = acc0;
+        for (int r = 0; r < n_r; ++r) {
+            mbar_wait(full_u32 + 8 * stage, phase);
+            const unsigned char* base = my + stage * stage_pitch;
+            P v = has_src ? *reinterpret_cast<const P*>(base) : pack_fill<T, VEC>(T(1));
+            for (int j = 0; j < nr; ++j) mul(v, *reinterpret_cast<const P*>(base + (src_rows + j) * row_pitch));
+            if (r == 0) {
+                for (int j = 0; j < nsm; ++j)
+                    mul(sm, *reinterpret_cast<const P*>(base + (rows_item + j) * row_pitch));
+                if (has_own) own = *reinterpret_cast<const P*>(base + (rows_item + nsm) * row_pitch);
+                scale = sm;
+                mul(scale, own);
+            }
+            const int e = e_row[stage];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_u32 + 8 * stage);
+            if (r & 1) add(acc1, v); else add(acc0, v);
+            if (wbeta && active) {
+                mul(v, scale);
+                st<T, VEC>(bptr + (long long)e * B, v);
+            }
+            if (++stage == n_stage) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+        if (wout && active) {
+            add(acc0, acc1);
+            mul(acc0, sm);
+            st<T, VEC>(optr + (long long)s * B, acc0);
+            if (wbel) {
+                mul(acc0, own);
+                st<T, VEC>(lptr + (long long)s * B, acc0);
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 jt_ratio_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n) {
@@ -376,6 +660,9 @@ struct jt_plan {
         int phase, begin, end, level;
         size_t prefix_off[kMaxSyLog2 + 1];
         long long blocks[kMaxSyLog2 + 1];
+        bool tma_ok;          // every task fits the TMA kernel's stage (rows per stage <= kTmaMaxRows)
+        int min_nr;           // smallest n_r of the launch
+        long long total_s;    // sum of n_s
     };
     std::vector<Launch> launches;
     std::vector<int> prefix;
@@ -423,10 +710,61 @@ void pick_tile(long long Bv, int& bx_log2, int& sy_log2) {
     sy_log2 = 8 - bx_log2;
 }
 
+int g_tma_enabled = -1;   // JT_DISABLE_TMA=1 forces the LDG kernel (debugging / A-B timing)
+
+bool tma_enabled() {
+    if (g_tma_enabled < 0) {
+        const char* e = getenv("JT_DISABLE_TMA");
+        g_tma_enabled = (e && e[0] == '1') ? 0 : 1;
+    }
+    return g_tma_enabled == 1;
+}
+
+template <typename T>
+int launch_tma(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
+    const int ct = a.Bv >= 256 ? 256 : (a.Bv >= 128 ? 128 : 64);
+    const long long tiles = (a.Bv + ct - 1) / ct;
+    // chunk of s per CTA: aim at ~8 CTAs per SM over the launch, but keep >= 32 (s, r) items per
+    // CTA so the pipeline fill is amortised
+    int sy_log2 = 0;
+    const long long target = 148LL * 8;
+    while (sy_log2 < kMaxSyLog2 && (L.total_s * tiles) >> (sy_log2 + 1) >= target) ++sy_log2;
+    while (sy_log2 < kMaxSyLog2 && ((long long)L.min_nr << sy_log2) < 32) ++sy_log2;
+    a.sy_log2 = sy_log2;
+    a.bx_log2 = 0;
+    a.tasks = p->d_tasks + L.begin;
+    a.n_tasks = L.end - L.begin;
+    a.prefix = p->d_prefix + L.prefix_off[sy_log2];
+    const long long gx = L.blocks[sy_log2];
+    if (gx <= 0) return JT_OK;
+    if (gx > 2147483647LL || tiles > 65535)
+        return fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, tiles);
+    const size_t smem = (size_t)kTmaSlots * ct * 16 + 2 * kTmaSlots * 8 + kTmaSlots * 4 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        JT_CUDA(cudaFuncSetAttribute(jt_project_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kTmaSlots * 256 * 16 + 1024));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)gx, (unsigned)tiles, 1);
+    jt_project_tma_kernel<T><<<grid, ct + 32, smem, stream>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    JT_CUDA(cudaGetLastError());
+    return JT_OK;
+}
+
 template <typename T, int VEC>
 int launch_tasks(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
+    if (L.phase != JT_PHASE_INIT && VEC * sizeof(T) == 16 && L.tma_ok && a.Bv >= 64 && tma_enabled())
+        return launch_tma<T>(p, L, a, stream);
     int bx_log2, sy_log2;
     pick_tile(a.Bv, bx_log2, sy_log2);
+    if (L.phase == JT_PHASE_INIT) {
+        // a thread walks ~32 rows of s so the per-instance factor offsets stay in registers
+        sy_log2 = sy_log2 + 5 > kMaxSyLog2 ? kMaxSyLog2 : sy_log2 + 5;
+        while (sy_log2 > 8 - bx_log2 && (L.total_s >> sy_log2) * ((a.Bv + (1LL << bx_log2) - 1) >> bx_log2) < 148 * 4)
+            --sy_log2;
+    }
     a.bx_log2 = bx_log2;
     a.sy_log2 = sy_log2;
     a.tasks = p->d_tasks + L.begin;
@@ -606,6 +944,17 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
             return bad("launch descriptor", i);
         for (int t = L.begin; t < L.end; ++t)
             if ((p->tasks[t].kind == JT_KIND_INIT) != (L.phase == JT_PHASE_INIT)) return bad("task kind vs phase", i);
+        L.tma_ok = true;
+        L.min_nr = 2147483647;
+        L.total_s = 0;
+        for (int t = L.begin; t < L.end; ++t) {
+            const DTask& k = p->tasks[t];
+            const int rows = (k.src >= 0 ? 1 : 0) + (k.rmsg_end - k.rmsg_begin) + (k.smsg_end - k.smsg_begin) +
+                             (k.own >= 0 ? 1 : 0);
+            if (rows < 1 || rows > kTmaMaxRows || k.rmsg_end != k.smsg_begin) L.tma_ok = false;
+            L.min_nr = k.n_r < L.min_nr ? k.n_r : L.min_nr;
+            L.total_s += k.n_s;
+        }
         // block prefix per tile shape: a block covers 2^sy consecutive values of s of one task
         for (int sy = 0; sy <= kMaxSyLog2; ++sy) {
             L.prefix_off[sy] = p->prefix.size();
@@ -777,6 +1126,17 @@ int jt_evidence_errors(jt_plan* p, int64_t B, int dtype, void* workspace, void* 
                             static_cast<cudaStream_t>(stream)));
     JT_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     *out = (int64_t)v;
+    return JT_OK;
+}
+
+int jt_copy_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                 size_t rows, int to_host, void* stream) {
+    if (!dst || !src || width_bytes > dst_pitch || width_bytes > src_pitch)
+        return fail(JT_ERR_INVALID, "bad argument");
+    if (!rows || !width_bytes) return JT_OK;
+    JT_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows,
+                              to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice,
+                              static_cast<cudaStream_t>(stream)));
     return JT_OK;
 }
 

@@ -47,6 +47,8 @@ SIGNATURES = {
                                     ctypes.c_int, ctypes.c_void_p]),
     "jt_evidence_errors": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_void_p, _i64p]),
+    "jt_copy_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                    ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]),
     "jt_ratio": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                 ctypes.c_int, ctypes.c_void_p]),
     "jt_contract": (ctypes.c_int, [_c_void_pp, ctypes.c_int, _i32p, ctypes.c_int64, _i32p,
@@ -186,3 +188,8 @@ def contract(op_ptrs, tables, maps, n_s, n_r, n_slo, n_rlo, B, dtype, out_ptr, s
 def ratio(new_ptr, old_ptr, out_ptr, n, dtype, stream):
     """``jt_ratio``: out = new / old with x / 0 = 0."""
     check(lib().jt_ratio(new_ptr, old_ptr, out_ptr, n, dtype_code(dtype), stream))
+
+
+def copy_rows(dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, rows, to_host, stream):
+    """``jt_copy_rows``: strided row copy device <-> pinned host on ``stream``."""
+    check(lib().jt_copy_rows(dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, rows, int(to_host), stream))

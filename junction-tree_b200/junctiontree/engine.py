@@ -190,3 +190,103 @@ class Engine:
 def make_plan(tree, node_vars, sizes, factors=None, factor_to_clique=None, evidence_vars=(),
               full_sizes=None):
     return sch.Plan(tree, node_vars, sizes, factors, factor_to_clique, evidence_vars, full_sizes)
+
+
+class BatchPipeline:
+    """End-to-end streaming of a large batch in chunks over several CUDA streams.
+
+    Per chunk: pinned int32 evidence -> device, ``jt_propagate`` (init, collect, distribute,
+    marginal), per-factor beliefs -> pinned host.  Chunks alternate between ``n_streams``
+    streams, each with its own workspace, so the PCIe copies of one chunk overlap the kernels of
+    another.  The host result keeps the batch-innermost layout ``[fout_entries, B]``; per-factor
+    ``[B, *shape]`` arrays are strided views of it (``factor_views``), so no transpose is done on
+    either side.
+    """
+
+    def __init__(self, engine, B, dtype, chunk=16384, n_streams=2):
+        t = require_cuda()
+        self.engine, self.B, self.dtype = engine, int(B), np.dtype(dtype)
+        plan = engine.plan
+        self.chunk = int(min(chunk, B))
+        self.bounds = [(lo, min(lo + self.chunk, self.B)) for lo in range(0, self.B, self.chunk)]
+        n_streams = max(1, min(n_streams, len(self.bounds)))
+        engine.dev.upload()
+        self.n_ev = len(plan.evidence_vars)
+        self.slots = []
+        for _ in range(n_streams):
+            slot = {
+                "stream": t.cuda.Stream(),
+                "ws": engine.new_workspace(self.chunk, self.dtype),
+                "fout": t.empty((plan.fout_entries, self.chunk), dtype=torch_dtype(self.dtype), device="cuda"),
+                "ev": t.empty((self.chunk, max(self.n_ev, 1)), dtype=t.int32, device="cuda"),
+            }
+            self.slots.append(slot)
+        # a ragged last chunk needs buffers of its own pitch
+        self.tail = None
+        last = self.bounds[-1][1] - self.bounds[-1][0]
+        if last != self.chunk:
+            self.tail = {
+                "stream": self.slots[(len(self.bounds) - 1) % n_streams]["stream"],
+                "ws": engine.new_workspace(last, self.dtype),
+                "fout": t.empty((plan.fout_entries, last), dtype=torch_dtype(self.dtype), device="cuda"),
+                "ev": t.empty((last, max(self.n_ev, 1)), dtype=t.int32, device="cuda"),
+            }
+
+    def host_output(self):
+        """Pinned ``[fout_entries, B]`` host buffer for :meth:`run`."""
+        t = torch()
+        return t.empty((self.engine.plan.fout_entries, self.B), dtype=torch_dtype(self.dtype)).pin_memory()
+
+    def factor_views(self, out_host):
+        """Per-factor ``[B, *shape]`` NumPy views of the host buffer."""
+        plan = self.engine.plan
+        arr = out_host.numpy()
+        return [
+            np.moveaxis(arr[plan.fout_off[f]:plan.fout_off[f] + plan.fout_size[f]]
+                        .reshape(tuple(plan.fout_shape[f]) + (self.B,)), -1, 0)
+            for f in range(len(plan.factors))
+        ]
+
+    def run(self, factor_dev, batched, ev_host, out_host, sync=False):
+        """Enqueue the whole batch.  ``ev_host``: pinned int32 ``[B, |E|]`` (or None);
+        ``out_host``: tensor from :meth:`host_output`.  The calling stream waits for all chunks."""
+        t = torch()
+        plan, dev = self.engine.plan, self.engine.dev
+        if batched:
+            raise ValueError("per-instance factor tables are not streamed; use Engine.propagate")
+        cur = t.cuda.current_stream()
+        item = self.dtype.itemsize
+        for slot in self.slots:
+            slot["stream"].wait_stream(cur)
+        for i, (lo, hi) in enumerate(self.bounds):
+            n = hi - lo
+            slot = self.tail if (self.tail is not None and n != self.chunk) else self.slots[i % len(self.slots)]
+            stream = slot["stream"]
+            with t.cuda.stream(stream):
+                ev_ptr = None
+                if self.n_ev:
+                    slot["ev"].copy_(ev_host[lo:hi], non_blocking=True)
+                    ev_ptr = slot["ev"].data_ptr()
+                dev.propagate(factor_dev.data_ptr(), False, ev_ptr, n, self.dtype, slot["ws"].data_ptr(),
+                              slot["fout"].data_ptr(), 0, stream.cuda_stream)
+                _native.copy_rows(out_host.data_ptr() + lo * item, self.B * item, slot["fout"].data_ptr(),
+                                  n * item, n * item, plan.fout_entries, True, stream.cuda_stream)
+        for slot in self.slots:
+            cur.wait_stream(slot["stream"])
+        if sync:
+            cur.synchronize()
+
+    def evidence_errors(self):
+        total = 0
+        for slot in self.slots + ([self.tail] if self.tail else []):
+            n = slot["fout"].shape[1]
+            total += self.engine.dev.evidence_errors(n, self.dtype, slot["ws"].data_ptr(),
+                                                     slot["stream"].cuda_stream)
+        return total
+
+
+def _pipeline(self, B, dtype, chunk=16384, n_streams=2):
+    return BatchPipeline(self, B, dtype, chunk, n_streams)
+
+
+Engine.pipeline = _pipeline

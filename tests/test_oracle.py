@@ -1,0 +1,145 @@
+"""The oracles are pinned here (CPU only): the NumPy restatement against the unmodified
+reference's recorded outputs (tests/golden, produced by tests/golden/make_golden.py), against
+brute force, and the schedule interpreter against both."""
+
+import numpy as np
+import pytest
+
+import jt_workloads as wl
+from helpers import RTOL_F64, assert_close, compile_net, load_golden, tuplify
+from oracle import brute, plan_interp, ref_fixed
+
+
+def test_golden_file_covers_the_reference_fixtures():
+    cases, arrays = load_golden()
+    names = {c["name"] for c in cases}
+    for expected in ("sprinkler", "sprinkler_wet", "sprinkler_wet_rain", "huang_darwiche", "wisconsin",
+                     "scalar_node", "child_all_shared", "two_children_3d", "grandchild_shared"):
+        assert expected in names
+    # the reference's own known-answer numbers (tests/test_junctiontree.py:245-292, 422-525)
+    hd = next(c for c in cases if c["name"] == "huang_darwiche")
+    np.testing.assert_allclose(arrays[hd["outputs"][0]], [0.5, 0.5])
+    np.testing.assert_allclose(arrays[hd["outputs"][3]].sum(axis=0), [0.32, 0.68])
+    np.testing.assert_allclose(arrays[hd["outputs"][4]].sum(axis=0), [0.535, 0.465])
+    wi = next(c for c in cases if c["name"] == "wisconsin")
+    np.testing.assert_allclose(arrays[wi["outputs"][2]].sum(axis=1), [0.75, 0.25])
+    np.testing.assert_allclose(arrays[wi["outputs"][3]].sum(axis=0), [0.546, 0.454])
+    # the reference defect D3 is visible in the recorded vectors
+    wet = next(c for c in cases if c["name"] == "sprinkler_wet")
+    assert wet["outputs_valid"] == [True, True, True, False]
+
+
+def test_ref_fixed_compute_beliefs_matches_reference_on_its_trees():
+    cases, arrays = load_golden()
+    checked = 0
+    for case in cases:
+        if "beliefs" not in case:
+            continue
+        if case["kind"] == "operator":
+            pots = [arrays[k] for k in case["potentials"]]
+            node_vars = case["variables"]
+        else:
+            node_vars = case["maxcliques"] + case["separators"]
+            sizes = dict(case["sizes"])
+            sizes.update({v: 1 for v in case["slices"]})
+            pots = [arrays[k] for k in case["psi"]] + \
+                   [np.ones(tuple(sizes[v] for v in s)) for s in case["separators"]]
+        got = ref_fixed.compute_beliefs(tuplify(case["tree"]), pots, node_vars)
+        for k, key in enumerate(case["beliefs"]):
+            if case["beliefs_valid"][k]:
+                assert_close(got[k], arrays[key], RTOL_F64, "%s node %d" % (case["name"], k))
+                checked += 1
+    assert checked >= 90
+
+
+def test_ref_fixed_propagate_matches_reference_outputs():
+    """Factor outputs do not depend on the tree, so our own host compile can be used."""
+    cases, arrays = load_golden()
+    checked = 0
+    for case in cases:
+        if case["kind"] != "end_to_end":
+            continue
+        values = [arrays[k] for k in case["values"]]
+        sizes = dict(case["sizes"])
+        sizes.update({v: 1 for v in case["slices"]})
+        net = {"factors": case["factors"], "sizes": sizes}
+        tree, seps, mc, f2c, eff, _ = compile_net(net)
+        outs, _ = ref_fixed.propagate(tree, seps, mc, f2c, case["factors"], eff, values)
+        for f, key in enumerate(case["outputs"]):
+            if case["outputs_valid"][f]:
+                assert_close(outs[f], arrays[key], RTOL_F64, "%s factor %d" % (case["name"], f))
+                checked += 1
+    assert checked >= 40
+
+
+NETS = [wl.sprinkler(), wl.huang_darwiche(), wl.wisconsin(), wl.random_dag(12, 3, 2, 3, 8, 5),
+        wl.random_dag(10, 4, 2, 4, 10, 21), wl.ising(4), wl.large_state_tree((4, 6, 8, 4, 6, 8))]
+
+
+@pytest.mark.parametrize("net", NETS, ids=lambda n: n["name"])
+def test_ref_fixed_matches_brute_force(net):
+    tree, seps, mc, f2c, eff, evars = compile_net(net)
+    B = 3
+    ev = wl.draw_evidence(net, B) if evars else None
+    outs, ys = ref_fixed.propagate_batch(tree, seps, mc, f2c, net["factors"], net["sizes"], net["values"],
+                                         evars, ev, n=B)
+    nodes = mc + seps
+    for b in range(B):
+        evd = {v: int(ev[b][i]) for i, v in enumerate(evars)} if evars else None
+        truth = brute.factor_graph_marginals(net["factors"], net["values"], nodes + net["factors"], evd)
+        for k in range(len(nodes)):
+            assert_close(ys[k][b], truth[k], 1e-11, "node %d" % k)
+        for f in range(len(net["factors"])):
+            assert_close(outs[f][b], truth[len(nodes) + f], 1e-11, "factor %d" % f)
+
+
+@pytest.mark.parametrize("net", NETS + [wl.dag37()], ids=lambda n: n["name"])
+def test_schedule_interpreter_matches_ref_fixed(net):
+    """The compiled plan (index tables, task wiring, launch order), interpreted in NumPy,
+    reproduces the oracle -- this is what the CUDA kernels execute."""
+    from junctiontree import schedule as sch
+    tree, seps, mc, f2c, eff, evars = compile_net(net)
+    plan = sch.Plan(tree, mc + seps, eff, net["factors"], f2c, evars, net["sizes"])
+    B = 2
+    ev = wl.draw_evidence(net, B) if evars else None
+    work, fout = plan_interp.run(plan, B, factor_in=plan_interp.flatten_factors(plan, net["values"]), evidence=ev)
+    outs, ys = ref_fixed.propagate_batch(tree, seps, mc, f2c, net["factors"], net["sizes"], net["values"],
+                                         evars, ev, n=B)
+    for k in range(len(mc) + len(seps)):
+        assert_close(plan_interp.node_array(plan, work, k, B), ys[k], 1e-13, "node %d" % k)
+    for f in range(len(net["factors"])):
+        assert_close(plan_interp.factor_array(plan, fout, f, B), outs[f], 1e-13, "factor %d" % f)
+
+
+def test_split_tables_equal_direct_index_arithmetic():
+    """hi/lo table pairs reproduce sum_v digit_v * stride_v exactly, for spaces larger than one
+    table (bit-exact index maps)."""
+    from junctiontree import schedule as sch
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        nv = int(rng.integers(1, 7))
+        variables = list(range(nv))
+        sizes = {v: int(rng.integers(1, 9)) for v in variables}
+        space = sch._Space(variables, sizes)
+        target = [v for v in variables if rng.random() < 0.6]
+        rng.shuffle(target)
+        strides = dict(zip(target, sch._row_major_strides([sizes[v] for v in target])))
+        hi, lo = space.tables(strides)
+        assert len(hi) == space.n_hi and len(lo) == space.n_lo and space.n_hi * space.n_lo == space.n
+        x = np.arange(space.n)
+        got = hi[x // space.n_lo] + lo[x % space.n_lo]
+        digits = np.unravel_index(x, space.shape) if nv else ()
+        want = sum((digits[i] * strides.get(v, 0) for i, v in enumerate(variables)), np.zeros(space.n, np.int64))
+        assert np.array_equal(got, want)
+
+
+def test_invariants_on_a_large_tree():
+    """Size-independent properties on config 2's shape: all nodes share one Z and neighbours
+    agree on the separator marginal."""
+    net = wl.dag37()
+    tree, seps, mc, f2c, eff, evars = compile_net(net, with_evidence=False)
+    _, ys = ref_fixed.propagate(tree, seps, mc, f2c, net["factors"], net["sizes"], net["values"])
+    Z = ys[0].sum()
+    np.testing.assert_allclose(Z, 1.0, rtol=1e-12)       # CPTs of a Bayesian network
+    for y in ys:
+        np.testing.assert_allclose(y.sum(), Z, rtol=1e-12)

@@ -157,6 +157,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -497,17 +500,44 @@ __global__ void __launch_bounds__(kThreads + 32, 2) jt_project_tma_kernel(const 
     __syncthreads();
 
     if (warp == n_cwarps) {
-        // ---------------- producer: one thread issues every copy of this CTA ----------------
-        if (lane != 0) return;
+        // ---------------- producer warp: lane k owns row k of every stage ----------------
+        // Row order inside a stage: [src] [r-dependent messages] [s-only messages] [own].
+        const int src_rows = has_src ? 1 : 0;
+        const int jm = lane - src_rows;                       // message index of this lane's row
+        const bool is_src = has_src && lane == 0;
+        const bool is_rmsg = jm >= 0 && jm < nr;
+        const bool is_smsg = jm >= nr && jm < nr + nsm;
+        const bool is_own = has_own && lane == rows_stage - 1;
+        if (lane >= rows_stage) return;
+        const unsigned pmask = (1u << rows_stage) - 1u;
+        const bool per_item = is_src || is_rmsg;              // fetched for every (s, r), else with r = 0 only
+
         const int* __restrict__ tab = a.tab;
-        const DMsg* __restrict__ msgs = a.msgs + m0;
         const T* work = static_cast<const T*>(a.work);
-        const long long colE = col0v * VEC;
         const int n_slo = tk->n_slo, n_rlo = tk->n_rlo, n_rhi = n_r / n_rlo;
-        const int* __restrict__ t_rhi = tab + tk->src_rhi;
-        const int* __restrict__ t_rlo = tab + tk->src_rlo;
-        const long long src = tk->src, own = tk->own;
-        const int nm = nr + nsm;
+        // per-lane row description, loaded once
+        long long base = 0, eoff = 0;
+        const int* t_ahi = tab;
+        const int* t_alo = tab;
+        const int* t_bhi = tab;
+        const int* t_blo = tab;
+        if (is_src) {
+            base = tk->src;
+            t_ahi = tab + tk->src_shi; t_alo = tab + tk->src_slo;
+            t_bhi = tab + tk->src_rhi; t_blo = tab + tk->src_rlo;
+        } else if (is_rmsg || is_smsg) {
+            const DMsg* m = a.msgs + m0 + jm;
+            base = m->off;
+            eoff = m->eoff;
+            t_ahi = tab + m->a_hi; t_alo = tab + m->a_lo;
+            t_bhi = tab + m->b_hi; t_blo = tab + m->b_lo;
+        } else {
+            base = tk->own;
+        }
+        const T* origin = work + eoff + col0v * VEC;
+        const uint32_t dst0 = slots_u32 + (uint32_t)lane * (uint32_t)row_pitch;
+        const uint32_t stage_bytes = (uint32_t)rows_stage * (uint32_t)row_pitch;
+
         int s_hi = 0, s_lo = s0;
         if (n_slo < n_s) {
             s_hi = s0 / n_slo;
@@ -516,53 +546,23 @@ __global__ void __launch_bounds__(kThreads + 32, 2) jt_project_tma_kernel(const 
         int stage = 0;
         uint32_t phase = 0;
         for (int s = s0; s < s1; ++s) {
-            const int s_off = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo);
-            const T* mrow[kTmaMaxRows];                  // message row pointers at r = 0
-#pragma unroll
-            for (int j = 0; j < kTmaMaxRows; ++j) {
-                mrow[j] = work;
-                if (j < nm) {
-                    const DMsg* m = msgs + j;
-                    const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
-                    mrow[j] = work + m->eoff + idx * B + colE;
-                }
-            }
-            int r = 0;
+            const int s_idx = is_own ? s : __ldg(t_ahi + s_hi) + __ldg(t_alo + s_lo);
+            const T* rowp = origin + (base + s_idx) * B;
+            bool first = true;
             for (int rh = 0; rh < n_rhi; ++rh) {
-                const int e_hi = s_off + __ldg(t_rhi + rh);
-                int mh[kTmaMaxRows];
-#pragma unroll
-                for (int j = 0; j < kTmaMaxRows; ++j) mh[j] = (j < nr) ? __ldg(tab + msgs[j].b_hi + rh) : 0;
-                for (int rl = 0; rl < n_rlo; ++rl, ++r) {
-                    const int e = e_hi + __ldg(t_rlo + rl);
+                const int h = per_item ? __ldg(t_bhi + rh) : 0;
+                for (int rl = 0; rl < n_rlo; ++rl) {
                     const uint32_t full = full_u32 + 8 * stage;
+                    const int e = per_item ? h + __ldg(t_blo + rl) : 0;
                     mbar_wait(empty_u32 + 8 * stage, phase ^ 1);
-                    e_row[stage] = e;
-                    const int rows_now = rows_item + (r == 0 ? rows_extra : 0);
-                    mbar_arrive_expect_tx(full, (uint32_t)rows_now * row_bytes);
-                    uint32_t dst = slots_u32 + (uint32_t)(stage * rows_stage) * (uint32_t)row_pitch;
-                    if (has_src) {
-                        bulk_g2s(dst, work + (src + e) * B + colE, row_bytes, full);
-                        dst += row_pitch;
+                    if (per_item || first) {
+                        if (is_src) e_row[stage] = s_idx + e;
+                        mbar_expect_tx(full, row_bytes);
+                        bulk_g2s(dst0 + (uint32_t)stage * stage_bytes, rowp + (long long)e * B, row_bytes, full);
                     }
-#pragma unroll
-                    for (int j = 0; j < kTmaMaxRows; ++j) {
-                        if (j < nr) {
-                            const long long off = (long long)(mh[j] + __ldg(tab + msgs[j].b_lo + rl)) * B;
-                            bulk_g2s(dst, mrow[j] + off, row_bytes, full);
-                            dst += row_pitch;
-                        }
-                    }
-                    if (r == 0) {
-#pragma unroll
-                        for (int j = 0; j < kTmaMaxRows; ++j) {
-                            if (j >= nr && j < nm) {
-                                bulk_g2s(dst, mrow[j], row_bytes, full);
-                                dst += row_pitch;
-                            }
-                        }
-                        if (has_own) bulk_g2s(dst, work + (own + s) * B + colE, row_bytes, full);
-                    }
+                    first = false;
+                    __syncwarp(pmask);                       // every lane's expect_tx precedes the arrive
+                    if (lane == 0) mbar_arrive(full);
                     if (++stage == n_stage) {
                         stage = 0;
                         phase ^= 1;
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(kThreads + 32, 2) jt_project_tma_kernel(const 
     T* lptr = work + (wbel ? tk->bel : 0) * B + col;
     const unsigned char* my = smem_raw + t * 16;
     const int stage_pitch = rows_stage * row_pitch;
-    const int src_rows = has_src ? 1 : 0;
+    const int src_rows = has_src ? 1 : 0;   // consumer-side copy
 
     int stage = 0;
     uint32_t phase = 0;

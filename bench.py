@@ -221,15 +221,15 @@ def run_gpu(args):
     fout = torch.empty((plan.fout_entries, B), dtype=engine_dtype(dtype), device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     ev_ptr = ev_dev.data_ptr() if evars else None
-    flags = _native.JT_SEP_BELIEFS
+    flags = _native.JT_SEP_BELIEFS | (0 if args.no_uniform else _native.JT_UNIFORM)
 
     def hot_path(events=None):
         if events is not None:
             events[0].record()
-        engine.dev.init(fdev.data_ptr(), batched, ev_ptr, B, dtype, ws.data_ptr(), stream)
+        engine.dev.init(fdev.data_ptr(), batched, ev_ptr, B, dtype, ws.data_ptr(), flags, stream)
         if events is not None:
             events[1].record()
-        engine.dev.collect(B, dtype, ws.data_ptr(), stream)
+        engine.dev.collect(B, dtype, ws.data_ptr(), flags, stream)
         engine.dev.distribute(B, dtype, ws.data_ptr(), flags, stream)
         if events is not None:
             events[2].record()
@@ -299,10 +299,17 @@ def run_gpu(args):
     # the message-passing kernel moves everything but the init write (w * sum n_C)
     A = w * plan.algorithmic_entries(with_init=True)
     A_msg = w * plan.algorithmic_entries(with_init=False)
-    msg_launches = sum(1 for L in plan.launches_arr if L[0] in (1, 2, 3))
+    uniform = not args.no_uniform and plan.uni_entries > 0
+    msg_phases = (2, 3, 8) if uniform else (1, 2, 3)     # batch launches of collect + distribute
+    msg_launches = sum(1 for L in plan.launches_arr if L[0] in msg_phases)
     msg_ms_per_launch = msg_ms / args.steps / max(msg_launches, 1)
     achieved = A_msg * B / (msg_ms / args.steps / 1e3) / 1e9
     step_gbs = A * B / (ms_per_step / 1e3) / 1e9
+    # bytes this schedule has to move through HBM (uniform operands are read once, not per instance)
+    S_all = w * plan.scheduled_entries(uniform=uniform)
+    n_init = sum(plan.node_size[c] for c in range(plan.n_cliques) if not (uniform and plan.uniform[c]))
+    S_msg = S_all - w * n_init
+    scheduled = S_msg * B / (msg_ms / args.steps / 1e3) / 1e9
 
     cpu = None
     if not args.skip_cpu:
@@ -321,18 +328,27 @@ def run_gpu(args):
             "parallelism": "batch-sharded x%d, no data-path collective" % world,
             "cliques": plan.n_cliques, "clique_entries": plan.clique_entries, "sep_entries": plan.sep_entries,
             "levels": plan.max_depth, "algorithmic_bytes_per_propagation": A,
+            "scheduled_bytes_per_propagation": S_all, "uniform_mode": bool(uniform),
+            "uniform_clique_entries": plan.uni_entries if uniform else 0,
             "step": "evidence slicing + clique init + collect + distribute (clique and separator beliefs)",
             "l2": "inputs larger than L2 (working set %.1f GB per GPU)" % (plan.work_entries * B * w / 1e9),
             "step_gbs_algorithmic": step_gbs, "init_ms_per_step": init_ms / args.steps,
             "message_passing_ms_per_step": msg_ms / args.steps,
         },
         "roofline": {
-            "bound": "hbm", "kernel": "jt_project_kernel<%s,%d>" % ("double" if w == 8 else "float",
-                                                                     pick_vec(B, w)),
+            "bound": "hbm", "kernel": "jt_project_tma_kernel<%s>" % ("double" if w == 8 else "float"),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": peak_src, "traffic": None,
             "launches_per_step": msg_launches, "avg_launch_ms": msg_ms_per_launch,
             "algorithmic_bytes_per_launch": A_msg * B / max(msg_launches, 1),
+            "scheduled_bytes_per_launch": S_msg * B / max(msg_launches, 1),
+            "scheduled_gbs": scheduled, "scheduled_frac": scheduled / peak,
+            "note": ("achieved/frac use SURVEY.md 8d's algorithmic bytes A (every potential per instance in HBM); "
+                     "uniform mode keeps potentials and up-messages that no evidence reaches once per batch, so "
+                     "the schedule moves fewer bytes than A and frac can exceed 1 -- scheduled_* count the bytes "
+                     "this schedule must move and are the figure to compare with dram traffic")
+                    if uniform else "per-instance potentials: scheduled bytes = algorithmic bytes + re-reads of "
+                                    "psi_C by cliques with several children",
         },
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT,
@@ -373,6 +389,8 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--chunk", type=int, default=16384, help="instances per pipeline chunk (e2e)")
     ap.add_argument("--no-evidence", action="store_true")
+    ap.add_argument("--no-uniform", action="store_true",
+                    help="materialise every potential and message per instance (general path)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-per-core", type=int, default=256, help="CPU baseline: instances per core")
     args = ap.parse_args()

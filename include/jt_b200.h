@@ -17,16 +17,27 @@
  * Conventions: plain C types only; every function returns JT_OK or an error code and never
  * throws; jt_last_error_string() describes the last error of the calling thread.  The caller
  * owns every device buffer.  All device work is enqueued on the caller's stream and the library
- * never synchronises (so calls can be captured into a CUDA graph after jt_plan_upload).  A plan
- * is immutable after jt_plan_upload and may be shared; a workspace belongs to one stream at a
- * time.  There is no CPU fallback: without a CUDA device the compute entry points fail.
+ * never synchronises (except jt_evidence_errors), so calls can be captured into a CUDA graph
+ * after jt_plan_upload.  A plan is immutable after jt_plan_upload and may be shared; a
+ * workspace belongs to one stream at a time.  There is no CPU fallback: without a CUDA device
+ * the compute entry points fail.
  *
  * Device memory layout: batch-innermost.  A node (clique or separator) with n entries and a
  * batch of B independent propagations is stored as [n][B]; element (entry e, instance b) of the
  * node at entry offset `off` lives at workspace[(off + e) * B + b].  Workspace regions, in
  * entries: [ cliques | separator beliefs | up-messages | down-messages ], i.e. the first
  * (clique_entries + sep_entries) rows are the reference's node order `maxcliques + separators`
- * (junctiontree.py:317-323).  Entry offsets of nodes come from jt_plan_node_range().
+ * (junctiontree.py:317-323).  Entry offsets of nodes come from jt_plan_node_range().  After the
+ * [entries][B] block the workspace holds the per-instance factor offsets (int32 [F][B]), an
+ * error counter and the *uniform workspace*: one more copy of the same regions with B = 1
+ * (byte offsets: jt_workspace_layout).
+ *
+ * Uniform mode (JT_UNIFORM): with factor tables shared by the batch, a clique potential whose
+ * factors contain no observed variable, and an up-message of a subtree that contains none, are
+ * the same for every instance.  They are computed once into the uniform workspace and the batch
+ * kernels broadcast them instead of streaming [n][B] rows; every belief and every down-message
+ * is still computed and stored per instance, so the results are identical.  jt_propagate
+ * enables it automatically when factors_batched = 0.
  *
  * Plan blob (produced by junctiontree/schedule.py, Plan.to_blob): little-endian int64 words
  *   header[JT_H_WORDS], node_off[n_nodes], node_size[n_nodes], fin_off[F], fin_size[F],
@@ -50,7 +61,7 @@
 extern "C" {
 #endif
 
-#define JT_ABI_VERSION 3
+#define JT_ABI_VERSION 4
 
 /* status codes */
 #define JT_OK 0
@@ -62,9 +73,11 @@ extern "C" {
 #define JT_F32 0
 #define JT_F64 1
 
-/* flags of jt_distribute / jt_propagate */
-#define JT_SEP_BELIEFS 1   /* also write separator beliefs (up*down), computation.py:210 */
+/* flags of the stage calls */
+#define JT_SEP_BELIEFS 1   /* distribute: also write separator beliefs (up*down), computation.py:210 */
 #define JT_SKIP_MARGINAL 2 /* jt_propagate: stop after distribute */
+#define JT_UNIFORM 4       /* init/collect/distribute: uniform mode (pass the same value to all three) */
+#define JT_NO_UNIFORM 8    /* jt_propagate: do not enable uniform mode automatically */
 
 /* plan blob header words */
 #define JT_MAGIC 0x324E4C5042544ALL
@@ -72,20 +85,27 @@ enum {
     JT_H_MAGIC, JT_H_VERSION, JT_H_NCLIQUES, JT_H_NSEPS, JT_H_NFACTORS, JT_H_NEVID,
     JT_H_CLIQUE_ENTRIES, JT_H_SEP_ENTRIES, JT_H_FIN_ENTRIES, JT_H_FOUT_ENTRIES, JT_H_NTAB,
     JT_H_NTASKS, JT_H_NMSGS, JT_H_NLAUNCHES, JT_H_MAXDEPTH, JT_H_NEVF, JT_H_ROOT_ENTRIES,
-    JT_H_WORDS
+    JT_H_UNI_ENTRIES, JT_H_WORDS
 };
 #define JT_TASK_WORDS 24
 enum {
     JT_T_KIND, JT_T_SRC, JT_T_OUT, JT_T_BETA, JT_T_BEL, JT_T_OWN, JT_T_NS, JT_T_NR, JT_T_NSLO,
     JT_T_NRLO, JT_T_SRC_SHI, JT_T_SRC_SLO, JT_T_SRC_RHI, JT_T_SRC_RLO, JT_T_RMSG_BEGIN,
-    JT_T_RMSG_END, JT_T_SMSG_BEGIN, JT_T_SMSG_END, JT_T_OUT_SPACE, JT_T_NODE, JT_T_AUX
+    JT_T_RMSG_END, JT_T_SMSG_BEGIN, JT_T_SMSG_END, JT_T_OUT_SPACE, JT_T_NODE, JT_T_AUX, JT_T_FLAGS
 };
-#define JT_MSG_WORDS 6
-enum { JT_M_OFF, JT_M_AHI, JT_M_ALO, JT_M_BHI, JT_M_BLO, JT_M_FID };
+/* task flags, honoured in uniform mode only */
+#define JT_TF_SRC_UNIFORM 1   /* src is the potential of a clique no evidence touches */
+#define JT_TF_OWN_UNIFORM 2   /* the own up-message is uniform */
+#define JT_TF_TASK_UNIFORM 4  /* every input is uniform: the task runs in the uniform workspace */
+#define JT_MSG_WORDS 8
+enum { JT_M_OFF, JT_M_AHI, JT_M_ALO, JT_M_BHI, JT_M_BLO, JT_M_FID, JT_M_UNI };
 #define JT_LAUNCH_WORDS 4
 enum { JT_L_PHASE, JT_L_BEGIN, JT_L_END, JT_L_LEVEL };
 enum { JT_KIND_PROJECT = 0, JT_KIND_INIT = 1 };
-enum { JT_PHASE_INIT, JT_PHASE_COLLECT, JT_PHASE_DIST_PRE, JT_PHASE_DIST_MAIN, JT_PHASE_MARGINAL };
+enum {
+    JT_PHASE_INIT, JT_PHASE_COLLECT, JT_PHASE_DIST_PRE, JT_PHASE_DIST_MAIN, JT_PHASE_MARGINAL,
+    JT_PHASE_INIT_UNIFORM, JT_PHASE_INIT_INSTANCE, JT_PHASE_COLLECT_UNIFORM, JT_PHASE_COLLECT_INSTANCE
+};
 
 typedef struct jt_plan jt_plan;
 
@@ -104,8 +124,11 @@ int jt_plan_query(const jt_plan* plan, int what, int64_t* out);
 int jt_plan_node_range(const jt_plan* plan, int node, int64_t* offset, int64_t* count);
 /* entry offset of separator node k's up / down message buffers */
 int jt_plan_message_offsets(const jt_plan* plan, int sep_node, int64_t* up, int64_t* down);
-/* bytes of workspace for a batch of B (includes the evidence-offset scratch) */
+/* bytes of workspace for a batch of B */
 int jt_workspace_bytes(const jt_plan* plan, int64_t B, int dtype, size_t* out);
+/* byte offsets inside the workspace: out4 = { factor offsets, error counter, uniform workspace,
+ * total size }; the [entries][B] block starts at 0 */
+int jt_workspace_layout(const jt_plan* plan, int64_t B, int dtype, int64_t* out4);
 /* copy the schedule tables to the current CUDA device (idempotent) */
 int jt_plan_upload(jt_plan* plan);
 
@@ -118,10 +141,11 @@ int jt_plan_upload(jt_plan* plan);
  * evidence      : int32 [B][n_evid] observed states (row-major), or NULL when the plan has no
  *                 per-instance evidence variables.  States outside [0, card) are clamped and
  *                 counted; see jt_evidence_errors.
+ * flags         : JT_UNIFORM must be passed consistently to init, collect and distribute.
  */
 int jt_init(jt_plan* plan, const void* factor_tables, int factors_batched, const int32_t* evidence,
-            int64_t B, int dtype, void* workspace, void* stream);
-int jt_collect(jt_plan* plan, int64_t B, int dtype, void* workspace, void* stream);
+            int64_t B, int dtype, void* workspace, int flags, void* stream);
+int jt_collect(jt_plan* plan, int64_t B, int dtype, void* workspace, int flags, void* stream);
 int jt_distribute(jt_plan* plan, int64_t B, int dtype, void* workspace, int flags, void* stream);
 /* factor_out: [fout_entries][B] values of `dtype` */
 int jt_marginal(jt_plan* plan, int64_t B, int dtype, void* workspace, void* factor_out, void* stream);

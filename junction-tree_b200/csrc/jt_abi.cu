@@ -1,0 +1,698 @@
+// libjt_b200: C ABI (include/jt_b200.h) over the sm_100a kernels of jt_kernels.cuh.
+// Plan parsing and validation, workspace layout, launch configuration.
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/jt_b200.h"
+#include "jt_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------
+// host side
+
+struct jt_plan {
+    std::vector<int64_t> hdr, node_off, node_size, fin_off, fin_size, fout_off, fout_size;
+    std::vector<int> ev_card, evf_ptr, evf_var, evf_stride;
+    std::vector<DTask> tasks;
+    std::vector<DMsg> msgs;
+    std::vector<int> tab;
+    struct Launch {
+        int phase, begin, end, level;
+        size_t prefix_off[kMaxSyLog2 + 1];
+        long long blocks[kMaxSyLog2 + 1];
+        bool tma_ok;          // every task fits the TMA kernel's stage (rows per stage <= kTmaMaxRows)
+        int min_nr;           // smallest n_r of the launch
+        long long total_s;    // sum of n_s
+    };
+    std::vector<Launch> launches;
+    std::vector<int> prefix;
+
+    int device = -1;
+    DTask* d_tasks = nullptr;
+    DMsg* d_msgs = nullptr;
+    int* d_tab = nullptr;
+    int* d_prefix = nullptr;
+    int* d_ev = nullptr;   // ev_card | evf_ptr | evf_var | evf_stride
+};
+
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t dtype_size(int dtype) { return dtype == JT_F64 ? 8 : 4; }
+
+// [ work: entries x B | fbase: F x B int32 | error counter | uniform workspace: entries x 1 ]
+struct WorkspaceLayout {
+    size_t work_bytes, fbase_off, err_off, uni_off, total;
+};
+
+WorkspaceLayout workspace_layout(const jt_plan* p, int64_t B, int dtype) {
+    WorkspaceLayout w;
+    const int64_t entries = p->hdr[JT_H_CLIQUE_ENTRIES] + 3 * p->hdr[JT_H_SEP_ENTRIES];
+    w.work_bytes = align_up((size_t)entries * (size_t)B * dtype_size(dtype), 256);
+    w.fbase_off = w.work_bytes;
+    const size_t fbase = p->hdr[JT_H_NEVID] > 0 ? (size_t)p->hdr[JT_H_NFACTORS] * (size_t)B * 4 : 0;
+    w.err_off = w.fbase_off + align_up(fbase, 256);
+    w.uni_off = w.err_off + 256;
+    const size_t uni = p->hdr[JT_H_UNI_ENTRIES] > 0 ? (size_t)entries * dtype_size(dtype) : 0;
+    w.total = w.uni_off + align_up(uni, 256);
+    return w;
+}
+
+int pick_vec(int64_t B, int dtype) {
+    const int maxv = dtype == JT_F64 ? 2 : 4;
+    for (int v = maxv; v > 1; v >>= 1)
+        if (B % v == 0) return v;
+    return 1;
+}
+
+// tile shape for a batch of Bv vectors: bx = min(256, pow2ceil(Bv)), sy = 256 / bx
+void pick_tile(long long Bv, int& bx_log2, int& sy_log2) {
+    bx_log2 = 0;
+    while ((1LL << bx_log2) < Bv && bx_log2 < 8) ++bx_log2;
+    sy_log2 = 8 - bx_log2;
+}
+
+int g_tma_enabled = -1;   // JT_DISABLE_TMA=1 forces the LDG kernel (debugging / A-B timing)
+
+bool tma_enabled() {
+    if (g_tma_enabled < 0) {
+        const char* e = getenv("JT_DISABLE_TMA");
+        g_tma_enabled = (e && e[0] == '1') ? 0 : 1;
+    }
+    return g_tma_enabled == 1;
+}
+
+template <typename T>
+int launch_tma(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
+    const int ct = a.Bv >= 256 ? 256 : (a.Bv >= 128 ? 128 : 64);
+    const long long tiles = (a.Bv + ct - 1) / ct;
+    // chunk of s per CTA: aim at ~8 CTAs per SM over the launch, but keep >= 32 (s, r) items per
+    // CTA so the pipeline fill is amortised
+    int sy_log2 = 0;
+    const long long target = 148LL * 8;
+    while (sy_log2 < kMaxSyLog2 && (L.total_s * tiles) >> (sy_log2 + 1) >= target) ++sy_log2;
+    while (sy_log2 < kMaxSyLog2 && ((long long)L.min_nr << sy_log2) < 32) ++sy_log2;
+    a.sy_log2 = sy_log2;
+    a.bx_log2 = 0;
+    a.tasks = p->d_tasks + L.begin;
+    a.n_tasks = L.end - L.begin;
+    a.prefix = p->d_prefix + L.prefix_off[sy_log2];
+    const long long gx = L.blocks[sy_log2];
+    if (gx <= 0) return JT_OK;
+    if (gx > 2147483647LL || tiles > 65535)
+        return fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, tiles);
+    // ring rows, then barriers / row indices / scalar operands (TmaAux)
+    const size_t smem = (size_t)kTmaSlots * ct * 16 + sizeof(TmaAux<T>);
+    static bool attr_set = false;
+    if (!attr_set) {
+        JT_CUDA(cudaFuncSetAttribute(jt_project_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kTmaSlots * 256 * 16 + (int)sizeof(TmaAux<T>)));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)gx, (unsigned)tiles, 1);
+    // consumer warps + row producer warp + uniform warp
+    jt_project_tma_kernel<T><<<grid, ct + 64, smem, stream>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    JT_CUDA(cudaGetLastError());
+    return JT_OK;
+}
+
+template <typename T, int VEC>
+int launch_tasks(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
+    const bool is_init = L.phase == JT_PHASE_INIT || L.phase == JT_PHASE_INIT_UNIFORM ||
+                         L.phase == JT_PHASE_INIT_INSTANCE;
+    if (!is_init && VEC * sizeof(T) == 16 && L.tma_ok && a.Bv >= 64 && tma_enabled())
+        return launch_tma<T>(p, L, a, stream);
+    int bx_log2, sy_log2;
+    pick_tile(a.Bv, bx_log2, sy_log2);
+    if (is_init) {
+        // a thread walks ~32 rows of s so the per-instance factor offsets stay in registers
+        sy_log2 = sy_log2 + 5 > kMaxSyLog2 ? kMaxSyLog2 : sy_log2 + 5;
+        while (sy_log2 > 8 - bx_log2 && (L.total_s >> sy_log2) * ((a.Bv + (1LL << bx_log2) - 1) >> bx_log2) < 148 * 4)
+            --sy_log2;
+    }
+    a.bx_log2 = bx_log2;
+    a.sy_log2 = sy_log2;
+    a.tasks = p->d_tasks + L.begin;
+    a.n_tasks = L.end - L.begin;
+    a.prefix = p->d_prefix + L.prefix_off[sy_log2];
+    const long long gx = L.blocks[sy_log2];
+    const long long gy = (a.Bv + (1LL << bx_log2) - 1) >> bx_log2;
+    if (gx <= 0) return JT_OK;
+    if (gx > 2147483647LL || gy > 65535)
+        return fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
+    dim3 grid((unsigned)gx, (unsigned)gy, 1);
+    if (is_init)
+        jt_init_kernel<T, VEC><<<grid, kThreads, 0, stream>>>(a);
+    else
+        jt_project_kernel<T, VEC><<<grid, kThreads, 0, stream>>>(a);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    JT_CUDA(cudaGetLastError());
+    return JT_OK;
+}
+
+int dispatch(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec,
+             cudaStream_t stream) {
+    if (dtype == JT_F64) {
+        if (vec == 2) return launch_tasks<double, 2>(p, L, a, stream);
+        return launch_tasks<double, 1>(p, L, a, stream);
+    }
+    if (vec == 4) return launch_tasks<float, 4>(p, L, a, stream);
+    if (vec == 2) return launch_tasks<float, 2>(p, L, a, stream);
+    return launch_tasks<float, 1>(p, L, a, stream);
+}
+
+int check_common(const jt_plan* p, int64_t B, int dtype, const void* workspace) {
+    if (!p) return fail(JT_ERR_INVALID, "plan is null");
+    if (B <= 0) return fail(JT_ERR_INVALID, "batch size must be positive");
+    if (dtype != JT_F32 && dtype != JT_F64) return fail(JT_ERR_INVALID, "dtype must be JT_F32 or JT_F64");
+    if (!workspace) return fail(JT_ERR_INVALID, "workspace is null");
+    if (p->device < 0) return fail(JT_ERR_INVALID, "plan not uploaded: call jt_plan_upload first");
+    return JT_OK;
+}
+
+KArgs base_args(const jt_plan* p, int64_t B, int dtype, void* workspace, int vec) {
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.msgs = p->d_msgs;
+    a.tab = p->d_tab;
+    a.work = workspace;
+    a.B = B;
+    a.Bv = B / vec;
+    return a;
+}
+
+// Launches of one phase, in plan order.
+int run_phase(jt_plan* p, int phase, const KArgs& a, int dtype, int vec, cudaStream_t stream) {
+    for (const auto& L : p->launches) {
+        if (L.phase != phase) continue;
+        int rc = dispatch(p, L, a, dtype, vec, stream);
+        if (rc != JT_OK) return rc;
+    }
+    return JT_OK;
+}
+
+// A phase executed once for the whole batch: an ordinary B = 1 launch on the uniform workspace.
+int run_phase_uniform(jt_plan* p, int phase, KArgs a, int dtype, void* uni_ws, cudaStream_t stream) {
+    a.work = uni_ws;
+    a.uni = nullptr;
+    a.uniform = 0;
+    a.fbase = nullptr;
+    a.B = 1;
+    a.Bv = 1;
+    return run_phase(p, phase, a, dtype, 1, stream);
+}
+
+bool uniform_mode(const jt_plan* p, int flags) {
+    return (flags & JT_UNIFORM) && p->hdr[JT_H_UNI_ENTRIES] > 0;
+}
+
+void* uniform_ws(const jt_plan* p, int64_t B, int dtype, void* workspace) {
+    return static_cast<char*>(workspace) + workspace_layout(p, B, dtype).uni_off;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jt_abi_version(void) { return JT_ABI_VERSION; }
+
+const char* jt_last_error_string(void) { return g_err; }
+
+int64_t jt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
+    if (!blob || !out) return fail(JT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (nbytes < JT_H_WORDS * 8 || nbytes % 8) return fail(JT_ERR_INVALID, "plan blob too short or misaligned");
+    const int64_t* w = static_cast<const int64_t*>(blob);
+    std::vector<int64_t> copy;
+    if (reinterpret_cast<uintptr_t>(blob) % 8) {   // tolerate unaligned input
+        copy.resize(nbytes / 8);
+        memcpy(copy.data(), blob, nbytes);
+        w = copy.data();
+    }
+    if (w[JT_H_MAGIC] != JT_MAGIC) return fail(JT_ERR_INVALID, "bad plan magic");
+    if (w[JT_H_VERSION] != JT_ABI_VERSION)
+        return fail(JT_ERR_INVALID, "plan version %lld, library expects %d", (long long)w[JT_H_VERSION], JT_ABI_VERSION);
+    for (int i = 2; i < JT_H_WORDS; ++i)
+        if (w[i] < 0) return fail(JT_ERR_INVALID, "negative header word %d", i);
+    jt_plan* p = new (std::nothrow) jt_plan;
+    if (!p) return fail(JT_ERR_NOMEM, "out of host memory");
+    p->hdr.assign(w, w + JT_H_WORDS);
+    const int64_t n_nodes = w[JT_H_NCLIQUES] + w[JT_H_NSEPS];
+    const int64_t F = w[JT_H_NFACTORS], n_evid = w[JT_H_NEVID], n_evf = w[JT_H_NEVF];
+    const int64_t n_tasks = w[JT_H_NTASKS], n_msgs = w[JT_H_NMSGS], n_launch = w[JT_H_NLAUNCHES];
+    const int64_t n_tab = w[JT_H_NTAB];
+    const int64_t evf_ptr_n = F > 0 ? F + 1 : 0;
+    const int64_t words = JT_H_WORDS + 2 * n_nodes + 4 * F + n_evid + evf_ptr_n + 2 * n_evf +
+                          n_tasks * JT_TASK_WORDS + n_msgs * JT_MSG_WORDS + n_launch * JT_LAUNCH_WORDS;
+    const int64_t tab_words = (n_tab + 1) / 2;
+    if ((int64_t)(nbytes / 8) != words + tab_words) {
+        delete p;
+        return fail(JT_ERR_INVALID, "plan blob size mismatch: %zu bytes, expected %lld", nbytes,
+                    (long long)(words + tab_words) * 8);
+    }
+    const int64_t* q = w + JT_H_WORDS;
+    auto take64 = [&](std::vector<int64_t>& v, int64_t n) { v.assign(q, q + n); q += n; };
+    auto take32 = [&](std::vector<int>& v, int64_t n) {
+        v.resize(n);
+        for (int64_t i = 0; i < n; ++i) v[i] = (int)q[i];
+        q += n;
+    };
+    take64(p->node_off, n_nodes);
+    take64(p->node_size, n_nodes);
+    take64(p->fin_off, F);
+    take64(p->fin_size, F);
+    take64(p->fout_off, F);
+    take64(p->fout_size, F);
+    take32(p->ev_card, n_evid);
+    take32(p->evf_ptr, evf_ptr_n);
+    take32(p->evf_var, n_evf);
+    take32(p->evf_stride, n_evf);
+
+    const int64_t work_entries = w[JT_H_CLIQUE_ENTRIES] + 3 * w[JT_H_SEP_ENTRIES];
+    auto bad = [&](const char* what, int64_t i) {
+        delete p;
+        return fail(JT_ERR_INVALID, "malformed plan: %s (item %lld)", what, (long long)i);
+    };
+    for (int64_t k = 0; k < n_evf; ++k)
+        if (p->evf_var[k] < 0 || p->evf_var[k] >= n_evid) return bad("evidence variable index", k);
+    for (int64_t f = 0; f + 1 < evf_ptr_n; ++f)
+        if (p->evf_ptr[f] > p->evf_ptr[f + 1] || p->evf_ptr[f + 1] > n_evf) return bad("evidence pointer", f);
+
+    p->tasks.resize(n_tasks);
+    for (int64_t i = 0; i < n_tasks; ++i, q += JT_TASK_WORDS) {
+        DTask& t = p->tasks[i];
+        t.src = q[JT_T_SRC]; t.out = q[JT_T_OUT]; t.beta = q[JT_T_BETA]; t.bel = q[JT_T_BEL]; t.own = q[JT_T_OWN];
+        if (q[JT_T_NS] <= 0 || q[JT_T_NS] > 2147483647LL || q[JT_T_NR] <= 0 || q[JT_T_NR] > 2147483647LL)
+            return bad("task index-space size", i);
+        t.n_s = (int)q[JT_T_NS]; t.n_r = (int)q[JT_T_NR]; t.n_slo = (int)q[JT_T_NSLO]; t.n_rlo = (int)q[JT_T_NRLO];
+        if (t.n_slo <= 0 || t.n_rlo <= 0 || t.n_s % t.n_slo || t.n_r % t.n_rlo) return bad("task table split", i);
+        t.src_shi = (int)q[JT_T_SRC_SHI]; t.src_slo = (int)q[JT_T_SRC_SLO];
+        t.src_rhi = (int)q[JT_T_SRC_RHI]; t.src_rlo = (int)q[JT_T_SRC_RLO];
+        t.rmsg_begin = (int)q[JT_T_RMSG_BEGIN]; t.rmsg_end = (int)q[JT_T_RMSG_END];
+        t.smsg_begin = (int)q[JT_T_SMSG_BEGIN]; t.smsg_end = (int)q[JT_T_SMSG_END];
+        t.kind = (int)q[JT_T_KIND]; t.out_space = (int)q[JT_T_OUT_SPACE];
+        t.flags = (int)q[JT_T_FLAGS]; t.pad = 0;
+        if (t.rmsg_begin < 0 || t.rmsg_begin > t.rmsg_end || t.rmsg_end > n_msgs || t.smsg_begin < 0 ||
+            t.smsg_begin > t.smsg_end || t.smsg_end > n_msgs)
+            return bad("task message range", i);
+        const int n_shi = t.n_s / t.n_slo, n_rhi = t.n_r / t.n_rlo;
+        if (t.kind == JT_KIND_PROJECT) {
+            if (t.src_shi < 0 || t.src_shi + n_shi > n_tab || t.src_slo < 0 || t.src_slo + t.n_slo > n_tab ||
+                t.src_rhi < 0 || t.src_rhi + n_rhi > n_tab || t.src_rlo < 0 || t.src_rlo + t.n_rlo > n_tab)
+                return bad("task table range", i);
+        } else if (t.kind != JT_KIND_INIT) {
+            return bad("task kind", i);
+        }
+        for (long long off : {t.src, t.beta, t.bel, t.own})
+            if (off < -1 || off >= work_entries) return bad("task buffer offset", i);
+        if (t.out < -1) return bad("task output offset", i);
+        if (t.out_space == 0 && t.out >= work_entries) return bad("task output offset", i);
+        if (t.out_space == 1 && t.out + t.n_s > w[JT_H_FOUT_ENTRIES]) return bad("factor output range", i);
+    }
+    p->msgs.resize(n_msgs);
+    for (int64_t i = 0; i < n_msgs; ++i, q += JT_MSG_WORDS) {
+        DMsg& m = p->msgs[i];
+        m.off = q[JT_M_OFF];
+        m.a_hi = (int)q[JT_M_AHI]; m.a_lo = (int)q[JT_M_ALO]; m.b_hi = (int)q[JT_M_BHI]; m.b_lo = (int)q[JT_M_BLO];
+        m.fid = (int)q[JT_M_FID]; m.uni = q[JT_M_UNI] ? 1 : 0; m.eoff = 0;
+        if (m.off < 0 || m.a_hi < 0 || m.a_lo < 0 || m.b_hi < 0 || m.b_lo < 0 || m.a_hi >= n_tab + 1 ||
+            m.a_lo >= n_tab + 1 || m.b_hi >= n_tab + 1 || m.b_lo >= n_tab + 1 || m.fid >= F)
+            return bad("message descriptor", i);
+    }
+    p->launches.resize(n_launch);
+    for (int64_t i = 0; i < n_launch; ++i, q += JT_LAUNCH_WORDS) {
+        jt_plan::Launch& L = p->launches[i];
+        L.phase = (int)q[JT_L_PHASE]; L.begin = (int)q[JT_L_BEGIN]; L.end = (int)q[JT_L_END]; L.level = (int)q[JT_L_LEVEL];
+        if (L.phase < JT_PHASE_INIT || L.phase > JT_PHASE_COLLECT_INSTANCE || L.begin < 0 || L.begin >= L.end || L.end > n_tasks)
+            return bad("launch descriptor", i);
+        for (int t = L.begin; t < L.end; ++t)
+            if ((p->tasks[t].kind == JT_KIND_INIT) != (L.phase == JT_PHASE_INIT || L.phase == JT_PHASE_INIT_UNIFORM ||
+                                                        L.phase == JT_PHASE_INIT_INSTANCE))
+                return bad("task kind vs phase", i);
+        L.tma_ok = true;
+        L.min_nr = 2147483647;
+        L.total_s = 0;
+        for (int t = L.begin; t < L.end; ++t) {
+            const DTask& k = p->tasks[t];
+            const int rows = (k.src >= 0 ? 1 : 0) + (k.rmsg_end - k.rmsg_begin) + (k.smsg_end - k.smsg_begin) +
+                             (k.own >= 0 ? 1 : 0);
+            if (rows < 1 || rows > kTmaMaxRows || k.rmsg_end != k.smsg_begin) L.tma_ok = false;
+            L.min_nr = k.n_r < L.min_nr ? k.n_r : L.min_nr;
+            L.total_s += k.n_s;
+        }
+        // block prefix per tile shape: a block covers 2^sy consecutive values of s of one task
+        for (int sy = 0; sy <= kMaxSyLog2; ++sy) {
+            L.prefix_off[sy] = p->prefix.size();
+            long long acc = 0;
+            for (int t = L.begin; t < L.end; ++t) {
+                p->prefix.push_back((int)acc);
+                acc += ((long long)p->tasks[t].n_s + (1 << sy) - 1) >> sy;
+                if (acc > 2147483647LL) return bad("launch too large", i);
+            }
+            p->prefix.push_back((int)acc);
+            L.blocks[sy] = acc;
+        }
+    }
+    const int32_t* tabp = reinterpret_cast<const int32_t*>(q);
+    p->tab.assign(tabp, tabp + n_tab);
+    *out = p;
+    return JT_OK;
+}
+
+void jt_plan_destroy(jt_plan* p) {
+    if (!p) return;
+    if (p->device >= 0) {
+        cudaFree(p->d_tasks);
+        cudaFree(p->d_msgs);
+        cudaFree(p->d_tab);
+        cudaFree(p->d_prefix);
+        cudaFree(p->d_ev);
+    }
+    delete p;
+}
+
+int jt_plan_query(const jt_plan* p, int what, int64_t* out) {
+    if (!p || !out || what < 0 || what >= JT_H_WORDS) return fail(JT_ERR_INVALID, "bad query");
+    *out = p->hdr[what];
+    return JT_OK;
+}
+
+int jt_plan_node_range(const jt_plan* p, int node, int64_t* offset, int64_t* count) {
+    if (!p || node < 0 || node >= (int)p->node_off.size()) return fail(JT_ERR_INVALID, "bad node index");
+    if (offset) *offset = p->node_off[node];
+    if (count) *count = p->node_size[node];
+    return JT_OK;
+}
+
+int jt_plan_message_offsets(const jt_plan* p, int node, int64_t* up, int64_t* down) {
+    if (!p) return fail(JT_ERR_INVALID, "plan is null");
+    const int64_t n_c = p->hdr[JT_H_NCLIQUES];
+    if (node < n_c || node >= (int64_t)p->node_off.size()) return fail(JT_ERR_INVALID, "not a separator node");
+    const int64_t rel = p->node_off[node] - p->hdr[JT_H_CLIQUE_ENTRIES];
+    const int64_t up_base = p->hdr[JT_H_CLIQUE_ENTRIES] + p->hdr[JT_H_SEP_ENTRIES];
+    if (up) *up = up_base + rel;
+    if (down) *down = up_base + p->hdr[JT_H_SEP_ENTRIES] + rel;
+    return JT_OK;
+}
+
+int jt_workspace_bytes(const jt_plan* p, int64_t B, int dtype, size_t* out) {
+    if (!p || !out || B <= 0 || (dtype != JT_F32 && dtype != JT_F64)) return fail(JT_ERR_INVALID, "bad argument");
+    *out = workspace_layout(p, B, dtype).total;
+    return JT_OK;
+}
+
+int jt_workspace_layout(const jt_plan* p, int64_t B, int dtype, int64_t* out4) {
+    if (!p || !out4 || B <= 0 || (dtype != JT_F32 && dtype != JT_F64)) return fail(JT_ERR_INVALID, "bad argument");
+    const WorkspaceLayout w = workspace_layout(p, B, dtype);
+    out4[0] = (int64_t)w.fbase_off;
+    out4[1] = (int64_t)w.err_off;
+    out4[2] = (int64_t)w.uni_off;
+    out4[3] = (int64_t)w.total;
+    return JT_OK;
+}
+
+int jt_plan_upload(jt_plan* p) {
+    if (!p) return fail(JT_ERR_INVALID, "plan is null");
+    int dev = -1;
+    JT_CUDA(cudaGetDevice(&dev));
+    if (p->device == dev) return JT_OK;
+    if (p->device >= 0) return fail(JT_ERR_INVALID, "plan already uploaded to device %d", p->device);
+    auto up = [](auto** dst, const auto& v) -> cudaError_t {
+        const size_t bytes = v.size() * sizeof(v[0]);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), bytes ? bytes : 16);
+        if (e != cudaSuccess || !bytes) return e;
+        return cudaMemcpy(*dst, v.data(), bytes, cudaMemcpyHostToDevice);
+    };
+    JT_CUDA(up(&p->d_tasks, p->tasks));
+    JT_CUDA(up(&p->d_msgs, p->msgs));
+    JT_CUDA(up(&p->d_tab, p->tab));
+    JT_CUDA(up(&p->d_prefix, p->prefix));
+    std::vector<int> ev;
+    ev.insert(ev.end(), p->ev_card.begin(), p->ev_card.end());
+    ev.insert(ev.end(), p->evf_ptr.begin(), p->evf_ptr.end());
+    ev.insert(ev.end(), p->evf_var.begin(), p->evf_var.end());
+    ev.insert(ev.end(), p->evf_stride.begin(), p->evf_stride.end());
+    JT_CUDA(up(&p->d_ev, ev));
+    p->device = dev;
+    return JT_OK;
+}
+
+int jt_init(jt_plan* p, const void* factor_tables, int factors_batched, const int32_t* evidence, int64_t B,
+            int dtype, void* workspace, int flags, void* stream_) {
+    int rc = check_common(p, B, dtype, workspace);
+    if (rc != JT_OK) return rc;
+    if ((flags & JT_UNIFORM) && factors_batched)
+        return fail(JT_ERR_INVALID, "JT_UNIFORM requires factor tables shared by the batch");
+    if (p->hdr[JT_H_NFACTORS] == 0) return fail(JT_ERR_INVALID, "plan has no factors: nothing to initialise");
+    if (!factor_tables) return fail(JT_ERR_INVALID, "factor_tables is null");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const WorkspaceLayout wl = workspace_layout(p, B, dtype);
+    const int n_evid = (int)p->hdr[JT_H_NEVID];
+    const int vec = pick_vec(B, dtype);
+    KArgs a = base_args(p, B, dtype, workspace, vec);
+    a.fin = factor_tables;
+    a.fin_batched = factors_batched ? 1 : 0;
+    if (n_evid > 0) {
+        if (!evidence) return fail(JT_ERR_INVALID, "plan has %d evidence variables but evidence is null", n_evid);
+        if (factors_batched) return fail(JT_ERR_INVALID, "per-instance factor tables cannot be combined with evidence indices");
+        int* fbase = reinterpret_cast<int*>(static_cast<char*>(workspace) + wl.fbase_off);
+        unsigned long long* err = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + wl.err_off);
+        const int F = (int)p->hdr[JT_H_NFACTORS];
+        const int* d_card = p->d_ev;
+        const int* d_ptr = d_card + p->ev_card.size();
+        const int* d_var = d_ptr + p->evf_ptr.size();
+        const int* d_stride = d_var + p->evf_var.size();
+        const long long blocks = (B + kThreads - 1) / kThreads;
+        jt_evidence_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(evidence, n_evid, d_card, d_ptr, d_var,
+                                                                      d_stride, F, B, fbase, err);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        JT_CUDA(cudaGetLastError());
+        a.fbase = fbase;
+    }
+    if (!uniform_mode(p, flags)) return run_phase(p, JT_PHASE_INIT, a, dtype, vec, stream);
+    // uniform mode: potentials no evidence touches are written once, the others per instance
+    rc = run_phase_uniform(p, JT_PHASE_INIT_UNIFORM, a, dtype, uniform_ws(p, B, dtype, workspace), stream);
+    if (rc != JT_OK) return rc;
+    return run_phase(p, JT_PHASE_INIT_INSTANCE, a, dtype, vec, stream);
+}
+
+int jt_collect(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, void* stream_) {
+    int rc = check_common(p, B, dtype, workspace);
+    if (rc != JT_OK) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int vec = pick_vec(B, dtype);
+    KArgs a = base_args(p, B, dtype, workspace, vec);
+    a.flags = flags;
+    if (!uniform_mode(p, flags)) return run_phase(p, JT_PHASE_COLLECT, a, dtype, vec, stream);
+    // uniform mode: evidence-free subtrees are collected once (B = 1), then the rest per instance
+    void* uni = uniform_ws(p, B, dtype, workspace);
+    rc = run_phase_uniform(p, JT_PHASE_COLLECT_UNIFORM, a, dtype, uni, stream);
+    if (rc != JT_OK) return rc;
+    a.uni = uni;
+    a.uniform = 1;
+    return run_phase(p, JT_PHASE_COLLECT_INSTANCE, a, dtype, vec, stream);
+}
+
+int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, void* stream_) {
+    int rc = check_common(p, B, dtype, workspace);
+    if (rc != JT_OK) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int vec = pick_vec(B, dtype);
+    KArgs a = base_args(p, B, dtype, workspace, vec);
+    a.flags = flags;
+    if (uniform_mode(p, flags)) {
+        a.uni = uniform_ws(p, B, dtype, workspace);
+        a.uniform = 1;
+    }
+    // per level: the tasks that only read psi_C, then the task that overwrites it with beta_C
+    for (const auto& L : p->launches) {
+        if (L.phase != JT_PHASE_DIST_PRE && L.phase != JT_PHASE_DIST_MAIN) continue;
+        rc = dispatch(p, L, a, dtype, vec, stream);
+        if (rc != JT_OK) return rc;
+    }
+    return JT_OK;
+}
+
+int jt_marginal(jt_plan* p, int64_t B, int dtype, void* workspace, void* factor_out, void* stream) {
+    int rc = check_common(p, B, dtype, workspace);
+    if (rc != JT_OK) return rc;
+    if (!factor_out) return fail(JT_ERR_INVALID, "factor_out is null");
+    const int vec = pick_vec(B, dtype);
+    KArgs a = base_args(p, B, dtype, workspace, vec);
+    a.fout = factor_out;
+    return run_phase(p, JT_PHASE_MARGINAL, a, dtype, vec, static_cast<cudaStream_t>(stream));
+}
+
+int jt_propagate(jt_plan* p, const void* factor_tables, int factors_batched, const int32_t* evidence, int64_t B,
+                 int dtype, void* workspace, void* factor_out, int flags, void* stream) {
+    // shared factor tables: potentials and messages no evidence reaches are computed once
+    if (factors_batched) flags &= ~JT_UNIFORM;
+    else if (!(flags & JT_NO_UNIFORM)) flags |= JT_UNIFORM;
+    int rc = jt_init(p, factor_tables, factors_batched, evidence, B, dtype, workspace, flags, stream);
+    if (rc != JT_OK) return rc;
+    rc = jt_collect(p, B, dtype, workspace, flags, stream);
+    if (rc != JT_OK) return rc;
+    rc = jt_distribute(p, B, dtype, workspace, flags, stream);
+    if (rc != JT_OK) return rc;
+    if (flags & JT_SKIP_MARGINAL) return JT_OK;
+    return jt_marginal(p, B, dtype, workspace, factor_out, stream);
+}
+
+int jt_evidence_errors(jt_plan* p, int64_t B, int dtype, void* workspace, void* stream, int64_t* out) {
+    int rc = check_common(p, B, dtype, workspace);
+    if (rc != JT_OK) return rc;
+    if (!out) return fail(JT_ERR_INVALID, "out is null");
+    const WorkspaceLayout wl = workspace_layout(p, B, dtype);
+    unsigned long long v = 0;
+    JT_CUDA(cudaMemcpyAsync(&v, static_cast<char*>(workspace) + wl.err_off, sizeof(v), cudaMemcpyDeviceToHost,
+                            static_cast<cudaStream_t>(stream)));
+    JT_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    *out = (int64_t)v;
+    return JT_OK;
+}
+
+int jt_copy_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                 size_t rows, int to_host, void* stream) {
+    if (!dst || !src || width_bytes > dst_pitch || width_bytes > src_pitch)
+        return fail(JT_ERR_INVALID, "bad argument");
+    if (!rows || !width_bytes) return JT_OK;
+    JT_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows,
+                              to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice,
+                              static_cast<cudaStream_t>(stream)));
+    return JT_OK;
+}
+
+int jt_ratio(const void* new_values, const void* old_values, void* out, int64_t n, int dtype, void* stream_) {
+    if (!new_values || !old_values || !out || n < 0) return fail(JT_ERR_INVALID, "bad argument");
+    if (dtype != JT_F32 && dtype != JT_F64) return fail(JT_ERR_INVALID, "dtype must be JT_F32 or JT_F64");
+    if (n == 0) return JT_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    long long blocks = (n + kThreads - 1) / kThreads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (dtype == JT_F64)
+        jt_ratio_kernel<double><<<(unsigned)blocks, kThreads, 0, stream>>>(
+            static_cast<const double*>(new_values), static_cast<const double*>(old_values),
+            static_cast<double*>(out), n);
+    else
+        jt_ratio_kernel<float><<<(unsigned)blocks, kThreads, 0, stream>>>(
+            static_cast<const float*>(new_values), static_cast<const float*>(old_values),
+            static_cast<float*>(out), n);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    JT_CUDA(cudaGetLastError());
+    return JT_OK;
+}
+
+int jt_contract(const void* const* ops, int n_ops, const int32_t* tables, int64_t n_tab, const int32_t* maps,
+                int64_t n_s, int64_t n_r, int64_t n_slo, int64_t n_rlo, int64_t B, int dtype, void* out,
+                void* stream_) {
+    if (!ops || n_ops <= 0 || !tables || !maps || !out) return fail(JT_ERR_INVALID, "null argument");
+    if (n_s <= 0 || n_r <= 0 || n_slo <= 0 || n_rlo <= 0 || n_s % n_slo || n_r % n_rlo || n_s > 2147483647LL ||
+        n_r > 2147483647LL || B <= 0 || n_tab <= 0)
+        return fail(JT_ERR_INVALID, "bad index-space sizes");
+    if (dtype != JT_F32 && dtype != JT_F64) return fail(JT_ERR_INVALID, "dtype must be JT_F32 or JT_F64");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t w = dtype_size(dtype);
+    const int n_shi = (int)(n_s / n_slo), n_rhi = (int)(n_r / n_rlo);
+    for (int j = 0; j < n_ops; ++j) {
+        const int32_t* m = maps + 4 * j;
+        if (m[0] < 0 || m[0] + n_shi > n_tab || m[1] < 0 || m[1] + n_slo > n_tab || m[2] < 0 ||
+            m[2] + n_rhi > n_tab || m[3] < 0 || m[3] + n_rlo > n_tab)
+            return fail(JT_ERR_INVALID, "operand %d: table range", j);
+    }
+    int vec = pick_vec(B, dtype);
+    auto misaligned = [&](const void* ptr) { return reinterpret_cast<uintptr_t>(ptr) % (w * vec) != 0; };
+    while (vec > 1) {
+        bool bad = misaligned(out);
+        for (int j = 0; j < n_ops; ++j) bad = bad || misaligned(ops[j]);
+        if (!bad) break;
+        vec >>= 1;
+    }
+    // device scratch: [DTask | DMsg x n_ops | prefix(2) | tables]
+    const size_t msg_off = align_up(sizeof(DTask), 16);
+    const size_t prefix_off = align_up(msg_off + sizeof(DMsg) * n_ops, 16);
+    const size_t tab_off = align_up(prefix_off + 2 * sizeof(int), 16);
+    const size_t total = tab_off + (size_t)n_tab * 4;
+    std::vector<char> host(total, 0);
+    int bx_log2, sy_log2;
+    pick_tile(B / vec, bx_log2, sy_log2);
+    DTask t;
+    memset(&t, 0, sizeof(t));
+    t.src = t.beta = t.bel = t.own = -1;
+    t.out = 0;
+    t.n_s = (int)n_s; t.n_r = (int)n_r; t.n_slo = (int)n_slo; t.n_rlo = (int)n_rlo;
+    // no src operand: point the (unused) src maps at operand 0's tables so every read is in range
+    t.src_shi = maps[0]; t.src_slo = maps[1]; t.src_rhi = maps[2]; t.src_rlo = maps[3];
+    t.rmsg_begin = 0; t.rmsg_end = n_ops; t.smsg_begin = t.smsg_end = n_ops;
+    t.kind = JT_KIND_PROJECT; t.out_space = 1;
+    memcpy(host.data(), &t, sizeof(t));
+    const char* out_c = static_cast<const char*>(out);
+    for (int j = 0; j < n_ops; ++j) {
+        DMsg m;
+        memset(&m, 0, sizeof(m));
+        const ptrdiff_t delta = static_cast<const char*>(ops[j]) - out_c;
+        if (delta % (ptrdiff_t)w) return fail(JT_ERR_INVALID, "operand %d misaligned relative to out", j);
+        m.eoff = delta / (ptrdiff_t)w;
+        m.a_hi = maps[4 * j]; m.a_lo = maps[4 * j + 1]; m.b_hi = maps[4 * j + 2]; m.b_lo = maps[4 * j + 3];
+        m.fid = -1;
+        memcpy(host.data() + msg_off + sizeof(DMsg) * j, &m, sizeof(m));
+    }
+    const long long blocks = ((long long)n_s + (1 << sy_log2) - 1) >> sy_log2;
+    int prefix[2] = {0, (int)blocks};
+    memcpy(host.data() + prefix_off, prefix, sizeof(prefix));
+    memcpy(host.data() + tab_off, tables, (size_t)n_tab * 4);
+    char* dev = nullptr;
+    JT_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dev), total, stream));
+    cudaError_t e = cudaMemcpyAsync(dev, host.data(), total, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(dev, stream);
+        return fail(JT_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+    }
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tasks = reinterpret_cast<const DTask*>(dev);
+    a.msgs = reinterpret_cast<const DMsg*>(dev + msg_off);
+    a.prefix = reinterpret_cast<const int*>(dev + prefix_off);
+    a.tab = reinterpret_cast<const int*>(dev + tab_off);
+    a.work = out;   // operands are addressed relative to `out` (DMsg::eoff)
+    a.fout = out;
+    a.B = B;
+    a.Bv = B / vec;
+    a.n_tasks = 1;
+    a.bx_log2 = bx_log2;
+    a.sy_log2 = sy_log2;
+    const long long gy = (a.Bv + (1LL << bx_log2) - 1) >> bx_log2;
+    int rc = JT_OK;
+    if (blocks > 2147483647LL || gy > 65535) {
+        rc = fail(JT_ERR_INVALID, "launch grid exceeds CUDA limits; split the batch");
+    } else {
+        dim3 grid((unsigned)blocks, (unsigned)gy, 1);
+        if (dtype == JT_F64) {
+            if (vec == 2) jt_project_kernel<double, 2><<<grid, kThreads, 0, stream>>>(a);
+            else jt_project_kernel<double, 1><<<grid, kThreads, 0, stream>>>(a);
+        } else {
+            if (vec == 4) jt_project_kernel<float, 4><<<grid, kThreads, 0, stream>>>(a);
+            else if (vec == 2) jt_project_kernel<float, 2><<<grid, kThreads, 0, stream>>>(a);
+            else jt_project_kernel<float, 1><<<grid, kThreads, 0, stream>>>(a);
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(JT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    cudaFreeAsync(dev, stream);
+    return rc;
+}
+
+}  // extern "C"

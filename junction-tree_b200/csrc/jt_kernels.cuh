@@ -1,0 +1,795 @@
+// Device side of libjt_b200: descriptors, mbarrier/TMA primitives and the sm_100a kernels.
+// Included by jt_abi.cu only.  Task semantics: include/jt_b200.h; schedule: junctiontree/schedule.py.
+//
+// Everything on this path is HBM-bound (2 flops per 8..16 bytes), so the kernels are built
+// around coalesced 16-byte accesses on the batch-innermost layout [entry][B]; all index
+// arithmetic is table-driven and warp-uniform.
+#pragma once
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// error handling
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define JT_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(JT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// device-side descriptors
+
+struct DTask {
+    long long src, out, beta, bel, own;  // entry offsets, -1 = absent
+    int n_s, n_r, n_slo, n_rlo;
+    int src_shi, src_slo, src_rhi, src_rlo;
+    int rmsg_begin, rmsg_end, smsg_begin, smsg_end;
+    int kind, out_space;
+    int flags, pad;       // JT_TF_* (honoured in uniform mode only)
+};
+
+struct DMsg {
+    long long off;    // entry offset (multiplied by B on the device)
+    long long eoff;   // element offset added as is (jt_contract operands; 0 inside a plan)
+    int a_hi, a_lo, b_hi, b_lo;
+    int fid;          // init: factor index
+    int uni;          // message buffer is uniform (read from the uniform workspace in uniform mode)
+};
+
+struct KArgs {
+    const DTask* tasks;   // first task of this launch
+    const DMsg* msgs;     // all messages of the plan
+    const int* tab;       // all index tables
+    const int* prefix;    // [n_tasks + 1] first block of each task for this launch / tile shape
+    void* work;
+    const void* uni;      // uniform workspace (same entry offsets, B = 1), or null
+    void* fout;
+    const void* fin;
+    const int* fbase;     // [F][B] per-instance factor base offsets, or null
+    long long B;          // instances (row pitch in elements)
+    long long Bv;         // B / VEC
+    int n_tasks;
+    int bx_log2;          // batch-tile width in vectors (log2)
+    int sy_log2;          // rows of s per block (log2)
+    int flags;
+    int fin_batched;
+    int uniform;          // honour the uniform-operand flags of tasks and messages
+};
+
+constexpr int kThreads = 256;
+constexpr int kMaxSyLog2 = 12;  // largest chunk of s per block: 4096
+constexpr int kRegMsgs = 4;   // r-dependent messages kept in registers
+constexpr int kUnroll = 4;    // independent row loads in flight per thread
+
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) Pack {
+    T v[VEC];
+};
+
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> pack_fill(T x) {
+    Pack<T, VEC> p;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) p.v[i] = x;
+    return p;
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> ld(const T* p) {
+    return *reinterpret_cast<const Pack<T, VEC>*>(p);
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void st(T* p, const Pack<T, VEC>& x) {
+    *reinterpret_cast<Pack<T, VEC>*>(p) = x;
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void mul(Pack<T, VEC>& a, const Pack<T, VEC>& b) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) a.v[i] *= b.v[i];
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void add(Pack<T, VEC>& a, const Pack<T, VEC>& b) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) a.v[i] += b.v[i];
+}
+
+// Locate the task of this block; s0 = first output index of the block's chunk of 2^sy_log2.
+__device__ __forceinline__ const DTask* locate_chunk(const KArgs& a, int& s0) {
+    const int bid = blockIdx.x;
+    int lo = 0, hi = a.n_tasks;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a.prefix + mid) <= bid) lo = mid; else hi = mid;
+    }
+    s0 = (bid - __ldg(a.prefix + lo)) << a.sy_log2;
+    return a.tasks + lo;
+}
+
+// Locate the task of this block and the output index s of this thread (2^sy_log2 rows of s per
+// block, 2^bx_log2 batch vectors per row).
+__device__ __forceinline__ const DTask* locate(const KArgs& a, int& s, long long& bv) {
+    const int tx = threadIdx.x & ((1 << a.bx_log2) - 1);
+    const int ty = threadIdx.x >> a.bx_log2;
+    bv = ((long long)blockIdx.y << a.bx_log2) + tx;
+    int s0;
+    const DTask* tk = locate_chunk(a, s0);
+    s = s0 + ty;
+    return tk;
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy (TMA) primitives, inline PTX for sm_100a
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "JT_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra JT_DONE_%=;\n"
+        "bra JT_WAIT_%=;\n"
+        "JT_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// evidence slicing (V1): per-instance base offset of every factor table
+//   fbase[f][b] = sum over observed axes k of factor f:  state[b][var_k] * stride_k
+// Pure integer arithmetic; out-of-range states are clamped and counted.
+
+__global__ void __launch_bounds__(kThreads)
+jt_evidence_kernel(const int* __restrict__ evidence, int n_evid, const int* __restrict__ ev_card,
+                   const int* __restrict__ evf_ptr, const int* __restrict__ evf_var,
+                   const int* __restrict__ evf_stride, int n_factors, long long B,
+                   int* __restrict__ fbase, unsigned long long* __restrict__ errors) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int* row = evidence + b * n_evid;
+    unsigned bad = 0;
+    for (int f = 0; f < n_factors; ++f) {
+        int acc = 0;
+        for (int k = evf_ptr[f]; k < evf_ptr[f + 1]; ++k) {
+            const int var = evf_var[k];
+            int state = row[var];
+            const int card = ev_card[var];
+            if (state < 0 || state >= card) {
+                ++bad;
+                state = state < 0 ? 0 : card - 1;
+            }
+            acc += state * evf_stride[k];
+        }
+        fbase[(long long)f * B + b] = acc;
+    }
+    if (bad) atomicAdd(errors, (unsigned long long)bad);
+}
+
+// ------------------------------------------------------------------------------------------
+// clique initialisation (E0 + V1): psi_C[s][b] = prod_f phi_f[ A_f(s) + fbase[f][b] ]
+
+// A thread owns VEC batch columns and walks its rows of the block's chunk of s, so the
+// per-instance factor offsets (which do not depend on s) are read once and kept in registers.
+constexpr int kInitRegFactors = 6;
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
+    typedef Pack<T, VEC> P;
+    int s;
+    long long bv;
+    const DTask* tk = locate(a, s, bv);
+    const int n_s = tk->n_s;
+    if (s >= n_s || bv >= a.Bv) return;
+    const int rows = kThreads >> a.bx_log2;                       // rows of s handled per step
+    const int s_end = min(n_s, (s - (int)(threadIdx.x >> a.bx_log2)) + (1 << a.sy_log2));
+    const int* __restrict__ tab = a.tab;
+    const DMsg* __restrict__ msgs = a.msgs;
+    const long long B = a.B, col = bv * VEC;
+    const int n_slo = tk->n_slo;
+    int s_hi = 0, s_lo = s;
+    if (n_slo < n_s) {
+        s_hi = s / n_slo;
+        s_lo = s - s_hi * n_slo;
+    }
+    const T* __restrict__ fin = static_cast<const T*>(a.fin);
+    const int f0 = tk->smsg_begin, nf = tk->smsg_end - f0;
+    const bool gather = !a.fin_batched && a.fbase != nullptr;
+
+    // per-factor, per-instance base offsets (evidence slicing), resident in registers
+    int fb[kInitRegFactors][VEC];
+#pragma unroll
+    for (int j = 0; j < kInitRegFactors; ++j) {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) fb[j][u] = 0;
+        if (gather && j < nf) {
+            const int* p = a.fbase + (long long)msgs[f0 + j].fid * B + col;
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) fb[j][u] = p[u];
+        }
+    }
+
+    T* out = static_cast<T*>(a.work) + tk->out * B + col;
+    for (; s < s_end; s += rows) {
+        P val = pack_fill<T, VEC>(T(1));
+#pragma unroll
+        for (int j = 0; j < kInitRegFactors; ++j) {
+            if (j < nf) {
+                const DMsg* m = msgs + f0 + j;
+                const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+                if (a.fin_batched) {
+                    mul(val, ld<T, VEC>(fin + idx * B + col));
+                } else {
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) val.v[u] *= __ldg(fin + idx + fb[j][u]);
+                }
+            }
+        }
+        for (int j = kInitRegFactors; j < nf; ++j) {   // rare: many factors in one clique
+            const DMsg* m = msgs + f0 + j;
+            const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+            if (a.fin_batched) {
+                mul(val, ld<T, VEC>(fin + idx * B + col));
+            } else {
+                const int* p = a.fbase ? a.fbase + (long long)m->fid * B + col : nullptr;
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) val.v[u] *= __ldg(fin + idx + (p ? p[u] : 0));
+            }
+        }
+        st<T, VEC>(out + (long long)s * B, val);
+        s_lo += rows;
+        while (s_lo >= n_slo) {
+            s_lo -= n_slo;
+            ++s_hi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// projection task (collect E1+E2, distribute E3+E4+M1+E5, marginal E6, contract)
+//
+// Uniform operands (KArgs::uniform): an operand flagged uniform (the potential of a clique no
+// evidence touches, an up-message of an evidence-free subtree) is identical for every instance;
+// it lives once in the uniform workspace (same entry offsets, B = 1) and is broadcast.
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
+    typedef Pack<T, VEC> P;
+    int s;
+    long long bv;
+    const DTask* tk = locate(a, s, bv);
+    const int n_s = tk->n_s;
+    if (s >= n_s || bv >= a.Bv) return;
+
+    const int* __restrict__ tab = a.tab;
+    const DMsg* __restrict__ msgs = a.msgs;
+    const long long B = a.B, col = bv * VEC;
+    T* work = static_cast<T*>(a.work);
+    const T* uni = static_cast<const T*>(a.uni);
+    const bool um = a.uniform != 0;
+    const int tflags = um ? tk->flags : 0;
+
+    const int n_slo = tk->n_slo;
+    int s_hi = 0, s_lo = s;
+    if (n_slo < n_s) {
+        s_hi = s / n_slo;
+        s_lo = s - s_hi * n_slo;
+    }
+
+    // messages that do not depend on r, and the task's own up-message
+    P sm = pack_fill<T, VEC>(T(1));
+    for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
+        const DMsg* m = msgs + j;
+        const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+        if (um && m->uni) mul(sm, pack_fill<T, VEC>(__ldg(uni + idx)));
+        else mul(sm, ld<T, VEC>(work + m->eoff + idx * B + col));
+    }
+    const bool has_own = tk->own >= 0;
+    P own = pack_fill<T, VEC>(T(1));
+    if (has_own) {
+        if (tflags & JT_TF_OWN_UNIFORM) own = pack_fill<T, VEC>(__ldg(uni + tk->own + s));
+        else own = ld<T, VEC>(work + (tk->own + s) * B + col);
+    }
+
+    // r-dependent messages: the first kRegMsgs are tracked in registers.  mptr/mpitch address
+    // either a [n][B] row (pitch B) or the uniform copy (pitch 1, scalar broadcast).
+    const int rm0 = tk->rmsg_begin;
+    const int nr = tk->rmsg_end - rm0;
+    const T* mptr[kRegMsgs];
+    int mbhi[kRegMsgs], mblo[kRegMsgs];
+    unsigned umask = 0;
+#pragma unroll
+    for (int j = 0; j < kRegMsgs; ++j) {
+        mptr[j] = work;
+        mbhi[j] = mblo[j] = 0;
+        if (j < nr) {
+            const DMsg* m = msgs + rm0 + j;
+            const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+            if (um && m->uni) {
+                umask |= 1u << j;
+                mptr[j] = uni + idx;
+            } else {
+                mptr[j] = work + m->eoff + idx * B + col;
+            }
+            mbhi[j] = m->b_hi;
+            mblo[j] = m->b_lo;
+        }
+    }
+
+    const bool has_src = tk->src >= 0;
+    const bool src_uni = (tflags & JT_TF_SRC_UNIFORM) != 0;
+    const long long s_off = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo);
+    const T* sptr = src_uni ? uni + tk->src + s_off : work + ((has_src ? tk->src : 0) + s_off) * B + col;
+    const long long spitch = src_uni ? 1 : B;
+    const bool wbeta = tk->beta >= 0;
+    T* bptr = work + ((wbeta ? tk->beta : 0) + s_off) * B + col;
+    P scale = sm;
+    mul(scale, own);
+
+    const int n_rlo = tk->n_rlo;
+    const int n_rhi = tk->n_r / n_rlo;
+    const int* __restrict__ t_rhi = tab + tk->src_rhi;
+    const int* __restrict__ t_rlo = tab + tk->src_rlo;
+
+    P acc[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) acc[u] = pack_fill<T, VEC>(T(0));
+
+    for (int rh = 0; rh < n_rhi; ++rh) {
+        const long long e_hi = __ldg(t_rhi + rh);
+        long long mh[kRegMsgs];
+#pragma unroll
+        for (int j = 0; j < kRegMsgs; ++j) mh[j] = (j < nr) ? (long long)__ldg(tab + mbhi[j] + rh) : 0;
+
+        int rl = 0;
+        for (; rl + kUnroll <= n_rlo; rl += kUnroll) {
+            long long e[kUnroll];
+            P v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) e[u] = e_hi + __ldg(t_rlo + rl + u);
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (!has_src) v[u] = pack_fill<T, VEC>(T(1));
+                else if (src_uni) v[u] = pack_fill<T, VEC>(__ldg(sptr + e[u]));
+                else v[u] = ld<T, VEC>(sptr + e[u] * B);
+            }
+#pragma unroll
+            for (int j = 0; j < kRegMsgs; ++j) {
+                if (j < nr) {
+                    P w[kUnroll];
+                    if ((umask >> j) & 1u) {
+#pragma unroll
+                        for (int u = 0; u < kUnroll; ++u)
+                            w[u] = pack_fill<T, VEC>(__ldg(mptr[j] + mh[j] + __ldg(tab + mblo[j] + rl + u)));
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < kUnroll; ++u)
+                            w[u] = ld<T, VEC>(mptr[j] + (mh[j] + __ldg(tab + mblo[j] + rl + u)) * B);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) mul(v[u], w[u]);
+                }
+            }
+            for (int j = kRegMsgs; j < nr; ++j) {   // rare: more than kRegMsgs r-dependent messages
+                const DMsg* m = msgs + rm0 + j;
+                const long long base = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo) +
+                                       __ldg(tab + m->b_hi + rh);
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const long long idx = base + __ldg(tab + m->b_lo + rl + u);
+                    if (um && m->uni) mul(v[u], pack_fill<T, VEC>(__ldg(uni + idx)));
+                    else mul(v[u], ld<T, VEC>(work + m->eoff + idx * B + col));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) add(acc[u], v[u]);
+            if (wbeta) {
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    mul(v[u], scale);
+                    st<T, VEC>(bptr + e[u] * B, v[u]);
+                }
+            }
+        }
+        for (; rl < n_rlo; ++rl) {
+            const long long e = e_hi + __ldg(t_rlo + rl);
+            P v;
+            if (!has_src) v = pack_fill<T, VEC>(T(1));
+            else if (src_uni) v = pack_fill<T, VEC>(__ldg(sptr + e));
+            else v = ld<T, VEC>(sptr + e * spitch);
+#pragma unroll
+            for (int j = 0; j < kRegMsgs; ++j) {
+                if (j < nr) {
+                    const long long d = mh[j] + __ldg(tab + mblo[j] + rl);
+                    if ((umask >> j) & 1u) mul(v, pack_fill<T, VEC>(__ldg(mptr[j] + d)));
+                    else mul(v, ld<T, VEC>(mptr[j] + d * B));
+                }
+            }
+            for (int j = kRegMsgs; j < nr; ++j) {
+                const DMsg* m = msgs + rm0 + j;
+                const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo) +
+                                      __ldg(tab + m->b_hi + rh) + __ldg(tab + m->b_lo + rl);
+                if (um && m->uni) mul(v, pack_fill<T, VEC>(__ldg(uni + idx)));
+                else mul(v, ld<T, VEC>(work + m->eoff + idx * B + col));
+            }
+            add(acc[0], v);
+            if (wbeta) {
+                mul(v, scale);
+                st<T, VEC>(bptr + e * B, v);
+            }
+        }
+    }
+
+    if (tk->out >= 0) {
+        // pairwise combination of the partial sums
+        add(acc[0], acc[1]);
+        add(acc[2], acc[3]);
+        add(acc[0], acc[2]);
+        P o = acc[0];
+        mul(o, sm);
+        T* obase = tk->out_space ? static_cast<T*>(a.fout) : work;
+        st<T, VEC>(obase + (tk->out + s) * B + col, o);
+        if (tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS)) {
+            mul(o, own);
+            st<T, VEC>(work + (tk->bel + s) * B + col, o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA-pipelined projection (same task semantics as jt_project_kernel).
+//
+// The LDG kernel above keeps every in-flight row in registers, so its memory-level parallelism
+// is capped by occupancy (ncu, round 1: 22 % warps active, DRAM 33-53 %).  Here the CTA is
+// specialised into three roles:
+//   * row producer warp: lane k owns the k-th streamed operand of the task (clique row,
+//     message rows, own up-message), walks the (s, r) index space and issues 1-D bulk async
+//     copies (cp.async.bulk, SASS UBLKCP) of whole batch-tile rows into a shared-memory ring
+//     guarded by full/empty mbarriers.  A stage holds the rows of one (s, r) item; operands
+//     that depend on s only ride along with the r = 0 item.  Bytes in flight = ring size
+//     (~96 KB per CTA, two CTAs per SM), independent of register pressure;
+//   * uniform warp: operands that are identical for every instance (uniform mode) are scalars;
+//     lane l resolves item 32 b + l of a double-buffered batch, so the L2 latency of the
+//     scalar reads is paid once per 32 items;
+//   * consumer warps: one thread per 16-byte batch vector multiplies the operands out of
+//     shared memory, accumulates over r and stores beliefs and messages with coalesced
+//     16-byte stores.
+
+constexpr int kTmaSlots = 24;     // ring size in rows (one row = 16 bytes x consumer threads)
+constexpr int kTmaMaxRows = 8;    // operands per task supported (src + messages + own)
+constexpr int kUBatch = 32;       // items resolved per batch by the uniform warp
+
+// Shared-memory bookkeeping that follows the ring rows.
+template <typename T>
+struct TmaAux {
+    unsigned long long full[kTmaSlots];
+    unsigned long long empty[kTmaSlots];
+    unsigned long long u_full[2];
+    unsigned long long u_empty[2];
+    int e_row[kTmaSlots];                       // clique row index of the item in each stage
+    int u_e[2][kUBatch];                        // same, produced by the uniform warp
+    T u_val[2][kUBatch][4];                     // products of the scalar operands: item, s-only, own
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const KArgs a) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    typedef Pack<T, VEC> P;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+
+    const int ct = blockDim.x - 64;                      // consumer threads = batch vectors per tile
+    const int row_pitch = ct * 16;                       // bytes per ring row
+    TmaAux<T>* aux = reinterpret_cast<TmaAux<T>*>(smem_raw + kTmaSlots * row_pitch);
+    const uint32_t slots_u32 = smem_u32(smem_raw);
+    const uint32_t full_u32 = smem_u32(aux->full), empty_u32 = smem_u32(aux->empty);
+    const uint32_t ufull_u32 = smem_u32(aux->u_full), uempty_u32 = smem_u32(aux->u_empty);
+
+    int s0;
+    const DTask* tk = locate_chunk(a, s0);
+    const int n_s = tk->n_s;
+    const int s1 = min(n_s, s0 + (1 << a.sy_log2));
+    const long long col0v = (long long)blockIdx.y * ct;
+    const int ncols = (int)min((long long)ct, a.Bv - col0v);
+    const uint32_t row_bytes = (uint32_t)ncols * 16u;
+
+    // operands in order: [src] [r-dependent messages] [s-only messages] [own]
+    const bool um = a.uniform != 0;
+    const int tflags = um ? tk->flags : 0;
+    const int has_src = tk->src >= 0 ? 1 : 0, has_own = tk->own >= 0 ? 1 : 0;
+    const int m0 = tk->rmsg_begin;
+    const int nr = tk->rmsg_end - m0;
+    const int nsm = tk->smsg_end - tk->smsg_begin;
+    const int n_ops = has_src + nr + nsm + has_own;
+    const int n_item_ops = has_src + nr;                 // needed for every (s, r); the rest with r = 0
+    unsigned umask = 0;                                  // bit k: operand k is uniform (a scalar)
+    if (has_src && (tflags & JT_TF_SRC_UNIFORM)) umask |= 1u;
+    if (um)
+        for (int j = 0; j < nr + nsm; ++j)
+            if (a.msgs[m0 + j].uni) umask |= 1u << (has_src + j);
+    if (has_own && (tflags & JT_TF_OWN_UNIFORM)) umask |= 1u << (n_ops - 1);
+    const unsigned rowmask = ((1u << n_ops) - 1u) & ~umask;     // operands that stream ring rows
+    const int n_rows = __popc(rowmask);
+    const int n_stage = n_rows > 0 ? kTmaSlots / n_rows : 1;
+    const int n_r = tk->n_r;
+    const int n_items = (s1 - s0) * n_r;
+    const long long B = a.B;
+    const bool src_uni = (umask & 1u) && has_src;
+
+    const int n_cwarps = ct >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < n_stage; ++i) {
+            mbar_init(full_u32 + 8 * i, n_rows > 0 ? n_rows : 1);    // every row lane arrives per item
+            mbar_init(empty_u32 + 8 * i, n_cwarps);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(ufull_u32 + 8 * i, 1);
+            mbar_init(uempty_u32 + 8 * i, n_cwarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == n_cwarps) {
+        // ---------------- row producer warp: lane k streams the k-th row operand ----------------
+        if (lane >= n_rows) return;
+        int op = 0;                                       // operand index of this lane
+        for (int seen = -1; op < n_ops; ++op)
+            if (((rowmask >> op) & 1u) && ++seen == lane) break;
+        const int jm = op - has_src;
+        const bool is_src = has_src && op == 0;
+        const bool is_own = has_own && op == n_ops - 1;
+        const bool per_item = op < n_item_ops;            // else fetched with r = 0 only
+
+        const int* __restrict__ tab = a.tab;
+        const int n_slo = tk->n_slo, n_rlo = tk->n_rlo, n_rhi = n_r / n_rlo;
+        long long base = 0, eoff = 0;
+        const int* t_ahi = tab;
+        const int* t_alo = tab;
+        const int* t_bhi = tab;
+        const int* t_blo = tab;
+        if (is_src) {
+            base = tk->src;
+            t_ahi = tab + tk->src_shi; t_alo = tab + tk->src_slo;
+            t_bhi = tab + tk->src_rhi; t_blo = tab + tk->src_rlo;
+        } else if (!is_own) {
+            const DMsg* m = a.msgs + m0 + jm;
+            base = m->off;
+            eoff = m->eoff;
+            t_ahi = tab + m->a_hi; t_alo = tab + m->a_lo;
+            t_bhi = tab + m->b_hi; t_blo = tab + m->b_lo;
+        } else {
+            base = tk->own;
+        }
+        const T* origin = static_cast<const T*>(a.work) + eoff + col0v * VEC;
+        const uint32_t dst0 = slots_u32 + (uint32_t)lane * (uint32_t)row_pitch;
+        const uint32_t stage_bytes = (uint32_t)n_rows * (uint32_t)row_pitch;
+
+        int s_hi = 0, s_lo = s0;
+        if (n_slo < n_s) {
+            s_hi = s0 / n_slo;
+            s_lo = s0 - s_hi * n_slo;
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int s = s0; s < s1; ++s) {
+            const int s_idx = is_own ? s : __ldg(t_ahi + s_hi) + __ldg(t_alo + s_lo);
+            const T* rowp = origin + (base + s_idx) * B;
+            bool first = true;
+            for (int rh = 0; rh < n_rhi; ++rh) {
+                const int h = per_item ? __ldg(t_bhi + rh) : 0;
+                for (int rl = 0; rl < n_rlo; ++rl) {
+                    const uint32_t full = full_u32 + 8 * stage;
+                    const int e = per_item ? h + __ldg(t_blo + rl) : 0;
+                    mbar_wait(empty_u32 + 8 * stage, phase ^ 1);
+                    if (is_src) aux->e_row[stage] = s_idx + e;
+                    if (per_item || first) {
+                        mbar_expect_tx(full, row_bytes);
+                        bulk_g2s(dst0 + (uint32_t)stage * stage_bytes, rowp + (long long)e * B, row_bytes, full);
+                    }
+                    first = false;
+                    mbar_arrive(full);
+                    if (++stage == n_stage) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+            if (++s_lo == n_slo) {
+                s_lo = 0;
+                ++s_hi;
+            }
+        }
+        return;
+    }
+
+    if (warp == n_cwarps + 1) {
+        // ---------------- uniform warp: scalar operands, 32 items per batch ----------------
+        // Lane l resolves item 32 b + l: its (s, r), the clique row index and the products of
+        // the uniform operands, read from the uniform workspace: [0] per-item operands (src,
+        // r-dependent messages), [1] s-only messages, [2] own.  One L2 round trip per batch.
+        if (umask == 0) return;
+        const int* __restrict__ tab = a.tab;
+        const T* __restrict__ uni = static_cast<const T*>(a.uni);
+        const int n_slo = tk->n_slo, n_rlo = tk->n_rlo;
+        for (int b = 0; b * kUBatch < n_items; ++b) {
+            const int buf = b & 1;
+            mbar_wait(uempty_u32 + 8 * buf, ((b >> 1) & 1) ^ 1);
+            const int i = b * kUBatch + lane;
+            if (i < n_items) {
+                const int ds = i / n_r;
+                const int r = i - ds * n_r;
+                const int s = s0 + ds;
+                int s_hi = 0, s_lo = s;
+                if (n_slo < n_s) {
+                    s_hi = s / n_slo;
+                    s_lo = s - s_hi * n_slo;
+                }
+                const int rh = r / n_rlo, rl = r - rh * n_rlo;
+                T item_prod = T(1), s_prod = T(1), own_val = T(1);
+                if (src_uni) {
+                    const int e = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo) +
+                                  __ldg(tab + tk->src_rhi + rh) + __ldg(tab + tk->src_rlo + rl);
+                    aux->u_e[buf][lane] = e;
+                    item_prod = __ldg(uni + tk->src + e);
+                }
+                for (int j = 0; j < nr + nsm; ++j) {
+                    if ((umask >> (has_src + j)) & 1u) {
+                        const DMsg* m = a.msgs + m0 + j;
+                        long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+                        if (j < nr) {
+                            idx += __ldg(tab + m->b_hi + rh) + __ldg(tab + m->b_lo + rl);
+                            item_prod *= __ldg(uni + idx);
+                        } else {
+                            s_prod *= __ldg(uni + idx);
+                        }
+                    }
+                }
+                if (has_own && ((umask >> (n_ops - 1)) & 1u)) own_val = __ldg(uni + tk->own + s);
+                T* out = aux->u_val[buf][lane];
+                out[0] = item_prod;
+                out[1] = s_prod;
+                out[2] = own_val;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ufull_u32 + 8 * buf);
+        }
+        return;
+    }
+
+    // ---------------- consumers: thread t owns batch vector col0v + t ----------------
+    const int t = threadIdx.x;
+    const bool active = t < ncols;
+    T* work = static_cast<T*>(a.work);
+    const long long col = (col0v + t) * VEC;
+    const bool wbeta = tk->beta >= 0, wout = tk->out >= 0;
+    const bool wbel = wout && tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS);
+    T* bptr = work + (wbeta ? tk->beta : 0) * B + col;
+    T* optr = (tk->out_space ? static_cast<T*>(a.fout) : work) + (wout ? tk->out : 0) * B + col;
+    T* lptr = work + (wbel ? tk->bel : 0) * B + col;
+    const unsigned char* my = smem_raw + t * 16;
+    const int stage_pitch = n_rows * row_pitch;
+    const bool any_uni = umask != 0, any_row = n_rows > 0;
+    // ring rows of a stage: the per-item operands first, then the per-s ones (own last)
+    const int n_item_rows = __popc(rowmask & ((1u << n_item_ops) - 1u));
+    const bool own_is_row = has_own && ((rowmask >> (n_ops - 1)) & 1u);
+    const int n_sm_rows = n_rows - n_item_rows - (own_is_row ? 1 : 0);
+
+    // The per-item loop is instantiated per number of streamed per-item operands so that it
+    // stays a few dozen instructions (ncu: the generic loop cost ~160 instructions per item).
+    auto consume = [&](auto ni_tag) {
+        constexpr int NI = decltype(ni_tag)::value;          // -1: run-time count
+        const int ni = NI >= 0 ? NI : n_item_rows;
+        int stage = 0, item = 0;
+        uint32_t phase = 0;
+        for (int s = s0; s < s1; ++s) {
+            P sm = pack_fill<T, VEC>(T(1)), own = sm, scale = sm;
+            P acc0 = pack_fill<T, VEC>(T(0)), acc1 = acc0;
+            for (int r = 0; r < n_r; ++r, ++item) {
+                const int ub = (item >> 5) & 1, ul = item & (kUBatch - 1);
+                if (any_uni && ul == 0) mbar_wait(ufull_u32 + 8 * ub, (item >> 6) & 1);
+                if (any_row) mbar_wait(full_u32 + 8 * stage, phase);
+                const unsigned char* row = my + stage * stage_pitch;
+                const T* uv = aux->u_val[ub][ul];
+                P v = pack_fill<T, VEC>(any_uni ? uv[0] : T(1));
+                if (NI >= 0) {
+#pragma unroll
+                    for (int k = 0; k < (NI >= 0 ? NI : 0); ++k)
+                        mul(v, *reinterpret_cast<const P*>(row + k * row_pitch));
+                } else {
+                    for (int k = 0; k < ni; ++k) mul(v, *reinterpret_cast<const P*>(row + k * row_pitch));
+                }
+                if (r == 0) {                                 // once per s: s-only operands and own
+                    const unsigned char* srow = row + ni * row_pitch;
+                    sm = pack_fill<T, VEC>(any_uni ? uv[1] : T(1));
+                    for (int k = 0; k < n_sm_rows; ++k) mul(sm, *reinterpret_cast<const P*>(srow + k * row_pitch));
+                    own = own_is_row ? *reinterpret_cast<const P*>(srow + n_sm_rows * row_pitch)
+                                     : pack_fill<T, VEC>(any_uni ? uv[2] : T(1));
+                    scale = sm;
+                    mul(scale, own);
+                }
+                const int e = src_uni ? aux->u_e[ub][ul] : aux->e_row[stage];
+                __syncwarp();
+                if (lane == 0) {
+                    if (any_row) mbar_arrive(empty_u32 + 8 * stage);
+                    if (any_uni && (ul == kUBatch - 1 || item == n_items - 1)) mbar_arrive(uempty_u32 + 8 * ub);
+                }
+                if (r & 1) add(acc1, v); else add(acc0, v);
+                if (wbeta && active) {
+                    mul(v, scale);
+                    st<T, VEC>(bptr + (long long)e * B, v);
+                }
+                if (any_row && ++stage == n_stage) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (wout && active) {
+                add(acc0, acc1);
+                mul(acc0, sm);
+                st<T, VEC>(optr + (long long)s * B, acc0);
+                if (wbel) {
+                    mul(acc0, own);
+                    st<T, VEC>(lptr + (long long)s * B, acc0);
+                }
+            }
+        }
+    };
+    switch (n_item_rows) {
+        case 0: consume(std::integral_constant<int, 0>{}); break;
+        case 1: consume(std::integral_constant<int, 1>{}); break;
+        case 2: consume(std::integral_constant<int, 2>{}); break;
+        case 3: consume(std::integral_constant<int, 3>{}); break;
+        default: consume(std::integral_constant<int, -1>{}); break;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+jt_ratio_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T d = b[i];
+        out[i] = d != T(0) ? a[i] / d : T(0);
+    }
+}
+
+static_assert(kUnroll == 4, "the pairwise combination above assumes four partial sums");
+
+}  // namespace

@@ -12,7 +12,8 @@ import numpy as np
 
 JT_OK = 0
 JT_F32, JT_F64 = 0, 1
-JT_SEP_BELIEFS, JT_SKIP_MARGINAL = 1, 2
+JT_SEP_BELIEFS, JT_SKIP_MARGINAL, JT_UNIFORM, JT_NO_UNIFORM = 1, 2, 4, 8
+ABI_VERSION = 4
 
 _LIB_NAME = "libjt_b200.so"
 _lib = None
@@ -33,11 +34,12 @@ SIGNATURES = {
     "jt_plan_message_offsets": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _i64p, _i64p]),
     "jt_workspace_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_size_t)]),
+    "jt_workspace_layout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, _i64p]),
     "jt_plan_upload": (ctypes.c_int, [ctypes.c_void_p]),
     "jt_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
-                               ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+                               ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "jt_collect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
-                                  ctypes.c_void_p]),
+                                  ctypes.c_int, ctypes.c_void_p]),
     "jt_distribute": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_int, ctypes.c_void_p]),
     "jt_marginal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
@@ -145,18 +147,24 @@ class DevicePlan:
         check(lib().jt_workspace_bytes(self._handle, B, dtype_code(dtype), ctypes.byref(out)))
         return out.value
 
+    def workspace_layout(self, B, dtype):
+        """Byte offsets ``{fbase, errors, uniform, total}`` inside a workspace."""
+        out = (ctypes.c_int64 * 4)()
+        check(lib().jt_workspace_layout(self._handle, B, dtype_code(dtype), out))
+        return {"fbase": out[0], "errors": out[1], "uniform": out[2], "total": out[3]}
+
     def upload(self):
         if not self.uploaded:
             check(lib().jt_plan_upload(self._handle))
             self.uploaded = True
 
     # stage calls: raw device pointers (ints) and a cudaStream_t (int)
-    def init(self, factors_ptr, batched, evidence_ptr, B, dtype, ws_ptr, stream):
+    def init(self, factors_ptr, batched, evidence_ptr, B, dtype, ws_ptr, flags, stream):
         check(lib().jt_init(self._handle, factors_ptr, int(batched), evidence_ptr, B, dtype_code(dtype),
-                            ws_ptr, stream))
+                            ws_ptr, flags, stream))
 
-    def collect(self, B, dtype, ws_ptr, stream):
-        check(lib().jt_collect(self._handle, B, dtype_code(dtype), ws_ptr, stream))
+    def collect(self, B, dtype, ws_ptr, flags, stream):
+        check(lib().jt_collect(self._handle, B, dtype_code(dtype), ws_ptr, flags, stream))
 
     def distribute(self, B, dtype, ws_ptr, flags, stream):
         check(lib().jt_distribute(self._handle, B, dtype_code(dtype), ws_ptr, flags, stream))

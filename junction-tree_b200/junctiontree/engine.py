@@ -63,8 +63,12 @@ class Engine:
         self.dev.upload()
         nbytes = self.dev.workspace_bytes(B, dtype)
         ws = t.empty(nbytes, dtype=t.uint8, device="cuda")
-        ws[-256:].zero_()   # evidence error counter
+        self.clear_evidence_errors(ws, B, dtype)
         return ws
+
+    def clear_evidence_errors(self, ws, B, dtype):
+        off = self.dev.workspace_layout(B, dtype)["errors"]
+        ws[off:off + 256].zero_()
 
     def release(self):
         self._workspaces.clear()
@@ -79,8 +83,7 @@ class Engine:
         """int32 ``[n_factors, B]`` per-instance factor base offsets written by ``jt_init``
         (workspace layout: include/jt_b200.h)."""
         t = torch()
-        work_bytes = self.plan.work_entries * B * np.dtype(dtype).itemsize
-        start = (work_bytes + 255) // 256 * 256
+        start = self.dev.workspace_layout(B, dtype)["fbase"]
         F = len(self.plan.factors)
         return ws[start:start + F * B * 4].view(t.int32).view(F, B)
 
@@ -145,15 +148,17 @@ class Engine:
         return torch().cuda.current_stream().cuda_stream
 
     def propagate(self, factor_dev, batched, evidence_dev, B, dtype, ws=None, sep_beliefs=False,
-                  marginal=True):
+                  marginal=True, uniform=True):
         """init + collect + distribute (+ marginal).  Returns ``(ws, factor_out)``; ``factor_out``
-        is a ``[fout_entries, B]`` tensor (``None`` when ``marginal`` is False)."""
+        is a ``[fout_entries, B]`` tensor (``None`` when ``marginal`` is False).  ``uniform``:
+        compute potentials and messages no evidence reaches once per batch (shared tables only;
+        results are identical)."""
         t = require_cuda()
         self.dev.upload()
         if ws is None:
             ws = self.workspace(B, dtype)
         fout = None
-        flags = (_native.JT_SEP_BELIEFS if sep_beliefs else 0)
+        flags = (_native.JT_SEP_BELIEFS if sep_beliefs else 0) | (0 if uniform else _native.JT_NO_UNIFORM)
         if marginal:
             fout = t.empty((self.plan.fout_entries, B), dtype=torch_dtype(dtype), device="cuda")
         else:
@@ -168,7 +173,7 @@ class Engine:
         """collect + distribute on clique potentials already stored in the workspace."""
         self.dev.upload()
         stream = self._stream()
-        self.dev.collect(B, dtype, ws.data_ptr(), stream)
+        self.dev.collect(B, dtype, ws.data_ptr(), 0, stream)
         self.dev.distribute(B, dtype, ws.data_ptr(), _native.JT_SEP_BELIEFS if sep_beliefs else 0, stream)
 
     # -----------------------------------------------------------------------------------------

@@ -147,7 +147,7 @@ class CliqueGraph():
         fdev, _ = engine.factors_to_device(xs, dtype)
         ws = engine.workspace(1, dtype)
         engine.dev.upload()
-        engine.dev.init(fdev.data_ptr(), False, None, 1, dtype, ws.data_ptr(), engine._stream())
+        engine.dev.init(fdev.data_ptr(), False, None, 1, dtype, ws.data_ptr(), 0, engine._stream())
         flat = engine.work_view(ws, 1, dtype)[:plan.clique_entries, 0].cpu().numpy()
         return [
             flat[plan.node_off[c]:plan.node_off[c] + plan.node_size[c]].reshape(tuple(plan.node_shape[c])).copy()
@@ -251,7 +251,7 @@ class JunctionTree():
         ]
 
     def propagate_batch(self, xs, evidence_vars=(), evidence=None, batch=None, dtype=None,
-                        nodes=False, device_output=False):
+                        nodes=False, device_output=False, uniform=True):
         """Many independent propagations over this tree in one pass.
 
         :param xs: factor tables shared by the whole batch (stored shapes, observed axes at full
@@ -264,6 +264,8 @@ class JunctionTree():
                       ``maxcliques + separators``)
         :param device_output: return CUDA tensors (views of the batch-innermost buffers) instead
                               of NumPy arrays
+        :param uniform: with shared tables, compute potentials and up-messages that no evidence
+                        reaches once per batch instead of once per instance (same results)
         :return: list of ``[B, *factor_shape]`` arrays (observed axes have length 1); with
                  ``nodes=True`` a pair ``(factor_outputs, node_beliefs)``
         """
@@ -289,11 +291,11 @@ class JunctionTree():
             raise ValueError("batch size unknown: give evidence, batched tables or batch=")
         fdev, batched = engine.factors_to_device(xs, dtype, B)
         edev = engine.evidence_to_device(evidence, B)
-        ws, fout = engine.propagate(fdev, batched, edev, B, dtype, sep_beliefs=nodes)
+        ws, fout = engine.propagate(fdev, batched, edev, B, dtype, sep_beliefs=nodes, uniform=uniform)
         if edev is not None:
             bad = engine.dev.evidence_errors(B, dtype, ws.data_ptr(), engine._stream())
             if bad:
-                ws[-256:].zero_()
+                engine.clear_evidence_errors(ws, B, dtype)
                 raise ValueError("%d evidence states are outside the range of their variable" % bad)
         outs = [engine.factor_tensor(fout, f, B) for f in range(len(plan.factors))]
         node_out = None

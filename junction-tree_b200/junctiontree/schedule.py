@@ -37,26 +37,32 @@ import numpy as np
 from . import construction as cons
 
 MAGIC = 0x324E4C5042544A  # "JTBPLN2"
-VERSION = 3
+VERSION = 4
 
 # header word indices (int64 words); mirrored in include/jt_b200.h
 H_MAGIC, H_VERSION, H_NCLIQUES, H_NSEPS, H_NFACTORS, H_NEVID, H_CLIQUE_ENTRIES, H_SEP_ENTRIES, \
     H_FIN_ENTRIES, H_FOUT_ENTRIES, H_NTAB, H_NTASKS, H_NMSGS, H_NLAUNCHES, H_MAXDEPTH, \
-    H_NEVF, H_ROOT_ENTRIES, H_WORDS = range(18)
+    H_NEVF, H_ROOT_ENTRIES, H_UNI_ENTRIES, H_WORDS = range(19)
 
 TASK_WORDS = 24
 (T_KIND, T_SRC, T_OUT, T_BETA, T_BEL, T_OWN, T_NS, T_NR, T_NSLO, T_NRLO, T_SRC_SHI, T_SRC_SLO,
  T_SRC_RHI, T_SRC_RLO, T_RMSG_BEGIN, T_RMSG_END, T_SMSG_BEGIN, T_SMSG_END, T_OUT_SPACE, T_NODE,
- T_AUX) = range(21)
+ T_AUX, T_FLAGS) = range(22)
 
-MSG_WORDS = 6
-M_OFF, M_AHI, M_ALO, M_BHI, M_BLO, M_FID = range(6)
+MSG_WORDS = 8
+M_OFF, M_AHI, M_ALO, M_BHI, M_BLO, M_FID, M_UNI = range(7)
+
+# task flags (honoured only when the run time enables uniform mode)
+TF_SRC_UNIFORM = 1     # src is the potential of a clique no evidence touches: read from the uniform workspace
+TF_OWN_UNIFORM = 2     # the task's own up-message is uniform
+TF_TASK_UNIFORM = 4    # every input is uniform: the task runs once, in the uniform workspace
 
 LAUNCH_WORDS = 4
 L_PHASE, L_BEGIN, L_END, L_LEVEL = range(4)
 
 KIND_PROJECT, KIND_INIT = 0, 1
-PHASE_INIT, PHASE_COLLECT, PHASE_DIST_PRE, PHASE_DIST_MAIN, PHASE_MARGINAL = range(5)
+(PHASE_INIT, PHASE_COLLECT, PHASE_DIST_PRE, PHASE_DIST_MAIN, PHASE_MARGINAL,
+ PHASE_INIT_UNIFORM, PHASE_INIT_INSTANCE, PHASE_COLLECT_UNIFORM, PHASE_COLLECT_INSTANCE) = range(9)
 SPACE_WORK, SPACE_FOUT = 0, 1
 
 #: trailing-axes table is grown while its length stays within this bound
@@ -240,6 +246,7 @@ class Plan:
         self.tasks, self.msgs, self.launches = [], [], []
 
         self._build_factor_tables()
+        self._find_uniform_cliques()
         self._build_init()
         self._build_collect()
         self._build_distribute()
@@ -296,10 +303,37 @@ class Plan:
                     self.evf_stride.append(st)
             self.evf_ptr.append(len(self.evf_var))
 
-    def _add_msg(self, off, s_space, r_space, stride_of, fid=-1):
+    def _find_uniform_cliques(self):
+        """Which potentials and up-messages are identical for every instance of a batch.
+
+        With factor tables shared by the batch, psi_C depends on the instance only through the
+        observed axes of its assigned factors, and an up-message only through the cliques below
+        it.  ``uniform[c]``: no factor of clique c contains an observed variable;
+        ``uniform_up[c]``: the same holds for the whole subtree of c.  In *uniform mode* such
+        operands are kept once, in a B = 1 copy of the workspace with the same entry offsets
+        (the uniform workspace), evidence-free subtrees are collected there once, and the batch
+        kernels broadcast them instead of streaming [n][B] rows.  Per-instance factor tables
+        switch uniform mode off at run time; the flags are then ignored.
+        """
+        self.uniform = [False] * self.n_cliques
+        self.uniform_up = [False] * self.n_cliques
+        self.uni_entries = 0
+        if self.factors is None or self.tree is None:
+            return
+        observed = set(self.evidence_vars)
+        touched = set(home for fv, home in zip(self.factors, self.factor_to_clique) if observed & set(fv))
+        if not self.children[self.root]:
+            touched.add(self.root)        # a single clique gets no distribute task: keep it per instance
+        for c in reversed(self.order):
+            self.uniform[c] = c not in touched
+            self.uniform_up[c] = self.uniform[c] and all(self.uniform_up[k] for _, k in self.children[c])
+        self.uni_entries = sum(self.node_size[c] for c in range(self.n_cliques) if self.uniform[c])
+
+    def _add_msg(self, off, s_space, r_space, stride_of, fid=-1, uniform=False):
         a_hi, a_lo = s_space.tables(stride_of)
         row = [0] * MSG_WORDS
         row[M_OFF] = off
+        row[M_UNI] = 1 if uniform else 0
         row[M_AHI], row[M_ALO] = self.tab.add(a_hi), self.tab.add(a_lo)
         if r_space is not None:
             b_hi, b_lo = r_space.tables(stride_of)
@@ -307,11 +341,13 @@ class Plan:
         row[M_FID] = fid
         self.msgs.append(row)
 
-    def _new_task(self, kind, s_space, r_space, node, src_node=None):
+    def _new_task(self, kind, s_space, r_space, node, src_node=None, src_is_psi=False):
         row = [0] * TASK_WORDS
         row[T_KIND] = kind
         for w in (T_SRC, T_OUT, T_BETA, T_BEL, T_OWN):
             row[w] = -1
+        if src_is_psi and src_node is not None and self.uniform[src_node]:
+            row[T_FLAGS] |= TF_SRC_UNIFORM
         row[T_NS], row[T_NSLO] = s_space.n, s_space.n_lo
         row[T_NR], row[T_NRLO] = (r_space.n, r_space.n_lo) if r_space is not None else (1, 1)
         row[T_NODE] = node
@@ -325,15 +361,15 @@ class Plan:
         return row
 
     def _attach_msgs(self, row, msgs, s_space, r_space):
-        """msgs: list of (workspace offset, separator node).  r-dependent ones first."""
-        rdep = [(off, sep) for off, sep in msgs if r_space.touches(set(self.node_vars[sep]))]
-        sonly = [(off, sep) for off, sep in msgs if not r_space.touches(set(self.node_vars[sep]))]
+        """msgs: list of (workspace offset, separator node, uniform).  r-dependent ones first."""
+        rdep = [m for m in msgs if r_space.touches(set(self.node_vars[m[1]]))]
+        sonly = [m for m in msgs if not r_space.touches(set(self.node_vars[m[1]]))]
         row[T_RMSG_BEGIN] = len(self.msgs)
-        for off, sep in rdep:
-            self._add_msg(off, s_space, r_space, self._strides(sep))
+        for off, sep, uni in rdep:
+            self._add_msg(off, s_space, r_space, self._strides(sep), uniform=uni)
         row[T_RMSG_END] = row[T_SMSG_BEGIN] = len(self.msgs)
-        for off, sep in sonly:
-            self._add_msg(off, s_space, None, self._strides(sep))
+        for off, sep, uni in sonly:
+            self._add_msg(off, s_space, None, self._strides(sep), uniform=uni)
         row[T_SMSG_END] = len(self.msgs)
 
     def _launch(self, phase, begin, level):
@@ -343,18 +379,27 @@ class Plan:
     # -----------------------------------------------------------------------------------------
 
     def _build_init(self):
-        """E0 + V1: psi_C = prod of assigned factors, observed axes gathered per instance."""
+        """E0 + V1: psi_C = prod of assigned factors, observed axes gathered per instance.
+
+        Uniform cliques come first, so one task list serves three launches: all cliques per
+        instance (general mode), the uniform ones once into the uniform workspace, the others
+        per instance (uniform mode)."""
         if self.factors is None:
             return
-        begin = len(self.tasks)
         by_clique = [[] for _ in range(self.n_cliques)]
         for f, home in enumerate(self.factor_to_clique):
             by_clique[home].append(f)
         self.clique_factors = by_clique
-        for c in range(self.n_cliques):
+        begin = len(self.tasks)
+        ordered = [c for c in range(self.n_cliques) if self.uniform[c]] + \
+                  [c for c in range(self.n_cliques) if not self.uniform[c]]
+        n_uniform = sum(self.uniform)
+        for c in ordered:
             s_space = _Space(self.node_vars[c], self.sizes)
             row = self._new_task(KIND_INIT, s_space, None, c)
             row[T_OUT] = self.node_off[c]
+            if self.uniform[c]:
+                row[T_FLAGS] |= TF_TASK_UNIFORM
             row[T_SMSG_BEGIN] = row[T_RMSG_BEGIN] = row[T_RMSG_END] = len(self.msgs)
             for f in by_clique[c]:
                 st = dict(zip(self.factors[f], _row_major_strides(self.fin_shape[f])))
@@ -364,27 +409,42 @@ class Plan:
                 self._add_msg(self.fin_off[f], s_space, None, st, fid=f)
             row[T_SMSG_END] = len(self.msgs)
             self.tasks.append(row)
-        self._launch(PHASE_INIT, begin, 0)
+        self._launch_split(PHASE_INIT, PHASE_INIT_UNIFORM, PHASE_INIT_INSTANCE, begin, begin + n_uniform, 0)
+
+    def _launch_split(self, phase_all, phase_uniform, phase_instance, begin, middle, level):
+        end = len(self.tasks)
+        if end > begin:
+            self.launches.append([phase_all, begin, end, level])
+        if middle > begin:
+            self.launches.append([phase_uniform, begin, middle, level])
+        if end > middle:
+            self.launches.append([phase_instance, middle, end, level])
 
     def _build_collect(self):
-        """E1 + E2: up-messages, deepest level first."""
+        """E1 + E2: up-messages, deepest level first (uniform subtrees first within a level)."""
         by_depth = {}
         for c in self.order:
             by_depth.setdefault(self.depth[c], []).append(c)
         self.by_depth = by_depth
         for d in range(self.max_depth, 0, -1):
             begin = len(self.tasks)
-            for c in by_depth[d]:
+            ordered = [c for c in by_depth[d] if self.uniform_up[c]] + \
+                      [c for c in by_depth[d] if not self.uniform_up[c]]
+            n_uniform = sum(1 for c in by_depth[d] if self.uniform_up[c])
+            for c in ordered:
                 psep = self.parent_sep[c]
                 s_space = _Space(self.node_vars[psep], self.sizes)
                 in_sep = set(self.node_vars[psep])
                 r_space = _Space([v for v in self.node_vars[c] if v not in in_sep], self.sizes)
-                row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c)
+                row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c, src_is_psi=True)
                 row[T_OUT] = self.up_off(psep)
-                self._attach_msgs(row, [(self.up_off(s), s) for s, _ in self.children[c]],
+                if self.uniform_up[c]:
+                    row[T_FLAGS] |= TF_TASK_UNIFORM
+                self._attach_msgs(row, [(self.up_off(s), s, self.uniform_up[k]) for s, k in self.children[c]],
                                   s_space, r_space)
                 self.tasks.append(row)
-            self._launch(PHASE_COLLECT, begin, d)
+            self._launch_split(PHASE_COLLECT, PHASE_COLLECT_UNIFORM, PHASE_COLLECT_INSTANCE,
+                               begin, begin + n_uniform, d)
 
     def _build_distribute(self):
         """E3 + E4 + M1 + E5 with a division-free exclude-one product, top level first.
@@ -401,26 +461,28 @@ class Plan:
                 kids = self.children[c]
                 incoming = []
                 if self.parent[c] >= 0:
-                    incoming.append((self.down_off(self.parent_sep[c]), self.parent_sep[c]))
-                incoming += [(self.up_off(s), s) for s, _ in kids]
+                    incoming.append((self.down_off(self.parent_sep[c]), self.parent_sep[c], False))
+                incoming += [(self.up_off(s), s, self.uniform_up[k]) for s, k in kids]
                 if not kids:
                     if self.parent[c] < 0:
                         continue  # single-clique tree: belief = potential
                     s_space = _Space(self.node_vars[c], self.sizes)
                     r_space = _Space([], self.sizes)
-                    row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c)
+                    row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c, src_is_psi=True)
                     row[T_BETA] = self.node_off[c]
                     self._attach_msgs(row, incoming, s_space, r_space)
                     main.append(row)
                     continue
-                for i, (sep, _) in enumerate(kids):
+                for i, (sep, kid) in enumerate(kids):
                     s_space = _Space(self.node_vars[sep], self.sizes)
                     in_sep = set(self.node_vars[sep])
                     r_space = _Space([v for v in self.node_vars[c] if v not in in_sep], self.sizes)
-                    row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c)
+                    row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c, src_is_psi=True)
                     row[T_OUT] = self.down_off(sep)
                     row[T_BEL] = self.bel_off(sep)
                     row[T_OWN] = self.up_off(sep)
+                    if self.uniform_up[kid]:
+                        row[T_FLAGS] |= TF_OWN_UNIFORM
                     others = [m for m in incoming if m[1] != sep]
                     writer = i == len(kids) - 1
                     if writer:
@@ -464,6 +526,30 @@ class Plan:
         n_root = self.node_size[self.root] if self.root >= 0 else 0
         return (4 if with_init else 3) * self.clique_entries - n_root + 6 * self.sep_entries
 
+    def scheduled_entries(self, uniform=True, sep_beliefs=True):
+        """Entries per instance this schedule reads + writes in HBM for init + collect +
+        distribute, every buffer counted once per consumer (the accounting of SURVEY.md 8d
+        applied to the schedule as built).  In uniform mode the potential of a uniform clique is
+        neither written nor read per instance (only its belief is written) and a uniform
+        up-message is not written or read per instance (only down-message and belief are)."""
+        total = 0
+        for c in self.order:
+            n = self.node_size[c]
+            kids = self.children[c]
+            reads = (0 if c == self.root else 1) + max(len(kids), 1 if c != self.root else 0)
+            if uniform and self.uniform[c]:
+                total += n if (kids or c != self.root) else 0       # belief write
+            else:
+                total += n * (1 + reads) + (n if (kids or c != self.root) else 0)
+            for s, k in kids:
+                ns = self.node_size[s]
+                if uniform and self.uniform_up[k]:
+                    total += ns * (2 + (1 if sep_beliefs else 0))       # down write + read, belief write
+                else:
+                    # up: write + parent's collect read + parent's distribute reads + own read
+                    total += ns * (5 + (1 if sep_beliefs else 0))
+        return total
+
     def header(self):
         h = np.zeros(H_WORDS, np.int64)
         h[H_MAGIC], h[H_VERSION] = MAGIC, VERSION
@@ -477,6 +563,7 @@ class Plan:
         h[H_MAXDEPTH] = self.max_depth
         h[H_NEVF] = len(self.evf_var)
         h[H_ROOT_ENTRIES] = self.node_size[self.root] if self.root >= 0 else 0
+        h[H_UNI_ENTRIES] = self.uni_entries
         return h
 
     def to_blob(self):
@@ -504,4 +591,7 @@ class Plan:
             "depth": self.max_depth, "tasks": len(self.tasks_arr), "launches": len(self.launches_arr),
             "table_entries": int(self.tables.size),
             "algorithmic_entries": self.algorithmic_entries(),
+            "uniform_clique_entries": self.uni_entries,
+            "uniform_up_entries": sum(self.node_size[self.parent_sep[c]] for c in self.order
+                                      if self.parent[c] >= 0 and self.uniform_up[c]),
         }

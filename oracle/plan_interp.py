@@ -26,27 +26,41 @@ def evidence_offsets(plan, evidence, B):
     return fbase
 
 
-def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np.float64):
+def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np.float64, uniform=False):
     """Execute the plan.  ``work``: [work_entries, B] (clique potentials preloaded when the init
     phase is skipped); ``factor_in``: flat shared factor tables (fin_entries) or per-instance
-    [fin_entries, B].  Returns (work, factor_out)."""
+    [fin_entries, B].  ``uniform``: keep the potentials of evidence-free cliques once, in the
+    uniform region, as the device does for shared factor tables.  Returns (work, factor_out)."""
     tab = plan.tables
-    if work is None:
-        work = np.zeros((plan.work_entries, B), dtype)
+    uni = np.zeros((plan.work_entries, 1), dtype)       # the uniform workspace: same offsets, B = 1
+    general = {sch.PHASE_INIT, sch.PHASE_COLLECT}
+    split = {sch.PHASE_INIT_UNIFORM, sch.PHASE_INIT_INSTANCE, sch.PHASE_COLLECT_UNIFORM, sch.PHASE_COLLECT_INSTANCE}
+    in_uni_ws = {sch.PHASE_INIT_UNIFORM, sch.PHASE_COLLECT_UNIFORM}
+    skip = general if uniform else split
+    launches = list(plan.launches_arr)
+    if uniform:   # evidence-free subtrees are collected first, once
+        launches = [L for L in launches if L[0] in in_uni_ws] + [L for L in launches if L[0] not in in_uni_ws]
+    real_work = work
     fout = np.zeros((plan.fout_entries, B), dtype)
     fbase = None
     if plan.factors is not None and plan.evidence_vars:
         fbase = evidence_offsets(plan, evidence, B)
-    for phase, begin, end, _level in plan.launches_arr:
-        if phases is not None and phase not in phases:
+    work = real_work if real_work is not None else np.zeros((plan.work_entries, B), dtype)
+    real_work = work
+    for phase, begin, end, _level in launches:
+        if (phases is not None and phase not in phases) or phase in skip:
             continue
+        # a launch in the uniform workspace is an ordinary B = 1 launch on that buffer
+        work = uni if phase in in_uni_ws else real_work
+        flagged = uniform and phase not in in_uni_ws
         # tasks of one launch are independent: evaluate all against the pre-launch state for
         # reads of other nodes, but in-place beta writes only touch the task's own clique
         for t in plan.tasks_arr[begin:end]:
             n_s, n_r, n_slo, n_rlo = (int(t[sch.T_NS]), int(t[sch.T_NR]),
                                       int(t[sch.T_NSLO]), int(t[sch.T_NRLO]))
             if t[sch.T_KIND] == sch.KIND_INIT:
-                val = np.ones((n_s, B), dtype)
+                to_uni = phase in in_uni_ws
+                val = np.ones((n_s, 1 if to_uni else B), dtype)
                 for m in plan.msgs_arr[t[sch.T_SMSG_BEGIN]:t[sch.T_SMSG_END]]:
                     a = _map(tab, m[sch.M_AHI], m[sch.M_ALO], n_s, n_slo)
                     f = int(m[sch.M_FID])
@@ -55,7 +69,7 @@ def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np
                         val = val * factor_in[idx, :]
                     else:
                         idx = m[sch.M_OFF] + a[:, None]
-                        if fbase is not None:
+                        if fbase is not None and not to_uni:
                             idx = idx + fbase[f][None, :]
                         val = val * factor_in[idx]
                 work[t[sch.T_OUT]:t[sch.T_OUT] + n_s] = val
@@ -63,17 +77,20 @@ def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np
             S = _map(tab, t[sch.T_SRC_SHI], t[sch.T_SRC_SLO], n_s, n_slo)
             R = _map(tab, t[sch.T_SRC_RHI], t[sch.T_SRC_RLO], n_r, n_rlo)
             e = t[sch.T_SRC] + S[:, None] + R[None, :]                       # [n_s, n_r]
-            term = work[e]                                                   # [n_s, n_r, B]
+            def buf(is_uniform):
+                return uni if (flagged and is_uniform) else work
+            term = buf(t[sch.T_FLAGS] & sch.TF_SRC_UNIFORM)[e]               # [n_s, n_r, B or 1]
             for m in plan.msgs_arr[t[sch.T_RMSG_BEGIN]:t[sch.T_RMSG_END]]:
                 a = _map(tab, m[sch.M_AHI], m[sch.M_ALO], n_s, n_slo)
                 b = _map(tab, m[sch.M_BHI], m[sch.M_BLO], n_r, n_rlo)
-                term = term * work[m[sch.M_OFF] + a[:, None] + b[None, :]]
-            sm = np.ones((n_s, B), dtype)
+                term = term * buf(m[sch.M_UNI])[m[sch.M_OFF] + a[:, None] + b[None, :]]
+            sm = np.ones((n_s, work.shape[1]), dtype)
             for m in plan.msgs_arr[t[sch.T_SMSG_BEGIN]:t[sch.T_SMSG_END]]:
                 a = _map(tab, m[sch.M_AHI], m[sch.M_ALO], n_s, n_slo)
-                sm = sm * work[m[sch.M_OFF] + a]
+                sm = sm * buf(m[sch.M_UNI])[m[sch.M_OFF] + a]
             out = term.sum(axis=1) * sm
-            own = work[t[sch.T_OWN]:t[sch.T_OWN] + n_s].copy() if t[sch.T_OWN] >= 0 else None
+            own = buf(t[sch.T_FLAGS] & sch.TF_OWN_UNIFORM)[t[sch.T_OWN]:t[sch.T_OWN] + n_s].copy() \
+                if t[sch.T_OWN] >= 0 else None
             if t[sch.T_OUT] >= 0:
                 if t[sch.T_OUT_SPACE] == sch.SPACE_FOUT:
                     fout[t[sch.T_OUT]:t[sch.T_OUT] + n_s] = out
@@ -86,7 +103,7 @@ def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np
                 if own is not None:
                     beta = beta * own[:, None, :]
                 work[t[sch.T_BETA] + S[:, None] + R[None, :]] = beta
-    return work, fout
+    return real_work, fout
 
 
 def node_array(plan, work, node, B):

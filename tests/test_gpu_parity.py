@@ -28,14 +28,15 @@ def _oracle(tree, net, evars, ev, B):
                                      net["factors"], net["sizes"], net["values"], evars, ev, n=B)
 
 
+@pytest.mark.parametrize("uniform", [True, False], ids=["uniform", "per_instance"])
 @pytest.mark.parametrize("net", _nets(), ids=lambda n: n["name"])
 @pytest.mark.parametrize("B", [1, 3, 8, 70, 300])
-def test_batched_propagation_f64(net, B):
+def test_batched_propagation_f64(net, B, uniform):
     import junctiontree as jt
     tree = jt.create_junction_tree(net["factors"], net["sizes"], order=net.get("order"))
     evars = net.get("evidence_vars", [])
     ev = wl.draw_evidence(net, B) if evars else None
-    outs, nodes = tree.propagate_batch(net["values"], evars, ev, batch=B, nodes=True)
+    outs, nodes = tree.propagate_batch(net["values"], evars, ev, batch=B, nodes=True, uniform=uniform)
     want_f, want_n = _oracle(tree, net, evars, ev, B)
     for k, (g, w) in enumerate(zip(nodes, want_n)):
         assert_close(g, w, RTOL_F64, "node %d" % k)
@@ -181,7 +182,7 @@ def test_evidence_slicing_is_bit_exact():
     edev = engine.evidence_to_device(ev, B)
     ws = engine.workspace(B, np.float64)
     engine.dev.upload()
-    engine.dev.init(fdev.data_ptr(), False, edev.data_ptr(), B, np.float64, ws.data_ptr(), engine._stream())
+    engine.dev.init(fdev.data_ptr(), False, edev.data_ptr(), B, np.float64, ws.data_ptr(), 0, engine._stream())
     torch.cuda.synchronize()
     fbase = engine.evidence_offsets_view(ws, B, np.float64).cpu().numpy()
     assert np.array_equal(fbase, plan_interp.evidence_offsets(plan, ev, B))

@@ -93,8 +93,9 @@ def test_ref_fixed_matches_brute_force(net):
             assert_close(outs[f][b], truth[len(nodes) + f], 1e-11, "factor %d" % f)
 
 
+@pytest.mark.parametrize("uniform", [False, True], ids=["per_instance_psi", "uniform_psi"])
 @pytest.mark.parametrize("net", NETS + [wl.dag37()], ids=lambda n: n["name"])
-def test_schedule_interpreter_matches_ref_fixed(net):
+def test_schedule_interpreter_matches_ref_fixed(net, uniform):
     """The compiled plan (index tables, task wiring, launch order), interpreted in NumPy,
     reproduces the oracle -- this is what the CUDA kernels execute."""
     from junctiontree import schedule as sch
@@ -102,9 +103,11 @@ def test_schedule_interpreter_matches_ref_fixed(net):
     plan = sch.Plan(tree, mc + seps, eff, net["factors"], f2c, evars, net["sizes"])
     B = 2
     ev = wl.draw_evidence(net, B) if evars else None
-    work, fout = plan_interp.run(plan, B, factor_in=plan_interp.flatten_factors(plan, net["values"]), evidence=ev)
+    work, fout = plan_interp.run(plan, B, factor_in=plan_interp.flatten_factors(plan, net["values"]), evidence=ev,
+                                 uniform=uniform)
     outs, ys = ref_fixed.propagate_batch(tree, seps, mc, f2c, net["factors"], net["sizes"], net["values"],
                                          evars, ev, n=B)
+    assert plan.uni_entries > 0
     for k in range(len(mc) + len(seps)):
         assert_close(plan_interp.node_array(plan, work, k, B), ys[k], 1e-13, "node %d" % k)
     for f in range(len(net["factors"])):

@@ -1,0 +1,198 @@
+"""Schedule emitter and the C ABI on a machine without a GPU: the library loads, exports every
+symbol the header declares, parses and validates plan blobs; no compute call is made."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import jt_workloads as wl
+from helpers import compile_net
+from junctiontree import _native
+from junctiontree import schedule as sch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "jt_b200.h")
+
+
+def _plan(net, with_evidence=True):
+    tree, seps, mc, f2c, eff, evars = compile_net(net, with_evidence)
+    return sch.Plan(tree, mc + seps, eff, net["factors"], f2c, evars, net["sizes"])
+
+
+def test_library_exports_every_declared_symbol():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(jt_[a-z_0-9]+)\s*\(", text))
+    assert len(declared) >= 18
+    lib = _native.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libjt_b200.so does not export %s" % name
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    assert lib.jt_abi_version() == _native.ABI_VERSION
+    assert ("#define JT_ABI_VERSION %d" % _native.ABI_VERSION) in open(HEADER).read()
+
+
+def test_header_constants_match_the_emitter():
+    text = open(HEADER).read()
+
+    def enum_after(marker):
+        for body in re.findall(r"enum\s*\{(.*?)\}", text, flags=re.S):
+            names = [n.strip().split("=")[0].strip() for n in body.split(",") if n.strip()]
+            if marker in names:
+                return names
+        raise AssertionError("no enum with %s" % marker)
+
+    hdr = enum_after("JT_H_MAGIC")
+    assert hdr.index("JT_H_WORDS") == sch.H_WORDS
+    assert hdr.index("JT_H_UNI_ENTRIES") == sch.H_UNI_ENTRIES
+    task = enum_after("JT_T_KIND")
+    assert task.index("JT_T_FLAGS") == sch.T_FLAGS and task.index("JT_T_NRLO") == sch.T_NRLO
+    msg = enum_after("JT_M_OFF")
+    assert msg.index("JT_M_UNI") == sch.M_UNI
+    phases = enum_after("JT_PHASE_INIT")
+    assert phases.index("JT_PHASE_COLLECT_INSTANCE") == sch.PHASE_COLLECT_INSTANCE
+    assert "#define JT_TASK_WORDS %d" % sch.TASK_WORDS in text
+    assert "#define JT_MSG_WORDS %d" % sch.MSG_WORDS in text
+    assert "0x%X" % sch.MAGIC in text.upper().replace("0X", "0x")
+
+
+@pytest.mark.parametrize("net", [wl.sprinkler(), wl.dag37(), wl.ising(4)], ids=lambda n: n["name"])
+def test_plan_blob_round_trip_through_the_c_parser(net):
+    plan = _plan(net)
+    dp = _native.DevicePlan(plan.to_blob())
+    assert dp.query(sch.H_NCLIQUES) == plan.n_cliques
+    assert dp.query(sch.H_NSEPS) == plan.n_seps
+    assert dp.query(sch.H_CLIQUE_ENTRIES) == plan.clique_entries
+    assert dp.query(sch.H_SEP_ENTRIES) == plan.sep_entries
+    assert dp.query(sch.H_NTASKS) == len(plan.tasks_arr)
+    assert dp.query(sch.H_UNI_ENTRIES) == plan.uni_entries
+    for k in range(len(plan.node_vars)):
+        assert dp.node_range(k) == (plan.node_off[k], plan.node_size[k])
+    for k in range(plan.n_cliques, len(plan.node_vars)):
+        assert dp.message_offsets(k) == (plan.up_off(k), plan.down_off(k))
+    B = 96
+    lay = dp.workspace_layout(B, np.float64)
+    assert lay["fbase"] >= plan.work_entries * B * 8
+    assert lay["total"] == dp.workspace_bytes(B, np.float64)
+    assert lay["total"] >= lay["uniform"] + plan.work_entries * 8
+    assert dp.workspace_bytes(B, np.float32) < dp.workspace_bytes(B, np.float64)
+    dp.close()
+
+
+def test_malformed_blobs_are_rejected():
+    plan = _plan(wl.huang_darwiche())
+    blob = plan.to_blob()
+    words = np.frombuffer(blob, np.int64).copy()
+
+    def rejected(w, nbytes=None):
+        data = w.tobytes()
+        if nbytes is not None:
+            data = data[:nbytes]
+        with pytest.raises(_native.NativeError):
+            _native.DevicePlan(data)
+
+    bad = words.copy(); bad[sch.H_MAGIC] += 1; rejected(bad)
+    bad = words.copy(); bad[sch.H_VERSION] = 1; rejected(bad)
+    bad = words.copy(); bad[sch.H_NTASKS] += 1; rejected(bad)
+    rejected(words, len(blob) - 8)
+    rejected(words, 64)
+    # a task whose table range leaves the table arena
+    n_nodes = plan.n_cliques + plan.n_seps
+    F = len(plan.factors)
+    task0 = sch.H_WORDS + 2 * n_nodes + 4 * F + len(plan.ev_card) + (F + 1) + 2 * len(plan.evf_var)
+    proj = next(i for i, t in enumerate(plan.tasks_arr) if t[sch.T_KIND] == sch.KIND_PROJECT)
+    bad = words.copy(); bad[task0 + proj * sch.TASK_WORDS + sch.T_SRC_SLO] = plan.tables.size + 5; rejected(bad)
+    bad = words.copy(); bad[task0 + proj * sch.TASK_WORDS + sch.T_NS] = 0; rejected(bad)
+    bad = words.copy(); bad[task0 + proj * sch.TASK_WORDS + sch.T_SRC] = plan.work_entries + 1; rejected(bad)
+    _native.DevicePlan(words.tobytes()).close()     # the untouched blob is fine
+
+
+def test_compute_entry_points_fail_without_an_uploaded_plan():
+    plan = _plan(wl.sprinkler())
+    dp = _native.DevicePlan(plan.to_blob())
+    with pytest.raises(_native.NativeError):
+        dp.collect(1, np.float64, 1 << 20, 0, None)      # not uploaded: refused before any CUDA call
+    with pytest.raises(TypeError):
+        dp.workspace_bytes(4, np.int32)
+
+
+@pytest.mark.parametrize("net", [wl.huang_darwiche(), wl.dag37(), wl.random_dag(30, 3, 2, 3, 30, 4)],
+                         ids=lambda n: n["name"])
+def test_schedule_structure(net):
+    """One collect task per non-root clique, one distribute task per child separator, exactly
+    one belief writer per clique, launches respect the data dependencies."""
+    plan = _plan(net)
+    T = plan.tasks_arr
+    phase_of = {}
+    for ph, b, e, lvl in plan.launches_arr:
+        for t in range(b, e):
+            phase_of.setdefault(t, []).append(int(ph))
+    collect = [t for t, p in phase_of.items() if sch.PHASE_COLLECT in p]
+    assert len(collect) == plan.n_cliques - 1
+    assert sorted(T[t][sch.T_OUT] for t in collect) == sorted(plan.up_off(s) for s in range(plan.n_cliques, plan.n_cliques + plan.n_seps))
+    dist = [t for t, p in phase_of.items() if sch.PHASE_DIST_PRE in p or sch.PHASE_DIST_MAIN in p]
+    writers = [t for t in dist if T[t][sch.T_BETA] >= 0]
+    assert sorted(T[t][sch.T_BETA] for t in writers) == sorted(plan.node_off[c] for c in range(plan.n_cliques))
+    assert sorted(T[t][sch.T_OUT] for t in dist if T[t][sch.T_OUT] >= 0) == \
+        sorted(plan.down_off(s) for s in range(plan.n_cliques, plan.n_cliques + plan.n_seps))
+    # dependency order: a buffer is read only after the launch that writes it (general mode)
+    written = set()
+    general = [L for L in plan.launches_arr if L[0] in (sch.PHASE_INIT, sch.PHASE_COLLECT, sch.PHASE_DIST_PRE,
+                                                         sch.PHASE_DIST_MAIN, sch.PHASE_MARGINAL)]
+    for ph, b, e, lvl in general:
+        outs = set()
+        for t in T[b:e]:
+            if t[sch.T_KIND] == sch.KIND_PROJECT:
+                assert t[sch.T_SRC] in written, "clique potential read before it is written"
+                for m in plan.msgs_arr[t[sch.T_RMSG_BEGIN]:t[sch.T_SMSG_END]]:
+                    assert m[sch.M_OFF] in written, "message read before it is written"
+                if t[sch.T_OWN] >= 0:
+                    assert t[sch.T_OWN] in written
+            if t[sch.T_OUT] >= 0 and t[sch.T_OUT_SPACE] == sch.SPACE_WORK:
+                outs.add(int(t[sch.T_OUT]))
+        written |= outs
+    # the split launches cover the general ones exactly
+    for all_ph, uni_ph, ins_ph in ((sch.PHASE_INIT, sch.PHASE_INIT_UNIFORM, sch.PHASE_INIT_INSTANCE),
+                                   (sch.PHASE_COLLECT, sch.PHASE_COLLECT_UNIFORM, sch.PHASE_COLLECT_INSTANCE)):
+        cover = lambda ph: sorted(t for L in plan.launches_arr if L[0] == ph for t in range(L[1], L[2]))
+        assert cover(all_ph) == sorted(cover(uni_ph) + cover(ins_ph))
+        for t in cover(uni_ph):
+            assert T[t][sch.T_FLAGS] & sch.TF_TASK_UNIFORM
+
+
+def test_uniform_flags_follow_the_evidence():
+    net = wl.dag37()
+    plan = _plan(net)
+    observed = set(net["evidence_vars"])
+    for c in range(plan.n_cliques):
+        touched = any(observed & set(net["factors"][f]) for f in plan.clique_factors[c])
+        assert plan.uniform[c] == (not touched)
+    for c in plan.order:
+        below = [c] + [k for k in plan.order if _is_below(plan, k, c)]
+        assert plan.uniform_up[c] == all(plan.uniform[k] for k in below)
+    assert plan.scheduled_entries(uniform=True) < plan.scheduled_entries(uniform=False)
+    assert plan.scheduled_entries(uniform=False) >= plan.algorithmic_entries()
+
+
+def _is_below(plan, k, c):
+    while plan.parent[k] >= 0:
+        k = plan.parent[k]
+        if k == c:
+            return True
+    return False
+
+
+def test_algorithmic_bytes_of_the_readme_network():
+    """A = 8 (4*16 - 8 + 6*4) = 640 bytes for config 1."""
+    plan = _plan(wl.sprinkler())
+    assert 8 * plan.algorithmic_entries() == 640
+
+
+def test_identical_tables_are_stored_once():
+    plan = _plan(wl.ising(6))
+    # the row sweep repeats the same clique structure: far fewer table entries than task maps
+    refs = sum(int(t[sch.T_NS]) // int(t[sch.T_NSLO]) + int(t[sch.T_NSLO]) for t in plan.tasks_arr)
+    assert plan.tables.size < refs / 2

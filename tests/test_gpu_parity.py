@@ -308,3 +308,69 @@ def test_properties_at_scale_dag37():
     want_f, _ = _oracle(tree, net, net["evidence_vars"], ev[:4], 4)
     for f, w in enumerate(want_f):
         assert_close(outs[f][:4], w, RTOL_F64, "factor %d" % f)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's configs at (or near) full size: size-independent properties checked on the
+# device for every instance, and the first instances against the oracle
+
+
+def _check_full_size(net, B, dtype, n_oracle, rtol_z, rtol):
+    import torch
+    import junctiontree as jt
+    tree = jt.create_junction_tree(net["factors"], net["sizes"], order=net.get("order"))
+    evars = net.get("evidence_vars", [])
+    ev = wl.draw_evidence(net, B) if evars else None
+    vals = [np.asarray(v, dtype) for v in net["values"]]
+    outs, nodes = tree.propagate_batch(vals, evars, ev, batch=B, nodes=True, device_output=True, dtype=dtype)
+    plan = tree.plan(evars)
+    # every clique and separator belief sums to the same partition function, per instance
+    Z = nodes[plan.root].reshape(B, -1).sum(dim=1, dtype=torch.float64)
+    assert bool(torch.isfinite(Z).all()) and bool((Z > 0).all())
+    for k, nd in enumerate(nodes):
+        zk = nd.reshape(B, -1).sum(dim=1, dtype=torch.float64)
+        assert float(((zk - Z).abs() / Z).max()) < rtol_z, "node %d" % k
+    # separator belief = marginal of the child clique belief (checked on a few edges)
+    edges = [(c, s, k) for c in plan.order for s, k in plan.children[c]]
+    for c, s, k in edges[:: max(1, len(edges) // 12)]:
+        kv, sv = plan.node_vars[k], plan.node_vars[s]
+        axes = [1 + i for i, v in enumerate(kv) if v not in sv]
+        marg = nodes[k].sum(dim=axes, dtype=torch.float64) if axes else nodes[k].double()
+        kept = [v for v in kv if v in sv]
+        marg = marg.permute([0] + [1 + kept.index(v) for v in sv])
+        ref = nodes[s].double()
+        assert float(((marg - ref).abs() / ref.abs().clamp_min(1e-300)).max()) < rtol_z * 10
+    # the first instances against the NumPy oracle
+    if n_oracle:
+        net64 = dict(net)
+        net64["values"] = [np.asarray(v, np.float64) for v in vals]
+        want_f, want_n = _oracle(tree, net64, evars, ev[:n_oracle] if ev is not None else None, n_oracle)
+        for f, w in enumerate(want_f):
+            assert_close(outs[f][:n_oracle].cpu().numpy(), w, rtol, "factor %d" % f)
+        for k in list(range(0, len(nodes), max(1, len(nodes) // 40))):
+            assert_close(nodes[k][:n_oracle].cpu().numpy(), want_n[k], rtol, "node %d" % k)
+    del outs, nodes
+    tree.clique_tree._engines.clear()
+    torch.cuda.empty_cache()
+
+
+def test_config3_ising_16x16_float64():
+    """Binary 16 x 16 Ising grid, row-sweep order: 240 cliques of up to 2^17 entries, batch 128
+    (half of BASELINE's 256 so that the 76 GB workspace leaves room on a shared box)."""
+    _check_full_size(wl.ising(16), 128, np.float64, 1, 1e-11, RTOL_F64)
+
+
+def test_config4_large_state_tree_float64_and_float32():
+    """Six variables of 64-128 states, four 3-variable cliques of 786,432 entries, batch 512."""
+    _check_full_size(wl.large_state_tree(), 512, np.float64, 2, 1e-11, RTOL_F64)
+    _check_full_size(wl.large_state_tree(), 512, np.float32, 2, 2e-5, RTOL_F32)
+
+
+def test_config5_dag500_chunk():
+    """500-node DAG, 424 cliques up to 1.8M entries: one 1024-instance chunk of the 1M batch."""
+    _check_full_size(wl.dag500(), 1024, np.float64, 1, 1e-11, RTOL_F64)
+
+
+def test_config2_dag37_full_batch():
+    """Config 2 at its full batch of 65,536 instances."""
+    _check_full_size(wl.dag37(), 65536, np.float64, 8, 1e-11, RTOL_F64)

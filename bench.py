@@ -290,6 +290,7 @@ def run_gpu(args):
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
 
     ms_per_step = total_ms / args.steps
@@ -364,6 +365,7 @@ def run_gpu(args):
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 def pick_vec(B, w):

@@ -545,7 +545,11 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     if (has_own && (tflags & JT_TF_OWN_UNIFORM)) umask |= 1u << (n_ops - 1);
     const unsigned rowmask = ((1u << n_ops) - 1u) & ~umask;     // operands that stream ring rows
     const int n_rows = __popc(rowmask);
-    const int n_stage = n_rows > 0 ? kTmaSlots / n_rows : 1;
+    // a stage groups G consecutive items so that one barrier round trip covers G * n_rows rows
+    int G = n_rows > 0 ? kTmaSlots / (4 * n_rows) : 1;
+    G = G < 1 ? 1 : (G > 4 ? 4 : G);
+    const int n_plane = n_rows * G;                      // producer lanes = ring rows per stage
+    const int n_stage = n_rows > 0 ? kTmaSlots / n_plane : 1;
     const int n_r = tk->n_r;
     const int n_items = (s1 - s0) * n_r;
     const long long B = a.B;
@@ -555,7 +559,7 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < n_stage; ++i) {
-            mbar_init(full_u32 + 8 * i, n_rows > 0 ? n_rows : 1);    // every row lane arrives per item
+            mbar_init(full_u32 + 8 * i, n_plane > 0 ? n_plane : 1);  // every producer lane arrives per stage
             mbar_init(empty_u32 + 8 * i, n_cwarps);
         }
         for (int i = 0; i < 2; ++i) {
@@ -567,18 +571,22 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     __syncthreads();
 
     if (warp == n_cwarps) {
-        // ---------------- row producer warp: lane k streams the k-th row operand ----------------
-        if (lane >= n_rows) return;
+        // ---------------- row producer warp ----------------
+        // A stage holds G consecutive (s, r) items; lane g * n_rows + k streams the k-th row
+        // operand of sub-item g, so one trip through the barriers moves up to G * n_rows rows
+        // and the G address chains run in parallel lanes.
+        if (lane >= n_plane) return;
+        const int g = lane / n_rows, k = lane - g * n_rows;
         int op = 0;                                       // operand index of this lane
         for (int seen = -1; op < n_ops; ++op)
-            if (((rowmask >> op) & 1u) && ++seen == lane) break;
+            if (((rowmask >> op) & 1u) && ++seen == k) break;
         const int jm = op - has_src;
         const bool is_src = has_src && op == 0;
         const bool is_own = has_own && op == n_ops - 1;
         const bool per_item = op < n_item_ops;            // else fetched with r = 0 only
 
         const int* __restrict__ tab = a.tab;
-        const int n_slo = tk->n_slo, n_rlo = tk->n_rlo, n_rhi = n_r / n_rlo;
+        const int n_slo = tk->n_slo, n_rlo = tk->n_rlo;
         long long base = 0, eoff = 0;
         const int* t_ahi = tab;
         const int* t_alo = tab;
@@ -599,41 +607,47 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
         }
         const T* origin = static_cast<const T*>(a.work) + eoff + col0v * VEC;
         const uint32_t dst0 = slots_u32 + (uint32_t)lane * (uint32_t)row_pitch;
-        const uint32_t stage_bytes = (uint32_t)n_rows * (uint32_t)row_pitch;
+        const uint32_t stage_bytes = (uint32_t)n_plane * (uint32_t)row_pitch;
 
-        int s_hi = 0, s_lo = s0;
-        if (n_slo < n_s) {
-            s_hi = s0 / n_slo;
-            s_lo = s0 - s_hi * n_slo;
-        }
         int stage = 0;
         uint32_t phase = 0;
-        for (int s = s0; s < s1; ++s) {
-            const int s_idx = is_own ? s : __ldg(t_ahi + s_hi) + __ldg(t_alo + s_lo);
-            const T* rowp = origin + (base + s_idx) * B;
-            bool first = true;
-            for (int rh = 0; rh < n_rhi; ++rh) {
-                const int h = per_item ? __ldg(t_bhi + rh) : 0;
-                for (int rl = 0; rl < n_rlo; ++rl) {
-                    const uint32_t full = full_u32 + 8 * stage;
-                    const int e = per_item ? h + __ldg(t_blo + rl) : 0;
-                    mbar_wait(empty_u32 + 8 * stage, phase ^ 1);
-                    if (is_src) aux->e_row[stage] = s_idx + e;
-                    if (per_item || first) {
-                        mbar_expect_tx(full, row_bytes);
-                        bulk_g2s(dst0 + (uint32_t)stage * stage_bytes, rowp + (long long)e * B, row_bytes, full);
-                    }
-                    first = false;
-                    mbar_arrive(full);
-                    if (++stage == n_stage) {
-                        stage = 0;
-                        phase ^= 1;
+        for (int i = g; i - g < n_items; i += G) {        // item of this lane in the current stage
+            const uint32_t full = full_u32 + 8 * stage;
+            const bool live = i < n_items;
+            int e = 0, s_idx = 0;
+            bool fetch = false;
+            if (live) {
+                const int ds = i / n_r;
+                const int r = i - ds * n_r;
+                const int s = s0 + ds;
+                fetch = per_item || r == 0;
+                if (fetch) {
+                    if (is_own) {
+                        s_idx = s;
+                    } else {
+                        int s_hi = 0, s_lo = s;
+                        if (n_slo < n_s) {
+                            s_hi = s / n_slo;
+                            s_lo = s - s_hi * n_slo;
+                        }
+                        s_idx = __ldg(t_ahi + s_hi) + __ldg(t_alo + s_lo);
+                        if (per_item) {
+                            const int rh = r / n_rlo, rl = r - rh * n_rlo;
+                            e = __ldg(t_bhi + rh) + __ldg(t_blo + rl);
+                        }
                     }
                 }
             }
-            if (++s_lo == n_slo) {
-                s_lo = 0;
-                ++s_hi;
+            mbar_wait(empty_u32 + 8 * stage, phase ^ 1);
+            if (fetch) {
+                if (is_src) aux->e_row[stage * G + g] = s_idx + e;
+                mbar_expect_tx(full, row_bytes);
+                bulk_g2s(dst0 + (uint32_t)stage * stage_bytes, origin + (base + s_idx + e) * B, row_bytes, full);
+            }
+            mbar_arrive(full);
+            if (++stage == n_stage) {
+                stage = 0;
+                phase ^= 1;
             }
         }
         return;
@@ -704,7 +718,7 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     T* optr = (tk->out_space ? static_cast<T*>(a.fout) : work) + (wout ? tk->out : 0) * B + col;
     T* lptr = work + (wbel ? tk->bel : 0) * B + col;
     const unsigned char* my = smem_raw + t * 16;
-    const int stage_pitch = n_rows * row_pitch;
+    const int stage_pitch = n_plane * row_pitch;
     const bool any_uni = umask != 0, any_row = n_rows > 0;
     // ring rows of a stage: the per-item operands first, then the per-s ones (own last)
     const int n_item_rows = __popc(rowmask & ((1u << n_item_ops) - 1u));
@@ -716,57 +730,67 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     auto consume = [&](auto ni_tag) {
         constexpr int NI = decltype(ni_tag)::value;          // -1: run-time count
         const int ni = NI >= 0 ? NI : n_item_rows;
-        int stage = 0, item = 0;
+        const int sub_pitch = n_rows * row_pitch;            // rows of one sub-item
+        int stage = 0, item = 0, s = s0, r = 0;
         uint32_t phase = 0;
-        for (int s = s0; s < s1; ++s) {
-            P sm = pack_fill<T, VEC>(T(1)), own = sm, scale = sm;
-            P acc0 = pack_fill<T, VEC>(T(0)), acc1 = acc0;
-            for (int r = 0; r < n_r; ++r, ++item) {
+        P sm = pack_fill<T, VEC>(T(1)), own = sm, scale = sm;
+        P acc0 = pack_fill<T, VEC>(T(0)), acc1 = acc0;
+        while (item < n_items) {
+            if (any_row) mbar_wait(full_u32 + 8 * stage, phase);
+            const unsigned char* sub = my + stage * stage_pitch;
+            for (int g = 0; g < G && item < n_items; ++g, ++item, sub += sub_pitch) {
                 const int ub = (item >> 5) & 1, ul = item & (kUBatch - 1);
                 if (any_uni && ul == 0) mbar_wait(ufull_u32 + 8 * ub, (item >> 6) & 1);
-                if (any_row) mbar_wait(full_u32 + 8 * stage, phase);
-                const unsigned char* row = my + stage * stage_pitch;
                 const T* uv = aux->u_val[ub][ul];
                 P v = pack_fill<T, VEC>(any_uni ? uv[0] : T(1));
                 if (NI >= 0) {
 #pragma unroll
                     for (int k = 0; k < (NI >= 0 ? NI : 0); ++k)
-                        mul(v, *reinterpret_cast<const P*>(row + k * row_pitch));
+                        mul(v, *reinterpret_cast<const P*>(sub + k * row_pitch));
                 } else {
-                    for (int k = 0; k < ni; ++k) mul(v, *reinterpret_cast<const P*>(row + k * row_pitch));
+                    for (int k = 0; k < ni; ++k) mul(v, *reinterpret_cast<const P*>(sub + k * row_pitch));
                 }
                 if (r == 0) {                                 // once per s: s-only operands and own
-                    const unsigned char* srow = row + ni * row_pitch;
+                    const unsigned char* srow = sub + ni * row_pitch;
                     sm = pack_fill<T, VEC>(any_uni ? uv[1] : T(1));
                     for (int k = 0; k < n_sm_rows; ++k) mul(sm, *reinterpret_cast<const P*>(srow + k * row_pitch));
                     own = own_is_row ? *reinterpret_cast<const P*>(srow + n_sm_rows * row_pitch)
                                      : pack_fill<T, VEC>(any_uni ? uv[2] : T(1));
                     scale = sm;
                     mul(scale, own);
+                    acc0 = pack_fill<T, VEC>(T(0));
+                    acc1 = acc0;
                 }
-                const int e = src_uni ? aux->u_e[ub][ul] : aux->e_row[stage];
-                __syncwarp();
-                if (lane == 0) {
-                    if (any_row) mbar_arrive(empty_u32 + 8 * stage);
-                    if (any_uni && (ul == kUBatch - 1 || item == n_items - 1)) mbar_arrive(uempty_u32 + 8 * ub);
+                const int e = src_uni ? aux->u_e[ub][ul] : aux->e_row[stage * G + g];
+                if (any_uni && (ul == kUBatch - 1 || item == n_items - 1)) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(uempty_u32 + 8 * ub);
                 }
                 if (r & 1) add(acc1, v); else add(acc0, v);
                 if (wbeta && active) {
                     mul(v, scale);
                     st<T, VEC>(bptr + (long long)e * B, v);
                 }
-                if (any_row && ++stage == n_stage) {
-                    stage = 0;
-                    phase ^= 1;
+                if (++r == n_r) {
+                    r = 0;
+                    if (wout && active) {
+                        add(acc0, acc1);
+                        mul(acc0, sm);
+                        st<T, VEC>(optr + (long long)s * B, acc0);
+                        if (wbel) {
+                            mul(acc0, own);
+                            st<T, VEC>(lptr + (long long)s * B, acc0);
+                        }
+                    }
+                    ++s;
                 }
             }
-            if (wout && active) {
-                add(acc0, acc1);
-                mul(acc0, sm);
-                st<T, VEC>(optr + (long long)s * B, acc0);
-                if (wbel) {
-                    mul(acc0, own);
-                    st<T, VEC>(lptr + (long long)s * B, acc0);
+            if (any_row) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_u32 + 8 * stage);
+                if (++stage == n_stage) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
         }

@@ -19,6 +19,8 @@
 // ------------------------------------------------------------------------------------------
 // host side
 
+constexpr int kItemLog2Max = 24;
+
 struct jt_plan {
     std::vector<int64_t> hdr, node_off, node_size, fin_off, fin_size, fout_off, fout_size;
     std::vector<int> ev_card, evf_ptr, evf_var, evf_stride;
@@ -29,6 +31,11 @@ struct jt_plan {
         int phase, begin, end, level;
         size_t prefix_off[kMaxSyLog2 + 1];
         long long blocks[kMaxSyLog2 + 1];
+        // TMA kernel: per-task chunks sized for ~2^j (s, r) items per CTA, j = 0..kItemLog2Max;
+        // layout per j: [n_tasks + 1] block prefix, [n_tasks] log2 chunk
+        size_t item_prefix_off[kItemLog2Max + 1];
+        long long item_blocks[kItemLog2Max + 1];
+        long long total_items;
         bool tma_ok;          // every task fits the TMA kernel's stage (rows per stage <= kTmaMaxRows)
         int min_nr;           // smallest n_r of the launch
         long long total_s;    // sum of n_s
@@ -96,18 +103,17 @@ template <typename T>
 int launch_tma(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
     const int ct = a.Bv >= 256 ? 256 : (a.Bv >= 128 ? 128 : 64);
     const long long tiles = (a.Bv + ct - 1) / ct;
-    // chunk of s per CTA: aim at ~8 CTAs per SM over the launch, but keep >= 32 (s, r) items per
-    // CTA so the pipeline fill is amortised
-    int sy_log2 = 0;
+    // (s, r) items per CTA: aim at ~8 CTAs per SM over the launch, but keep >= 64 items per CTA
+    // so the pipeline fill is amortised; every task gets its own chunk of s for that item count
+    int j = 6;
     const long long target = 148LL * 8;
-    while (sy_log2 < kMaxSyLog2 && (L.total_s * tiles) >> (sy_log2 + 1) >= target) ++sy_log2;
-    while (sy_log2 < kMaxSyLog2 && ((long long)L.min_nr << sy_log2) < 32) ++sy_log2;
-    a.sy_log2 = sy_log2;
+    while (j < kItemLog2Max && (L.total_items * tiles) >> (j + 1) >= target) ++j;
+    a.sy_log2 = 0;
     a.bx_log2 = 0;
     a.tasks = p->d_tasks + L.begin;
     a.n_tasks = L.end - L.begin;
-    a.prefix = p->d_prefix + L.prefix_off[sy_log2];
-    const long long gx = L.blocks[sy_log2];
+    a.prefix = p->d_prefix + L.item_prefix_off[j];
+    const long long gx = L.item_blocks[j];
     if (gx <= 0) return JT_OK;
     if (gx > 2147483647LL || tiles > 65535)
         return fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, tiles);
@@ -345,6 +351,28 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
         L.tma_ok = true;
         L.min_nr = 2147483647;
         L.total_s = 0;
+        L.total_items = 0;
+        for (int t = L.begin; t < L.end; ++t) L.total_items += (long long)p->tasks[t].n_s * p->tasks[t].n_r;
+        for (int j = 0; j <= kItemLog2Max; ++j) {
+            L.item_prefix_off[j] = p->prefix.size();
+            long long acc = 0;
+            std::vector<int> chunk;
+            for (int t = L.begin; t < L.end; ++t) {
+                const DTask& k = p->tasks[t];
+                int nr_log2 = 0;
+                while ((1LL << nr_log2) < k.n_r) ++nr_log2;
+                int c = j - nr_log2;
+                c = c < 0 ? 0 : (c > 30 ? 30 : c);
+                while (c > 0 && (1LL << c) >= 2LL * k.n_s) --c;      // no larger than the task
+                p->prefix.push_back((int)acc);
+                chunk.push_back(c);
+                acc += ((long long)k.n_s + (1LL << c) - 1) >> c;
+                if (acc > 2147483647LL) return bad("launch too large", i);
+            }
+            p->prefix.push_back((int)acc);
+            p->prefix.insert(p->prefix.end(), chunk.begin(), chunk.end());
+            L.item_blocks[j] = acc;
+        }
         for (int t = L.begin; t < L.end; ++t) {
             const DTask& k = p->tasks[t];
             const int rows = (k.src >= 0 ? 1 : 0) + (k.rmsg_end - k.rmsg_begin) + (k.smsg_end - k.smsg_begin) +

@@ -520,10 +520,23 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     const uint32_t full_u32 = smem_u32(aux->full), empty_u32 = smem_u32(aux->empty);
     const uint32_t ufull_u32 = smem_u32(aux->u_full), uempty_u32 = smem_u32(aux->u_empty);
 
-    int s0;
-    const DTask* tk = locate_chunk(a, s0);
+    // block -> (task, chunk of s): per-task chunk sizes (a.prefix: [n_tasks + 1] first block of
+    // each task, then [n_tasks] log2 of the task's chunk) balance the (s, r) items per CTA
+    int s0, chunk_log2;
+    const DTask* tk;
+    {
+        const int bid = blockIdx.x;
+        int lo = 0, hi = a.n_tasks;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(a.prefix + mid) <= bid) lo = mid; else hi = mid;
+        }
+        chunk_log2 = __ldg(a.prefix + a.n_tasks + 1 + lo);
+        s0 = (bid - __ldg(a.prefix + lo)) << chunk_log2;
+        tk = a.tasks + lo;
+    }
     const int n_s = tk->n_s;
-    const int s1 = min(n_s, s0 + (1 << a.sy_log2));
+    const int s1 = min(n_s, s0 + (1 << chunk_log2));
     const long long col0v = (long long)blockIdx.y * ct;
     const int ncols = (int)min((long long)ct, a.Bv - col0v);
     const uint32_t row_bytes = (uint32_t)ncols * 16u;

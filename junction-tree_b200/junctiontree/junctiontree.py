@@ -241,10 +241,12 @@ class JunctionTree():
         sizes.update(_effective_sizes(fg.factors, xs))
         engine = self._engine(sizes)
         dtype = np.dtype(dtype) if dtype is not None else _result_dtype(xs)
-        fdev, _ = engine.factors_to_device(xs, dtype)
-        _, fout = engine.propagate(fdev, False, None, 1, dtype)
         plan = engine.plan
-        flat = fout[:, 0].cpu().numpy()
+        # single instance: launch-bound, so the whole call (tables in, propagate, beliefs out)
+        # is one CUDA-graph replay over static buffers
+        graphed = engine.graphed(1, dtype)
+        graphed.set_factors(xs)
+        flat = graphed.run().numpy()[:, 0]
         return [
             flat[plan.fout_off[f]:plan.fout_off[f] + plan.fout_size[f]].reshape(tuple(plan.fout_shape[f])).copy()
             for f in range(len(plan.factors))

@@ -389,7 +389,7 @@ def main():
     ap.add_argument("--config", default="dag37")
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--chunk", type=int, default=16384, help="instances per pipeline chunk (e2e)")
+    ap.add_argument("--chunk", type=int, default=8192, help="instances per pipeline chunk (e2e)")
     ap.add_argument("--no-evidence", action="store_true")
     ap.add_argument("--no-uniform", action="store_true",
                     help="materialise every potential and message per instance (general path)")

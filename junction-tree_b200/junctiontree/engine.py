@@ -208,7 +208,7 @@ class BatchPipeline:
     either side.
     """
 
-    def __init__(self, engine, B, dtype, chunk=16384, n_streams=2):
+    def __init__(self, engine, B, dtype, chunk=8192, n_streams=2):
         t = require_cuda()
         self.engine, self.B, self.dtype = engine, int(B), np.dtype(dtype)
         plan = engine.plan
@@ -290,7 +290,7 @@ class BatchPipeline:
         return total
 
 
-def _pipeline(self, B, dtype, chunk=16384, n_streams=2):
+def _pipeline(self, B, dtype, chunk=8192, n_streams=2):
     return BatchPipeline(self, B, dtype, chunk, n_streams)
 
 

@@ -374,3 +374,31 @@ def test_config5_dag500_chunk():
 def test_config2_dag37_full_batch():
     """Config 2 at its full batch of 65,536 instances."""
     _check_full_size(wl.dag37(), 65536, np.float64, 8, 1e-11, RTOL_F64)
+
+
+def test_star_tree_with_many_messages():
+    """A clique with nine neighbours whose separators all depend on summed-out axes: more
+    r-dependent messages than the kernels keep in registers / ring rows (generic paths)."""
+    from junctiontree import computation as comp
+    from oracle import brute
+    rng = np.random.default_rng(11)
+    centre = list("abcdefgh")
+    sizes = {v: 2 for v in centre}
+    node_vars = [centre]
+    pots = [rng.random((2,) * 8) + 0.1]
+    tree = [0]
+    pairs = [("a", "b"), ("b", "c"), ("c", "d"), ("d", "e"), ("e", "f"), ("f", "g"), ("g", "h"), ("h", "a"), ("a", "e")]
+    n = len(pairs)
+    for i, (u, v) in enumerate(pairs):
+        leaf = "z%d" % i
+        sizes[leaf] = 3
+        node_vars.append([u, leaf, v])
+        pots.append(rng.random((2, 3, 2)) + 0.1)
+    for i, (u, v) in enumerate(pairs):
+        node_vars.append([v, u])                      # separator axis order differs from the cliques
+        pots.append(np.ones((2, 2)))
+        tree.append((1 + n + i, [1 + i]))
+    got = comp.compute_beliefs(tree, pots, node_vars)
+    want = brute.tree_beliefs(tree, node_vars, pots)
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert_close(g, w, RTOL_F64, "node %d" % k)

@@ -40,6 +40,18 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(args, uniform):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu launch list
+    (profiles/r01_traffic.json), when one exists for this exact configuration."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            table = json.load(fh)
+        key = "%s:%d:%s:%s" % (args.config, args.batch, args.dtype, "uniform" if uniform else "per_instance")
+        return table[key]["traffic_per_launch"]
+    except Exception:
+        return None
+
+
 def make_net(name):
     if name == "dag37":
         return wl.dag37()
@@ -339,7 +351,7 @@ def run_gpu(args):
         "roofline": {
             "bound": "hbm", "kernel": "jt_project_tma_kernel<%s>" % ("double" if w == 8 else "float"),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_source": peak_src, "traffic": None,
+            "peak_source": peak_src, "traffic": load_traffic(args, uniform),
             "launches_per_step": msg_launches, "avg_launch_ms": msg_ms_per_launch,
             "algorithmic_bytes_per_launch": A_msg * B / max(msg_launches, 1),
             "scheduled_bytes_per_launch": S_msg * B / max(msg_launches, 1),

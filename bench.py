@@ -190,7 +190,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_line(json.dumps(line))
 
 
 def workload_name(args):
@@ -374,7 +374,7 @@ def run_gpu(args):
         "gpu_launches_e2e": int(e2e_launches),
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    print_line(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -408,10 +408,22 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-per-core", type=int, default=256, help="CPU baseline: instances per core")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything libraries print there meanwhile (e.g. NCCL's
+    # version banner) goes to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(saved, "w")
+    global print_line
+    print_line = lambda text: (out.write(text + "\n"), out.flush())
     if args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)
+
+
+def print_line(text):
+    print(text)
 
 
 if __name__ == "__main__":

@@ -38,6 +38,7 @@ struct jt_plan {
         long long total_items;
         bool tma_ok;          // every task fits the TMA kernel's stage (rows per stage <= kTmaMaxRows)
         int min_nr;           // smallest n_r of the launch
+        int max_nr;           // largest n_r of the launch
         long long total_s;    // sum of n_s
     };
     std::vector<Launch> launches;
@@ -99,6 +100,12 @@ bool tma_enabled() {
     return g_tma_enabled == 1;
 }
 
+// Few instances and long reductions with too few output indices to fill the machine: split r.
+bool use_splitr(const jt_plan::Launch& L, long long B, bool is_init) {
+    if (is_init || B > 64 || L.max_nr < 128) return false;
+    return L.max_nr >= 4096 || L.total_s * B < 65536;
+}
+
 template <typename T>
 int launch_tma(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
     const int ct = a.Bv >= 256 ? 256 : (a.Bv >= 128 ? 128 : 64);
@@ -141,6 +148,23 @@ int launch_tasks(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream
         return launch_tma<T>(p, L, a, stream);
     int bx_log2, sy_log2;
     pick_tile(a.Bv, bx_log2, sy_log2);
+    if (VEC == 1 && use_splitr(L, a.B, is_init)) {
+        // few instances, long reductions: one block per output index, threads split r
+        a.bx_log2 = bx_log2;
+        a.sy_log2 = 0;
+        a.tasks = p->d_tasks + L.begin;
+        a.n_tasks = L.end - L.begin;
+        a.prefix = p->d_prefix + L.prefix_off[0];
+        const long long gx = L.blocks[0];
+        const long long gy = (a.B + (1LL << bx_log2) - 1) >> bx_log2;
+        if (gx <= 0) return JT_OK;
+        if (gx > 2147483647LL || gy > 65535)
+            return fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
+        jt_project_splitr_kernel<T><<<dim3((unsigned)gx, (unsigned)gy, 1), kThreads, 0, stream>>>(a);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        JT_CUDA(cudaGetLastError());
+        return JT_OK;
+    }
     if (is_init) {
         // a thread walks ~32 rows of s so the per-instance factor offsets stay in registers
         sy_log2 = sy_log2 + 5 > kMaxSyLog2 ? kMaxSyLog2 : sy_log2 + 5;
@@ -167,8 +191,15 @@ int launch_tasks(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream
     return JT_OK;
 }
 
-int dispatch(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec,
+int dispatch(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a_in, int dtype, int vec,
              cudaStream_t stream) {
+    KArgs a = a_in;
+    const bool is_init = L.phase == JT_PHASE_INIT || L.phase == JT_PHASE_INIT_UNIFORM ||
+                         L.phase == JT_PHASE_INIT_INSTANCE;
+    if (use_splitr(L, a.B, is_init)) {                  // split-r kernel: scalar batch lanes
+        vec = 1;
+        a.Bv = a.B;
+    }
     if (dtype == JT_F64) {
         if (vec == 2) return launch_tasks<double, 2>(p, L, a, stream);
         return launch_tasks<double, 1>(p, L, a, stream);
@@ -187,7 +218,7 @@ int check_common(const jt_plan* p, int64_t B, int dtype, const void* workspace) 
     return JT_OK;
 }
 
-KArgs base_args(const jt_plan* p, int64_t B, int dtype, void* workspace, int vec) {
+KArgs base_args(const jt_plan* p, int64_t B, void* workspace, int vec) {
     KArgs a;
     memset(&a, 0, sizeof(a));
     a.msgs = p->d_msgs;
@@ -350,6 +381,7 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
                 return bad("task kind vs phase", i);
         L.tma_ok = true;
         L.min_nr = 2147483647;
+        L.max_nr = 0;
         L.total_s = 0;
         L.total_items = 0;
         for (int t = L.begin; t < L.end; ++t) L.total_items += (long long)p->tasks[t].n_s * p->tasks[t].n_r;
@@ -379,6 +411,7 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
                              (k.own >= 0 ? 1 : 0);
             if (rows < 1 || rows > kTmaMaxRows || k.rmsg_end != k.smsg_begin) L.tma_ok = false;
             L.min_nr = k.n_r < L.min_nr ? k.n_r : L.min_nr;
+            L.max_nr = k.n_r > L.max_nr ? k.n_r : L.max_nr;
             L.total_s += k.n_s;
         }
         // block prefix per tile shape: a block covers 2^sy consecutive values of s of one task
@@ -490,7 +523,7 @@ int jt_init(jt_plan* p, const void* factor_tables, int factors_batched, const in
     const WorkspaceLayout wl = workspace_layout(p, B, dtype);
     const int n_evid = (int)p->hdr[JT_H_NEVID];
     const int vec = pick_vec(B, dtype);
-    KArgs a = base_args(p, B, dtype, workspace, vec);
+    KArgs a = base_args(p, B, workspace, vec);
     a.fin = factor_tables;
     a.fin_batched = factors_batched ? 1 : 0;
     if (n_evid > 0) {
@@ -522,7 +555,7 @@ int jt_collect(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, voi
     if (rc != JT_OK) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int vec = pick_vec(B, dtype);
-    KArgs a = base_args(p, B, dtype, workspace, vec);
+    KArgs a = base_args(p, B, workspace, vec);
     a.flags = flags;
     if (!uniform_mode(p, flags)) return run_phase(p, JT_PHASE_COLLECT, a, dtype, vec, stream);
     // uniform mode: evidence-free subtrees are collected once (B = 1), then the rest per instance
@@ -539,7 +572,7 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
     if (rc != JT_OK) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int vec = pick_vec(B, dtype);
-    KArgs a = base_args(p, B, dtype, workspace, vec);
+    KArgs a = base_args(p, B, workspace, vec);
     a.flags = flags;
     if (uniform_mode(p, flags)) {
         a.uni = uniform_ws(p, B, dtype, workspace);
@@ -559,7 +592,7 @@ int jt_marginal(jt_plan* p, int64_t B, int dtype, void* workspace, void* factor_
     if (rc != JT_OK) return rc;
     if (!factor_out) return fail(JT_ERR_INVALID, "factor_out is null");
     const int vec = pick_vec(B, dtype);
-    KArgs a = base_args(p, B, dtype, workspace, vec);
+    KArgs a = base_args(p, B, workspace, vec);
     a.fout = factor_out;
     return run_phase(p, JT_PHASE_MARGINAL, a, dtype, vec, static_cast<cudaStream_t>(stream));
 }

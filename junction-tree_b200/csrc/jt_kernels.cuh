@@ -145,9 +145,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -469,6 +466,89 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
             mul(o, own);
             st<T, VEC>(work + (tk->bel + s) * B + col, o);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Split-r projection for small batches (same task semantics as jt_project_kernel).
+//
+// With few instances and a long reduction (a single propagation marginalising a 2^17-entry
+// clique to a 2-entry factor scope) the s-parallel kernels leave all but a handful of threads
+// idle.  Here a block owns one output index s; its threads are laid out as 2^bx_log2 batch lanes
+// times 256 / 2^bx_log2 r-lanes, every r-lane strides over r, and the partial sums are combined
+// by a fixed-order tree in shared memory (deterministic).  beta rows are written by whichever
+// lane visits them, exactly once.
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) jt_project_splitr_kernel(const KArgs a) {
+    __shared__ T red[kThreads];
+    const int bx_log2 = a.bx_log2;
+    const int tx = threadIdx.x & ((1 << bx_log2) - 1);
+    const int rz = threadIdx.x >> bx_log2, RZ = kThreads >> bx_log2;
+    const long long b = ((long long)blockIdx.y << bx_log2) + tx;
+    const bool valid = b < a.B;
+    int s;
+    const DTask* tk = locate_chunk(a, s);             // prefix for chunks of one s: s0 == s
+    const int n_s = tk->n_s;
+
+    const int* __restrict__ tab = a.tab;
+    const DMsg* __restrict__ msgs = a.msgs;
+    const long long B = a.B, col = valid ? b : 0;
+    T* work = static_cast<T*>(a.work);
+    const T* uni = static_cast<const T*>(a.uni);
+    const bool um = a.uniform != 0;
+    const int tflags = um ? tk->flags : 0;
+
+    const int n_slo = tk->n_slo;
+    int s_hi = 0, s_lo = s;
+    if (n_slo < n_s) {
+        s_hi = s / n_slo;
+        s_lo = s - s_hi * n_slo;
+    }
+    T sm = T(1);
+    for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
+        const DMsg* m = msgs + j;
+        const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+        sm *= (um && m->uni) ? __ldg(uni + idx) : work[m->eoff + idx * B + col];
+    }
+    T own = T(1);
+    if (tk->own >= 0)
+        own = (tflags & JT_TF_OWN_UNIFORM) ? __ldg(uni + tk->own + s) : work[(tk->own + s) * B + col];
+    const T scale = sm * own;
+
+    const bool has_src = tk->src >= 0, src_uni = (tflags & JT_TF_SRC_UNIFORM) != 0;
+    const bool wbeta = tk->beta >= 0;
+    const long long s_off = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo);
+    const int rm0 = tk->rmsg_begin, nr = tk->rmsg_end - rm0;
+    const int n_r = tk->n_r, n_rlo = tk->n_rlo;
+
+    T acc = T(0);
+    for (int r = rz; r < n_r; r += RZ) {
+        const int rh = r / n_rlo, rl = r - rh * n_rlo;
+        const long long e = s_off + __ldg(tab + tk->src_rhi + rh) + __ldg(tab + tk->src_rlo + rl);
+        T v = T(1);
+        if (has_src) v = src_uni ? __ldg(uni + tk->src + e) : work[(tk->src + e) * B + col];
+        for (int j = 0; j < nr; ++j) {
+            const DMsg* m = msgs + rm0 + j;
+            const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo) +
+                                  __ldg(tab + m->b_hi + rh) + __ldg(tab + m->b_lo + rl);
+            v *= (um && m->uni) ? __ldg(uni + idx) : work[m->eoff + idx * B + col];
+        }
+        acc += v;
+        if (wbeta && valid) work[(tk->beta + e) * B + col] = v * scale;
+    }
+
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int stride = RZ >> 1; stride > 0; stride >>= 1) {
+        if (rz < stride) red[threadIdx.x] += red[threadIdx.x + (stride << bx_log2)];
+        __syncthreads();
+    }
+    if (rz == 0 && valid && tk->out >= 0) {
+        T o = red[threadIdx.x] * sm;
+        T* obase = tk->out_space ? static_cast<T*>(a.fout) : work;
+        obase[(tk->out + s) * B + col] = o;
+        if (tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS)) work[(tk->bel + s) * B + col] = o * own;
     }
 }
 

@@ -26,6 +26,32 @@ def shard_sizes(total, world_size):
             for r in range(world_size)]
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that pinned host
+    buffers (first touch) and the copy threads are local to the GPU's PCIe root.  With eight
+    ranks streaming results to the host at once, remote-socket buffers halve the aggregate
+    device->host rate.  Best effort: silently does nothing when the topology is not exposed."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def init_from_env(backend=None):
     """Initialise ``torch.distributed`` from RANK / WORLD_SIZE / MASTER_* (torchrun); binds the
     process to ``cuda:LOCAL_RANK`` when the backend is NCCL.  Returns ``(rank, world_size)``."""
@@ -36,7 +62,10 @@ def init_from_env(backend=None):
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
-        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", str(rank))))
+        local = int(os.environ.get("LOCAL_RANK", str(rank)))
+        torch.cuda.set_device(local)
+        if world > 1:
+            bind_to_gpu_numa_node(local)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")

@@ -402,3 +402,28 @@ def test_star_tree_with_many_messages():
     want = brute.tree_beliefs(tree, node_vars, pots)
     for k, (g, w) in enumerate(zip(got, want)):
         assert_close(g, w, RTOL_F64, "node %d" % k)
+
+
+@pytest.mark.parametrize("B", [1, 5, 64])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_split_r_small_batches(B, dtype):
+    """Few instances, long reductions (a 2^13-entry clique with 2- and 4-entry neighbours): the
+    split-r kernel, including belief writes and uniform operands."""
+    import junctiontree as jt
+    rng = np.random.default_rng(4)
+    big = ["v%02d" % i for i in range(13)]
+    factors = [big, ["v00", "w0"], ["v05", "v06", "w1"], ["w1", "w2"], ["v12"]]
+    sizes = {v: 2 for v in big}
+    sizes.update(w0=3, w1=2, w2=4)
+    values = [np.asarray(rng.random([sizes[v] for v in f]) + 0.05, dtype) for f in factors]
+    net = {"factors": factors, "sizes": sizes, "values": values, "evidence_vars": ["w2"], "seed": 3}
+    tree = jt.create_junction_tree(factors, sizes)
+    ev = wl.draw_evidence(net, B)
+    outs, nodes = tree.propagate_batch(values, ["w2"], ev, nodes=True)
+    net64 = dict(net, values=[np.asarray(v, np.float64) for v in values])
+    want_f, want_n = _oracle(tree, net64, ["w2"], ev, B)
+    rtol = RTOL_F64 if dtype == np.float64 else RTOL_F32
+    for k, (g, w) in enumerate(zip(nodes, want_n)):
+        assert_close(g, w, rtol, "node %d" % k)
+    for f, (g, w) in enumerate(zip(outs, want_f)):
+        assert_close(g, w, rtol, "factor %d" % f)

@@ -18,6 +18,10 @@ from . import engine as eng
 from . import schedule as sch
 
 
+#: batches larger than this with host output are streamed through the chunked pipeline
+_STREAM_THRESHOLD = 4096
+
+
 def create_junction_tree(factors, sizes, order=None):
     """Create a Junction tree for a given factor graph.
 
@@ -252,6 +256,34 @@ class JunctionTree():
             for f in range(len(plan.factors))
         ]
 
+    def _propagate_streamed(self, engine, fdev, evidence, B, dtype):
+        """Host-in / host-out propagation of a large batch through ``engine.BatchPipeline``."""
+        t = eng.require_cuda()
+        plan = engine.plan
+        per_instance = engine.dev.workspace_bytes(2, dtype) - engine.dev.workspace_bytes(1, dtype)
+        per_instance += plan.fout_entries * np.dtype(dtype).itemsize
+        free, _ = t.cuda.mem_get_info()
+        chunk = int(max(1, min(8192, B, (free // 3) // max(per_instance, 1))))
+        chunk = max(2, chunk - chunk % 2) if chunk > 1 else 1
+        pipe = engine.pipeline(B, dtype, chunk=chunk)
+        ev_host = None
+        if plan.evidence_vars:
+            if evidence is None:
+                raise ValueError("the plan has evidence variables %r but no evidence was given"
+                                 % (plan.evidence_vars,))
+            ev_host = t.from_numpy(np.ascontiguousarray(evidence, dtype=np.int32))
+            if tuple(ev_host.shape) != (B, len(plan.evidence_vars)):
+                raise ValueError("evidence must have shape [%d, %d], got %s"
+                                 % (B, len(plan.evidence_vars), tuple(ev_host.shape)))
+            ev_host = ev_host.pin_memory()
+        out_host = pipe.host_output()
+        pipe.run(fdev, False, ev_host, out_host, sync=True)
+        if ev_host is not None:
+            bad = pipe.evidence_errors()
+            if bad:
+                raise ValueError("%d evidence states are outside the range of their variable" % bad)
+        return pipe.factor_views(out_host)
+
     def propagate_batch(self, xs, evidence_vars=(), evidence=None, batch=None, dtype=None,
                         nodes=False, device_output=False, uniform=True):
         """Many independent propagations over this tree in one pass.
@@ -292,6 +324,10 @@ class JunctionTree():
         else:
             raise ValueError("batch size unknown: give evidence, batched tables or batch=")
         fdev, batched = engine.factors_to_device(xs, dtype, B)
+        if not nodes and not device_output and not batched and B > _STREAM_THRESHOLD:
+            # large batches with host output: stream chunks over two CUDA streams, sized to the
+            # free device memory (config 5 needs ~80 MB of workspace per instance)
+            return self._propagate_streamed(engine, fdev, evidence, B, dtype)
         edev = engine.evidence_to_device(evidence, B)
         ws, fout = engine.propagate(fdev, batched, edev, B, dtype, sep_beliefs=nodes, uniform=uniform)
         if edev is not None:

@@ -427,3 +427,25 @@ def test_split_r_small_batches(B, dtype):
         assert_close(g, w, rtol, "node %d" % k)
     for f, (g, w) in enumerate(zip(outs, want_f)):
         assert_close(g, w, rtol, "factor %d" % f)
+
+
+def test_large_batch_is_streamed_in_chunks():
+    """Host-in / host-out batches above the streaming threshold go through the chunked
+    two-stream pipeline (ragged last chunk included) and give the same numbers."""
+    import junctiontree as jt
+    net = wl.random_dag(14, 3, 2, 3, 8, 2)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    B = 3 * 8192 + 1234
+    ev = wl.draw_evidence(net, B)
+    outs = tree.propagate_batch(net["values"], net["evidence_vars"], ev)
+    assert all(o.shape[0] == B for o in outs)
+    direct = tree.propagate_batch(net["values"], net["evidence_vars"], ev, device_output=True)
+    for f, (a, b) in enumerate(zip(outs, direct)):
+        assert_close(a, b.cpu().numpy(), 1e-14, "factor %d" % f)
+    pick = [0, 1, 8191, 8192, 3 * 8192, B - 1]
+    want_f, _ = _oracle(tree, net, net["evidence_vars"], ev[pick], len(pick))
+    for f, w in enumerate(want_f):
+        assert_close(outs[f][pick], w, RTOL_F64, "factor %d" % f)
+    ev[B - 3, 1] = -1
+    with pytest.raises(ValueError):
+        tree.propagate_batch(net["values"], net["evidence_vars"], ev)

@@ -41,7 +41,7 @@
  *
  * Plan blob (produced by junctiontree/schedule.py, Plan.to_blob): little-endian int64 words
  *   header[JT_H_WORDS], node_off[n_nodes], node_size[n_nodes], fin_off[F], fin_size[F],
- *   fout_off[F], fout_size[F], ev_card[n_evid], evf_ptr[F+1 or 0], evf_var[n_evf],
+ *   fout_off[n_out], fout_size[n_out], ev_card[n_evid], evf_ptr[F+1 or 0], evf_var[n_evf],
  *   evf_stride[n_evf], tasks[n_tasks][JT_TASK_WORDS], msgs[n_msgs][JT_MSG_WORDS],
  *   launches[n_launches][JT_LAUNCH_WORDS], then int32 tables[n_tab (padded to even)].
  *
@@ -61,7 +61,7 @@
 extern "C" {
 #endif
 
-#define JT_ABI_VERSION 4
+#define JT_ABI_VERSION 5
 
 /* status codes */
 #define JT_OK 0
@@ -85,7 +85,7 @@ enum {
     JT_H_MAGIC, JT_H_VERSION, JT_H_NCLIQUES, JT_H_NSEPS, JT_H_NFACTORS, JT_H_NEVID,
     JT_H_CLIQUE_ENTRIES, JT_H_SEP_ENTRIES, JT_H_FIN_ENTRIES, JT_H_FOUT_ENTRIES, JT_H_NTAB,
     JT_H_NTASKS, JT_H_NMSGS, JT_H_NLAUNCHES, JT_H_MAXDEPTH, JT_H_NEVF, JT_H_ROOT_ENTRIES,
-    JT_H_UNI_ENTRIES, JT_H_WORDS
+    JT_H_UNI_ENTRIES, JT_H_NOUT, JT_H_WORDS
 };
 #define JT_TASK_WORDS 24
 enum {
@@ -153,6 +153,12 @@ int jt_marginal(jt_plan* plan, int64_t B, int dtype, void* workspace, void* fact
 int jt_propagate(jt_plan* plan, const void* factor_tables, int factors_batched,
                  const int32_t* evidence, int64_t B, int dtype, void* workspace, void* factor_out,
                  int flags, void* stream);
+/* Output stage: divide every output scope of factor_out ([fout_entries][B], as written by
+ * jt_marginal) by its sum over the scope, per instance; the sum of scope 0 -- the partition
+ * function Z = P(evidence) that the reference computes at the root and discards,
+ * computation.py:90-96 -- is written as log Z to logz[B] when logz is not NULL.  A scope whose sum
+ * is 0 (impossible evidence) becomes all zeros and log Z = -inf. */
+int jt_normalize(jt_plan* plan, int64_t B, int dtype, void* factor_out, void* logz, void* stream);
 /* number of out-of-range evidence states seen by jt_init calls on this workspace since it was
  * last zeroed (synchronises the stream) */
 int jt_evidence_errors(jt_plan* plan, int64_t B, int dtype, void* workspace, void* stream, int64_t* out);

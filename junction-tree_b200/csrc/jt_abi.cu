@@ -50,6 +50,7 @@ struct jt_plan {
     int* d_tab = nullptr;
     int* d_prefix = nullptr;
     int* d_ev = nullptr;   // ev_card | evf_ptr | evf_var | evf_stride
+    long long* d_out = nullptr;   // fout_off | fout_size
 };
 
 namespace {
@@ -288,11 +289,11 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
     if (!p) return fail(JT_ERR_NOMEM, "out of host memory");
     p->hdr.assign(w, w + JT_H_WORDS);
     const int64_t n_nodes = w[JT_H_NCLIQUES] + w[JT_H_NSEPS];
-    const int64_t F = w[JT_H_NFACTORS], n_evid = w[JT_H_NEVID], n_evf = w[JT_H_NEVF];
+    const int64_t F = w[JT_H_NFACTORS], n_evid = w[JT_H_NEVID], n_evf = w[JT_H_NEVF], n_out = w[JT_H_NOUT];
     const int64_t n_tasks = w[JT_H_NTASKS], n_msgs = w[JT_H_NMSGS], n_launch = w[JT_H_NLAUNCHES];
     const int64_t n_tab = w[JT_H_NTAB];
     const int64_t evf_ptr_n = F > 0 ? F + 1 : 0;
-    const int64_t words = JT_H_WORDS + 2 * n_nodes + 4 * F + n_evid + evf_ptr_n + 2 * n_evf +
+    const int64_t words = JT_H_WORDS + 2 * n_nodes + 2 * F + 2 * n_out + n_evid + evf_ptr_n + 2 * n_evf +
                           n_tasks * JT_TASK_WORDS + n_msgs * JT_MSG_WORDS + n_launch * JT_LAUNCH_WORDS;
     const int64_t tab_words = (n_tab + 1) / 2;
     if ((int64_t)(nbytes / 8) != words + tab_words) {
@@ -311,8 +312,13 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
     take64(p->node_size, n_nodes);
     take64(p->fin_off, F);
     take64(p->fin_size, F);
-    take64(p->fout_off, F);
-    take64(p->fout_size, F);
+    take64(p->fout_off, n_out);
+    take64(p->fout_size, n_out);
+    for (int64_t k = 0; k < n_out; ++k)
+        if (p->fout_off[k] < 0 || p->fout_size[k] <= 0 || p->fout_off[k] + p->fout_size[k] > w[JT_H_FOUT_ENTRIES]) {
+            delete p;
+            return fail(JT_ERR_INVALID, "malformed plan: output scope %lld", (long long)k);
+        }
     take32(p->ev_card, n_evid);
     take32(p->evf_ptr, evf_ptr_n);
     take32(p->evf_var, n_evf);
@@ -441,6 +447,7 @@ void jt_plan_destroy(jt_plan* p) {
         cudaFree(p->d_tab);
         cudaFree(p->d_prefix);
         cudaFree(p->d_ev);
+        cudaFree(p->d_out);
     }
     delete p;
 }
@@ -507,6 +514,9 @@ int jt_plan_upload(jt_plan* p) {
     ev.insert(ev.end(), p->evf_var.begin(), p->evf_var.end());
     ev.insert(ev.end(), p->evf_stride.begin(), p->evf_stride.end());
     JT_CUDA(up(&p->d_ev, ev));
+    std::vector<long long> outs(p->fout_off.begin(), p->fout_off.end());
+    outs.insert(outs.end(), p->fout_size.begin(), p->fout_size.end());
+    JT_CUDA(up(&p->d_out, outs));
     p->device = dev;
     return JT_OK;
 }
@@ -610,6 +620,25 @@ int jt_propagate(jt_plan* p, const void* factor_tables, int factors_batched, con
     if (rc != JT_OK) return rc;
     if (flags & JT_SKIP_MARGINAL) return JT_OK;
     return jt_marginal(p, B, dtype, workspace, factor_out, stream);
+}
+
+int jt_normalize(jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, void* stream_) {
+    int rc = check_common(p, B, dtype, factor_out);
+    if (rc != JT_OK) return rc;
+    const int n_out = (int)p->fout_off.size();
+    if (n_out == 0) return JT_OK;
+    if (n_out > 65535) return fail(JT_ERR_INVALID, "too many output scopes for one launch");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    dim3 grid((unsigned)((B + kThreads - 1) / kThreads), (unsigned)n_out, 1);
+    if (dtype == JT_F64)
+        jt_normalize_kernel<double><<<grid, kThreads, 0, stream>>>(static_cast<double*>(factor_out), p->d_out,
+                                                                  p->d_out + n_out, B, static_cast<double*>(logz));
+    else
+        jt_normalize_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<float*>(factor_out), p->d_out,
+                                                                 p->d_out + n_out, B, static_cast<float*>(logz));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    JT_CUDA(cudaGetLastError());
+    return JT_OK;
 }
 
 int jt_evidence_errors(jt_plan* p, int64_t B, int dtype, void* workspace, void* stream, int64_t* out) {

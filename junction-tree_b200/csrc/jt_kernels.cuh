@@ -897,6 +897,23 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     }
 }
 
+// Output stage: normalise every output scope per instance; log Z from scope 0.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+jt_normalize_kernel(T* __restrict__ fout, const long long* __restrict__ out_off,
+                    const long long* __restrict__ out_size, long long B, T* __restrict__ logz) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int k = blockIdx.y;
+    T* col = fout + out_off[k] * B + b;
+    const long long n = out_size[k];
+    T z = T(0);
+    for (long long e = 0; e < n; ++e) z += col[e * B];
+    const T inv = z > T(0) ? T(1) / z : T(0);
+    for (long long e = 0; e < n; ++e) col[e * B] *= inv;
+    if (k == 0 && logz) logz[b] = log(z);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 jt_ratio_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n) {

@@ -13,7 +13,7 @@ import numpy as np
 JT_OK = 0
 JT_F32, JT_F64 = 0, 1
 JT_SEP_BELIEFS, JT_SKIP_MARGINAL, JT_UNIFORM, JT_NO_UNIFORM = 1, 2, 4, 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _LIB_NAME = "libjt_b200.so"
 _lib = None
@@ -47,6 +47,8 @@ SIGNATURES = {
     "jt_propagate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                     ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_int, ctypes.c_void_p]),
+    "jt_normalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p]),
     "jt_evidence_errors": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_void_p, _i64p]),
     "jt_copy_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
@@ -175,6 +177,9 @@ class DevicePlan:
     def propagate(self, factors_ptr, batched, evidence_ptr, B, dtype, ws_ptr, out_ptr, flags, stream):
         check(lib().jt_propagate(self._handle, factors_ptr, int(batched), evidence_ptr, B,
                                  dtype_code(dtype), ws_ptr, out_ptr, flags, stream))
+
+    def normalize(self, B, dtype, out_ptr, logz_ptr, stream):
+        check(lib().jt_normalize(self._handle, B, dtype_code(dtype), out_ptr, logz_ptr, stream))
 
     def evidence_errors(self, B, dtype, ws_ptr, stream):
         out = ctypes.c_int64()

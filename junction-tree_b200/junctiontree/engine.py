@@ -208,9 +208,11 @@ class BatchPipeline:
     either side.
     """
 
-    def __init__(self, engine, B, dtype, chunk=8192, n_streams=2):
+    def __init__(self, engine, B, dtype, chunk=8192, n_streams=2, normalize=False, log_z=False):
         t = require_cuda()
         self.engine, self.B, self.dtype = engine, int(B), np.dtype(dtype)
+        self.normalize, self.log_z = bool(normalize), bool(log_z)
+        self.host_logz = t.empty(self.B, dtype=torch_dtype(dtype)).pin_memory() if log_z else None
         plan = engine.plan
         self.chunk = int(min(chunk, B))
         self.bounds = [(lo, min(lo + self.chunk, self.B)) for lo in range(0, self.B, self.chunk)]
@@ -224,6 +226,7 @@ class BatchPipeline:
                 "ws": engine.new_workspace(self.chunk, self.dtype),
                 "fout": t.empty((plan.fout_entries, self.chunk), dtype=torch_dtype(self.dtype), device="cuda"),
                 "ev": t.empty((self.chunk, max(self.n_ev, 1)), dtype=t.int32, device="cuda"),
+                "logz": t.empty(self.chunk, dtype=torch_dtype(self.dtype), device="cuda"),
             }
             self.slots.append(slot)
         # a ragged last chunk needs buffers of its own pitch
@@ -235,6 +238,7 @@ class BatchPipeline:
                 "ws": engine.new_workspace(last, self.dtype),
                 "fout": t.empty((plan.fout_entries, last), dtype=torch_dtype(self.dtype), device="cuda"),
                 "ev": t.empty((last, max(self.n_ev, 1)), dtype=t.int32, device="cuda"),
+                "logz": t.empty(last, dtype=torch_dtype(self.dtype), device="cuda"),
             }
 
     def host_output(self):
@@ -249,7 +253,7 @@ class BatchPipeline:
         return [
             np.moveaxis(arr[plan.fout_off[f]:plan.fout_off[f] + plan.fout_size[f]]
                         .reshape(tuple(plan.fout_shape[f]) + (self.B,)), -1, 0)
-            for f in range(len(plan.factors))
+            for f in range(len(plan.fout_off))
         ]
 
     def run(self, factor_dev, batched, ev_host, out_host, sync=False):
@@ -274,6 +278,15 @@ class BatchPipeline:
                     ev_ptr = slot["ev"].data_ptr()
                 dev.propagate(factor_dev.data_ptr(), False, ev_ptr, n, self.dtype, slot["ws"].data_ptr(),
                               slot["fout"].data_ptr(), 0, stream.cuda_stream)
+                if self.normalize or self.log_z:
+                    # output stage: per-scope normalisation and log Z = log P(evidence)
+                    if self.normalize:
+                        dev.normalize(n, self.dtype, slot["fout"].data_ptr(),
+                                      slot["logz"].data_ptr() if self.log_z else None, stream.cuda_stream)
+                    else:
+                        slot["logz"].copy_(t.log(slot["fout"][:plan.fout_size[0]].sum(dim=0)))
+                    if self.log_z:
+                        self.host_logz[lo:hi].copy_(slot["logz"], non_blocking=True)
                 _native.copy_rows(out_host.data_ptr() + lo * item, self.B * item, slot["fout"].data_ptr(),
                                   n * item, n * item, plan.fout_entries, True, stream.cuda_stream)
         for slot in self.slots:
@@ -290,8 +303,8 @@ class BatchPipeline:
         return total
 
 
-def _pipeline(self, B, dtype, chunk=8192, n_streams=2):
-    return BatchPipeline(self, B, dtype, chunk, n_streams)
+def _pipeline(self, B, dtype, chunk=8192, n_streams=2, normalize=False, log_z=False):
+    return BatchPipeline(self, B, dtype, chunk, n_streams, normalize, log_z)
 
 
 Engine.pipeline = _pipeline

@@ -124,14 +124,15 @@ class CliqueGraph():
         f2c = self.factor_to_maxclique
         return [f2c[i] for i in range(len(self.factor_graph.factors))]   # list or dict (reference D13)
 
-    def _engine(self, sizes, tree=None, separators=(), evidence_vars=(), full_sizes=None):
+    def _engine(self, sizes, tree=None, separators=(), evidence_vars=(), full_sizes=None, outputs=None):
         key = (tuple(sizes.get(v) for c in self.maxcliques for v in c), tree is not None,
-               tuple(evidence_vars), tuple(tuple(c) for c in self.maxcliques), tuple(self._f2c()))
+               tuple(evidence_vars), tuple(tuple(c) for c in self.maxcliques), tuple(self._f2c()),
+               None if outputs is None else tuple(tuple(o) for o in outputs))
         hit = self._engines.get(key)
         if hit is None:
             node_vars = list(self.maxcliques) + ([list(s) for s in separators] if tree is not None else [])
             plan = sch.Plan(tree, node_vars, sizes, self.factor_graph.factors, self._f2c(),
-                            evidence_vars, full_sizes)
+                            evidence_vars, full_sizes, outputs)
             hit = eng.Engine(plan)
             self._engines[key] = hit
         return hit
@@ -187,7 +188,7 @@ class CliqueGraph():
         flat = fout[:, 0].cpu().numpy()
         return [
             flat[plan.fout_off[f]:plan.fout_off[f] + plan.fout_size[f]].reshape(tuple(plan.fout_shape[f])).copy()
-            for f in range(len(plan.factors))
+            for f in range(len(plan.fout_off))
         ]
 
 
@@ -219,8 +220,8 @@ class JunctionTree():
     # The underlying triangulated clique graph
     clique_tree = attr.ib()
 
-    def _engine(self, sizes, evidence_vars=(), full_sizes=None):
-        return self.clique_tree._engine(sizes, self.tree, self.separators, evidence_vars, full_sizes)
+    def _engine(self, sizes, evidence_vars=(), full_sizes=None, outputs=None):
+        return self.clique_tree._engine(sizes, self.tree, self.separators, evidence_vars, full_sizes, outputs)
 
     def plan(self, evidence_vars=(), sizes=None):
         """The compiled schedule for the current variable sizes (``schedule.Plan``)."""
@@ -253,19 +254,74 @@ class JunctionTree():
         flat = graphed.run().numpy()[:, 0]
         return [
             flat[plan.fout_off[f]:plan.fout_off[f] + plan.fout_size[f]].reshape(tuple(plan.fout_shape[f])).copy()
-            for f in range(len(plan.factors))
+            for f in range(len(plan.fout_off))
         ]
+
+    def marginals_batch(self, xs, variables=None, evidence_vars=(), evidence=None, batch=None, dtype=None,
+                        normalize=True):
+        """Posterior marginals of single variables for a batch of evidence (output stage on the
+        device: the step after the propagation path).
+
+        :param variables: variables to report (default: every unobserved variable)
+        :param normalize: divide each marginal by its sum (the default) or return the
+                          unnormalised beliefs, as ``propagate`` does
+        :return: ``(marginals, log_z)``: ``{variable: array [B, size]}`` and ``log_z [B]``, the log
+                 of the partition function P(evidence) of every instance -- the quantity the
+                 reference computes at the root and discards (``computation.py:90-96``)
+        """
+        t = eng.require_cuda()
+        fg = self.clique_tree.factor_graph
+        evidence_vars = list(evidence_vars)
+        full = dict(fg.sizes)
+        full.update(_effective_sizes(fg.factors, xs))
+        eff = dict(full)
+        for v in evidence_vars:
+            eff[v] = 1
+        if variables is None:
+            seen = []
+            for fv in fg.factors:
+                for v in fv:
+                    if v not in seen and v not in evidence_vars:
+                        seen.append(v)
+            variables = seen
+        variables = list(variables)
+        engine = self._engine(eff, evidence_vars, full, outputs=[[v] for v in variables])
+        plan = engine.plan
+        dtype = np.dtype(dtype) if dtype is not None else _result_dtype(xs)
+        B = int(evidence.shape[0]) if evidence is not None else int(batch) if batch is not None else None
+        if B is None:
+            raise ValueError("batch size unknown: give evidence or batch=")
+        fdev, batched = engine.factors_to_device(xs, dtype)
+        ev_host = None
+        if plan.evidence_vars:
+            if evidence is None:
+                raise ValueError("the plan has evidence variables %r but no evidence was given" % (plan.evidence_vars,))
+            ev_host = t.from_numpy(np.ascontiguousarray(evidence, dtype=np.int32)).pin_memory()
+            if tuple(ev_host.shape) != (B, len(plan.evidence_vars)):
+                raise ValueError("evidence must have shape [%d, %d]" % (B, len(plan.evidence_vars)))
+        pipe = engine.pipeline(B, dtype, chunk=self._chunk_for(engine, B, dtype), normalize=normalize, log_z=True)
+        out_host = pipe.host_output()
+        pipe.run(fdev, False, ev_host, out_host, sync=True)
+        if ev_host is not None and pipe.evidence_errors():
+            raise ValueError("evidence states outside the range of their variable")
+        views = pipe.factor_views(out_host)
+        return dict(zip(variables, views)), pipe.host_logz.numpy()
+
+    @staticmethod
+    def _chunk_for(engine, B, dtype):
+        """Instances per pipeline chunk: at most 8192, and a third of the free device memory."""
+        t = eng.torch()
+        per_instance = engine.dev.workspace_bytes(2, dtype) - engine.dev.workspace_bytes(1, dtype)
+        per_instance += engine.plan.fout_entries * np.dtype(dtype).itemsize
+        free, _ = t.cuda.mem_get_info()
+        chunk = int(max(1, min(8192, B, (free // 3) // max(per_instance, 1))))
+        return max(2, chunk - chunk % 2) if chunk > 1 else 1
 
     def _propagate_streamed(self, engine, fdev, evidence, B, dtype):
         """Host-in / host-out propagation of a large batch through ``engine.BatchPipeline``."""
         t = eng.require_cuda()
         plan = engine.plan
-        per_instance = engine.dev.workspace_bytes(2, dtype) - engine.dev.workspace_bytes(1, dtype)
-        per_instance += plan.fout_entries * np.dtype(dtype).itemsize
-        free, _ = t.cuda.mem_get_info()
-        chunk = int(max(1, min(8192, B, (free // 3) // max(per_instance, 1))))
-        chunk = max(2, chunk - chunk % 2) if chunk > 1 else 1
-        pipe = engine.pipeline(B, dtype, chunk=chunk)
+        pipe = engine.pipeline(B, dtype, chunk=self._chunk_for(engine, B, dtype))
         ev_host = None
         if plan.evidence_vars:
             if evidence is None:
@@ -335,7 +391,7 @@ class JunctionTree():
             if bad:
                 engine.clear_evidence_errors(ws, B, dtype)
                 raise ValueError("%d evidence states are outside the range of their variable" % bad)
-        outs = [engine.factor_tensor(fout, f, B) for f in range(len(plan.factors))]
+        outs = [engine.factor_tensor(fout, f, B) for f in range(len(plan.fout_off))]
         node_out = None
         if nodes:
             node_out = [engine.node_tensor(ws, k, B, dtype) for k in range(len(plan.node_vars))]

@@ -37,12 +37,12 @@ import numpy as np
 from . import construction as cons
 
 MAGIC = 0x324E4C5042544A  # "JTBPLN2"
-VERSION = 4
+VERSION = 5
 
 # header word indices (int64 words); mirrored in include/jt_b200.h
 H_MAGIC, H_VERSION, H_NCLIQUES, H_NSEPS, H_NFACTORS, H_NEVID, H_CLIQUE_ENTRIES, H_SEP_ENTRIES, \
     H_FIN_ENTRIES, H_FOUT_ENTRIES, H_NTAB, H_NTASKS, H_NMSGS, H_NLAUNCHES, H_MAXDEPTH, \
-    H_NEVF, H_ROOT_ENTRIES, H_UNI_ENTRIES, H_WORDS = range(19)
+    H_NEVF, H_ROOT_ENTRIES, H_UNI_ENTRIES, H_NOUT, H_WORDS = range(20)
 
 TASK_WORDS = 24
 (T_KIND, T_SRC, T_OUT, T_BETA, T_BEL, T_OWN, T_NS, T_NR, T_NSLO, T_NRLO, T_SRC_SHI, T_SRC_SLO,
@@ -175,10 +175,12 @@ class Plan:
     :param evidence_vars: ordered list of variables observed per instance; their effective
                           size must be 1 and ``full_sizes`` gives the size of the factor axis
     :param full_sizes: ``{var: size}`` of the factor tables as stored (defaults to ``sizes``)
+    :param outputs: scopes (variable lists) the marginal stage sums the clique beliefs down to;
+                    default: the factor scopes, as ``CliqueGraph.marginalize`` of the reference
     """
 
     def __init__(self, tree, node_vars, sizes, factors=None, factor_to_clique=None,
-                 evidence_vars=(), full_sizes=None):
+                 evidence_vars=(), full_sizes=None, outputs=None):
         self.tree = tree
         self.node_vars = [list(v) for v in node_vars]
         self.sizes = dict(sizes)
@@ -186,6 +188,7 @@ class Plan:
         self.factor_to_clique = None if factor_to_clique is None else list(factor_to_clique)
         self.evidence_vars = list(evidence_vars)
         self.full_sizes = dict(full_sizes) if full_sizes is not None else dict(sizes)
+        self.outputs = None if outputs is None else [list(o) for o in outputs]
         for v in self.evidence_vars:
             if int(self.sizes[v]) != 1:
                 raise ValueError("observed variable %r must have effective size 1" % (v,))
@@ -275,6 +278,7 @@ class Plan:
     def _build_factor_tables(self):
         self.fin_off, self.fin_size, self.fin_shape = [], [], []
         self.fout_off, self.fout_size, self.fout_shape = [], [], []
+        self.out_scopes, self.out_clique = [], []
         self.evf_ptr, self.evf_var, self.evf_stride = [0], [], []
         self.ev_card = [int(self.full_sizes[v]) for v in self.evidence_vars]
         self.fin_entries = self.fout_entries = 0
@@ -288,20 +292,35 @@ class Plan:
             if not set(fv) <= set(self.node_vars[home]):
                 raise ValueError("factor %d is not contained in its clique %d" % (f, home))
             full = [int(self.full_sizes[v]) if v in ev_index else int(self.sizes[v]) for v in fv]
-            eff = [int(self.sizes[v]) for v in fv]
             self.fin_shape.append(full)
-            self.fout_shape.append(eff)
             self.fin_off.append(self.fin_entries)
             self.fin_size.append(_prod(full))
             self.fin_entries += _prod(full)
-            self.fout_off.append(self.fout_entries)
-            self.fout_size.append(_prod(eff))
-            self.fout_entries += _prod(eff)
             for v, st in zip(fv, _row_major_strides(full)):
                 if v in ev_index:
                     self.evf_var.append(ev_index[v])
                     self.evf_stride.append(st)
             self.evf_ptr.append(len(self.evf_var))
+        # output scopes of the marginal stage
+        if self.outputs is None:
+            scopes = [(list(fv), home) for fv, home in zip(self.factors, self.factor_to_clique)]
+        else:
+            scopes = []
+            for scope in self.outputs:
+                if len(set(scope)) != len(scope):
+                    raise ValueError("duplicate variable in output scope %r" % (scope,))
+                holders = [c for c in range(self.n_cliques) if set(scope) <= set(self.node_vars[c])]
+                if not holders:
+                    raise ValueError("no clique contains the output scope %r" % (scope,))
+                scopes.append((list(scope), min(holders, key=lambda c: (self.node_size[c], c))))
+        for scope, home in scopes:
+            eff = [int(self.sizes[v]) for v in scope]
+            self.out_scopes.append(scope)
+            self.out_clique.append(home)
+            self.fout_shape.append(eff)
+            self.fout_off.append(self.fout_entries)
+            self.fout_size.append(_prod(eff))
+            self.fout_entries += _prod(eff)
 
     def _find_uniform_cliques(self):
         """Which potentials and up-messages are identical for every instance of a batch.
@@ -501,19 +520,18 @@ class Plan:
                 self._launch(phase, begin, d)
 
     def _build_marginal(self):
-        """E6: per-factor output = clique belief summed down to the factor scope."""
+        """E6: per output scope (by default per factor) = clique belief summed down to the scope."""
         if self.factors is None:
             return
         begin = len(self.tasks)
-        for f, fv in enumerate(self.factors):
-            c = self.factor_to_clique[f]
-            s_space = _Space(fv, self.sizes)
-            in_f = set(fv)
+        for k, (scope, c) in enumerate(zip(self.out_scopes, self.out_clique)):
+            s_space = _Space(scope, self.sizes)
+            in_f = set(scope)
             r_space = _Space([v for v in self.node_vars[c] if v not in in_f], self.sizes)
             row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c)
-            row[T_OUT] = self.fout_off[f]
+            row[T_OUT] = self.fout_off[k]
             row[T_OUT_SPACE] = SPACE_FOUT
-            row[T_AUX] = f
+            row[T_AUX] = k
             row[T_RMSG_BEGIN] = row[T_RMSG_END] = row[T_SMSG_BEGIN] = row[T_SMSG_END] = len(self.msgs)
             self.tasks.append(row)
         self._launch(PHASE_MARGINAL, begin, 0)
@@ -564,6 +582,7 @@ class Plan:
         h[H_NEVF] = len(self.evf_var)
         h[H_ROOT_ENTRIES] = self.node_size[self.root] if self.root >= 0 else 0
         h[H_UNI_ENTRIES] = self.uni_entries
+        h[H_NOUT] = len(self.fout_off)
         return h
 
     def to_blob(self):

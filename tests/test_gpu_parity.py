@@ -449,3 +449,26 @@ def test_large_batch_is_streamed_in_chunks():
     ev[B - 3, 1] = -1
     with pytest.raises(ValueError):
         tree.propagate_batch(net["values"], net["evidence_vars"], ev)
+
+
+def test_marginals_batch_output_stage():
+    """Normalised single-variable posteriors and log Z per instance (device output stage)."""
+    import junctiontree as jt
+    from oracle import brute
+    net = wl.random_dag(14, 3, 2, 4, 8, 6)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    B = 37
+    ev = wl.draw_evidence(net, B)
+    evars = net["evidence_vars"]
+    marg, log_z = tree.marginals_batch(net["values"], None, evars, ev)
+    free = [v for v in sorted(net["sizes"]) if v not in evars]
+    assert sorted(marg) == free and log_z.shape == (B,)
+    for b in range(0, B, 6):
+        evd = {v: int(ev[b][i]) for i, v in enumerate(evars)}
+        truth = brute.factor_graph_marginals(net["factors"], net["values"], [[v] for v in free], evd)
+        for v, tr in zip(free, truth):
+            assert_close(marg[v][b], tr / tr.sum(), 1e-11, "P(%s | e) instance %d" % (v, b))
+            assert_close(log_z[b], np.log(tr.sum()), 1e-11, "log Z instance %d" % b)
+    raw, _ = tree.marginals_batch(net["values"], free[:3], evars, ev, normalize=False)
+    for v in free[:3]:
+        assert_close(raw[v] / raw[v].sum(axis=1, keepdims=True), marg[v], 1e-12, v)

@@ -472,3 +472,31 @@ def test_marginals_batch_output_stage():
     raw, _ = tree.marginals_batch(net["values"], free[:3], evars, ev, normalize=False)
     for v in free[:3]:
         assert_close(raw[v] / raw[v].sum(axis=1, keepdims=True), marg[v], 1e-12, v)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_networks_fuzz(seed):
+    """Random DAGs (2-5 states, up to 5 parents), random evidence sets (not only leaves), random
+    batch sizes crossing the kernel selection thresholds (LDG / split-r / TMA, odd and even B)."""
+    import junctiontree as jt
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(5, 15))
+    net = wl.random_dag(n, int(rng.integers(1, 6)), 2, int(rng.integers(2, 6)), int(rng.integers(2, n + 1)), 500 + seed)
+    labels = sorted(net["sizes"])
+    k = int(rng.integers(0, max(1, n // 2)))
+    net["evidence_vars"] = sorted(rng.choice(labels, size=k, replace=False).tolist())
+    B = int(rng.choice([1, 2, 7, 33, 64, 129, 256, 301, 640]))
+    dtype = np.float64 if seed % 3 else np.float32
+    vals = [np.asarray(v, dtype) for v in net["values"]]
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    evars = net["evidence_vars"]
+    ev = wl.draw_evidence(net, B) if evars else None
+    outs, nodes = tree.propagate_batch(vals, evars, ev, batch=B, nodes=True, uniform=bool(seed % 2))
+    pick = sorted(set([0, B - 1, B // 2]))
+    net64 = dict(net, values=[np.asarray(v, np.float64) for v in vals])
+    want_f, want_n = _oracle(tree, net64, evars, ev[pick] if ev is not None else None, len(pick))
+    rtol = RTOL_F64 if dtype == np.float64 else RTOL_F32
+    for kk, w in enumerate(want_n):
+        assert_close(nodes[kk][pick], w, rtol, "node %d" % kk)
+    for f, w in enumerate(want_f):
+        assert_close(outs[f][pick], w, rtol, "factor %d" % f)

@@ -818,83 +818,109 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     const bool own_is_row = has_own && ((rowmask >> (n_ops - 1)) & 1u);
     const int n_sm_rows = n_rows - n_item_rows - (own_is_row ? 1 : 0);
 
-    // The per-item loop is instantiated per number of streamed per-item operands so that it
-    // stays a few dozen instructions (ncu: the generic loop cost ~160 instructions per item).
-    auto consume = [&](auto ni_tag) {
+    // The per-item code is instantiated per number of streamed per-item operands and per
+    // "writes beliefs", and the (s, r) loops are kept nested, so that an item costs a few dozen
+    // instructions (ncu, round 1: a generic flattened loop made the consumers issue-bound at
+    // ~100-160 instructions per item).
+    auto consume = [&](auto ni_tag, auto wbeta_tag) {
         constexpr int NI = decltype(ni_tag)::value;          // -1: run-time count
+        constexpr bool WB = decltype(wbeta_tag)::value;
         const int ni = NI >= 0 ? NI : n_item_rows;
         const int sub_pitch = n_rows * row_pitch;            // rows of one sub-item
-        int stage = 0, item = 0, s = s0, r = 0;
-        uint32_t phase = 0;
-        P sm = pack_fill<T, VEC>(T(1)), own = sm, scale = sm;
-        P acc0 = pack_fill<T, VEC>(T(0)), acc1 = acc0;
-        while (item < n_items) {
-            if (any_row) mbar_wait(full_u32 + 8 * stage, phase);
-            const unsigned char* sub = my + stage * stage_pitch;
-            for (int g = 0; g < G && item < n_items; ++g, ++item, sub += sub_pitch) {
-                const int ub = (item >> 5) & 1, ul = item & (kUBatch - 1);
-                if (any_uni && ul == 0) mbar_wait(ufull_u32 + 8 * ub, (item >> 6) & 1);
-                const T* uv = aux->u_val[ub][ul];
-                P v = pack_fill<T, VEC>(any_uni ? uv[0] : T(1));
-                if (NI >= 0) {
+        int stage = 0, g = 0, ub = 0, ul = 0;
+        uint32_t phase = 0, uphase = 0;
+        const unsigned char* sub = my;
+        const T* uv = aux->u_val[0][0];
+
+        auto begin_item = [&]() {
+            if (any_row && g == 0) mbar_wait(full_u32 + 8 * stage, phase);
+            if (any_uni && ul == 0) mbar_wait(ufull_u32 + 8 * ub, uphase);
+            sub = my + stage * stage_pitch + g * sub_pitch;
+            uv = aux->u_val[ub][ul];
+        };
+        auto release_stage = [&]() {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_u32 + 8 * stage);
+            g = 0;
+            if (++stage == n_stage) {
+                stage = 0;
+                phase ^= 1;
+            }
+        };
+        auto release_batch = [&]() {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(uempty_u32 + 8 * ub);
+            ul = 0;
+            ub ^= 1;
+            if (ub == 0) uphase ^= 1;
+        };
+        auto end_item = [&]() {
+            if (any_uni && ++ul == kUBatch) release_batch();
+            if (any_row && ++g == G) release_stage();
+        };
+        auto item_value = [&]() {
+            P v = pack_fill<T, VEC>(any_uni ? uv[0] : T(1));
+            if (NI >= 0) {
 #pragma unroll
-                    for (int k = 0; k < (NI >= 0 ? NI : 0); ++k)
-                        mul(v, *reinterpret_cast<const P*>(sub + k * row_pitch));
-                } else {
-                    for (int k = 0; k < ni; ++k) mul(v, *reinterpret_cast<const P*>(sub + k * row_pitch));
-                }
-                if (r == 0) {                                 // once per s: s-only operands and own
-                    const unsigned char* srow = sub + ni * row_pitch;
-                    sm = pack_fill<T, VEC>(any_uni ? uv[1] : T(1));
-                    for (int k = 0; k < n_sm_rows; ++k) mul(sm, *reinterpret_cast<const P*>(srow + k * row_pitch));
-                    own = own_is_row ? *reinterpret_cast<const P*>(srow + n_sm_rows * row_pitch)
-                                     : pack_fill<T, VEC>(any_uni ? uv[2] : T(1));
-                    scale = sm;
-                    mul(scale, own);
-                    acc0 = pack_fill<T, VEC>(T(0));
-                    acc1 = acc0;
-                }
+                for (int k = 0; k < (NI >= 0 ? NI : 0); ++k) mul(v, *reinterpret_cast<const P*>(sub + k * row_pitch));
+            } else {
+                for (int k = 0; k < ni; ++k) mul(v, *reinterpret_cast<const P*>(sub + k * row_pitch));
+            }
+            return v;
+        };
+        auto store_beta = [&](P v, const P& scale) {
+            if (WB) {
                 const int e = src_uni ? aux->u_e[ub][ul] : aux->e_row[stage * G + g];
-                if (any_uni && (ul == kUBatch - 1 || item == n_items - 1)) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(uempty_u32 + 8 * ub);
-                }
-                if (r & 1) add(acc1, v); else add(acc0, v);
-                if (wbeta && active) {
+                if (active) {
                     mul(v, scale);
                     st<T, VEC>(bptr + (long long)e * B, v);
                 }
-                if (++r == n_r) {
-                    r = 0;
-                    if (wout && active) {
-                        add(acc0, acc1);
-                        mul(acc0, sm);
-                        st<T, VEC>(optr + (long long)s * B, acc0);
-                        if (wbel) {
-                            mul(acc0, own);
-                            st<T, VEC>(lptr + (long long)s * B, acc0);
-                        }
-                    }
-                    ++s;
-                }
             }
-            if (any_row) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty_u32 + 8 * stage);
-                if (++stage == n_stage) {
-                    stage = 0;
-                    phase ^= 1;
+        };
+
+        for (int s = s0; s < s1; ++s) {
+            // r = 0: the item that also carries the s-only operands and own
+            begin_item();
+            P acc0 = item_value(), acc1 = pack_fill<T, VEC>(T(0));
+            const unsigned char* srow = sub + ni * row_pitch;
+            P sm = pack_fill<T, VEC>(any_uni ? uv[1] : T(1));
+            for (int k = 0; k < n_sm_rows; ++k) mul(sm, *reinterpret_cast<const P*>(srow + k * row_pitch));
+            const P own = own_is_row ? *reinterpret_cast<const P*>(srow + n_sm_rows * row_pitch)
+                                     : pack_fill<T, VEC>(any_uni ? uv[2] : T(1));
+            P scale = sm;
+            mul(scale, own);
+            store_beta(acc0, scale);
+            end_item();
+            for (int r = 1; r < n_r; ++r) {
+                begin_item();
+                const P v = item_value();
+                if (r & 1) add(acc1, v); else add(acc0, v);
+                store_beta(v, scale);
+                end_item();
+            }
+            if (wout && active) {
+                add(acc0, acc1);
+                mul(acc0, sm);
+                st<T, VEC>(optr + (long long)s * B, acc0);
+                if (wbel) {
+                    mul(acc0, own);
+                    st<T, VEC>(lptr + (long long)s * B, acc0);
                 }
             }
         }
+        if (any_uni && ul != 0) release_batch();              // partially used last batch / stage
+        if (any_row && g != 0) release_stage();
     };
-    switch (n_item_rows) {
-        case 0: consume(std::integral_constant<int, 0>{}); break;
-        case 1: consume(std::integral_constant<int, 1>{}); break;
-        case 2: consume(std::integral_constant<int, 2>{}); break;
-        case 3: consume(std::integral_constant<int, 3>{}); break;
-        default: consume(std::integral_constant<int, -1>{}); break;
-    }
+    auto dispatch_ni = [&](auto wbeta_tag) {
+        switch (n_item_rows) {
+            case 0: consume(std::integral_constant<int, 0>{}, wbeta_tag); break;
+            case 1: consume(std::integral_constant<int, 1>{}, wbeta_tag); break;
+            case 2: consume(std::integral_constant<int, 2>{}, wbeta_tag); break;
+            case 3: consume(std::integral_constant<int, 3>{}, wbeta_tag); break;
+            default: consume(std::integral_constant<int, -1>{}, wbeta_tag); break;
+        }
+    };
+    if (wbeta) dispatch_ni(std::true_type{}); else dispatch_ni(std::false_type{});
 }
 
 // Output stage: normalise every output scope per instance; log Z from scope 0.

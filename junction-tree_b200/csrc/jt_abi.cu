@@ -107,10 +107,10 @@ bool use_splitr(const jt_plan::Launch& L, long long B, bool is_init) {
     return L.max_nr >= 4096 || L.total_s * B < 65536;
 }
 
-template <typename T>
-int launch_tma(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
-    const int ct = a.Bv >= 256 ? 256 : (a.Bv >= 128 ? 128 : 64);
-    const long long tiles = (a.Bv + ct - 1) / ct;
+template <typename T, int VPT>
+int launch_tma_vpt(const jt_plan* p, const jt_plan::Launch& L, KArgs a, int ct, cudaStream_t stream) {
+    const int tw = ct * VPT;
+    const long long tiles = (a.Bv + tw - 1) / tw;
     // (s, r) items per CTA: aim at ~8 CTAs per SM over the launch, but keep >= 64 items per CTA
     // so the pipeline fill is amortised; every task gets its own chunk of s for that item count
     int j = 6;
@@ -126,19 +126,35 @@ int launch_tma(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t
     if (gx > 2147483647LL || tiles > 65535)
         return fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, tiles);
     // ring rows, then barriers / row indices / scalar operands (TmaAux)
-    const size_t smem = (size_t)kTmaSlots * ct * 16 + sizeof(TmaAux<T>);
+    const size_t smem = (size_t)(kTmaSlots / VPT) * tw * 16 + sizeof(TmaAux<T>);
     static bool attr_set = false;
     if (!attr_set) {
-        JT_CUDA(cudaFuncSetAttribute(jt_project_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        JT_CUDA(cudaFuncSetAttribute(jt_project_tma_kernel<T, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kTmaSlots * 256 * 16 + (int)sizeof(TmaAux<T>)));
         attr_set = true;
     }
     dim3 grid((unsigned)gx, (unsigned)tiles, 1);
     // consumer warps + row producer warp + uniform warp
-    jt_project_tma_kernel<T><<<grid, ct + 64, smem, stream>>>(a);
+    jt_project_tma_kernel<T, VPT><<<grid, ct + 64, smem, stream>>>(a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     JT_CUDA(cudaGetLastError());
     return JT_OK;
+}
+
+int g_tma_vpt = -1;   // JT_TMA_VPT=1|2 overrides the vectors-per-thread choice (A-B timing)
+
+template <typename T>
+int launch_tma(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
+    if (g_tma_vpt < 0) {
+        const char* e = getenv("JT_TMA_VPT");
+        g_tma_vpt = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+    }
+    const int ct = a.Bv >= 256 ? 256 : (a.Bv >= 128 ? 128 : 64);
+    // two vectors per consumer thread once the batch fills 512-vector tiles: halves the control
+    // instructions per byte of the consumers
+    const bool two = g_tma_vpt ? g_tma_vpt == 2 : a.Bv >= 512;
+    if (two && ct == 256) return launch_tma_vpt<T, 2>(p, L, a, ct, stream);
+    return launch_tma_vpt<T, 1>(p, L, a, ct, stream);
 }
 
 template <typename T, int VEC>

@@ -587,15 +587,19 @@ struct TmaAux {
     T u_val[2][kUBatch][4];                     // products of the scalar operands: item, s-only, own
 };
 
-template <typename T>
+// VPT: 16-byte batch vectors per consumer thread.  The ring holds kTmaSlots / VPT rows of
+// ct * VPT vectors, so the shared-memory footprint (and bytes in flight) is the same.
+template <typename T, int VPT>
 __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const KArgs a) {
     constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int kSlots = kTmaSlots / VPT;
     typedef Pack<T, VEC> P;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
-    const int ct = blockDim.x - 64;                      // consumer threads = batch vectors per tile
-    const int row_pitch = ct * 16;                       // bytes per ring row
-    TmaAux<T>* aux = reinterpret_cast<TmaAux<T>*>(smem_raw + kTmaSlots * row_pitch);
+    const int ct = blockDim.x - 64;                      // consumer threads
+    const int tw = ct * VPT;                             // batch vectors per tile
+    const int row_pitch = tw * 16;                       // bytes per ring row
+    TmaAux<T>* aux = reinterpret_cast<TmaAux<T>*>(smem_raw + kSlots * row_pitch);
     const uint32_t slots_u32 = smem_u32(smem_raw);
     const uint32_t full_u32 = smem_u32(aux->full), empty_u32 = smem_u32(aux->empty);
     const uint32_t ufull_u32 = smem_u32(aux->u_full), uempty_u32 = smem_u32(aux->u_empty);
@@ -617,8 +621,8 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     }
     const int n_s = tk->n_s;
     const int s1 = min(n_s, s0 + (1 << chunk_log2));
-    const long long col0v = (long long)blockIdx.y * ct;
-    const int ncols = (int)min((long long)ct, a.Bv - col0v);
+    const long long col0v = (long long)blockIdx.y * tw;
+    const int ncols = (int)min((long long)tw, a.Bv - col0v);
     const uint32_t row_bytes = (uint32_t)ncols * 16u;
 
     // operands in order: [src] [r-dependent messages] [s-only messages] [own]
@@ -639,10 +643,10 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     const unsigned rowmask = ((1u << n_ops) - 1u) & ~umask;     // operands that stream ring rows
     const int n_rows = __popc(rowmask);
     // a stage groups G consecutive items so that one barrier round trip covers G * n_rows rows
-    int G = n_rows > 0 ? kTmaSlots / (4 * n_rows) : 1;
+    int G = n_rows > 0 ? kSlots / (4 * n_rows) : 1;
     G = G < 1 ? 1 : (G > 4 ? 4 : G);
     const int n_plane = n_rows * G;                      // producer lanes = ring rows per stage
-    const int n_stage = n_rows > 0 ? kTmaSlots / n_plane : 1;
+    const int n_stage = n_rows > 0 ? kSlots / n_plane : 1;
     const int n_r = tk->n_r;
     const int n_items = (s1 - s0) * n_r;
     const long long B = a.B;
@@ -800,17 +804,21 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
         return;
     }
 
-    // ---------------- consumers: thread t owns batch vector col0v + t ----------------
+    // ---------------- consumers: thread t owns batch vectors col0v + t + v * ct, v < VPT ----------------
     const int t = threadIdx.x;
-    const bool active = t < ncols;
+    bool active[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) active[v] = t + v * ct < ncols;
     T* work = static_cast<T*>(a.work);
     const long long col = (col0v + t) * VEC;
+    const long long vstep = (long long)ct * VEC;         // elements between the vectors of a thread
     const bool wbeta = tk->beta >= 0, wout = tk->out >= 0;
     const bool wbel = wout && tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS);
     T* bptr = work + (wbeta ? tk->beta : 0) * B + col;
     T* optr = (tk->out_space ? static_cast<T*>(a.fout) : work) + (wout ? tk->out : 0) * B + col;
     T* lptr = work + (wbel ? tk->bel : 0) * B + col;
     const unsigned char* my = smem_raw + t * 16;
+    const int vpitch = ct * 16;                          // bytes between the vectors of a thread
     const int stage_pitch = n_plane * row_pitch;
     const bool any_uni = umask != 0, any_row = n_rows > 0;
     // ring rows of a stage: the per-item operands first, then the per-s ones (own last)
@@ -818,10 +826,15 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     const bool own_is_row = has_own && ((rowmask >> (n_ops - 1)) & 1u);
     const int n_sm_rows = n_rows - n_item_rows - (own_is_row ? 1 : 0);
 
+    struct PV {
+        P v[VPT];
+    };
+
     // The per-item code is instantiated per number of streamed per-item operands and per
     // "writes beliefs", and the (s, r) loops are kept nested, so that an item costs a few dozen
     // instructions (ncu, round 1: a generic flattened loop made the consumers issue-bound at
-    // ~100-160 instructions per item).
+    // ~100-160 instructions per item); with VPT = 2 a thread covers 32 bytes of every row, which
+    // halves the control instructions per byte again.
     auto consume = [&](auto ni_tag, auto wbeta_tag) {
         constexpr int NI = decltype(ni_tag)::value;          // -1: run-time count
         constexpr bool WB = decltype(wbeta_tag)::value;
@@ -858,22 +871,38 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
             if (any_uni && ++ul == kUBatch) release_batch();
             if (any_row && ++g == G) release_stage();
         };
-        auto item_value = [&]() {
-            P v = pack_fill<T, VEC>(any_uni ? uv[0] : T(1));
-            if (NI >= 0) {
+        auto load_row = [&](const unsigned char* row, PV& x) {
 #pragma unroll
-                for (int k = 0; k < (NI >= 0 ? NI : 0); ++k) mul(v, *reinterpret_cast<const P*>(sub + k * row_pitch));
-            } else {
-                for (int k = 0; k < ni; ++k) mul(v, *reinterpret_cast<const P*>(sub + k * row_pitch));
-            }
-            return v;
+            for (int v = 0; v < VPT; ++v) x.v[v] = *reinterpret_cast<const P*>(row + v * vpitch);
         };
-        auto store_beta = [&](P v, const P& scale) {
+        auto item_value = [&]() {
+            PV val;
+            const P u = pack_fill<T, VEC>(any_uni ? uv[0] : T(1));
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) val.v[v] = u;
+            const int n = NI >= 0 ? NI : ni;
+#pragma unroll
+            for (int k = 0; k < (NI >= 0 ? NI : 8); ++k) {
+                if (k < n) {
+                    PV x;
+                    load_row(sub + k * row_pitch, x);
+#pragma unroll
+                    for (int v = 0; v < VPT; ++v) mul(val.v[v], x.v[v]);
+                }
+            }
+            return val;
+        };
+        auto store_beta = [&](const PV& val, const PV& scale) {
             if (WB) {
                 const int e = src_uni ? aux->u_e[ub][ul] : aux->e_row[stage * G + g];
-                if (active) {
-                    mul(v, scale);
-                    st<T, VEC>(bptr + (long long)e * B, v);
+                T* dst = bptr + (long long)e * B;
+#pragma unroll
+                for (int v = 0; v < VPT; ++v) {
+                    if (active[v]) {
+                        P x = val.v[v];
+                        mul(x, scale.v[v]);
+                        st<T, VEC>(dst + v * vstep, x);
+                    }
                 }
             }
         };
@@ -881,30 +910,52 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
         for (int s = s0; s < s1; ++s) {
             // r = 0: the item that also carries the s-only operands and own
             begin_item();
-            P acc0 = item_value(), acc1 = pack_fill<T, VEC>(T(0));
+            PV acc0 = item_value(), acc1, sm, own, scale;
             const unsigned char* srow = sub + ni * row_pitch;
-            P sm = pack_fill<T, VEC>(any_uni ? uv[1] : T(1));
-            for (int k = 0; k < n_sm_rows; ++k) mul(sm, *reinterpret_cast<const P*>(srow + k * row_pitch));
-            const P own = own_is_row ? *reinterpret_cast<const P*>(srow + n_sm_rows * row_pitch)
-                                     : pack_fill<T, VEC>(any_uni ? uv[2] : T(1));
-            P scale = sm;
-            mul(scale, own);
+            const P u1 = pack_fill<T, VEC>(any_uni ? uv[1] : T(1)), u2 = pack_fill<T, VEC>(any_uni ? uv[2] : T(1));
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) {
+                acc1.v[v] = pack_fill<T, VEC>(T(0));
+                sm.v[v] = u1;
+                own.v[v] = u2;
+            }
+            for (int k = 0; k < n_sm_rows; ++k) {
+                PV x;
+                load_row(srow + k * row_pitch, x);
+#pragma unroll
+                for (int v = 0; v < VPT; ++v) mul(sm.v[v], x.v[v]);
+            }
+            if (own_is_row) load_row(srow + n_sm_rows * row_pitch, own);
+#pragma unroll
+            for (int v = 0; v < VPT; ++v) {
+                scale.v[v] = sm.v[v];
+                mul(scale.v[v], own.v[v]);
+            }
             store_beta(acc0, scale);
             end_item();
             for (int r = 1; r < n_r; ++r) {
                 begin_item();
-                const P v = item_value();
-                if (r & 1) add(acc1, v); else add(acc0, v);
-                store_beta(v, scale);
+                const PV val = item_value();
+#pragma unroll
+                for (int v = 0; v < VPT; ++v) {
+                    if (r & 1) add(acc1.v[v], val.v[v]); else add(acc0.v[v], val.v[v]);
+                }
+                store_beta(val, scale);
                 end_item();
             }
-            if (wout && active) {
-                add(acc0, acc1);
-                mul(acc0, sm);
-                st<T, VEC>(optr + (long long)s * B, acc0);
-                if (wbel) {
-                    mul(acc0, own);
-                    st<T, VEC>(lptr + (long long)s * B, acc0);
+            if (wout) {
+#pragma unroll
+                for (int v = 0; v < VPT; ++v) {
+                    if (active[v]) {
+                        P o = acc0.v[v];
+                        add(o, acc1.v[v]);
+                        mul(o, sm.v[v]);
+                        st<T, VEC>(optr + (long long)s * B + v * vstep, o);
+                        if (wbel) {
+                            mul(o, own.v[v]);
+                            st<T, VEC>(lptr + (long long)s * B + v * vstep, o);
+                        }
+                    }
                 }
             }
         }

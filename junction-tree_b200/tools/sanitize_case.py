@@ -1,0 +1,43 @@
+"""Small propagation exercising every kernel (TMA ring, uniform warp, LDG, split-r, init), meant
+to be run under compute-sanitizer:
+
+    compute-sanitizer --tool memcheck  python junction-tree_b200/tools/sanitize_case.py
+    compute-sanitizer --tool racecheck python junction-tree_b200/tools/sanitize_case.py
+"""
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.dirname(os.path.dirname(HERE)), os.path.dirname(HERE)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import jt_workloads as wl  # noqa: E402
+import junctiontree as jt  # noqa: E402
+from oracle import ref_fixed  # noqa: E402
+
+
+def main():
+    net = wl.random_dag(14, 3, 2, 3, 8, 2)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    ct = tree.clique_tree
+    for B, dtype, uniform in ((300, np.float64, True), (1030, np.float64, True), (520, np.float32, False), (5, np.float64, True)):
+        ev = wl.draw_evidence(net, B)
+        vals = [np.asarray(v, dtype) for v in net["values"]]
+        outs, nodes = tree.propagate_batch(vals, net["evidence_vars"], ev, nodes=True, uniform=uniform)
+        want_f, want_n = ref_fixed.propagate_batch(tree.tree, tree.separators, ct.maxcliques, ct.factor_to_maxclique,
+                                                   net["factors"], net["sizes"], net["values"], net["evidence_vars"],
+                                                   ev[:2], n=2)
+        rtol = 1e-12 if dtype == np.float64 else 1e-5
+        for g, w in zip(list(outs) + list(nodes), list(want_f) + list(want_n)):
+            np.testing.assert_allclose(g[:2], w, rtol=rtol)
+        print("ok", B, np.dtype(dtype).name, "uniform" if uniform else "per-instance")
+    tree.propagate(net["values"])
+    print("done")
+
+
+if __name__ == "__main__":
+    main()

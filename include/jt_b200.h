@@ -78,6 +78,9 @@ extern "C" {
 #define JT_SKIP_MARGINAL 2 /* jt_propagate: stop after distribute */
 #define JT_UNIFORM 4       /* init/collect/distribute: uniform mode (pass the same value to all three) */
 #define JT_NO_UNIFORM 8    /* jt_propagate: do not enable uniform mode automatically */
+#define JT_UNIFORM_VALID 16 /* uniform mode: the uniform workspace of this workspace already holds the
+                              potentials and up-messages of these factor tables (an earlier call with
+                              the same tables and the same workspace): skip recomputing them */
 
 /* plan blob header words */
 #define JT_MAGIC 0x324E4C5042544ALL

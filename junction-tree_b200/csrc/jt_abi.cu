@@ -571,8 +571,10 @@ int jt_init(jt_plan* p, const void* factor_tables, int factors_batched, const in
     }
     if (!uniform_mode(p, flags)) return run_phase(p, JT_PHASE_INIT, a, dtype, vec, stream);
     // uniform mode: potentials no evidence touches are written once, the others per instance
-    rc = run_phase_uniform(p, JT_PHASE_INIT_UNIFORM, a, dtype, uniform_ws(p, B, dtype, workspace), stream);
-    if (rc != JT_OK) return rc;
+    if (!(flags & JT_UNIFORM_VALID)) {
+        rc = run_phase_uniform(p, JT_PHASE_INIT_UNIFORM, a, dtype, uniform_ws(p, B, dtype, workspace), stream);
+        if (rc != JT_OK) return rc;
+    }
     return run_phase(p, JT_PHASE_INIT_INSTANCE, a, dtype, vec, stream);
 }
 
@@ -586,8 +588,10 @@ int jt_collect(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, voi
     if (!uniform_mode(p, flags)) return run_phase(p, JT_PHASE_COLLECT, a, dtype, vec, stream);
     // uniform mode: evidence-free subtrees are collected once (B = 1), then the rest per instance
     void* uni = uniform_ws(p, B, dtype, workspace);
-    rc = run_phase_uniform(p, JT_PHASE_COLLECT_UNIFORM, a, dtype, uni, stream);
-    if (rc != JT_OK) return rc;
+    if (!(flags & JT_UNIFORM_VALID)) {
+        rc = run_phase_uniform(p, JT_PHASE_COLLECT_UNIFORM, a, dtype, uni, stream);
+        if (rc != JT_OK) return rc;
+    }
     a.uni = uni;
     a.uniform = 1;
     return run_phase(p, JT_PHASE_COLLECT_INSTANCE, a, dtype, vec, stream);

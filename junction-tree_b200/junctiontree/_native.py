@@ -12,7 +12,7 @@ import numpy as np
 
 JT_OK = 0
 JT_F32, JT_F64 = 0, 1
-JT_SEP_BELIEFS, JT_SKIP_MARGINAL, JT_UNIFORM, JT_NO_UNIFORM = 1, 2, 4, 8
+JT_SEP_BELIEFS, JT_SKIP_MARGINAL, JT_UNIFORM, JT_NO_UNIFORM, JT_UNIFORM_VALID = 1, 2, 4, 8, 16
 ABI_VERSION = 5
 
 _LIB_NAME = "libjt_b200.so"

@@ -267,6 +267,9 @@ class BatchPipeline:
         item = self.dtype.itemsize
         for slot in self.slots:
             slot["stream"].wait_stream(cur)
+        # the factor tables are the same for every chunk of this call: the uniform workspace of
+        # a slot is computed by the first chunk that uses the slot and reused by the later ones
+        primed = set()
         for i, (lo, hi) in enumerate(self.bounds):
             n = hi - lo
             slot = self.tail if (self.tail is not None and n != self.chunk) else self.slots[i % len(self.slots)]
@@ -276,8 +279,10 @@ class BatchPipeline:
                 if self.n_ev:
                     slot["ev"].copy_(ev_host[lo:hi], non_blocking=True)
                     ev_ptr = slot["ev"].data_ptr()
+                flags = _native.JT_UNIFORM_VALID if id(slot) in primed else 0
+                primed.add(id(slot))
                 dev.propagate(factor_dev.data_ptr(), False, ev_ptr, n, self.dtype, slot["ws"].data_ptr(),
-                              slot["fout"].data_ptr(), 0, stream.cuda_stream)
+                              slot["fout"].data_ptr(), flags, stream.cuda_stream)
                 if self.normalize or self.log_z:
                     # output stage: per-scope normalisation and log Z = log P(evidence)
                     if self.normalize:

@@ -1,4 +1,5 @@
 import os
+import subprocess
 import sys
 
 import pytest
@@ -11,6 +12,15 @@ for path in (ROOT, os.path.join(ROOT, "junction-tree_b200")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_sessionstart(session):
+    """The shared library is a build product (git-ignored): build it when a fresh checkout has
+    none, so that the ABI tests can load it (nvcc cross-compiles without a GPU)."""
+    lib = os.path.join(ROOT, "junction-tree_b200", "junctiontree", "libjt_b200.so")
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "junction-tree_b200", "csrc")],
+                              stdout=subprocess.DEVNULL)
 
 
 def pytest_collection_modifyitems(config, items):

@@ -61,7 +61,7 @@
 extern "C" {
 #endif
 
-#define JT_ABI_VERSION 5
+#define JT_ABI_VERSION 6
 
 /* status codes */
 #define JT_OK 0
@@ -78,6 +78,9 @@ extern "C" {
 #define JT_SKIP_MARGINAL 2 /* jt_propagate: stop after distribute */
 #define JT_UNIFORM 4       /* init/collect/distribute: uniform mode (pass the same value to all three) */
 #define JT_NO_UNIFORM 8    /* jt_propagate: do not enable uniform mode automatically */
+#define JT_NO_BELIEFS 32    /* distribute/marginal/propagate: only messages and outputs are wanted -- clique
+                              beliefs are not written and jt_marginal computes the outputs directly from
+                              psi_C and the incoming messages (pass the same value to both stages) */
 #define JT_UNIFORM_VALID 16 /* uniform mode: the uniform workspace of this workspace already holds the
                               potentials and up-messages of these factor tables (an earlier call with
                               the same tables and the same workspace): skip recomputing them */
@@ -107,7 +110,8 @@ enum { JT_L_PHASE, JT_L_BEGIN, JT_L_END, JT_L_LEVEL };
 enum { JT_KIND_PROJECT = 0, JT_KIND_INIT = 1 };
 enum {
     JT_PHASE_INIT, JT_PHASE_COLLECT, JT_PHASE_DIST_PRE, JT_PHASE_DIST_MAIN, JT_PHASE_MARGINAL,
-    JT_PHASE_INIT_UNIFORM, JT_PHASE_INIT_INSTANCE, JT_PHASE_COLLECT_UNIFORM, JT_PHASE_COLLECT_INSTANCE
+    JT_PHASE_INIT_UNIFORM, JT_PHASE_INIT_INSTANCE, JT_PHASE_COLLECT_UNIFORM, JT_PHASE_COLLECT_INSTANCE,
+    JT_PHASE_DIST_MAIN_MESSAGES, JT_PHASE_MARGINAL_DIRECT
 };
 
 typedef struct jt_plan jt_plan;
@@ -151,7 +155,7 @@ int jt_init(jt_plan* plan, const void* factor_tables, int factors_batched, const
 int jt_collect(jt_plan* plan, int64_t B, int dtype, void* workspace, int flags, void* stream);
 int jt_distribute(jt_plan* plan, int64_t B, int dtype, void* workspace, int flags, void* stream);
 /* factor_out: [fout_entries][B] values of `dtype` */
-int jt_marginal(jt_plan* plan, int64_t B, int dtype, void* workspace, void* factor_out, void* stream);
+int jt_marginal(jt_plan* plan, int64_t B, int dtype, void* workspace, void* factor_out, int flags, void* stream);
 /* init + collect + distribute (+ marginal unless JT_SKIP_MARGINAL) */
 int jt_propagate(jt_plan* plan, const void* factor_tables, int factors_batched,
                  const int32_t* evidence, int64_t B, int dtype, void* workspace, void* factor_out,

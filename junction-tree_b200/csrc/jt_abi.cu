@@ -395,7 +395,7 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
     for (int64_t i = 0; i < n_launch; ++i, q += JT_LAUNCH_WORDS) {
         jt_plan::Launch& L = p->launches[i];
         L.phase = (int)q[JT_L_PHASE]; L.begin = (int)q[JT_L_BEGIN]; L.end = (int)q[JT_L_END]; L.level = (int)q[JT_L_LEVEL];
-        if (L.phase < JT_PHASE_INIT || L.phase > JT_PHASE_COLLECT_INSTANCE || L.begin < 0 || L.begin >= L.end || L.end > n_tasks)
+        if (L.phase < JT_PHASE_INIT || L.phase > JT_PHASE_MARGINAL_DIRECT || L.begin < 0 || L.begin >= L.end || L.end > n_tasks)
             return bad("launch descriptor", i);
         for (int t = L.begin; t < L.end; ++t)
             if ((p->tasks[t].kind == JT_KIND_INIT) != (L.phase == JT_PHASE_INIT || L.phase == JT_PHASE_INIT_UNIFORM ||
@@ -609,22 +609,30 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
         a.uniform = 1;
     }
     // per level: the tasks that only read psi_C, then the task that overwrites it with beta_C
+    // (JT_NO_BELIEFS: only the message-sending tasks, and the kernels skip the belief stores)
+    const int main_phase = (flags & JT_NO_BELIEFS) ? JT_PHASE_DIST_MAIN_MESSAGES : JT_PHASE_DIST_MAIN;
     for (const auto& L : p->launches) {
-        if (L.phase != JT_PHASE_DIST_PRE && L.phase != JT_PHASE_DIST_MAIN) continue;
+        if (L.phase != JT_PHASE_DIST_PRE && L.phase != main_phase) continue;
         rc = dispatch(p, L, a, dtype, vec, stream);
         if (rc != JT_OK) return rc;
     }
     return JT_OK;
 }
 
-int jt_marginal(jt_plan* p, int64_t B, int dtype, void* workspace, void* factor_out, void* stream) {
+int jt_marginal(jt_plan* p, int64_t B, int dtype, void* workspace, void* factor_out, int flags, void* stream) {
     int rc = check_common(p, B, dtype, workspace);
     if (rc != JT_OK) return rc;
     if (!factor_out) return fail(JT_ERR_INVALID, "factor_out is null");
     const int vec = pick_vec(B, dtype);
     KArgs a = base_args(p, B, workspace, vec);
     a.fout = factor_out;
-    return run_phase(p, JT_PHASE_MARGINAL, a, dtype, vec, static_cast<cudaStream_t>(stream));
+    if (!(flags & JT_NO_BELIEFS)) return run_phase(p, JT_PHASE_MARGINAL, a, dtype, vec, static_cast<cudaStream_t>(stream));
+    // outputs straight from psi_C and the incoming messages (the beliefs were not written)
+    if (uniform_mode(p, flags)) {
+        a.uni = uniform_ws(p, B, dtype, workspace);
+        a.uniform = 1;
+    }
+    return run_phase(p, JT_PHASE_MARGINAL_DIRECT, a, dtype, vec, static_cast<cudaStream_t>(stream));
 }
 
 int jt_propagate(jt_plan* p, const void* factor_tables, int factors_batched, const int32_t* evidence, int64_t B,
@@ -639,7 +647,7 @@ int jt_propagate(jt_plan* p, const void* factor_tables, int factors_batched, con
     rc = jt_distribute(p, B, dtype, workspace, flags, stream);
     if (rc != JT_OK) return rc;
     if (flags & JT_SKIP_MARGINAL) return JT_OK;
-    return jt_marginal(p, B, dtype, workspace, factor_out, stream);
+    return jt_marginal(p, B, dtype, workspace, factor_out, flags, stream);
 }
 
 int jt_normalize(jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, void* stream_) {

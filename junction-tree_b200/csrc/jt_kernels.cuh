@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
     const long long s_off = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo);
     const T* sptr = src_uni ? uni + tk->src + s_off : work + ((has_src ? tk->src : 0) + s_off) * B + col;
     const long long spitch = src_uni ? 1 : B;
-    const bool wbeta = tk->beta >= 0;
+    const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS);
     T* bptr = work + ((wbeta ? tk->beta : 0) + s_off) * B + col;
     P scale = sm;
     mul(scale, own);
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(kThreads) jt_project_splitr_kernel(const KArgs
     const T scale = sm * own;
 
     const bool has_src = tk->src >= 0, src_uni = (tflags & JT_TF_SRC_UNIFORM) != 0;
-    const bool wbeta = tk->beta >= 0;
+    const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS);
     const long long s_off = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo);
     const int rm0 = tk->rmsg_begin, nr = tk->rmsg_end - rm0;
     const int n_r = tk->n_r, n_rlo = tk->n_rlo;
@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     T* work = static_cast<T*>(a.work);
     const long long col = (col0v + t) * VEC;
     const long long vstep = (long long)ct * VEC;         // elements between the vectors of a thread
-    const bool wbeta = tk->beta >= 0, wout = tk->out >= 0;
+    const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS), wout = tk->out >= 0;
     const bool wbel = wout && tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS);
     T* bptr = work + (wbeta ? tk->beta : 0) * B + col;
     T* optr = (tk->out_space ? static_cast<T*>(a.fout) : work) + (wout ? tk->out : 0) * B + col;

@@ -12,8 +12,8 @@ import numpy as np
 
 JT_OK = 0
 JT_F32, JT_F64 = 0, 1
-JT_SEP_BELIEFS, JT_SKIP_MARGINAL, JT_UNIFORM, JT_NO_UNIFORM, JT_UNIFORM_VALID = 1, 2, 4, 8, 16
-ABI_VERSION = 5
+JT_SEP_BELIEFS, JT_SKIP_MARGINAL, JT_UNIFORM, JT_NO_UNIFORM, JT_UNIFORM_VALID, JT_NO_BELIEFS = 1, 2, 4, 8, 16, 32
+ABI_VERSION = 6
 
 _LIB_NAME = "libjt_b200.so"
 _lib = None
@@ -43,7 +43,7 @@ SIGNATURES = {
     "jt_distribute": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_int, ctypes.c_void_p]),
     "jt_marginal": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
-                                   ctypes.c_void_p, ctypes.c_void_p]),
+                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "jt_propagate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                     ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_int, ctypes.c_void_p]),
@@ -171,8 +171,8 @@ class DevicePlan:
     def distribute(self, B, dtype, ws_ptr, flags, stream):
         check(lib().jt_distribute(self._handle, B, dtype_code(dtype), ws_ptr, flags, stream))
 
-    def marginal(self, B, dtype, ws_ptr, out_ptr, stream):
-        check(lib().jt_marginal(self._handle, B, dtype_code(dtype), ws_ptr, out_ptr, stream))
+    def marginal(self, B, dtype, ws_ptr, out_ptr, stream, flags=0):
+        check(lib().jt_marginal(self._handle, B, dtype_code(dtype), ws_ptr, out_ptr, flags, stream))
 
     def propagate(self, factors_ptr, batched, evidence_ptr, B, dtype, ws_ptr, out_ptr, flags, stream):
         check(lib().jt_propagate(self._handle, factors_ptr, int(batched), evidence_ptr, B,

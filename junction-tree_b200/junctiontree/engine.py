@@ -148,7 +148,7 @@ class Engine:
         return torch().cuda.current_stream().cuda_stream
 
     def propagate(self, factor_dev, batched, evidence_dev, B, dtype, ws=None, sep_beliefs=False,
-                  marginal=True, uniform=True):
+                  marginal=True, uniform=True, beliefs=True):
         """init + collect + distribute (+ marginal).  Returns ``(ws, factor_out)``; ``factor_out``
         is a ``[fout_entries, B]`` tensor (``None`` when ``marginal`` is False).  ``uniform``:
         compute potentials and messages no evidence reaches once per batch (shared tables only;
@@ -159,6 +159,8 @@ class Engine:
             ws = self.workspace(B, dtype)
         fout = None
         flags = (_native.JT_SEP_BELIEFS if sep_beliefs else 0) | (0 if uniform else _native.JT_NO_UNIFORM)
+        if not beliefs:       # only the outputs are wanted: no clique belief is written
+            flags |= _native.JT_NO_BELIEFS
         if marginal:
             fout = t.empty((self.plan.fout_entries, B), dtype=torch_dtype(dtype), device="cuda")
         else:
@@ -279,7 +281,8 @@ class BatchPipeline:
                 if self.n_ev:
                     slot["ev"].copy_(ev_host[lo:hi], non_blocking=True)
                     ev_ptr = slot["ev"].data_ptr()
-                flags = _native.JT_UNIFORM_VALID if id(slot) in primed else 0
+                # host output only: clique beliefs are never read, so they are not written
+                flags = _native.JT_NO_BELIEFS | (_native.JT_UNIFORM_VALID if id(slot) in primed else 0)
                 primed.add(id(slot))
                 dev.propagate(factor_dev.data_ptr(), False, ev_ptr, n, self.dtype, slot["ws"].data_ptr(),
                               slot["fout"].data_ptr(), flags, stream.cuda_stream)
@@ -339,6 +342,7 @@ class GraphedPropagation:
         self.fout = t.zeros_like(self.host_out, device="cuda")
         self.ws = engine.new_workspace(self.B, dtype)
         flags = (_native.JT_SEP_BELIEFS if sep_beliefs else 0) | (0 if uniform else _native.JT_NO_UNIFORM)
+        flags |= _native.JT_NO_BELIEFS
         ev_ptr = self.evidence.data_ptr() if n_ev else None
 
         def enqueue(stream):

@@ -184,7 +184,7 @@ class CliqueGraph():
         work[:plan.clique_entries, 0].copy_(t.from_numpy(host))
         fout = t.empty((plan.fout_entries, 1), dtype=eng.torch_dtype(dtype), device="cuda")
         engine.dev.upload()
-        engine.dev.marginal(1, dtype, ws.data_ptr(), fout.data_ptr(), engine._stream())
+        engine.dev.marginal(1, dtype, ws.data_ptr(), fout.data_ptr(), engine._stream(), 0)
         flat = fout[:, 0].cpu().numpy()
         return [
             flat[plan.fout_off[f]:plan.fout_off[f] + plan.fout_size[f]].reshape(tuple(plan.fout_shape[f])).copy()
@@ -385,7 +385,8 @@ class JunctionTree():
             # free device memory (config 5 needs ~80 MB of workspace per instance)
             return self._propagate_streamed(engine, fdev, evidence, B, dtype)
         edev = engine.evidence_to_device(evidence, B)
-        ws, fout = engine.propagate(fdev, batched, edev, B, dtype, sep_beliefs=nodes, uniform=uniform)
+        ws, fout = engine.propagate(fdev, batched, edev, B, dtype, sep_beliefs=nodes, uniform=uniform,
+                                    beliefs=nodes)
         if edev is not None:
             bad = engine.dev.evidence_errors(B, dtype, ws.data_ptr(), engine._stream())
             if bad:

@@ -37,7 +37,7 @@ import numpy as np
 from . import construction as cons
 
 MAGIC = 0x324E4C5042544A  # "JTBPLN2"
-VERSION = 5
+VERSION = 6
 
 # header word indices (int64 words); mirrored in include/jt_b200.h
 H_MAGIC, H_VERSION, H_NCLIQUES, H_NSEPS, H_NFACTORS, H_NEVID, H_CLIQUE_ENTRIES, H_SEP_ENTRIES, \
@@ -62,7 +62,8 @@ L_PHASE, L_BEGIN, L_END, L_LEVEL = range(4)
 
 KIND_PROJECT, KIND_INIT = 0, 1
 (PHASE_INIT, PHASE_COLLECT, PHASE_DIST_PRE, PHASE_DIST_MAIN, PHASE_MARGINAL,
- PHASE_INIT_UNIFORM, PHASE_INIT_INSTANCE, PHASE_COLLECT_UNIFORM, PHASE_COLLECT_INSTANCE) = range(9)
+ PHASE_INIT_UNIFORM, PHASE_INIT_INSTANCE, PHASE_COLLECT_UNIFORM, PHASE_COLLECT_INSTANCE,
+ PHASE_DIST_MAIN_MESSAGES, PHASE_MARGINAL_DIRECT) = range(11)
 SPACE_WORK, SPACE_FOUT = 0, 1
 
 #: trailing-axes table is grown while its length stays within this bound
@@ -508,19 +509,30 @@ class Plan:
                         row[T_BETA] = self.node_off[c]
                     # messages are appended when the task is placed (keeps ranges contiguous)
                     (main if writer else pre).append((row, others, s_space, r_space))
+            # tasks that send a message first, the belief-only ones (leaves) last: when clique
+            # beliefs are not wanted the launch stops before them
+            main.sort(key=lambda item: 0 if isinstance(item, tuple) else 1)
             for phase, group in ((PHASE_DIST_PRE, pre), (PHASE_DIST_MAIN, main)):
                 begin = len(self.tasks)
+                n_sending = 0
                 for item in group:
                     if isinstance(item, tuple):
                         row, others, s_space, r_space = item
                         self._attach_msgs(row, others, s_space, r_space)
                         self.tasks.append(row)
+                        n_sending += 1
                     else:
                         self.tasks.append(item)
                 self._launch(phase, begin, d)
+                if phase == PHASE_DIST_MAIN and n_sending:
+                    self.launches.append([PHASE_DIST_MAIN_MESSAGES, begin, begin + n_sending, d])
 
     def _build_marginal(self):
-        """E6: per output scope (by default per factor) = clique belief summed down to the scope."""
+        """E6: per output scope (by default per factor) = clique belief summed down to the scope.
+
+        Two forms: from the stored belief beta_C (``PHASE_MARGINAL``), or *direct* from psi_C
+        times every incoming message (``PHASE_MARGINAL_DIRECT``), which does not need the clique
+        beliefs to be written at all -- used when only the outputs are wanted."""
         if self.factors is None:
             return
         begin = len(self.tasks)
@@ -535,6 +547,24 @@ class Plan:
             row[T_RMSG_BEGIN] = row[T_RMSG_END] = row[T_SMSG_BEGIN] = row[T_SMSG_END] = len(self.msgs)
             self.tasks.append(row)
         self._launch(PHASE_MARGINAL, begin, 0)
+        if self.tree is None:
+            return
+        begin = len(self.tasks)
+        for k, (scope, c) in enumerate(zip(self.out_scopes, self.out_clique)):
+            s_space = _Space(scope, self.sizes)
+            in_f = set(scope)
+            r_space = _Space([v for v in self.node_vars[c] if v not in in_f], self.sizes)
+            row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c, src_is_psi=True)
+            row[T_OUT] = self.fout_off[k]
+            row[T_OUT_SPACE] = SPACE_FOUT
+            row[T_AUX] = k
+            incoming = []
+            if self.parent[c] >= 0:
+                incoming.append((self.down_off(self.parent_sep[c]), self.parent_sep[c], False))
+            incoming += [(self.up_off(sp), sp, self.uniform_up[kid]) for sp, kid in self.children[c]]
+            self._attach_msgs(row, incoming, s_space, r_space)
+            self.tasks.append(row)
+        self._launch(PHASE_MARGINAL_DIRECT, begin, 0)
 
     # -----------------------------------------------------------------------------------------
 

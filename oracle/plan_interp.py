@@ -26,7 +26,8 @@ def evidence_offsets(plan, evidence, B):
     return fbase
 
 
-def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np.float64, uniform=False):
+def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np.float64, uniform=False,
+        beliefs=True):
     """Execute the plan.  ``work``: [work_entries, B] (clique potentials preloaded when the init
     phase is skipped); ``factor_in``: flat shared factor tables (fin_entries) or per-instance
     [fin_entries, B].  ``uniform``: keep the potentials of evidence-free cliques once, in the
@@ -36,7 +37,11 @@ def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np
     general = {sch.PHASE_INIT, sch.PHASE_COLLECT}
     split = {sch.PHASE_INIT_UNIFORM, sch.PHASE_INIT_INSTANCE, sch.PHASE_COLLECT_UNIFORM, sch.PHASE_COLLECT_INSTANCE}
     in_uni_ws = {sch.PHASE_INIT_UNIFORM, sch.PHASE_COLLECT_UNIFORM}
-    skip = general if uniform else split
+    skip = set(general if uniform else split)
+    # beliefs=False: messages and outputs only -- no clique belief is written, outputs come
+    # straight from psi_C and the incoming messages
+    skip |= ({sch.PHASE_DIST_MAIN, sch.PHASE_MARGINAL} if not beliefs else
+             {sch.PHASE_DIST_MAIN_MESSAGES, sch.PHASE_MARGINAL_DIRECT})
     launches = list(plan.launches_arr)
     if uniform:   # evidence-free subtrees are collected first, once
         launches = [L for L in launches if L[0] in in_uni_ws] + [L for L in launches if L[0] not in in_uni_ws]
@@ -98,7 +103,7 @@ def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np
                     work[t[sch.T_OUT]:t[sch.T_OUT] + n_s] = out
             if t[sch.T_BEL] >= 0:
                 work[t[sch.T_BEL]:t[sch.T_BEL] + n_s] = out * own
-            if t[sch.T_BETA] >= 0:
+            if t[sch.T_BETA] >= 0 and beliefs:
                 beta = term * sm[:, None, :]
                 if own is not None:
                     beta = beta * own[:, None, :]

@@ -146,3 +146,21 @@ def test_invariants_on_a_large_tree():
     np.testing.assert_allclose(Z, 1.0, rtol=1e-12)       # CPTs of a Bayesian network
     for y in ys:
         np.testing.assert_allclose(y.sum(), Z, rtol=1e-12)
+
+
+@pytest.mark.parametrize("uniform", [False, True], ids=["per_instance_psi", "uniform_psi"])
+@pytest.mark.parametrize("net", NETS, ids=lambda n: n["name"])
+def test_direct_marginals_without_clique_beliefs(net, uniform):
+    """JT_NO_BELIEFS schedule: message-sending distribute tasks only, outputs computed straight
+    from psi_C and the incoming messages -- same factor outputs, no clique belief written."""
+    from junctiontree import schedule as sch
+    tree, seps, mc, f2c, eff, evars = compile_net(net)
+    plan = sch.Plan(tree, mc + seps, eff, net["factors"], f2c, evars, net["sizes"])
+    B = 2
+    ev = wl.draw_evidence(net, B) if evars else None
+    work, fout = plan_interp.run(plan, B, factor_in=plan_interp.flatten_factors(plan, net["values"]), evidence=ev,
+                                 uniform=uniform, beliefs=False)
+    outs, _ = ref_fixed.propagate_batch(tree, seps, mc, f2c, net["factors"], net["sizes"], net["values"],
+                                        evars, ev, n=B)
+    for f in range(len(net["factors"])):
+        assert_close(plan_interp.factor_array(plan, fout, f, B), outs[f], 1e-13, "factor %d" % f)

@@ -51,6 +51,7 @@ struct jt_plan {
     int* d_prefix = nullptr;
     int* d_ev = nullptr;   // ev_card | evf_ptr | evf_var | evf_stride
     long long* d_out = nullptr;   // fout_off | fout_size
+    mutable bool tma_attr_set[2][2] = {{false, false}, {false, false}};   // [f32|f64][VPT-1]
 };
 
 namespace {
@@ -127,7 +128,8 @@ int launch_tma_vpt(const jt_plan* p, const jt_plan::Launch& L, KArgs a, int ct, 
         return fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, tiles);
     // ring rows, then barriers / row indices / scalar operands (TmaAux)
     const size_t smem = (size_t)(kTmaSlots / VPT) * tw * 16 + sizeof(TmaAux<T>);
-    static bool attr_set = false;
+    // opt in to > 48 KB of dynamic shared memory once per (plan = device, instantiation)
+    bool& attr_set = p->tma_attr_set[sizeof(T) == 8 ? 1 : 0][VPT - 1];
     if (!attr_set) {
         JT_CUDA(cudaFuncSetAttribute(jt_project_tma_kernel<T, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kTmaSlots * 256 * 16 + (int)sizeof(TmaAux<T>)));

@@ -226,6 +226,10 @@ def run_gpu(args):
     lo, hi = jdist.shard_bounds(B * world, world, rank)
     ev_host = torch.from_numpy(ev_all[lo:hi].copy()).pin_memory() if evars else None
 
+    sr_flag = {"sum_product": _native.JT_SR_SUM_PRODUCT, "max_product": _native.JT_SR_MAX_PRODUCT,
+               "log_sum_exp": _native.JT_SR_LOG_SUM_EXP, "max_sum": _native.JT_SR_MAX_SUM}[args.semiring]
+    if args.semiring in ("log_sum_exp", "max_sum"):          # log-domain laws take log potentials
+        net["values"] = [np.log(v) for v in net["values"]]
     fdev, batched = engine.factors_to_device(net["values"], dtype)
     ev_dev = ev_host.to("cuda") if evars else None
     ws = engine.workspace(B, dtype)
@@ -233,7 +237,7 @@ def run_gpu(args):
     fout = torch.empty((plan.fout_entries, B), dtype=engine_dtype(dtype), device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     ev_ptr = ev_dev.data_ptr() if evars else None
-    flags = _native.JT_SEP_BELIEFS | (0 if args.no_uniform else _native.JT_UNIFORM)
+    flags = _native.JT_SEP_BELIEFS | (0 if args.no_uniform else _native.JT_UNIFORM) | sr_flag
 
     def hot_path(events=None):
         if events is not None:
@@ -275,7 +279,7 @@ def run_gpu(args):
     msg_ms = sum(e[1].elapsed_time(e[2]) for e in ev_pairs)
 
     # ---- end to end through the public API: pinned host evidence in, per-factor beliefs out ----
-    pipe = engine.pipeline(B, dtype, chunk=args.chunk)
+    pipe = engine.pipeline(B, dtype, chunk=args.chunk, semiring=sr_flag)
     out_host = pipe.host_output()
     for _ in range(2):
         pipe.run(fdev, batched, ev_host, out_host)
@@ -297,7 +301,7 @@ def run_gpu(args):
     # posteriors of the unobserved variables + log P(evidence) instead of raw factor beliefs ----
     free_vars = [v for v in sorted(net["sizes"]) if v not in evars]
     m_engine = tree._engine(plan.sizes, evars, plan.full_sizes, outputs=[[v] for v in free_vars])
-    m_pipe = m_engine.pipeline(B, dtype, chunk=args.chunk, normalize=True, log_z=True)
+    m_pipe = m_engine.pipeline(B, dtype, chunk=args.chunk, normalize=True, log_z=True, semiring=sr_flag)
     m_out = m_pipe.host_output()
     m_fdev, _ = m_engine.factors_to_device(net["values"], dtype)
     for _ in range(2):
@@ -365,14 +369,16 @@ def run_gpu(args):
             "cliques": plan.n_cliques, "clique_entries": plan.clique_entries, "sep_entries": plan.sep_entries,
             "levels": plan.max_depth, "algorithmic_bytes_per_propagation": A,
             "scheduled_bytes_per_propagation": S_all, "uniform_mode": bool(uniform),
-            "uniform_clique_entries": plan.uni_entries if uniform else 0,
+            "uniform_clique_entries": plan.uni_entries if uniform else 0, "semiring": args.semiring,
             "step": "evidence slicing + clique init + collect + distribute (clique and separator beliefs)",
             "l2": "inputs larger than L2 (working set %.1f GB per GPU)" % (plan.work_entries * B * w / 1e9),
             "step_gbs_algorithmic": step_gbs, "init_ms_per_step": init_ms / args.steps,
             "message_passing_ms_per_step": msg_ms / args.steps,
         },
         "roofline": {
-            "bound": "hbm", "kernel": "jt_project_tma_kernel<%s>" % ("double" if w == 8 else "float"),
+            "bound": "hbm", "kernel": "jt_project_tma_kernel<%s, %s>" % (
+                {"sum_product": "SrSumProduct", "max_product": "SrMaxProduct", "log_sum_exp": "SrLogSumExp",
+                 "max_sum": "SrMaxSum"}[args.semiring], "double" if w == 8 else "float"),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": peak_src, "traffic": load_traffic(args, uniform),
             "launches_per_step": msg_launches, "avg_launch_ms": msg_ms_per_launch,
@@ -434,6 +440,9 @@ def main():
     ap.add_argument("--no-evidence", action="store_true")
     ap.add_argument("--no-uniform", action="store_true",
                     help="materialise every potential and message per instance (general path)")
+    ap.add_argument("--semiring", default="sum_product",
+                    choices=["sum_product", "max_product", "log_sum_exp", "max_sum"],
+                    help="distributive law of the kernels (default: the reference's sum-product)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-per-core", type=int, default=512, help="CPU baseline: instances per core")
     args = ap.parse_args()

@@ -61,7 +61,7 @@
 extern "C" {
 #endif
 
-#define JT_ABI_VERSION 6
+#define JT_ABI_VERSION 7
 
 /* status codes */
 #define JT_OK 0
@@ -84,6 +84,19 @@ extern "C" {
 #define JT_UNIFORM_VALID 16 /* uniform mode: the uniform workspace of this workspace already holds the
                               potentials and up-messages of these factor tables (an earlier call with
                               the same tables and the same workspace): skip recomputing them */
+
+/* Semiring ("distributive law", reference sum_product.py:2-3, junctiontree.py:300-305) of the stage
+ * calls, jt_normalize and jt_contract: which (+, x) pair the kernels use.  Pass the same value to
+ * every stage of one propagation.  Log-domain semirings take log potentials as factor tables.
+ *   sum-product  (+, *)           marginals and the partition function (the reference's only law)
+ *   max-product  (max, *)         max-marginals: the value of the best joint state per entry (MAP)
+ *   log-sum-exp  (logaddexp, +)   sum-product on log potentials, safe against underflow
+ *   max-sum      (max, +)         max-product on log potentials */
+#define JT_SR_SUM_PRODUCT 0x000
+#define JT_SR_MAX_PRODUCT 0x100
+#define JT_SR_LOG_SUM_EXP 0x200
+#define JT_SR_MAX_SUM 0x300
+#define JT_SR_MASK 0x300
 
 /* plan blob header words */
 #define JT_MAGIC 0x324E4C5042544ALL
@@ -164,8 +177,11 @@ int jt_propagate(jt_plan* plan, const void* factor_tables, int factors_batched,
  * jt_marginal) by its sum over the scope, per instance; the sum of scope 0 -- the partition
  * function Z = P(evidence) that the reference computes at the root and discards,
  * computation.py:90-96 -- is written as log Z to logz[B] when logz is not NULL.  A scope whose sum
- * is 0 (impossible evidence) becomes all zeros and log Z = -inf. */
-int jt_normalize(jt_plan* plan, int64_t B, int dtype, void* factor_out, void* logz, void* stream);
+ * is 0 (impossible evidence) becomes all zeros and log Z = -inf.  `flags` selects the semiring
+ * (JT_SR_*): the total is the semiring's reduction (sum / max / logsumexp) over the scope, the
+ * entries are divided by it (log domain: it is subtracted) and logz receives its logarithm (log
+ * domain: the total itself). */
+int jt_normalize(jt_plan* plan, int64_t B, int dtype, void* factor_out, void* logz, int flags, void* stream);
 /* number of out-of-range evidence states seen by jt_init calls on this workspace since it was
  * last zeroed (synchronises the stream) */
 int jt_evidence_errors(jt_plan* plan, int64_t B, int dtype, void* workspace, void* stream, int64_t* out);
@@ -175,11 +191,12 @@ int jt_evidence_errors(jt_plan* plan, int64_t B, int dtype, void* workspace, voi
  * out[s] = sum_r prod_j op_j[ A_j(s) + B_j(r) ], every operand and the output batch-innermost
  * ([n][B]).  `tables` (host, int32) holds all index tables; per operand j the four table
  * offsets are maps[4*j .. 4*j+3] = (a_hi, a_lo, b_hi, b_lo).  ops[j] are device pointers.
- * "project" is the case of one operand, "absorb" the case n_r = 1.
+ * "project" is the case of one operand, "absorb" the case n_r = 1.  `flags`: JT_SR_* semiring
+ * (sum and product above become the semiring's reduction and product).
  */
 int jt_contract(const void* const* ops, int n_ops, const int32_t* tables, int64_t n_tab,
                 const int32_t* maps, int64_t n_s, int64_t n_r, int64_t n_slo, int64_t n_rlo,
-                int64_t B, int dtype, void* out, void* stream);
+                int64_t B, int dtype, void* out, int flags, void* stream);
 
 /* Strided row copy between a device buffer and a (pinned) host buffer on `stream`
  * (cudaMemcpy2DAsync): `rows` rows of `width_bytes`; to_host = 1 for device -> host.  Used to

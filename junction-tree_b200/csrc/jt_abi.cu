@@ -1,5 +1,7 @@
-// libjt_b200: C ABI (include/jt_b200.h) over the sm_100a kernels of jt_kernels.cuh.
-// Plan parsing and validation, workspace layout, launch configuration.
+// libjt_b200: C ABI (include/jt_b200.h) over the sm_100a kernels.
+// Plan parsing and validation, workspace layout, stage sequencing.  The kernels live in
+// jt_kernels.cuh and are instantiated once per semiring by jt_sr_*.cu; this file picks the
+// launcher table by the JT_SR_* bits of the stage flags.
 
 #include <cuda_runtime.h>
 
@@ -10,49 +12,70 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
-#include <type_traits>
 #include <vector>
 
-#include "../../include/jt_b200.h"
-#include "jt_kernels.cuh"
+#include "jt_host.h"
 
 // ------------------------------------------------------------------------------------------
-// host side
+// error handling
 
-constexpr int kItemLog2Max = 24;
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> jt_g_launches{0};
 
-struct jt_plan {
-    std::vector<int64_t> hdr, node_off, node_size, fin_off, fin_size, fout_off, fout_size;
-    std::vector<int> ev_card, evf_ptr, evf_var, evf_stride;
-    std::vector<DTask> tasks;
-    std::vector<DMsg> msgs;
-    std::vector<int> tab;
-    struct Launch {
-        int phase, begin, end, level;
-        size_t prefix_off[kMaxSyLog2 + 1];
-        long long blocks[kMaxSyLog2 + 1];
-        // TMA kernel: per-task chunks sized for ~2^j (s, r) items per CTA, j = 0..kItemLog2Max;
-        // layout per j: [n_tasks + 1] block prefix, [n_tasks] log2 chunk
-        size_t item_prefix_off[kItemLog2Max + 1];
-        long long item_blocks[kItemLog2Max + 1];
-        long long total_items;
-        bool tma_ok;          // every task fits the TMA kernel's stage (rows per stage <= kTmaMaxRows)
-        int min_nr;           // smallest n_r of the launch
-        int max_nr;           // largest n_r of the launch
-        long long total_s;    // sum of n_s
-    };
-    std::vector<Launch> launches;
-    std::vector<int> prefix;
+int jt_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
 
-    int device = -1;
-    DTask* d_tasks = nullptr;
-    DMsg* d_msgs = nullptr;
-    int* d_tab = nullptr;
-    int* d_prefix = nullptr;
-    int* d_ev = nullptr;   // ev_card | evf_ptr | evf_var | evf_stride
-    long long* d_out = nullptr;   // fout_off | fout_size
-    mutable bool tma_attr_set[2][2] = {{false, false}, {false, false}};   // [f32|f64][VPT-1]
-};
+#define fail jt_fail
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// evidence slicing (V1): per-instance base offset of every factor table
+//   fbase[f][b] = sum over observed axes k of factor f:  state[b][var_k] * stride_k
+// Pure integer arithmetic; out-of-range states are clamped and counted.
+
+__global__ void __launch_bounds__(kThreads)
+jt_evidence_kernel(const int* __restrict__ evidence, int n_evid, const int* __restrict__ ev_card,
+                   const int* __restrict__ evf_ptr, const int* __restrict__ evf_var,
+                   const int* __restrict__ evf_stride, int n_factors, long long B,
+                   int* __restrict__ fbase, unsigned long long* __restrict__ errors) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int* row = evidence + b * n_evid;
+    unsigned bad = 0;
+    for (int f = 0; f < n_factors; ++f) {
+        int acc = 0;
+        for (int k = evf_ptr[f]; k < evf_ptr[f + 1]; ++k) {
+            const int var = evf_var[k];
+            int state = row[var];
+            const int card = ev_card[var];
+            if (state < 0 || state >= card) {
+                ++bad;
+                state = state < 0 ? 0 : card - 1;
+            }
+            acc += state * evf_stride[k];
+        }
+        fbase[(long long)f * B + b] = acc;
+    }
+    if (bad) atomicAdd(errors, (unsigned long long)bad);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+jt_ratio_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T d = b[i];
+        out[i] = d != T(0) ? a[i] / d : T(0);
+    }
+}
+
+}  // namespace
 
 namespace {
 
@@ -85,147 +108,20 @@ int pick_vec(int64_t B, int dtype) {
     return 1;
 }
 
+const jt_sr_launchers* launchers(int flags) {
+    switch (flags & JT_SR_MASK) {
+        case JT_SR_MAX_PRODUCT: return jt_sr_max_product();
+        case JT_SR_LOG_SUM_EXP: return jt_sr_log_sum_exp();
+        case JT_SR_MAX_SUM: return jt_sr_max_sum();
+        default: return jt_sr_sum_product();
+    }
+}
+
 // tile shape for a batch of Bv vectors: bx = min(256, pow2ceil(Bv)), sy = 256 / bx
 void pick_tile(long long Bv, int& bx_log2, int& sy_log2) {
     bx_log2 = 0;
     while ((1LL << bx_log2) < Bv && bx_log2 < 8) ++bx_log2;
     sy_log2 = 8 - bx_log2;
-}
-
-int g_tma_enabled = -1;   // JT_DISABLE_TMA=1 forces the LDG kernel (debugging / A-B timing)
-
-bool tma_enabled() {
-    if (g_tma_enabled < 0) {
-        const char* e = getenv("JT_DISABLE_TMA");
-        g_tma_enabled = (e && e[0] == '1') ? 0 : 1;
-    }
-    return g_tma_enabled == 1;
-}
-
-// Few instances and long reductions with too few output indices to fill the machine: split r.
-bool use_splitr(const jt_plan::Launch& L, long long B, bool is_init) {
-    if (is_init || B > 64 || L.max_nr < 128) return false;
-    return L.max_nr >= 4096 || L.total_s * B < 65536;
-}
-
-template <typename T, int VPT>
-int launch_tma_vpt(const jt_plan* p, const jt_plan::Launch& L, KArgs a, int ct, cudaStream_t stream) {
-    const int tw = ct * VPT;
-    const long long tiles = (a.Bv + tw - 1) / tw;
-    // (s, r) items per CTA: aim at ~8 CTAs per SM over the launch, but keep >= 64 items per CTA
-    // so the pipeline fill is amortised; every task gets its own chunk of s for that item count
-    int j = 6;
-    const long long target = 148LL * 8;
-    while (j < kItemLog2Max && (L.total_items * tiles) >> (j + 1) >= target) ++j;
-    a.sy_log2 = 0;
-    a.bx_log2 = 0;
-    a.tasks = p->d_tasks + L.begin;
-    a.n_tasks = L.end - L.begin;
-    a.prefix = p->d_prefix + L.item_prefix_off[j];
-    const long long gx = L.item_blocks[j];
-    if (gx <= 0) return JT_OK;
-    if (gx > 2147483647LL || tiles > 65535)
-        return fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, tiles);
-    // ring rows, then barriers / row indices / scalar operands (TmaAux)
-    const size_t smem = (size_t)(kTmaSlots / VPT) * tw * 16 + sizeof(TmaAux<T>);
-    // opt in to > 48 KB of dynamic shared memory once per (plan = device, instantiation)
-    bool& attr_set = p->tma_attr_set[sizeof(T) == 8 ? 1 : 0][VPT - 1];
-    if (!attr_set) {
-        JT_CUDA(cudaFuncSetAttribute(jt_project_tma_kernel<T, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kTmaSlots * 256 * 16 + (int)sizeof(TmaAux<T>)));
-        attr_set = true;
-    }
-    dim3 grid((unsigned)gx, (unsigned)tiles, 1);
-    // consumer warps + row producer warp + uniform warp
-    jt_project_tma_kernel<T, VPT><<<grid, ct + 64, smem, stream>>>(a);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    JT_CUDA(cudaGetLastError());
-    return JT_OK;
-}
-
-int g_tma_vpt = -1;   // JT_TMA_VPT=1|2 overrides the vectors-per-thread choice (A-B timing)
-
-template <typename T>
-int launch_tma(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
-    if (g_tma_vpt < 0) {
-        const char* e = getenv("JT_TMA_VPT");
-        g_tma_vpt = (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
-    }
-    const int ct = a.Bv >= 256 ? 256 : (a.Bv >= 128 ? 128 : 64);
-    // two vectors per consumer thread once the batch fills 512-vector tiles: halves the control
-    // instructions per byte of the consumers
-    const bool two = g_tma_vpt ? g_tma_vpt == 2 : a.Bv >= 512;
-    if (two && ct == 256) return launch_tma_vpt<T, 2>(p, L, a, ct, stream);
-    return launch_tma_vpt<T, 1>(p, L, a, ct, stream);
-}
-
-template <typename T, int VEC>
-int launch_tasks(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
-    const bool is_init = L.phase == JT_PHASE_INIT || L.phase == JT_PHASE_INIT_UNIFORM ||
-                         L.phase == JT_PHASE_INIT_INSTANCE;
-    if (!is_init && VEC * sizeof(T) == 16 && L.tma_ok && a.Bv >= 64 && tma_enabled())
-        return launch_tma<T>(p, L, a, stream);
-    int bx_log2, sy_log2;
-    pick_tile(a.Bv, bx_log2, sy_log2);
-    if (VEC == 1 && use_splitr(L, a.B, is_init)) {
-        // few instances, long reductions: one block per output index, threads split r
-        a.bx_log2 = bx_log2;
-        a.sy_log2 = 0;
-        a.tasks = p->d_tasks + L.begin;
-        a.n_tasks = L.end - L.begin;
-        a.prefix = p->d_prefix + L.prefix_off[0];
-        const long long gx = L.blocks[0];
-        const long long gy = (a.B + (1LL << bx_log2) - 1) >> bx_log2;
-        if (gx <= 0) return JT_OK;
-        if (gx > 2147483647LL || gy > 65535)
-            return fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
-        jt_project_splitr_kernel<T><<<dim3((unsigned)gx, (unsigned)gy, 1), kThreads, 0, stream>>>(a);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        JT_CUDA(cudaGetLastError());
-        return JT_OK;
-    }
-    if (is_init) {
-        // a thread walks ~32 rows of s so the per-instance factor offsets stay in registers
-        sy_log2 = sy_log2 + 5 > kMaxSyLog2 ? kMaxSyLog2 : sy_log2 + 5;
-        while (sy_log2 > 8 - bx_log2 && (L.total_s >> sy_log2) * ((a.Bv + (1LL << bx_log2) - 1) >> bx_log2) < 148 * 4)
-            --sy_log2;
-    }
-    a.bx_log2 = bx_log2;
-    a.sy_log2 = sy_log2;
-    a.tasks = p->d_tasks + L.begin;
-    a.n_tasks = L.end - L.begin;
-    a.prefix = p->d_prefix + L.prefix_off[sy_log2];
-    const long long gx = L.blocks[sy_log2];
-    const long long gy = (a.Bv + (1LL << bx_log2) - 1) >> bx_log2;
-    if (gx <= 0) return JT_OK;
-    if (gx > 2147483647LL || gy > 65535)
-        return fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
-    dim3 grid((unsigned)gx, (unsigned)gy, 1);
-    if (is_init)
-        jt_init_kernel<T, VEC><<<grid, kThreads, 0, stream>>>(a);
-    else
-        jt_project_kernel<T, VEC><<<grid, kThreads, 0, stream>>>(a);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    JT_CUDA(cudaGetLastError());
-    return JT_OK;
-}
-
-int dispatch(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a_in, int dtype, int vec,
-             cudaStream_t stream) {
-    KArgs a = a_in;
-    const bool is_init = L.phase == JT_PHASE_INIT || L.phase == JT_PHASE_INIT_UNIFORM ||
-                         L.phase == JT_PHASE_INIT_INSTANCE;
-    if (use_splitr(L, a.B, is_init)) {                  // split-r kernel: scalar batch lanes
-        vec = 1;
-        a.Bv = a.B;
-    }
-    if (dtype == JT_F64) {
-        if (vec == 2) return launch_tasks<double, 2>(p, L, a, stream);
-        return launch_tasks<double, 1>(p, L, a, stream);
-    }
-    if (vec == 4) return launch_tasks<float, 4>(p, L, a, stream);
-    if (vec == 2) return launch_tasks<float, 2>(p, L, a, stream);
-    return launch_tasks<float, 1>(p, L, a, stream);
 }
 
 int check_common(const jt_plan* p, int64_t B, int dtype, const void* workspace) {
@@ -252,7 +148,7 @@ KArgs base_args(const jt_plan* p, int64_t B, void* workspace, int vec) {
 int run_phase(jt_plan* p, int phase, const KArgs& a, int dtype, int vec, cudaStream_t stream) {
     for (const auto& L : p->launches) {
         if (L.phase != phase) continue;
-        int rc = dispatch(p, L, a, dtype, vec, stream);
+        int rc = launchers(a.flags)->dispatch(p, L, a, dtype, vec, stream);
         if (rc != JT_OK) return rc;
     }
     return JT_OK;
@@ -285,7 +181,7 @@ int jt_abi_version(void) { return JT_ABI_VERSION; }
 
 const char* jt_last_error_string(void) { return g_err; }
 
-int64_t jt_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int64_t jt_launch_count(void) { return jt_g_launches.load(std::memory_order_relaxed); }
 
 int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
     if (!blob || !out) return fail(JT_ERR_INVALID, "null argument");
@@ -554,6 +450,7 @@ int jt_init(jt_plan* p, const void* factor_tables, int factors_batched, const in
     KArgs a = base_args(p, B, workspace, vec);
     a.fin = factor_tables;
     a.fin_batched = factors_batched ? 1 : 0;
+    a.flags = flags;
     if (n_evid > 0) {
         if (!evidence) return fail(JT_ERR_INVALID, "plan has %d evidence variables but evidence is null", n_evid);
         if (factors_batched) return fail(JT_ERR_INVALID, "per-instance factor tables cannot be combined with evidence indices");
@@ -567,7 +464,7 @@ int jt_init(jt_plan* p, const void* factor_tables, int factors_batched, const in
         const long long blocks = (B + kThreads - 1) / kThreads;
         jt_evidence_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(evidence, n_evid, d_card, d_ptr, d_var,
                                                                       d_stride, F, B, fbase, err);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        jt_g_launches.fetch_add(1, std::memory_order_relaxed);
         JT_CUDA(cudaGetLastError());
         a.fbase = fbase;
     }
@@ -615,7 +512,7 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
     const int main_phase = (flags & JT_NO_BELIEFS) ? JT_PHASE_DIST_MAIN_MESSAGES : JT_PHASE_DIST_MAIN;
     for (const auto& L : p->launches) {
         if (L.phase != JT_PHASE_DIST_PRE && L.phase != main_phase) continue;
-        rc = dispatch(p, L, a, dtype, vec, stream);
+        rc = launchers(flags)->dispatch(p, L, a, dtype, vec, stream);
         if (rc != JT_OK) return rc;
     }
     return JT_OK;
@@ -628,6 +525,7 @@ int jt_marginal(jt_plan* p, int64_t B, int dtype, void* workspace, void* factor_
     const int vec = pick_vec(B, dtype);
     KArgs a = base_args(p, B, workspace, vec);
     a.fout = factor_out;
+    a.flags = flags;
     if (!(flags & JT_NO_BELIEFS)) return run_phase(p, JT_PHASE_MARGINAL, a, dtype, vec, static_cast<cudaStream_t>(stream));
     // outputs straight from psi_C and the incoming messages (the beliefs were not written)
     if (uniform_mode(p, flags)) {
@@ -652,23 +550,13 @@ int jt_propagate(jt_plan* p, const void* factor_tables, int factors_batched, con
     return jt_marginal(p, B, dtype, workspace, factor_out, flags, stream);
 }
 
-int jt_normalize(jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, void* stream_) {
+int jt_normalize(jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, int flags, void* stream) {
     int rc = check_common(p, B, dtype, factor_out);
     if (rc != JT_OK) return rc;
     const int n_out = (int)p->fout_off.size();
     if (n_out == 0) return JT_OK;
     if (n_out > 65535) return fail(JT_ERR_INVALID, "too many output scopes for one launch");
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    dim3 grid((unsigned)((B + kThreads - 1) / kThreads), (unsigned)n_out, 1);
-    if (dtype == JT_F64)
-        jt_normalize_kernel<double><<<grid, kThreads, 0, stream>>>(static_cast<double*>(factor_out), p->d_out,
-                                                                  p->d_out + n_out, B, static_cast<double*>(logz));
-    else
-        jt_normalize_kernel<float><<<grid, kThreads, 0, stream>>>(static_cast<float*>(factor_out), p->d_out,
-                                                                 p->d_out + n_out, B, static_cast<float*>(logz));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    JT_CUDA(cudaGetLastError());
-    return JT_OK;
+    return launchers(flags)->normalize(p, B, dtype, factor_out, logz, static_cast<cudaStream_t>(stream));
 }
 
 int jt_evidence_errors(jt_plan* p, int64_t B, int dtype, void* workspace, void* stream, int64_t* out) {
@@ -710,14 +598,14 @@ int jt_ratio(const void* new_values, const void* old_values, void* out, int64_t 
         jt_ratio_kernel<float><<<(unsigned)blocks, kThreads, 0, stream>>>(
             static_cast<const float*>(new_values), static_cast<const float*>(old_values),
             static_cast<float*>(out), n);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    jt_g_launches.fetch_add(1, std::memory_order_relaxed);
     JT_CUDA(cudaGetLastError());
     return JT_OK;
 }
 
 int jt_contract(const void* const* ops, int n_ops, const int32_t* tables, int64_t n_tab, const int32_t* maps,
                 int64_t n_s, int64_t n_r, int64_t n_slo, int64_t n_rlo, int64_t B, int dtype, void* out,
-                void* stream_) {
+                int flags, void* stream_) {
     if (!ops || n_ops <= 0 || !tables || !maps || !out) return fail(JT_ERR_INVALID, "null argument");
     if (n_s <= 0 || n_r <= 0 || n_slo <= 0 || n_rlo <= 0 || n_s % n_slo || n_r % n_rlo || n_s > 2147483647LL ||
         n_r > 2147483647LL || B <= 0 || n_tab <= 0)
@@ -798,18 +686,8 @@ int jt_contract(const void* const* ops, int n_ops, const int32_t* tables, int64_
     if (blocks > 2147483647LL || gy > 65535) {
         rc = fail(JT_ERR_INVALID, "launch grid exceeds CUDA limits; split the batch");
     } else {
-        dim3 grid((unsigned)blocks, (unsigned)gy, 1);
-        if (dtype == JT_F64) {
-            if (vec == 2) jt_project_kernel<double, 2><<<grid, kThreads, 0, stream>>>(a);
-            else jt_project_kernel<double, 1><<<grid, kThreads, 0, stream>>>(a);
-        } else {
-            if (vec == 4) jt_project_kernel<float, 4><<<grid, kThreads, 0, stream>>>(a);
-            else if (vec == 2) jt_project_kernel<float, 2><<<grid, kThreads, 0, stream>>>(a);
-            else jt_project_kernel<float, 1><<<grid, kThreads, 0, stream>>>(a);
-        }
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) rc = fail(JT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+        a.flags = flags;
+        rc = launchers(flags)->contract(a, blocks, gy, dtype, vec, stream);
     }
     cudaFreeAsync(dev, stream);
     return rc;

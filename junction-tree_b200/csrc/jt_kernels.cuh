@@ -1,76 +1,16 @@
-// Device side of libjt_b200: descriptors, mbarrier/TMA primitives and the sm_100a kernels.
-// Included by jt_abi.cu only.  Task semantics: include/jt_b200.h; schedule: junctiontree/schedule.py.
+// Device side of libjt_b200: mbarrier/TMA primitives, semirings and the sm_100a kernels.
+// Included through jt_launch.cuh by one translation unit per semiring (jt_sr_*.cu).
+// Task semantics: include/jt_b200.h; schedule: junctiontree/schedule.py.
 //
 // Everything on this path is HBM-bound (2 flops per 8..16 bytes), so the kernels are built
 // around coalesced 16-byte accesses on the batch-innermost layout [entry][B]; all index
 // arithmetic is table-driven and warp-uniform.
 #pragma once
 
+#include "jt_host.h"
+
 namespace {
 
-// ------------------------------------------------------------------------------------------
-// error handling
-
-thread_local char g_err[512] = "";
-std::atomic<int64_t> g_launches{0};
-
-int fail(int code, const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err, sizeof(g_err), fmt, ap);
-    va_end(ap);
-    return code;
-}
-
-#define JT_CUDA(call)                                                                      \
-    do {                                                                                   \
-        cudaError_t e_ = (call);                                                           \
-        if (e_ != cudaSuccess)                                                             \
-            return fail(JT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));      \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------
-// device-side descriptors
-
-struct DTask {
-    long long src, out, beta, bel, own;  // entry offsets, -1 = absent
-    int n_s, n_r, n_slo, n_rlo;
-    int src_shi, src_slo, src_rhi, src_rlo;
-    int rmsg_begin, rmsg_end, smsg_begin, smsg_end;
-    int kind, out_space;
-    int flags, pad;       // JT_TF_* (honoured in uniform mode only)
-};
-
-struct DMsg {
-    long long off;    // entry offset (multiplied by B on the device)
-    long long eoff;   // element offset added as is (jt_contract operands; 0 inside a plan)
-    int a_hi, a_lo, b_hi, b_lo;
-    int fid;          // init: factor index
-    int uni;          // message buffer is uniform (read from the uniform workspace in uniform mode)
-};
-
-struct KArgs {
-    const DTask* tasks;   // first task of this launch
-    const DMsg* msgs;     // all messages of the plan
-    const int* tab;       // all index tables
-    const int* prefix;    // [n_tasks + 1] first block of each task for this launch / tile shape
-    void* work;
-    const void* uni;      // uniform workspace (same entry offsets, B = 1), or null
-    void* fout;
-    const void* fin;
-    const int* fbase;     // [F][B] per-instance factor base offsets, or null
-    long long B;          // instances (row pitch in elements)
-    long long Bv;         // B / VEC
-    int n_tasks;
-    int bx_log2;          // batch-tile width in vectors (log2)
-    int sy_log2;          // rows of s per block (log2)
-    int flags;
-    int fin_batched;
-    int uniform;          // honour the uniform-operand flags of tasks and messages
-};
-
-constexpr int kThreads = 256;
-constexpr int kMaxSyLog2 = 12;  // largest chunk of s per block: 4096
 constexpr int kRegMsgs = 4;   // r-dependent messages kept in registers
 constexpr int kUnroll = 4;    // independent row loads in flight per thread
 
@@ -97,16 +37,132 @@ __device__ __forceinline__ void st(T* p, const Pack<T, VEC>& x) {
     *reinterpret_cast<Pack<T, VEC>*>(p) = x;
 }
 
-template <typename T, int VEC>
-__device__ __forceinline__ void mul(Pack<T, VEC>& a, const Pack<T, VEC>& b) {
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) a.v[i] *= b.v[i];
+// ------------------------------------------------------------------------------------------
+// Semirings ("distributive laws", reference sum_product.py:2-3 and junctiontree.py:300-305).
+// A semiring supplies the product (x), the running reduction (+) through an accumulator type,
+// and the output-stage operations.  SrSumProduct generates exactly the multiply / add code the
+// kernels had before they were parameterised.
+//   sum-product  (R, +, *)        marginals, partition function
+//   max-product  (R>=0, max, *)   max-marginals (MAP)
+//   log-sum-exp  (R, logaddexp, +) sum-product on log potentials, underflow-safe
+//   max-sum      (R, max, +)      max-product on log potentials
+
+struct SrSumProduct {
+    template <typename T> struct Acc { T v; };
+    template <typename T> __device__ __forceinline__ static T one() { return T(1); }
+    template <typename T> __device__ __forceinline__ static T mul(T a, T b) { return a * b; }
+    template <typename T> __device__ __forceinline__ static T add(T a, T b) { return a + b; }
+    template <typename T> __device__ __forceinline__ static Acc<T> acc_zero() { return {T(0)}; }
+    template <typename T> __device__ __forceinline__ static void accum(Acc<T>& a, T v) { a.v += v; }
+    template <typename T> __device__ __forceinline__ static void merge(Acc<T>& a, const Acc<T>& b) { a.v += b.v; }
+    template <typename T> __device__ __forceinline__ static T finish(const Acc<T>& a) { return a.v; }
+    // output stage: x (/) z with the (+)-identity mapped to itself, and log of a total
+    template <typename T> __device__ __forceinline__ static T unit(T x, T z) { return z > T(0) ? x / z : T(0); }
+    template <typename T> __device__ __forceinline__ static T log_of(T z) { return log(z); }
+};
+
+struct SrMaxProduct {
+    template <typename T> struct Acc { T v; };
+    template <typename T> __device__ __forceinline__ static T one() { return T(1); }
+    template <typename T> __device__ __forceinline__ static T mul(T a, T b) { return a * b; }
+    template <typename T> __device__ __forceinline__ static T add(T a, T b) { return a > b ? a : b; }
+    template <typename T> __device__ __forceinline__ static Acc<T> acc_zero() { return {T(-INFINITY)}; }
+    template <typename T> __device__ __forceinline__ static void accum(Acc<T>& a, T v) { a.v = v > a.v ? v : a.v; }
+    template <typename T> __device__ __forceinline__ static void merge(Acc<T>& a, const Acc<T>& b) { a.v = b.v > a.v ? b.v : a.v; }
+    template <typename T> __device__ __forceinline__ static T finish(const Acc<T>& a) { return a.v; }
+    template <typename T> __device__ __forceinline__ static T unit(T x, T z) { return z > T(0) ? x / z : T(0); }
+    template <typename T> __device__ __forceinline__ static T log_of(T z) { return log(z); }
+};
+
+struct SrMaxSum {
+    template <typename T> struct Acc { T v; };
+    template <typename T> __device__ __forceinline__ static T one() { return T(0); }
+    template <typename T> __device__ __forceinline__ static T mul(T a, T b) { return a + b; }
+    template <typename T> __device__ __forceinline__ static T add(T a, T b) { return a > b ? a : b; }
+    template <typename T> __device__ __forceinline__ static Acc<T> acc_zero() { return {T(-INFINITY)}; }
+    template <typename T> __device__ __forceinline__ static void accum(Acc<T>& a, T v) { a.v = v > a.v ? v : a.v; }
+    template <typename T> __device__ __forceinline__ static void merge(Acc<T>& a, const Acc<T>& b) { a.v = b.v > a.v ? b.v : a.v; }
+    template <typename T> __device__ __forceinline__ static T finish(const Acc<T>& a) { return a.v; }
+    template <typename T> __device__ __forceinline__ static T unit(T x, T z) { return z > T(-INFINITY) ? x - z : T(-INFINITY); }
+    template <typename T> __device__ __forceinline__ static T log_of(T z) { return z; }
+};
+
+// log-sum-exp: the running reduction keeps (max m, sum s of exp(v - m)), one exp per term
+struct SrLogSumExp {
+    template <typename T> struct Acc { T m, s; };
+    template <typename T> __device__ __forceinline__ static T one() { return T(0); }
+    template <typename T> __device__ __forceinline__ static T mul(T a, T b) { return a + b; }
+    template <typename T> __device__ __forceinline__ static T add(T a, T b) {
+        const T m = a > b ? a : b, n = a > b ? b : a;
+        return n > T(-INFINITY) ? m + log1p(exp(n - m)) : m;
+    }
+    template <typename T> __device__ __forceinline__ static Acc<T> acc_zero() { return {T(-INFINITY), T(0)}; }
+    template <typename T> __device__ __forceinline__ static void accum(Acc<T>& a, T v) {
+        if (v > a.m) {
+            a.s = a.s * exp(a.m - v) + T(1);
+            a.m = v;
+        } else if (v > T(-INFINITY)) {
+            a.s += exp(v - a.m);
+        }
+    }
+    template <typename T> __device__ __forceinline__ static void merge(Acc<T>& a, const Acc<T>& b) {
+        if (b.m > a.m) {
+            a.s = a.s * exp(a.m - b.m) + b.s;
+            a.m = b.m;
+        } else if (b.m > T(-INFINITY)) {
+            a.s += b.s * exp(b.m - a.m);
+        }
+    }
+    template <typename T> __device__ __forceinline__ static T finish(const Acc<T>& a) {
+        return a.s > T(0) ? a.m + log(a.s) : T(-INFINITY);
+    }
+    template <typename T> __device__ __forceinline__ static T unit(T x, T z) { return z > T(-INFINITY) ? x - z : T(-INFINITY); }
+    template <typename T> __device__ __forceinline__ static T log_of(T z) { return z; }
+};
+
+template <typename SR, typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> pack_one() {
+    return pack_fill<T, VEC>(SR::template one<T>());
 }
 
-template <typename T, int VEC>
-__device__ __forceinline__ void add(Pack<T, VEC>& a, const Pack<T, VEC>& b) {
+template <typename SR, typename T, int VEC>
+__device__ __forceinline__ void mul(Pack<T, VEC>& a, const Pack<T, VEC>& b) {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) a.v[i] += b.v[i];
+    for (int i = 0; i < VEC; ++i) a.v[i] = SR::mul(a.v[i], b.v[i]);
+}
+
+// accumulator of one batch vector
+template <typename SR, typename T, int VEC>
+struct AccPack {
+    typename SR::template Acc<T> a[VEC];
+};
+
+template <typename SR, typename T, int VEC>
+__device__ __forceinline__ AccPack<SR, T, VEC> acc_zero() {
+    AccPack<SR, T, VEC> x;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) x.a[i] = SR::template acc_zero<T>();
+    return x;
+}
+
+template <typename SR, typename T, int VEC>
+__device__ __forceinline__ void accum(AccPack<SR, T, VEC>& a, const Pack<T, VEC>& v) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) SR::accum(a.a[i], v.v[i]);
+}
+
+template <typename SR, typename T, int VEC>
+__device__ __forceinline__ void merge(AccPack<SR, T, VEC>& a, const AccPack<SR, T, VEC>& b) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) SR::merge(a.a[i], b.a[i]);
+}
+
+template <typename SR, typename T, int VEC>
+__device__ __forceinline__ Pack<T, VEC> finish(const AccPack<SR, T, VEC>& a) {
+    Pack<T, VEC> p;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) p.v[i] = SR::finish(a.a[i]);
+    return p;
 }
 
 // Locate the task of this block; s0 = first output index of the block's chunk of 2^sy_log2.
@@ -169,44 +225,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 // ------------------------------------------------------------------------------------------
-// evidence slicing (V1): per-instance base offset of every factor table
-//   fbase[f][b] = sum over observed axes k of factor f:  state[b][var_k] * stride_k
-// Pure integer arithmetic; out-of-range states are clamped and counted.
-
-__global__ void __launch_bounds__(kThreads)
-jt_evidence_kernel(const int* __restrict__ evidence, int n_evid, const int* __restrict__ ev_card,
-                   const int* __restrict__ evf_ptr, const int* __restrict__ evf_var,
-                   const int* __restrict__ evf_stride, int n_factors, long long B,
-                   int* __restrict__ fbase, unsigned long long* __restrict__ errors) {
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    const int* row = evidence + b * n_evid;
-    unsigned bad = 0;
-    for (int f = 0; f < n_factors; ++f) {
-        int acc = 0;
-        for (int k = evf_ptr[f]; k < evf_ptr[f + 1]; ++k) {
-            const int var = evf_var[k];
-            int state = row[var];
-            const int card = ev_card[var];
-            if (state < 0 || state >= card) {
-                ++bad;
-                state = state < 0 ? 0 : card - 1;
-            }
-            acc += state * evf_stride[k];
-        }
-        fbase[(long long)f * B + b] = acc;
-    }
-    if (bad) atomicAdd(errors, (unsigned long long)bad);
-}
-
-// ------------------------------------------------------------------------------------------
 // clique initialisation (E0 + V1): psi_C[s][b] = prod_f phi_f[ A_f(s) + fbase[f][b] ]
 
 // A thread owns VEC batch columns and walks its rows of the block's chunk of s, so the
 // per-instance factor offsets (which do not depend on s) are read once and kept in registers.
 constexpr int kInitRegFactors = 6;
 
-template <typename T, int VEC>
+template <typename SR, typename T, int VEC>
 __global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
     typedef Pack<T, VEC> P;
     int s;
@@ -244,17 +269,17 @@ __global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
 
     T* out = static_cast<T*>(a.work) + tk->out * B + col;
     for (; s < s_end; s += rows) {
-        P val = pack_fill<T, VEC>(T(1));
+        P val = pack_one<SR, T, VEC>();
 #pragma unroll
         for (int j = 0; j < kInitRegFactors; ++j) {
             if (j < nf) {
                 const DMsg* m = msgs + f0 + j;
                 const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
                 if (a.fin_batched) {
-                    mul(val, ld<T, VEC>(fin + idx * B + col));
+                    mul<SR>(val, ld<T, VEC>(fin + idx * B + col));
                 } else {
 #pragma unroll
-                    for (int u = 0; u < VEC; ++u) val.v[u] *= __ldg(fin + idx + fb[j][u]);
+                    for (int u = 0; u < VEC; ++u) val.v[u] = SR::mul(val.v[u], __ldg(fin + idx + fb[j][u]));
                 }
             }
         }
@@ -262,11 +287,11 @@ __global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
             const DMsg* m = msgs + f0 + j;
             const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
             if (a.fin_batched) {
-                mul(val, ld<T, VEC>(fin + idx * B + col));
+                mul<SR>(val, ld<T, VEC>(fin + idx * B + col));
             } else {
                 const int* p = a.fbase ? a.fbase + (long long)m->fid * B + col : nullptr;
 #pragma unroll
-                for (int u = 0; u < VEC; ++u) val.v[u] *= __ldg(fin + idx + (p ? p[u] : 0));
+                for (int u = 0; u < VEC; ++u) val.v[u] = SR::mul(val.v[u], __ldg(fin + idx + (p ? p[u] : 0)));
             }
         }
         st<T, VEC>(out + (long long)s * B, val);
@@ -285,9 +310,10 @@ __global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
 // evidence touches, an up-message of an evidence-free subtree) is identical for every instance;
 // it lives once in the uniform workspace (same entry offsets, B = 1) and is broadcast.
 
-template <typename T, int VEC>
+template <typename SR, typename T, int VEC>
 __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
     typedef Pack<T, VEC> P;
+    typedef AccPack<SR, T, VEC> A;
     int s;
     long long bv;
     const DTask* tk = locate(a, s, bv);
@@ -310,15 +336,15 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
     }
 
     // messages that do not depend on r, and the task's own up-message
-    P sm = pack_fill<T, VEC>(T(1));
+    P sm = pack_one<SR, T, VEC>();
     for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
         const DMsg* m = msgs + j;
         const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
-        if (um && m->uni) mul(sm, pack_fill<T, VEC>(__ldg(uni + idx)));
-        else mul(sm, ld<T, VEC>(work + m->eoff + idx * B + col));
+        if (um && m->uni) mul<SR>(sm, pack_fill<T, VEC>(__ldg(uni + idx)));
+        else mul<SR>(sm, ld<T, VEC>(work + m->eoff + idx * B + col));
     }
     const bool has_own = tk->own >= 0;
-    P own = pack_fill<T, VEC>(T(1));
+    P own = pack_one<SR, T, VEC>();
     if (has_own) {
         if (tflags & JT_TF_OWN_UNIFORM) own = pack_fill<T, VEC>(__ldg(uni + tk->own + s));
         else own = ld<T, VEC>(work + (tk->own + s) * B + col);
@@ -357,16 +383,16 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
     const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS);
     T* bptr = work + ((wbeta ? tk->beta : 0) + s_off) * B + col;
     P scale = sm;
-    mul(scale, own);
+    mul<SR>(scale, own);
 
     const int n_rlo = tk->n_rlo;
     const int n_rhi = tk->n_r / n_rlo;
     const int* __restrict__ t_rhi = tab + tk->src_rhi;
     const int* __restrict__ t_rlo = tab + tk->src_rlo;
 
-    P acc[kUnroll];
+    A acc[kUnroll];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) acc[u] = pack_fill<T, VEC>(T(0));
+    for (int u = 0; u < kUnroll; ++u) acc[u] = acc_zero<SR, T, VEC>();
 
     for (int rh = 0; rh < n_rhi; ++rh) {
         const long long e_hi = __ldg(t_rhi + rh);
@@ -382,7 +408,7 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
             for (int u = 0; u < kUnroll; ++u) e[u] = e_hi + __ldg(t_rlo + rl + u);
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                if (!has_src) v[u] = pack_fill<T, VEC>(T(1));
+                if (!has_src) v[u] = pack_one<SR, T, VEC>();
                 else if (src_uni) v[u] = pack_fill<T, VEC>(__ldg(sptr + e[u]));
                 else v[u] = ld<T, VEC>(sptr + e[u] * B);
             }
@@ -400,7 +426,7 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
                             w[u] = ld<T, VEC>(mptr[j] + (mh[j] + __ldg(tab + mblo[j] + rl + u)) * B);
                     }
 #pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) mul(v[u], w[u]);
+                    for (int u = 0; u < kUnroll; ++u) mul<SR>(v[u], w[u]);
                 }
             }
             for (int j = kRegMsgs; j < nr; ++j) {   // rare: more than kRegMsgs r-dependent messages
@@ -410,16 +436,16 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
                     const long long idx = base + __ldg(tab + m->b_lo + rl + u);
-                    if (um && m->uni) mul(v[u], pack_fill<T, VEC>(__ldg(uni + idx)));
-                    else mul(v[u], ld<T, VEC>(work + m->eoff + idx * B + col));
+                    if (um && m->uni) mul<SR>(v[u], pack_fill<T, VEC>(__ldg(uni + idx)));
+                    else mul<SR>(v[u], ld<T, VEC>(work + m->eoff + idx * B + col));
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kUnroll; ++u) add(acc[u], v[u]);
+            for (int u = 0; u < kUnroll; ++u) accum<SR>(acc[u], v[u]);
             if (wbeta) {
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    mul(v[u], scale);
+                    mul<SR>(v[u], scale);
                     st<T, VEC>(bptr + e[u] * B, v[u]);
                 }
             }
@@ -427,27 +453,27 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
         for (; rl < n_rlo; ++rl) {
             const long long e = e_hi + __ldg(t_rlo + rl);
             P v;
-            if (!has_src) v = pack_fill<T, VEC>(T(1));
+            if (!has_src) v = pack_one<SR, T, VEC>();
             else if (src_uni) v = pack_fill<T, VEC>(__ldg(sptr + e));
             else v = ld<T, VEC>(sptr + e * spitch);
 #pragma unroll
             for (int j = 0; j < kRegMsgs; ++j) {
                 if (j < nr) {
                     const long long d = mh[j] + __ldg(tab + mblo[j] + rl);
-                    if ((umask >> j) & 1u) mul(v, pack_fill<T, VEC>(__ldg(mptr[j] + d)));
-                    else mul(v, ld<T, VEC>(mptr[j] + d * B));
+                    if ((umask >> j) & 1u) mul<SR>(v, pack_fill<T, VEC>(__ldg(mptr[j] + d)));
+                    else mul<SR>(v, ld<T, VEC>(mptr[j] + d * B));
                 }
             }
             for (int j = kRegMsgs; j < nr; ++j) {
                 const DMsg* m = msgs + rm0 + j;
                 const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo) +
                                       __ldg(tab + m->b_hi + rh) + __ldg(tab + m->b_lo + rl);
-                if (um && m->uni) mul(v, pack_fill<T, VEC>(__ldg(uni + idx)));
-                else mul(v, ld<T, VEC>(work + m->eoff + idx * B + col));
+                if (um && m->uni) mul<SR>(v, pack_fill<T, VEC>(__ldg(uni + idx)));
+                else mul<SR>(v, ld<T, VEC>(work + m->eoff + idx * B + col));
             }
-            add(acc[0], v);
+            accum<SR>(acc[0], v);
             if (wbeta) {
-                mul(v, scale);
+                mul<SR>(v, scale);
                 st<T, VEC>(bptr + e * B, v);
             }
         }
@@ -455,15 +481,15 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
 
     if (tk->out >= 0) {
         // pairwise combination of the partial sums
-        add(acc[0], acc[1]);
-        add(acc[2], acc[3]);
-        add(acc[0], acc[2]);
-        P o = acc[0];
-        mul(o, sm);
+        merge<SR>(acc[0], acc[1]);
+        merge<SR>(acc[2], acc[3]);
+        merge<SR>(acc[0], acc[2]);
+        P o = finish<SR>(acc[0]);
+        mul<SR>(o, sm);
         T* obase = tk->out_space ? static_cast<T*>(a.fout) : work;
         st<T, VEC>(obase + (tk->out + s) * B + col, o);
         if (tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS)) {
-            mul(o, own);
+            mul<SR>(o, own);
             st<T, VEC>(work + (tk->bel + s) * B + col, o);
         }
     }
@@ -479,7 +505,7 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
 // by a fixed-order tree in shared memory (deterministic).  beta rows are written by whichever
 // lane visits them, exactly once.
 
-template <typename T>
+template <typename SR, typename T>
 __global__ void __launch_bounds__(kThreads) jt_project_splitr_kernel(const KArgs a) {
     __shared__ T red[kThreads];
     const int bx_log2 = a.bx_log2;
@@ -505,16 +531,16 @@ __global__ void __launch_bounds__(kThreads) jt_project_splitr_kernel(const KArgs
         s_hi = s / n_slo;
         s_lo = s - s_hi * n_slo;
     }
-    T sm = T(1);
+    T sm = SR::template one<T>();
     for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
         const DMsg* m = msgs + j;
         const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
-        sm *= (um && m->uni) ? __ldg(uni + idx) : work[m->eoff + idx * B + col];
+        sm = SR::mul(sm, (um && m->uni) ? __ldg(uni + idx) : work[m->eoff + idx * B + col]);
     }
-    T own = T(1);
+    T own = SR::template one<T>();
     if (tk->own >= 0)
         own = (tflags & JT_TF_OWN_UNIFORM) ? __ldg(uni + tk->own + s) : work[(tk->own + s) * B + col];
-    const T scale = sm * own;
+    const T scale = SR::mul(sm, own);
 
     const bool has_src = tk->src >= 0, src_uni = (tflags & JT_TF_SRC_UNIFORM) != 0;
     const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS);
@@ -522,33 +548,33 @@ __global__ void __launch_bounds__(kThreads) jt_project_splitr_kernel(const KArgs
     const int rm0 = tk->rmsg_begin, nr = tk->rmsg_end - rm0;
     const int n_r = tk->n_r, n_rlo = tk->n_rlo;
 
-    T acc = T(0);
+    typename SR::template Acc<T> acc = SR::template acc_zero<T>();
     for (int r = rz; r < n_r; r += RZ) {
         const int rh = r / n_rlo, rl = r - rh * n_rlo;
         const long long e = s_off + __ldg(tab + tk->src_rhi + rh) + __ldg(tab + tk->src_rlo + rl);
-        T v = T(1);
+        T v = SR::template one<T>();
         if (has_src) v = src_uni ? __ldg(uni + tk->src + e) : work[(tk->src + e) * B + col];
         for (int j = 0; j < nr; ++j) {
             const DMsg* m = msgs + rm0 + j;
             const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo) +
                                   __ldg(tab + m->b_hi + rh) + __ldg(tab + m->b_lo + rl);
-            v *= (um && m->uni) ? __ldg(uni + idx) : work[m->eoff + idx * B + col];
+            v = SR::mul(v, (um && m->uni) ? __ldg(uni + idx) : work[m->eoff + idx * B + col]);
         }
-        acc += v;
-        if (wbeta && valid) work[(tk->beta + e) * B + col] = v * scale;
+        SR::accum(acc, v);
+        if (wbeta && valid) work[(tk->beta + e) * B + col] = SR::mul(v, scale);
     }
 
-    red[threadIdx.x] = acc;
+    red[threadIdx.x] = SR::finish(acc);
     __syncthreads();
     for (int stride = RZ >> 1; stride > 0; stride >>= 1) {
-        if (rz < stride) red[threadIdx.x] += red[threadIdx.x + (stride << bx_log2)];
+        if (rz < stride) red[threadIdx.x] = SR::add(red[threadIdx.x], red[threadIdx.x + (stride << bx_log2)]);
         __syncthreads();
     }
     if (rz == 0 && valid && tk->out >= 0) {
-        T o = red[threadIdx.x] * sm;
+        T o = SR::mul(red[threadIdx.x], sm);
         T* obase = tk->out_space ? static_cast<T*>(a.fout) : work;
         obase[(tk->out + s) * B + col] = o;
-        if (tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS)) work[(tk->bel + s) * B + col] = o * own;
+        if (tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS)) work[(tk->bel + s) * B + col] = SR::mul(o, own);
     }
 }
 
@@ -572,7 +598,6 @@ __global__ void __launch_bounds__(kThreads) jt_project_splitr_kernel(const KArgs
 //     16-byte stores.
 
 constexpr int kTmaSlots = 24;     // ring size in rows (one row = 16 bytes x consumer threads)
-constexpr int kTmaMaxRows = 8;    // operands per task supported (src + messages + own)
 constexpr int kUBatch = 32;       // items resolved per batch by the uniform warp
 
 // Shared-memory bookkeeping that follows the ring rows.
@@ -589,11 +614,12 @@ struct TmaAux {
 
 // VPT: 16-byte batch vectors per consumer thread.  The ring holds kTmaSlots / VPT rows of
 // ct * VPT vectors, so the shared-memory footprint (and bytes in flight) is the same.
-template <typename T, int VPT>
+template <typename SR, typename T, int VPT>
 __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const KArgs a) {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int kSlots = kTmaSlots / VPT;
     typedef Pack<T, VEC> P;
+    typedef AccPack<SR, T, VEC> A;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int ct = blockDim.x - 64;                      // consumer threads
@@ -773,7 +799,8 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
                     s_lo = s - s_hi * n_slo;
                 }
                 const int rh = r / n_rlo, rl = r - rh * n_rlo;
-                T item_prod = T(1), s_prod = T(1), own_val = T(1);
+                const T one = SR::template one<T>();
+                T item_prod = one, s_prod = one, own_val = one;
                 if (src_uni) {
                     const int e = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo) +
                                   __ldg(tab + tk->src_rhi + rh) + __ldg(tab + tk->src_rlo + rl);
@@ -786,9 +813,9 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
                         long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
                         if (j < nr) {
                             idx += __ldg(tab + m->b_hi + rh) + __ldg(tab + m->b_lo + rl);
-                            item_prod *= __ldg(uni + idx);
+                            item_prod = SR::mul(item_prod, __ldg(uni + idx));
                         } else {
-                            s_prod *= __ldg(uni + idx);
+                            s_prod = SR::mul(s_prod, __ldg(uni + idx));
                         }
                     }
                 }
@@ -829,6 +856,10 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     struct PV {
         P v[VPT];
     };
+    struct AV {
+        A v[VPT];
+    };
+    const T one = SR::template one<T>();
 
     // The per-item code is instantiated per number of streamed per-item operands and per
     // "writes beliefs", and the (s, r) loops are kept nested, so that an item costs a few dozen
@@ -877,7 +908,7 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
         };
         auto item_value = [&]() {
             PV val;
-            const P u = pack_fill<T, VEC>(any_uni ? uv[0] : T(1));
+            const P u = pack_fill<T, VEC>(any_uni ? uv[0] : one);
 #pragma unroll
             for (int v = 0; v < VPT; ++v) val.v[v] = u;
             const int n = NI >= 0 ? NI : ni;
@@ -887,7 +918,7 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
                     PV x;
                     load_row(sub + k * row_pitch, x);
 #pragma unroll
-                    for (int v = 0; v < VPT; ++v) mul(val.v[v], x.v[v]);
+                    for (int v = 0; v < VPT; ++v) mul<SR>(val.v[v], x.v[v]);
                 }
             }
             return val;
@@ -900,7 +931,7 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
                 for (int v = 0; v < VPT; ++v) {
                     if (active[v]) {
                         P x = val.v[v];
-                        mul(x, scale.v[v]);
+                        mul<SR>(x, scale.v[v]);
                         st<T, VEC>(dst + v * vstep, x);
                     }
                 }
@@ -910,12 +941,16 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
         for (int s = s0; s < s1; ++s) {
             // r = 0: the item that also carries the s-only operands and own
             begin_item();
-            PV acc0 = item_value(), acc1, sm, own, scale;
+            const PV first = item_value();
+            PV sm, own, scale;
+            AV acc0, acc1;
             const unsigned char* srow = sub + ni * row_pitch;
-            const P u1 = pack_fill<T, VEC>(any_uni ? uv[1] : T(1)), u2 = pack_fill<T, VEC>(any_uni ? uv[2] : T(1));
+            const P u1 = pack_fill<T, VEC>(any_uni ? uv[1] : one), u2 = pack_fill<T, VEC>(any_uni ? uv[2] : one);
 #pragma unroll
             for (int v = 0; v < VPT; ++v) {
-                acc1.v[v] = pack_fill<T, VEC>(T(0));
+                acc0.v[v] = acc_zero<SR, T, VEC>();
+                acc1.v[v] = acc_zero<SR, T, VEC>();
+                accum<SR>(acc0.v[v], first.v[v]);
                 sm.v[v] = u1;
                 own.v[v] = u2;
             }
@@ -923,22 +958,22 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
                 PV x;
                 load_row(srow + k * row_pitch, x);
 #pragma unroll
-                for (int v = 0; v < VPT; ++v) mul(sm.v[v], x.v[v]);
+                for (int v = 0; v < VPT; ++v) mul<SR>(sm.v[v], x.v[v]);
             }
             if (own_is_row) load_row(srow + n_sm_rows * row_pitch, own);
 #pragma unroll
             for (int v = 0; v < VPT; ++v) {
                 scale.v[v] = sm.v[v];
-                mul(scale.v[v], own.v[v]);
+                mul<SR>(scale.v[v], own.v[v]);
             }
-            store_beta(acc0, scale);
+            store_beta(first, scale);
             end_item();
             for (int r = 1; r < n_r; ++r) {
                 begin_item();
                 const PV val = item_value();
 #pragma unroll
                 for (int v = 0; v < VPT; ++v) {
-                    if (r & 1) add(acc1.v[v], val.v[v]); else add(acc0.v[v], val.v[v]);
+                    if (r & 1) accum<SR>(acc1.v[v], val.v[v]); else accum<SR>(acc0.v[v], val.v[v]);
                 }
                 store_beta(val, scale);
                 end_item();
@@ -947,12 +982,12 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
 #pragma unroll
                 for (int v = 0; v < VPT; ++v) {
                     if (active[v]) {
-                        P o = acc0.v[v];
-                        add(o, acc1.v[v]);
-                        mul(o, sm.v[v]);
+                        merge<SR>(acc0.v[v], acc1.v[v]);
+                        P o = finish<SR>(acc0.v[v]);
+                        mul<SR>(o, sm.v[v]);
                         st<T, VEC>(optr + (long long)s * B + v * vstep, o);
                         if (wbel) {
-                            mul(o, own.v[v]);
+                            mul<SR>(o, own.v[v]);
                             st<T, VEC>(lptr + (long long)s * B + v * vstep, o);
                         }
                     }
@@ -975,7 +1010,7 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
 }
 
 // Output stage: normalise every output scope per instance; log Z from scope 0.
-template <typename T>
+template <typename SR, typename T>
 __global__ void __launch_bounds__(kThreads)
 jt_normalize_kernel(T* __restrict__ fout, const long long* __restrict__ out_off,
                     const long long* __restrict__ out_size, long long B, T* __restrict__ logz) {
@@ -984,21 +1019,11 @@ jt_normalize_kernel(T* __restrict__ fout, const long long* __restrict__ out_off,
     const int k = blockIdx.y;
     T* col = fout + out_off[k] * B + b;
     const long long n = out_size[k];
-    T z = T(0);
-    for (long long e = 0; e < n; ++e) z += col[e * B];
-    const T inv = z > T(0) ? T(1) / z : T(0);
-    for (long long e = 0; e < n; ++e) col[e * B] *= inv;
-    if (k == 0 && logz) logz[b] = log(z);
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
-jt_ratio_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const T d = b[i];
-        out[i] = d != T(0) ? a[i] / d : T(0);
-    }
+    typename SR::template Acc<T> acc = SR::template acc_zero<T>();
+    for (long long e = 0; e < n; ++e) SR::accum(acc, col[e * B]);
+    const T z = SR::finish(acc);
+    for (long long e = 0; e < n; ++e) col[e * B] = SR::unit(col[e * B], z);
+    if (k == 0 && logz) logz[b] = SR::log_of(z);
 }
 
 static_assert(kUnroll == 4, "the pairwise combination above assumes four partial sums");

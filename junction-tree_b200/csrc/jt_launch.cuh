@@ -1,0 +1,195 @@
+// Launch configuration of the sm_100a kernels, instantiated once per semiring.
+// A translation unit jt_sr_<name>.cu includes this header and expands JT_DEFINE_SEMIRING, which
+// instantiates every kernel of jt_kernels.cuh for that semiring and exports its launcher table
+// (jt_host.h: jt_sr_launchers).
+#pragma once
+
+#include <cstdlib>
+#include <type_traits>
+
+#include "jt_kernels.cuh"
+
+namespace {
+
+// tile shape for a batch of Bv vectors: bx = min(256, pow2ceil(Bv)), sy = 256 / bx
+inline void pick_tile(long long Bv, int& bx_log2, int& sy_log2) {
+    bx_log2 = 0;
+    while ((1LL << bx_log2) < Bv && bx_log2 < 8) ++bx_log2;
+    sy_log2 = 8 - bx_log2;
+}
+
+inline bool tma_enabled() {   // JT_DISABLE_TMA=1 forces the LDG kernel (debugging / A-B timing)
+    static const int enabled = [] {
+        const char* e = getenv("JT_DISABLE_TMA");
+        return (e && e[0] == '1') ? 0 : 1;
+    }();
+    return enabled == 1;
+}
+
+inline int tma_vpt_override() {   // JT_TMA_VPT=1|2 overrides the vectors-per-thread choice (A-B timing)
+    static const int vpt = [] {
+        const char* e = getenv("JT_TMA_VPT");
+        return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
+    }();
+    return vpt;
+}
+
+// Few instances and long reductions with too few output indices to fill the machine: split r.
+inline bool use_splitr(const jt_plan::Launch& L, long long B, bool is_init) {
+    if (is_init || B > 64 || L.max_nr < 128) return false;
+    return L.max_nr >= 4096 || L.total_s * B < 65536;
+}
+
+template <typename SR, int SR_ID>
+struct Launcher {
+    template <typename T, int VPT>
+    static int launch_tma_vpt(const jt_plan* p, const jt_plan::Launch& L, KArgs a, int ct, cudaStream_t stream) {
+        const int tw = ct * VPT;
+        const long long tiles = (a.Bv + tw - 1) / tw;
+        // (s, r) items per CTA: aim at ~8 CTAs per SM over the launch, but keep >= 64 items per CTA
+        // so the pipeline fill is amortised; every task gets its own chunk of s for that item count
+        int j = 6;
+        const long long target = 148LL * 8;
+        while (j < kItemLog2Max && (L.total_items * tiles) >> (j + 1) >= target) ++j;
+        a.sy_log2 = 0;
+        a.bx_log2 = 0;
+        a.tasks = p->d_tasks + L.begin;
+        a.n_tasks = L.end - L.begin;
+        a.prefix = p->d_prefix + L.item_prefix_off[j];
+        const long long gx = L.item_blocks[j];
+        if (gx <= 0) return JT_OK;
+        if (gx > 2147483647LL || tiles > 65535)
+            return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, tiles);
+        // ring rows, then barriers / row indices / scalar operands (TmaAux)
+        const size_t smem = (size_t)(kTmaSlots / VPT) * tw * 16 + sizeof(TmaAux<T>);
+        // opt in to > 48 KB of dynamic shared memory once per (plan = device, instantiation)
+        bool& attr_set = p->tma_attr_set[SR_ID][sizeof(T) == 8 ? 1 : 0][VPT - 1];
+        if (!attr_set) {
+            JT_CUDA(cudaFuncSetAttribute(jt_project_tma_kernel<SR, T, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kTmaSlots * 256 * 16 + (int)sizeof(TmaAux<T>)));
+            attr_set = true;
+        }
+        dim3 grid((unsigned)gx, (unsigned)tiles, 1);
+        // consumer warps + row producer warp + uniform warp
+        jt_project_tma_kernel<SR, T, VPT><<<grid, ct + 64, smem, stream>>>(a);
+        jt_g_launches.fetch_add(1, std::memory_order_relaxed);
+        JT_CUDA(cudaGetLastError());
+        return JT_OK;
+    }
+
+    template <typename T>
+    static int launch_tma(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
+        const int ct = a.Bv >= 256 ? 256 : (a.Bv >= 128 ? 128 : 64);
+        // two vectors per consumer thread once the batch fills 512-vector tiles: halves the control
+        // instructions per byte of the consumers
+        const int forced = tma_vpt_override();
+        const bool two = forced ? forced == 2 : a.Bv >= 512;
+        if (two && ct == 256) return launch_tma_vpt<T, 2>(p, L, a, ct, stream);
+        return launch_tma_vpt<T, 1>(p, L, a, ct, stream);
+    }
+
+    template <typename T, int VEC>
+    static int launch_tasks(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
+        const bool is_init = jt_is_init_phase(L.phase);
+        if (!is_init && VEC * sizeof(T) == 16 && L.tma_ok && a.Bv >= 64 && tma_enabled())
+            return launch_tma<T>(p, L, a, stream);
+        int bx_log2, sy_log2;
+        pick_tile(a.Bv, bx_log2, sy_log2);
+        if (VEC == 1 && use_splitr(L, a.B, is_init)) {
+            // few instances, long reductions: one block per output index, threads split r
+            a.bx_log2 = bx_log2;
+            a.sy_log2 = 0;
+            a.tasks = p->d_tasks + L.begin;
+            a.n_tasks = L.end - L.begin;
+            a.prefix = p->d_prefix + L.prefix_off[0];
+            const long long gx = L.blocks[0];
+            const long long gy = (a.B + (1LL << bx_log2) - 1) >> bx_log2;
+            if (gx <= 0) return JT_OK;
+            if (gx > 2147483647LL || gy > 65535)
+                return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
+            jt_project_splitr_kernel<SR, T><<<dim3((unsigned)gx, (unsigned)gy, 1), kThreads, 0, stream>>>(a);
+            jt_g_launches.fetch_add(1, std::memory_order_relaxed);
+            JT_CUDA(cudaGetLastError());
+            return JT_OK;
+        }
+        if (is_init) {
+            // a thread walks ~32 rows of s so the per-instance factor offsets stay in registers
+            sy_log2 = sy_log2 + 5 > kMaxSyLog2 ? kMaxSyLog2 : sy_log2 + 5;
+            while (sy_log2 > 8 - bx_log2 &&
+                   (L.total_s >> sy_log2) * ((a.Bv + (1LL << bx_log2) - 1) >> bx_log2) < 148 * 4)
+                --sy_log2;
+        }
+        a.bx_log2 = bx_log2;
+        a.sy_log2 = sy_log2;
+        a.tasks = p->d_tasks + L.begin;
+        a.n_tasks = L.end - L.begin;
+        a.prefix = p->d_prefix + L.prefix_off[sy_log2];
+        const long long gx = L.blocks[sy_log2];
+        const long long gy = (a.Bv + (1LL << bx_log2) - 1) >> bx_log2;
+        if (gx <= 0) return JT_OK;
+        if (gx > 2147483647LL || gy > 65535)
+            return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
+        dim3 grid((unsigned)gx, (unsigned)gy, 1);
+        if (is_init)
+            jt_init_kernel<SR, T, VEC><<<grid, kThreads, 0, stream>>>(a);
+        else
+            jt_project_kernel<SR, T, VEC><<<grid, kThreads, 0, stream>>>(a);
+        jt_g_launches.fetch_add(1, std::memory_order_relaxed);
+        JT_CUDA(cudaGetLastError());
+        return JT_OK;
+    }
+
+    static int dispatch(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a_in, int dtype, int vec,
+                        cudaStream_t stream) {
+        KArgs a = a_in;
+        if (use_splitr(L, a.B, jt_is_init_phase(L.phase))) {   // split-r kernel: scalar batch lanes
+            vec = 1;
+            a.Bv = a.B;
+        }
+        if (dtype == JT_F64) {
+            if (vec == 2) return launch_tasks<double, 2>(p, L, a, stream);
+            return launch_tasks<double, 1>(p, L, a, stream);
+        }
+        if (vec == 4) return launch_tasks<float, 4>(p, L, a, stream);
+        if (vec == 2) return launch_tasks<float, 2>(p, L, a, stream);
+        return launch_tasks<float, 1>(p, L, a, stream);
+    }
+
+    static int contract(const KArgs& a, long long blocks, long long gy, int dtype, int vec, cudaStream_t stream) {
+        dim3 grid((unsigned)blocks, (unsigned)gy, 1);
+        if (dtype == JT_F64) {
+            if (vec == 2) jt_project_kernel<SR, double, 2><<<grid, kThreads, 0, stream>>>(a);
+            else jt_project_kernel<SR, double, 1><<<grid, kThreads, 0, stream>>>(a);
+        } else {
+            if (vec == 4) jt_project_kernel<SR, float, 4><<<grid, kThreads, 0, stream>>>(a);
+            else if (vec == 2) jt_project_kernel<SR, float, 2><<<grid, kThreads, 0, stream>>>(a);
+            else jt_project_kernel<SR, float, 1><<<grid, kThreads, 0, stream>>>(a);
+        }
+        jt_g_launches.fetch_add(1, std::memory_order_relaxed);
+        JT_CUDA(cudaGetLastError());
+        return JT_OK;
+    }
+
+    static int normalize(const jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, cudaStream_t stream) {
+        const int n_out = (int)p->fout_off.size();
+        dim3 grid((unsigned)((B + kThreads - 1) / kThreads), (unsigned)n_out, 1);
+        if (dtype == JT_F64)
+            jt_normalize_kernel<SR, double><<<grid, kThreads, 0, stream>>>(
+                static_cast<double*>(factor_out), p->d_out, p->d_out + n_out, B, static_cast<double*>(logz));
+        else
+            jt_normalize_kernel<SR, float><<<grid, kThreads, 0, stream>>>(
+                static_cast<float*>(factor_out), p->d_out, p->d_out + n_out, B, static_cast<float*>(logz));
+        jt_g_launches.fetch_add(1, std::memory_order_relaxed);
+        JT_CUDA(cudaGetLastError());
+        return JT_OK;
+    }
+};
+
+}  // namespace
+
+#define JT_DEFINE_SEMIRING(SR, ID, NAME)                                                       \
+    const jt_sr_launchers* NAME() {                                                            \
+        static const jt_sr_launchers table = {&Launcher<SR, ID>::dispatch, &Launcher<SR, ID>::contract, \
+                                              &Launcher<SR, ID>::normalize};                   \
+        return &table;                                                                         \
+    }

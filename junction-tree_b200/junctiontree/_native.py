@@ -13,7 +13,9 @@ import numpy as np
 JT_OK = 0
 JT_F32, JT_F64 = 0, 1
 JT_SEP_BELIEFS, JT_SKIP_MARGINAL, JT_UNIFORM, JT_NO_UNIFORM, JT_UNIFORM_VALID, JT_NO_BELIEFS = 1, 2, 4, 8, 16, 32
-ABI_VERSION = 6
+# semiring bits of the stage flags (include/jt_b200.h JT_SR_*)
+JT_SR_SUM_PRODUCT, JT_SR_MAX_PRODUCT, JT_SR_LOG_SUM_EXP, JT_SR_MAX_SUM, JT_SR_MASK = 0x000, 0x100, 0x200, 0x300, 0x300
+ABI_VERSION = 7
 
 _LIB_NAME = "libjt_b200.so"
 _lib = None
@@ -48,7 +50,7 @@ SIGNATURES = {
                                     ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_int, ctypes.c_void_p]),
     "jt_normalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
-                                    ctypes.c_void_p, ctypes.c_void_p]),
+                                    ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "jt_evidence_errors": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_void_p, _i64p]),
     "jt_copy_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
@@ -57,7 +59,8 @@ SIGNATURES = {
                                 ctypes.c_int, ctypes.c_void_p]),
     "jt_contract": (ctypes.c_int, [_c_void_pp, ctypes.c_int, _i32p, ctypes.c_int64, _i32p,
                                    ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
-                                   ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+                                   ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                   ctypes.c_void_p]),
 }
 
 
@@ -178,8 +181,8 @@ class DevicePlan:
         check(lib().jt_propagate(self._handle, factors_ptr, int(batched), evidence_ptr, B,
                                  dtype_code(dtype), ws_ptr, out_ptr, flags, stream))
 
-    def normalize(self, B, dtype, out_ptr, logz_ptr, stream):
-        check(lib().jt_normalize(self._handle, B, dtype_code(dtype), out_ptr, logz_ptr, stream))
+    def normalize(self, B, dtype, out_ptr, logz_ptr, stream, flags=0):
+        check(lib().jt_normalize(self._handle, B, dtype_code(dtype), out_ptr, logz_ptr, flags, stream))
 
     def evidence_errors(self, B, dtype, ws_ptr, stream):
         out = ctypes.c_int64()
@@ -187,15 +190,15 @@ class DevicePlan:
         return out.value
 
 
-def contract(op_ptrs, tables, maps, n_s, n_r, n_slo, n_rlo, B, dtype, out_ptr, stream):
-    """``jt_contract``: out[s] = sum_r prod_j op_j[A_j(s) + B_j(r)]."""
+def contract(op_ptrs, tables, maps, n_s, n_r, n_slo, n_rlo, B, dtype, out_ptr, stream, flags=0):
+    """``jt_contract``: out[s] = sum_r prod_j op_j[A_j(s) + B_j(r)] (``flags``: JT_SR_* semiring)."""
     n = len(op_ptrs)
     ops = (ctypes.c_void_p * n)(*op_ptrs)
     tables = np.ascontiguousarray(tables, np.int32)
     maps = np.ascontiguousarray(maps, np.int32)
     check(lib().jt_contract(ops, n, tables.ctypes.data_as(_i32p), tables.size,
                             maps.ctypes.data_as(_i32p), n_s, n_r, n_slo, n_rlo, B, dtype_code(dtype),
-                            out_ptr, stream))
+                            out_ptr, flags, stream))
 
 
 def ratio(new_ptr, old_ptr, out_ptr, n, dtype, stream):

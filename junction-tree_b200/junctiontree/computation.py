@@ -20,6 +20,7 @@ from . import construction as cons
 from . import engine as eng
 from . import schedule as sch
 from .sum_product import SumProduct
+from .semirings import max_product, log_sum_exp, max_sum  # noqa: F401  (other laws, same surface)
 
 # The distributive law used by default.  The reference binds np.einsum here
 # (computation.py:4-9); this build binds the device contraction.
@@ -90,7 +91,7 @@ def _engine_for(tree, clique_vars, shapes):
     return engine, sizes
 
 
-def _compute_beliefs_device(tree, potentials, clique_vars):
+def _compute_beliefs_device(tree, potentials, clique_vars, semiring=0):
     t = eng.require_cuda()
     arrays = [np.asarray(p) for p in potentials]
     for a in arrays:
@@ -109,7 +110,7 @@ def _compute_beliefs_device(tree, potentials, clique_vars):
         full = np.broadcast_to(arrays[c], tuple(plan.node_shape[c]))   # size-1 axes (reference D7)
         host[plan.node_off[c]:plan.node_off[c] + plan.node_size[c]] = full.reshape(-1)
     work[:plan.clique_entries, 0].copy_(t.from_numpy(host))
-    engine.beliefs_from_potentials(work, 1, dtype, ws, sep_beliefs=True)
+    engine.beliefs_from_potentials(work, 1, dtype, ws, sep_beliefs=True, semiring=semiring)
     n_nodes = plan.clique_entries + plan.sep_entries
     flat = work[:n_nodes, 0].cpu().numpy()
     return [
@@ -164,12 +165,14 @@ def compute_beliefs(tree, potentials, clique_vars, dl=sum_product):
     :param potentials: list of numpy arrays for cliques in junction tree
     :param clique_vars: list of variables included in each clique in potentials list
     :param dl: distributive law; the default runs the compiled schedule on the GPU, a
-               ``SumProduct`` built around a user einsum function is called once per operator
+               ``SumProduct`` built around a user einsum function is called once per operator;
+               ``max_product`` / ``log_sum_exp`` / ``max_sum`` run the same schedule in another
+               semiring (``semirings.py``)
     :return: list of numpy arrays defining computed beliefs of each clique
 
     Inputs are never modified (reference ``computation.py:245``); the result lists the clique
     beliefs followed by the separator beliefs in ``clique_vars`` order.
     '''
     if getattr(dl, "on_device", False):
-        return _compute_beliefs_device(tree, potentials, clique_vars)
+        return _compute_beliefs_device(tree, potentials, clique_vars, getattr(dl, "semiring_flag", 0))
     return _compute_beliefs_plugin(tree, potentials, clique_vars, dl)

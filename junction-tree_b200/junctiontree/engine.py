@@ -148,17 +148,18 @@ class Engine:
         return torch().cuda.current_stream().cuda_stream
 
     def propagate(self, factor_dev, batched, evidence_dev, B, dtype, ws=None, sep_beliefs=False,
-                  marginal=True, uniform=True, beliefs=True):
+                  marginal=True, uniform=True, beliefs=True, semiring=0):
         """init + collect + distribute (+ marginal).  Returns ``(ws, factor_out)``; ``factor_out``
         is a ``[fout_entries, B]`` tensor (``None`` when ``marginal`` is False).  ``uniform``:
         compute potentials and messages no evidence reaches once per batch (shared tables only;
-        results are identical)."""
+        results are identical).  ``semiring``: a ``JT_SR_*`` flag (``semirings.py``)."""
         t = require_cuda()
         self.dev.upload()
         if ws is None:
             ws = self.workspace(B, dtype)
         fout = None
         flags = (_native.JT_SEP_BELIEFS if sep_beliefs else 0) | (0 if uniform else _native.JT_NO_UNIFORM)
+        flags |= semiring
         if not beliefs:       # only the outputs are wanted: no clique belief is written
             flags |= _native.JT_NO_BELIEFS
         if marginal:
@@ -171,12 +172,13 @@ class Engine:
                            flags, self._stream())
         return ws, fout
 
-    def beliefs_from_potentials(self, work, B, dtype, ws, sep_beliefs=True):
+    def beliefs_from_potentials(self, work, B, dtype, ws, sep_beliefs=True, semiring=0):
         """collect + distribute on clique potentials already stored in the workspace."""
         self.dev.upload()
         stream = self._stream()
-        self.dev.collect(B, dtype, ws.data_ptr(), 0, stream)
-        self.dev.distribute(B, dtype, ws.data_ptr(), _native.JT_SEP_BELIEFS if sep_beliefs else 0, stream)
+        self.dev.collect(B, dtype, ws.data_ptr(), semiring, stream)
+        self.dev.distribute(B, dtype, ws.data_ptr(), (_native.JT_SEP_BELIEFS if sep_beliefs else 0) | semiring,
+                            stream)
 
     # -----------------------------------------------------------------------------------------
     # views of results
@@ -210,10 +212,10 @@ class BatchPipeline:
     either side.
     """
 
-    def __init__(self, engine, B, dtype, chunk=8192, n_streams=2, normalize=False, log_z=False):
+    def __init__(self, engine, B, dtype, chunk=8192, n_streams=2, normalize=False, log_z=False, semiring=0):
         t = require_cuda()
         self.engine, self.B, self.dtype = engine, int(B), np.dtype(dtype)
-        self.normalize, self.log_z = bool(normalize), bool(log_z)
+        self.normalize, self.log_z, self.semiring = bool(normalize), bool(log_z), int(semiring)
         self.host_logz = t.empty(self.B, dtype=torch_dtype(dtype)).pin_memory() if log_z else None
         plan = engine.plan
         self.chunk = int(min(chunk, B))
@@ -283,6 +285,7 @@ class BatchPipeline:
                     ev_ptr = slot["ev"].data_ptr()
                 # host output only: clique beliefs are never read, so they are not written
                 flags = _native.JT_NO_BELIEFS | (_native.JT_UNIFORM_VALID if id(slot) in primed else 0)
+                flags |= self.semiring
                 primed.add(id(slot))
                 dev.propagate(factor_dev.data_ptr(), False, ev_ptr, n, self.dtype, slot["ws"].data_ptr(),
                               slot["fout"].data_ptr(), flags, stream.cuda_stream)
@@ -290,9 +293,10 @@ class BatchPipeline:
                     # output stage: per-scope normalisation and log Z = log P(evidence)
                     if self.normalize:
                         dev.normalize(n, self.dtype, slot["fout"].data_ptr(),
-                                      slot["logz"].data_ptr() if self.log_z else None, stream.cuda_stream)
+                                      slot["logz"].data_ptr() if self.log_z else None, stream.cuda_stream,
+                                      self.semiring)
                     else:
-                        slot["logz"].copy_(t.log(slot["fout"][:plan.fout_size[0]].sum(dim=0)))
+                        slot["logz"].copy_(_log_total(t, slot["fout"][:plan.fout_size[0]], self.semiring))
                     if self.log_z:
                         self.host_logz[lo:hi].copy_(slot["logz"], non_blocking=True)
                 _native.copy_rows(out_host.data_ptr() + lo * item, self.B * item, slot["fout"].data_ptr(),
@@ -311,8 +315,20 @@ class BatchPipeline:
         return total
 
 
-def _pipeline(self, B, dtype, chunk=8192, n_streams=2, normalize=False, log_z=False):
-    return BatchPipeline(self, B, dtype, chunk, n_streams, normalize, log_z)
+def _log_total(t, scope, semiring):
+    """log of the semiring total of one output scope ``[n, B]`` (plumbing for un-normalised
+    output with log Z; the normalising path does this inside ``jt_normalize``)."""
+    if semiring == _native.JT_SR_MAX_PRODUCT:
+        return t.log(scope.max(dim=0).values)
+    if semiring == _native.JT_SR_LOG_SUM_EXP:
+        return t.logsumexp(scope, dim=0)
+    if semiring == _native.JT_SR_MAX_SUM:
+        return scope.max(dim=0).values
+    return t.log(scope.sum(dim=0))
+
+
+def _pipeline(self, B, dtype, chunk=8192, n_streams=2, normalize=False, log_z=False, semiring=0):
+    return BatchPipeline(self, B, dtype, chunk, n_streams, normalize, log_z, semiring)
 
 
 Engine.pipeline = _pipeline
@@ -327,7 +343,7 @@ class GraphedPropagation:
     The library never synchronises or allocates in the stage calls, so they capture as is.
     """
 
-    def __init__(self, engine, B, dtype, sep_beliefs=False, uniform=True):
+    def __init__(self, engine, B, dtype, sep_beliefs=False, uniform=True, semiring=0):
         t = require_cuda()
         plan = engine.plan
         engine.dev.upload()
@@ -342,7 +358,7 @@ class GraphedPropagation:
         self.fout = t.zeros_like(self.host_out, device="cuda")
         self.ws = engine.new_workspace(self.B, dtype)
         flags = (_native.JT_SEP_BELIEFS if sep_beliefs else 0) | (0 if uniform else _native.JT_NO_UNIFORM)
-        flags |= _native.JT_NO_BELIEFS
+        flags |= _native.JT_NO_BELIEFS | int(semiring)
         ev_ptr = self.evidence.data_ptr() if n_ev else None
 
         def enqueue(stream):
@@ -381,11 +397,11 @@ class GraphedPropagation:
             host[plan.fin_off[f]:plan.fin_off[f] + plan.fin_size[f]] = a.reshape(-1)
 
 
-def _graphed(self, B, dtype, sep_beliefs=False, uniform=True):
-    key = ("graph", int(B), np.dtype(dtype).str, bool(sep_beliefs), bool(uniform))
+def _graphed(self, B, dtype, sep_beliefs=False, uniform=True, semiring=0):
+    key = ("graph", int(B), np.dtype(dtype).str, bool(sep_beliefs), bool(uniform), int(semiring))
     hit = self._workspaces.get(key)
     if hit is None:
-        hit = GraphedPropagation(self, B, dtype, sep_beliefs, uniform)
+        hit = GraphedPropagation(self, B, dtype, sep_beliefs, uniform, semiring)
         self._workspaces[key] = hit
     return hit
 

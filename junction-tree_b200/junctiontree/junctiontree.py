@@ -137,7 +137,7 @@ class CliqueGraph():
             self._engines[key] = hit
         return hit
 
-    def evaluate(self, xs):
+    def evaluate(self, xs, dl=None):
         """Compute maximum clique values based on factor values.
 
         GPU stage ``jt_init``.  Unlike the reference (``junctiontree.py:52-61``) a clique
@@ -152,14 +152,14 @@ class CliqueGraph():
         fdev, _ = engine.factors_to_device(xs, dtype)
         ws = engine.workspace(1, dtype)
         engine.dev.upload()
-        engine.dev.init(fdev.data_ptr(), False, None, 1, dtype, ws.data_ptr(), 0, engine._stream())
+        engine.dev.init(fdev.data_ptr(), False, None, 1, dtype, ws.data_ptr(), _semiring(dl), engine._stream())
         flat = engine.work_view(ws, 1, dtype)[:plan.clique_entries, 0].cpu().numpy()
         return [
             flat[plan.node_off[c]:plan.node_off[c] + plan.node_size[c]].reshape(tuple(plan.node_shape[c])).copy()
             for c in range(plan.n_cliques)
         ]
 
-    def marginalize(self, ys):
+    def marginalize(self, ys, dl=None):
         """Marginalize results for maxcliques to results for factors
 
         For each factor, take the maxclique it belongs to and sum out the axes that don't belong
@@ -184,12 +184,24 @@ class CliqueGraph():
         work[:plan.clique_entries, 0].copy_(t.from_numpy(host))
         fout = t.empty((plan.fout_entries, 1), dtype=eng.torch_dtype(dtype), device="cuda")
         engine.dev.upload()
-        engine.dev.marginal(1, dtype, ws.data_ptr(), fout.data_ptr(), engine._stream(), 0)
+        engine.dev.marginal(1, dtype, ws.data_ptr(), fout.data_ptr(), engine._stream(), _semiring(dl))
         flat = fout[:, 0].cpu().numpy()
         return [
             flat[plan.fout_off[f]:plan.fout_off[f] + plan.fout_size[f]].reshape(tuple(plan.fout_shape[f])).copy()
             for f in range(len(plan.fout_off))
         ]
+
+
+def _semiring(dl):
+    """``JT_SR_*`` flag of a distributive law (``None``: sum-product).  Only laws bound to the
+    device kernels are accepted here; a law built around a user einsum function goes through
+    ``computation.compute_beliefs(..., dl)``."""
+    if dl is None:
+        return 0
+    if not getattr(dl, "on_device", False):
+        raise ValueError("this entry point runs on the device kernels; a distributive law wrapping a user "
+                         "einsum function is only accepted by computation.compute_beliefs")
+    return int(dl.semiring_flag)
 
 
 def _result_dtype(arrays):
@@ -231,12 +243,15 @@ class JunctionTree():
             eff[v] = 1
         return self._engine(eff, evidence_vars, full).plan
 
-    def propagate(self, xs, dtype=None):
+    def propagate(self, xs, dtype=None, dl=None):
         """Run belief propagation on the Junction tree.
 
         :param xs: one array per factor (shape = sizes of the factor's variables; an observed
                    variable is conditioned on by slicing its axis to length 1, reference
                    ``README.md:148-166``)
+        :param dl: distributive law (default sum-product, the only one of the reference,
+                   ``junctiontree.py:300-305``); ``semirings.max_product`` returns max-marginals,
+                   ``log_sum_exp`` / ``max_sum`` work on log potentials
         :return: one array per factor with the same shape: the consistent (unnormalised)
                  clique belief summed down to the factor's variables (reference
                  ``junctiontree.py:297-331``)
@@ -249,7 +264,7 @@ class JunctionTree():
         plan = engine.plan
         # single instance: launch-bound, so the whole call (tables in, propagate, beliefs out)
         # is one CUDA-graph replay over static buffers
-        graphed = engine.graphed(1, dtype)
+        graphed = engine.graphed(1, dtype, semiring=_semiring(dl))
         graphed.set_factors(xs)
         flat = graphed.run().numpy()[:, 0]
         return [
@@ -258,13 +273,17 @@ class JunctionTree():
         ]
 
     def marginals_batch(self, xs, variables=None, evidence_vars=(), evidence=None, batch=None, dtype=None,
-                        normalize=True):
+                        normalize=True, dl=None):
         """Posterior marginals of single variables for a batch of evidence (output stage on the
         device: the step after the propagation path).
 
         :param variables: variables to report (default: every unobserved variable)
         :param normalize: divide each marginal by its sum (the default) or return the
                           unnormalised beliefs, as ``propagate`` does
+        :param dl: distributive law; with ``max_product`` / ``max_sum`` the marginals are
+                   max-marginals (their argmax is the MAP state when it is unique) and ``log_z`` is
+                   the log-probability of the best joint state; ``log_sum_exp`` / ``max_sum`` take
+                   log potentials and return log marginals
         :return: ``(marginals, log_z)``: ``{variable: array [B, size]}`` and ``log_z [B]``, the log
                  of the partition function P(evidence) of every instance -- the quantity the
                  reference computes at the root and discards (``computation.py:90-96``)
@@ -299,7 +318,8 @@ class JunctionTree():
             ev_host = t.from_numpy(np.ascontiguousarray(evidence, dtype=np.int32)).pin_memory()
             if tuple(ev_host.shape) != (B, len(plan.evidence_vars)):
                 raise ValueError("evidence must have shape [%d, %d]" % (B, len(plan.evidence_vars)))
-        pipe = engine.pipeline(B, dtype, chunk=self._chunk_for(engine, B, dtype), normalize=normalize, log_z=True)
+        pipe = engine.pipeline(B, dtype, chunk=self._chunk_for(engine, B, dtype), normalize=normalize, log_z=True,
+                               semiring=_semiring(dl))
         out_host = pipe.host_output()
         pipe.run(fdev, False, ev_host, out_host, sync=True)
         if ev_host is not None and pipe.evidence_errors():
@@ -317,11 +337,11 @@ class JunctionTree():
         chunk = int(max(1, min(8192, B, (free // 3) // max(per_instance, 1))))
         return max(2, chunk - chunk % 2) if chunk > 1 else 1
 
-    def _propagate_streamed(self, engine, fdev, evidence, B, dtype):
+    def _propagate_streamed(self, engine, fdev, evidence, B, dtype, semiring=0):
         """Host-in / host-out propagation of a large batch through ``engine.BatchPipeline``."""
         t = eng.require_cuda()
         plan = engine.plan
-        pipe = engine.pipeline(B, dtype, chunk=self._chunk_for(engine, B, dtype))
+        pipe = engine.pipeline(B, dtype, chunk=self._chunk_for(engine, B, dtype), semiring=semiring)
         ev_host = None
         if plan.evidence_vars:
             if evidence is None:
@@ -341,7 +361,7 @@ class JunctionTree():
         return pipe.factor_views(out_host)
 
     def propagate_batch(self, xs, evidence_vars=(), evidence=None, batch=None, dtype=None,
-                        nodes=False, device_output=False, uniform=True):
+                        nodes=False, device_output=False, uniform=True, dl=None):
         """Many independent propagations over this tree in one pass.
 
         :param xs: factor tables shared by the whole batch (stored shapes, observed axes at full
@@ -356,6 +376,7 @@ class JunctionTree():
                               of NumPy arrays
         :param uniform: with shared tables, compute potentials and up-messages that no evidence
                         reaches once per batch instead of once per instance (same results)
+        :param dl: distributive law (``semirings.py``); default sum-product
         :return: list of ``[B, *factor_shape]`` arrays (observed axes have length 1); with
                  ``nodes=True`` a pair ``(factor_outputs, node_beliefs)``
         """
@@ -383,10 +404,10 @@ class JunctionTree():
         if not nodes and not device_output and not batched and B > _STREAM_THRESHOLD:
             # large batches with host output: stream chunks over two CUDA streams, sized to the
             # free device memory (config 5 needs ~80 MB of workspace per instance)
-            return self._propagate_streamed(engine, fdev, evidence, B, dtype)
+            return self._propagate_streamed(engine, fdev, evidence, B, dtype, _semiring(dl))
         edev = engine.evidence_to_device(evidence, B)
         ws, fout = engine.propagate(fdev, batched, edev, B, dtype, sep_beliefs=nodes, uniform=uniform,
-                                    beliefs=nodes)
+                                    beliefs=nodes, semiring=_semiring(dl))
         if edev is not None:
             bad = engine.dev.evidence_errors(B, dtype, ws.data_ptr(), engine._stream())
             if bad:

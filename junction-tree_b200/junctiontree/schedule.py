@@ -37,7 +37,7 @@ import numpy as np
 from . import construction as cons
 
 MAGIC = 0x324E4C5042544A  # "JTBPLN2"
-VERSION = 6
+VERSION = 7
 
 # header word indices (int64 words); mirrored in include/jt_b200.h
 H_MAGIC, H_VERSION, H_NCLIQUES, H_NSEPS, H_NFACTORS, H_NEVID, H_CLIQUE_ENTRIES, H_SEP_ENTRIES, \

@@ -17,11 +17,12 @@ from . import engine as eng
 from .schedule import _Space, _row_major_strides
 
 
-def device_einsum(*args):
+def device_einsum(*args, semiring=_native.JT_SR_SUM_PRODUCT):
     """GPU einsum in NumPy's interleaved form: ``device_einsum(op0, [i, j], op1, [j], [i])``.
 
     Computes ``out[out_labels] = sum over the other labels of prod_k op_k`` for any number of
-    operands.  Labels are hashable; size-1 axes broadcast (as in ``np.einsum``); a label
+    operands; ``semiring`` (a ``JT_SR_*`` flag) replaces sum and product by another
+    distributive law (max / product, logaddexp / plus, max / plus).  Labels are hashable; size-1 axes broadcast (as in ``np.einsum``); a label
     repeated inside one operand takes its diagonal.  Every output label must occur in an
     operand.  float32 inputs give a float32 result only if all operands are float32 (the
     reference promotes to float64 through its float64 separators, ``junctiontree.py:311-315``).
@@ -85,7 +86,7 @@ def device_einsum(*args):
     out = t.empty(tuple(sizes[l] for l in out_labels), dtype=tdt, device="cuda")
     _native.contract([d.data_ptr() for d in dev_ops], np.concatenate(tables), np.asarray(maps),
                      s_space.n, r_space.n, s_space.n_lo, r_space.n_lo, 1, dtype, out.data_ptr(),
-                     t.cuda.current_stream().cuda_stream)
+                     t.cuda.current_stream().cuda_stream, semiring)
     if any_tensor:
         return out
     return out.cpu().numpy()
@@ -94,17 +95,20 @@ def device_einsum(*args):
 class SumProduct():
     ''' Sum-product distributive law '''
 
+    #: semiring of the device kernels (``JT_SR_*``); subclasses in ``semirings.py`` override it
+    semiring_flag = _native.JT_SR_SUM_PRODUCT
+    name = "sum-product"
+
     def __init__(self, einsum=None, *args, **kwargs):
         # `einsum` is the plugin hook of the reference (sum_product.py:6-12): any function with
         # np.einsum's interleaved calling convention.  None selects the sm_100a contraction.
-        self.func = einsum if einsum is not None else device_einsum
+        self.on_device = einsum is None
+        self.func = einsum if einsum is not None else self._device_einsum
         self.args = args
         self.kwargs = kwargs
 
-    @property
-    def on_device(self):
-        """True when contractions run through libjt_b200 (no injected einsum)."""
-        return self.func is device_einsum
+    def _device_einsum(self, *args):
+        return device_einsum(*args, semiring=self.semiring_flag)
 
     def einsum(self, *args, **kwargs):
         '''Einstein summation ``einsum(op0, vars0, op1, vars1, ..., out_vars)`` with arbitrary

@@ -11,15 +11,16 @@ import numpy as np
 from .ref_fixed import _einsum, slice_evidence
 
 
-def joint_marginals(arrays, var_lists, scopes):
-    """Marginals of prod_k arrays[k] (axes ``var_lists[k]``) onto each scope in ``scopes``."""
+def joint_marginals(arrays, var_lists, scopes, semiring="sum_product"):
+    """Marginals of prod_k arrays[k] (axes ``var_lists[k]``) onto each scope in ``scopes``
+    (``semiring``: the (+, x) pair, see ``ref_fixed.SEMIRINGS``)."""
     ops = []
     for a, vs in zip(arrays, var_lists):
         ops += [np.asarray(a, dtype=np.float64), list(vs)]
-    return [_einsum(*(ops + [list(scope)])) for scope in scopes]
+    return [_einsum(*(ops + [list(scope)]), semiring=semiring) for scope in scopes]
 
 
-def tree_beliefs(tree, node_list, potentials):
+def tree_beliefs(tree, node_list, potentials, semiring="sum_product"):
     """Beliefs of every node of a tree given *node* potentials (clique and separator arrays),
     in node-list order.  Same quantity as ``brute_force_sum_product`` of the reference tests,
     which multiplies every node potential (separator potentials are ones there)."""
@@ -33,12 +34,12 @@ def tree_beliefs(tree, node_list, potentials):
             stack.append(t)
     arrays = [potentials[i] for i in ids]
     var_lists = [node_list[i] for i in ids]
-    return joint_marginals(arrays, var_lists, node_list)
+    return joint_marginals(arrays, var_lists, node_list, semiring)
 
 
-def factor_graph_marginals(factors, values, scopes, evidence=None):
+def factor_graph_marginals(factors, values, scopes, evidence=None, semiring="sum_product"):
     """Marginals of the factor-graph joint onto ``scopes``; observed variables keep a size-1
     axis (evidence slicing semantics of the reference, ``computation.py:11-34``)."""
     if evidence:
         values = slice_evidence(values, factors, evidence)
-    return joint_marginals(values, factors, scopes)
+    return joint_marginals(values, factors, scopes, semiring)

@@ -10,6 +10,8 @@ import numpy as np
 
 from junctiontree import schedule as sch
 
+from .ref_fixed import semiring_ops
+
 
 def _map(tables, hi, lo, n, n_lo):
     x = np.arange(n, dtype=np.int64)
@@ -27,11 +29,13 @@ def evidence_offsets(plan, evidence, B):
 
 
 def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np.float64, uniform=False,
-        beliefs=True):
+        beliefs=True, semiring="sum_product"):
     """Execute the plan.  ``work``: [work_entries, B] (clique potentials preloaded when the init
     phase is skipped); ``factor_in``: flat shared factor tables (fin_entries) or per-instance
     [fin_entries, B].  ``uniform``: keep the potentials of evidence-free cliques once, in the
-    uniform region, as the device does for shared factor tables.  Returns (work, factor_out)."""
+    uniform region, as the device does for shared factor tables.  ``semiring``: the (+, x) pair
+    of the task (``ref_fixed.SEMIRINGS``).  Returns (work, factor_out)."""
+    mul, reduce_, one = semiring_ops(semiring)
     tab = plan.tables
     uni = np.zeros((plan.work_entries, 1), dtype)       # the uniform workspace: same offsets, B = 1
     general = {sch.PHASE_INIT, sch.PHASE_COLLECT}
@@ -65,18 +69,18 @@ def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np
                                       int(t[sch.T_NSLO]), int(t[sch.T_NRLO]))
             if t[sch.T_KIND] == sch.KIND_INIT:
                 to_uni = phase in in_uni_ws
-                val = np.ones((n_s, 1 if to_uni else B), dtype)
+                val = np.full((n_s, 1 if to_uni else B), one, dtype)
                 for m in plan.msgs_arr[t[sch.T_SMSG_BEGIN]:t[sch.T_SMSG_END]]:
                     a = _map(tab, m[sch.M_AHI], m[sch.M_ALO], n_s, n_slo)
                     f = int(m[sch.M_FID])
                     if factor_in.ndim == 2:
                         idx = m[sch.M_OFF] + a
-                        val = val * factor_in[idx, :]
+                        val = mul(val, factor_in[idx, :])
                     else:
                         idx = m[sch.M_OFF] + a[:, None]
                         if fbase is not None and not to_uni:
                             idx = idx + fbase[f][None, :]
-                        val = val * factor_in[idx]
+                        val = mul(val, factor_in[idx])
                 work[t[sch.T_OUT]:t[sch.T_OUT] + n_s] = val
                 continue
             S = _map(tab, t[sch.T_SRC_SHI], t[sch.T_SRC_SLO], n_s, n_slo)
@@ -88,12 +92,12 @@ def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np
             for m in plan.msgs_arr[t[sch.T_RMSG_BEGIN]:t[sch.T_RMSG_END]]:
                 a = _map(tab, m[sch.M_AHI], m[sch.M_ALO], n_s, n_slo)
                 b = _map(tab, m[sch.M_BHI], m[sch.M_BLO], n_r, n_rlo)
-                term = term * buf(m[sch.M_UNI])[m[sch.M_OFF] + a[:, None] + b[None, :]]
-            sm = np.ones((n_s, work.shape[1]), dtype)
+                term = mul(term, buf(m[sch.M_UNI])[m[sch.M_OFF] + a[:, None] + b[None, :]])
+            sm = np.full((n_s, work.shape[1]), one, dtype)
             for m in plan.msgs_arr[t[sch.T_SMSG_BEGIN]:t[sch.T_SMSG_END]]:
                 a = _map(tab, m[sch.M_AHI], m[sch.M_ALO], n_s, n_slo)
-                sm = sm * buf(m[sch.M_UNI])[m[sch.M_OFF] + a]
-            out = term.sum(axis=1) * sm
+                sm = mul(sm, buf(m[sch.M_UNI])[m[sch.M_OFF] + a])
+            out = mul(reduce_(term, 1), sm)
             own = buf(t[sch.T_FLAGS] & sch.TF_OWN_UNIFORM)[t[sch.T_OWN]:t[sch.T_OWN] + n_s].copy() \
                 if t[sch.T_OWN] >= 0 else None
             if t[sch.T_OUT] >= 0:
@@ -102,11 +106,11 @@ def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np
                 else:
                     work[t[sch.T_OUT]:t[sch.T_OUT] + n_s] = out
             if t[sch.T_BEL] >= 0:
-                work[t[sch.T_BEL]:t[sch.T_BEL] + n_s] = out * own
+                work[t[sch.T_BEL]:t[sch.T_BEL] + n_s] = mul(out, own)
             if t[sch.T_BETA] >= 0 and beliefs:
-                beta = term * sm[:, None, :]
+                beta = mul(term, sm[:, None, :])
                 if own is not None:
-                    beta = beta * own[:, None, :]
+                    beta = mul(beta, own[:, None, :])
                 work[t[sch.T_BETA] + S[:, None] + R[None, :]] = beta
     return real_work, fout
 

@@ -19,11 +19,67 @@ reference (tier T1; golden vectors under ``tests/golden/`` were produced by
 
 import numpy as np
 
+#: distributive laws: name -> (product, reduction over axes, multiplicative identity).
+#: "sum_product" is the reference's (np.einsum); the others restate the same contraction with
+#: another (+, x) pair by explicit broadcasting.  The log-domain laws are
+#: pinned through exact identities: log_sum_exp(log x) = log(sum_product(x)) and
+#: max_sum(log x) = log(max_product(x)); max_product is pinned by brute force over the joint.
+SEMIRINGS = ("sum_product", "max_product", "log_sum_exp", "max_sum")
 
-def _einsum(*args):
+
+def _logsumexp(x, axis):
+    m = np.max(x, axis=axis, keepdims=True)
+    m = np.where(np.isfinite(m), m, 0.0)
+    with np.errstate(divide="ignore"):
+        out = np.log(np.sum(np.exp(x - m), axis=axis, keepdims=True)) + m
+    return np.squeeze(out, axis=axis)
+
+
+def semiring_ops(semiring):
+    """(product, reduce(x, axes), one) of a distributive law."""
+    if semiring == "sum_product":
+        return np.multiply, lambda x, ax: np.sum(x, axis=ax), 1.0
+    if semiring == "max_product":
+        return np.multiply, lambda x, ax: np.max(x, axis=ax), 1.0
+    if semiring == "log_sum_exp":
+        return np.add, _logsumexp, 0.0
+    if semiring == "max_sum":
+        return np.add, lambda x, ax: np.max(x, axis=ax), 0.0
+    raise ValueError("unknown semiring %r" % (semiring,))
+
+
+def _semiring_einsum(semiring, args):
+    """The contraction of ``_einsum`` in another semiring: operands are aligned on the union of
+    their labels by broadcasting, combined with the product and reduced over the labels that
+    are not in the output."""
+    mul, reduce_, one = semiring_ops(semiring)
+    operands, label_lists, out_labels = args[0:-1:2], args[1:-1:2], list(args[-1])
+    order = list(out_labels)
+    for labels in label_lists:
+        for v in labels:
+            if v not in order:
+                order.append(v)
+    acc = np.asarray(one, dtype=np.float64)
+    for op, labels in zip(operands, label_lists):
+        op = np.asarray(op, dtype=np.float64)
+        perm = sorted(range(len(labels)), key=lambda i: order.index(labels[i]))
+        op = np.transpose(op, perm)
+        shape = [1] * len(order)
+        for axis_len, i in zip(op.shape, perm):
+            shape[order.index(labels[i])] = axis_len
+        acc = mul(acc, op.reshape(shape))
+    acc = np.broadcast_to(np.asarray(acc, dtype=np.float64), np.shape(acc) if np.ndim(acc) == len(order)
+                          else [1] * len(order))
+    rest = tuple(range(len(out_labels), len(order)))
+    return reduce_(acc, rest) if rest else np.array(acc)
+
+
+def _einsum(*args, semiring="sum_product"):
     """``np.einsum`` in interleaved form with arbitrary hashable labels
     (what ``SumProduct.einsum`` does, reference ``sum_product.py:14-35``)."""
     args = list(args)
+    if semiring != "sum_product":
+        return _semiring_einsum(semiring, args)
     label_lists = args[1::2] + [args[-1]]
     var_map = {}
     for labels in label_lists:
@@ -35,7 +91,7 @@ def _einsum(*args):
     return np.einsum(*args)
 
 
-def evaluate(factors, values, maxcliques, factor_to_maxclique, sizes):
+def evaluate(factors, values, maxcliques, factor_to_maxclique, sizes, semiring="sum_product"):
     """psi_C = product of the assigned factors, broadcast to the full clique shape.
 
     Follows ``CliqueGraph.evaluate`` (reference ``junctiontree.py:203-226``) and its einsum
@@ -49,12 +105,12 @@ def evaluate(factors, values, maxcliques, factor_to_maxclique, sizes):
         args = []
         for f in fs:
             args += [np.asarray(values[f], dtype=np.float64), list(factors[f])]
-        args += [np.ones(shape), list(cvars), list(cvars)]
-        out.append(_einsum(*args))
+        args += [np.full(shape, semiring_ops(semiring)[2]), list(cvars), list(cvars)]
+        out.append(_einsum(*args, semiring=semiring))
     return out
 
 
-def compute_beliefs(tree, potentials, clique_vars):
+def compute_beliefs(tree, potentials, clique_vars, semiring="sum_product"):
     """Shafer-Shenoy collect + distribute, returns beliefs in node order.
 
     Follows ``compute_beliefs`` (reference ``computation.py:37-246``): ``get_message``
@@ -63,6 +119,10 @@ def compute_beliefs(tree, potentials, clique_vars):
     (``:210``).  Iterative instead of recursive (defect D15).
     """
     beliefs = [np.array(p, dtype=np.float64) for p in potentials]
+    mul = semiring_ops(semiring)[0]
+
+    def _einsum(*args):
+        return globals()["_einsum"](*args, semiring=semiring)
 
     # flatten: pre-order list of (clique, parent_sep, [(sep, child) ...])
     nodes = []
@@ -98,7 +158,7 @@ def compute_beliefs(tree, potentials, clique_vars):
             args += [beliefs[c], clique_vars[c], clique_vars[s]]
             message = _einsum(*args)                          # E4
             down[s] = message
-            beliefs[s] = beliefs[s] * message                 # M1 (:210)
+            beliefs[s] = mul(beliefs[s], message)             # M1 (:210)
         args = [beliefs[c], clique_vars[c]]
         for m, mv in incoming:
             args += [m, mv]
@@ -107,21 +167,23 @@ def compute_beliefs(tree, potentials, clique_vars):
     return beliefs
 
 
-def marginalize(factors, maxcliques, factor_to_maxclique, ys):
+def marginalize(factors, maxcliques, factor_to_maxclique, ys, semiring="sum_product"):
     """Per-factor output = clique belief summed to the factor scope, axes in factor order
     (``CliqueGraph.marginalize``, reference ``junctiontree.py:229-274``)."""
     return [
-        _einsum(ys[home], list(maxcliques[home]), list(fv))
+        _einsum(ys[home], list(maxcliques[home]), list(fv), semiring=semiring)
         for fv, home in zip(factors, factor_to_maxclique)
     ]
 
 
-def propagate(tree, separators, maxcliques, factor_to_maxclique, factors, sizes, values):
+def propagate(tree, separators, maxcliques, factor_to_maxclique, factors, sizes, values,
+              semiring="sum_product"):
     """``JunctionTree.propagate`` (reference ``junctiontree.py:297-331``)."""
-    psi = evaluate(factors, values, maxcliques, factor_to_maxclique, sizes)
-    seps = [np.ones(tuple(int(sizes[v]) for v in s)) for s in separators]      # :311-315
-    ys = compute_beliefs(tree, psi + seps, list(maxcliques) + list(separators))
-    return marginalize(factors, maxcliques, factor_to_maxclique, ys), ys
+    psi = evaluate(factors, values, maxcliques, factor_to_maxclique, sizes, semiring)
+    one = semiring_ops(semiring)[2]
+    seps = [np.full(tuple(int(sizes[v]) for v in s), one) for s in separators]      # :311-315
+    ys = compute_beliefs(tree, psi + seps, list(maxcliques) + list(separators), semiring)
+    return marginalize(factors, maxcliques, factor_to_maxclique, ys, semiring), ys
 
 
 def slice_evidence(values, factors, evidence):
@@ -135,7 +197,7 @@ def slice_evidence(values, factors, evidence):
 
 
 def propagate_batch(tree, separators, maxcliques, factor_to_maxclique, factors, sizes, values,
-                    evidence_vars=(), evidence=None, n=None):
+                    evidence_vars=(), evidence=None, n=None, semiring="sum_product"):
     """Loop of independent propagations, one per evidence row.
 
     :param sizes: full sizes; observed variables are sliced to size 1 per instance
@@ -151,7 +213,7 @@ def propagate_batch(tree, separators, maxcliques, factor_to_maxclique, factors, 
     for b in range(B):
         ev = {v: int(evidence[b][i]) for i, v in enumerate(evidence_vars)}
         vals = slice_evidence(values, factors, ev)
-        fo, ys = propagate(tree, separators, maxcliques, factor_to_maxclique, factors, eff, vals)
+        fo, ys = propagate(tree, separators, maxcliques, factor_to_maxclique, factors, eff, vals, semiring)
         if outs is None:
             outs = [np.empty((B,) + o.shape) for o in fo]
             nodes = [np.empty((B,) + y.shape) for y in ys]

@@ -45,3 +45,30 @@ def compile_net(net, with_evidence=True):
     for v in evars:
         eff[v] = 1
     return tree, seps, mc, f2c, eff, evars
+
+
+SEMIRING_NAMES = ("max_product", "log_sum_exp", "max_sum")
+
+
+def semiring_inputs(values, semiring):
+    """Factor tables in the domain of ``semiring``: log potentials for the log-domain laws
+    (zeros become -inf)."""
+    if semiring in ("log_sum_exp", "max_sum"):
+        with np.errstate(divide="ignore"):
+            return [np.log(np.asarray(v, np.float64)) for v in values]
+    return [np.asarray(v, np.float64) for v in values]
+
+
+def assert_close_semiring(got, want, rtol, semiring, what=""):
+    """Product-domain laws: relative error as ``assert_close``.  Log-domain laws: an absolute
+    error of ``rtol`` on a log value *is* a relative error of ``rtol`` on the potential;
+    -inf (probability zero) must match exactly."""
+    if semiring in ("sum_product", "max_product"):
+        return assert_close(got, want, rtol, what)
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, "%s: shape %s vs %s" % (what, got.shape, want.shape)
+    ninf = np.isneginf(want)
+    assert np.array_equal(np.isneginf(got), ninf), "%s: -inf pattern differs" % what
+    g, w = got[~ninf], want[~ninf]
+    assert np.all(np.abs(g - w) <= rtol * np.maximum(1.0, np.abs(w))), \
+        "%s: max abs error %g" % (what, np.max(np.abs(g - w)) if g.size else 0.0)

@@ -47,7 +47,7 @@ def load_traffic(args, uniform):
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
             table = json.load(fh)
         key = "%s:%d:%s:%s" % (args.config, args.batch, args.dtype, "uniform" if uniform else "per_instance")
-        return table[key]["traffic_per_launch"]
+        return table[key]["traffic_per_launch"] if args.semiring == "sum_product" else None
     except Exception:
         return None
 
@@ -115,9 +115,12 @@ class ClockSampler(threading.Thread):
 _CPU = {}
 
 
-def _cpu_setup(name):
+def _cpu_setup(name, semiring="sum_product"):
     from junctiontree import construction as cons
     net = make_net(name)
+    if semiring in ("log_sum_exp", "max_sum"):
+        net["values"] = [np.log(v) for v in net["values"]]
+    _CPU["semiring"] = semiring
     _, mc, f2c = cons.find_triangulation(net["factors"], net["sizes"], net.get("order"))
     tree, seps = cons.construct_junction_tree(mc, net["sizes"])
     _CPU.update(net=net, mc=mc, f2c=f2c, tree=tree, seps=seps)
@@ -128,11 +131,11 @@ def _cpu_work(ev_rows):
     net = _CPU["net"]
     outs, _ = ref_fixed.propagate_batch(_CPU["tree"], _CPU["seps"], _CPU["mc"], _CPU["f2c"], net["factors"],
                                         net["sizes"], net["values"], net.get("evidence_vars", []), ev_rows,
-                                        n=len(ev_rows))
+                                        n=len(ev_rows), semiring=_CPU["semiring"])
     return float(sum(o.sum() for o in outs))
 
 
-def cpu_throughput(name, per_core, repeats=1, pool=None):
+def cpu_throughput(name, per_core, repeats=1, pool=None, semiring="sum_product"):
     """props/s of oracle/ref_fixed.py over all host cores on a bounded sample."""
     import multiprocessing as mp
     os.environ.setdefault("OMP_NUM_THREADS", "1")
@@ -141,7 +144,7 @@ def cpu_throughput(name, per_core, repeats=1, pool=None):
     net = make_net(name)
     own_pool = pool is None
     if own_pool:
-        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_setup, initargs=(name,))
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_setup, initargs=(name, semiring))
     try:
         n = per_core * cores
         ev = wl.draw_evidence(net, n) if net.get("evidence_vars") else np.zeros((n, 0), np.int32)
@@ -166,7 +169,7 @@ def run_reference(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_setup, initargs=(args.config,))
+    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_setup, initargs=(args.config, args.semiring))
     try:
         for _ in range(args.warmup):
             cpu_throughput(args.config, 1, pool=pool)
@@ -353,7 +356,7 @@ def run_gpu(args):
 
     cpu = None
     if not args.skip_cpu:
-        v, cores, n, dt = cpu_throughput(args.config, args.cpu_per_core)
+        v, cores, n, dt = cpu_throughput(args.config, args.cpu_per_core, semiring=args.semiring)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d instances of the same workload (%d per core, %.1f s) through oracle/ref_fixed.py "
                          "(NumPy restatement of the reference), %d processes" % (n, args.cpu_per_core, dt, cores)}

@@ -208,6 +208,58 @@ int jt_copy_rows(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
  * (The propagation schedule itself is division-free; this serves SumProduct.absorb(old=...).) */
 int jt_ratio(const void* new_values, const void* old_values, void* out, int64_t n, int dtype, void* stream);
 
+/*
+ * ---- compile phase on the host, in C++ (no CUDA call; works without a device) ----
+ *
+ * Replaces find_triangulation (junctiontree/construction.py:176-353) and construct_junction_tree
+ * (:522-601) of the reference -- with valid trees (the reference's are not) --
+ * and emits the plan blob that the reference's per-call Python bookkeeping corresponds to
+ * (computation.py:47-96,140-224; junctiontree.py:203-274).  Variables are integers 0..n_vars-1;
+ * the integer is also the tie-break rank.  Lists of variable lists are CSR pairs (ptr[n+1], data).
+ * Results of the two graph calls come back as a list of int32 arrays (jt_ibuf).
+ */
+typedef struct jt_ibuf jt_ibuf;
+int jt_ibuf_count(const jt_ibuf* buf);
+int64_t jt_ibuf_size(const jt_ibuf* buf, int k);           /* -1 when k is out of range */
+const int32_t* jt_ibuf_data(const jt_ibuf* buf, int k);
+void jt_ibuf_destroy(jt_ibuf* buf);
+/* frees a blob returned by jt_plan_build */
+void jt_free(void* blob);
+
+/* Min-fill elimination (ties: cluster weight, then rank; scores always those of the current
+ * graph) or the given elimination `order` (n_order entries, a permutation of the variables that
+ * occur in a factor; NULL for min-fill).  Every elimination cluster not contained in an earlier
+ * one is a maximal clique.  Output arrays: 0 clique_ptr, 1 clique_vars (ascending), 2
+ * factor_to_clique, 3 fill-in edges (pairs), 4 elimination order. */
+int jt_triangulate(int32_t n_vars, const int64_t* var_sizes, int32_t n_factors, const int32_t* factor_ptr,
+                   const int32_t* factor_vars, const int32_t* order, int32_t n_order, jt_ibuf** out);
+
+/* Maximum spanning tree over the clique graph (Kruskal: most shared variables first, then the
+ * lighter clique pair, then the pair index), unconnected components joined by empty separators,
+ * rooted at `root` or, with root = -1, at the centre of the tree (fewest levels).  Output
+ * arrays: 0 sep_ptr, 1 sep_vars (ascending), 2 parent[n_cliques] (-1 for the root), 3
+ * parent_sep[n_cliques] (node id n_cliques + k, -1 for the root), 4 cliques in breadth-first
+ * order.  The children of a clique are its successors in that order, in order of appearance. */
+int jt_junction_tree(int32_t n_vars, const int64_t* var_sizes, int32_t n_cliques, const int32_t* clique_ptr,
+                     const int32_t* clique_vars, int32_t root, jt_ibuf** out);
+
+/* Emit the plan blob (the input of jt_plan_create) for a tree.
+ *   sizes / full_sizes : effective size per variable (1 for observed ones) / size of the stored
+ *                        factor axes (NULL: same as sizes)
+ *   nodes              : cliques 0..n_cliques-1 then separators, axis order as listed
+ *   has_tree = 0       : bare clique graph (init and marginal stages only; n_seps ignored)
+ *   order/parent/parent_sep : the tree as produced by jt_junction_tree
+ *   n_factors = -1     : no factors (collect/distribute on given potentials: compute_beliefs)
+ *   n_outputs = -1     : marginalise to the factor scopes (CliqueGraph.marginalize); otherwise to
+ *                        the listed scopes, each from the smallest clique containing it
+ * Byte-identical to junctiontree/schedule.py Plan.to_blob() of this package for the same input. */
+int jt_plan_build(int32_t n_vars, const int64_t* sizes, const int64_t* full_sizes, int32_t n_cliques,
+                  int32_t n_seps, const int32_t* node_ptr, const int32_t* node_vars, int32_t has_tree,
+                  const int32_t* order, const int32_t* parent, const int32_t* parent_sep, int32_t n_factors,
+                  const int32_t* factor_ptr, const int32_t* factor_vars, const int32_t* factor_to_clique,
+                  int32_t n_evidence, const int32_t* evidence_vars, int32_t n_outputs,
+                  const int32_t* output_ptr, const int32_t* output_vars, void** blob, size_t* nbytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,20 +97,26 @@ struct SrLogSumExp {
         return n > T(-INFINITY) ? m + log1p(exp(n - m)) : m;
     }
     template <typename T> __device__ __forceinline__ static Acc<T> acc_zero() { return {T(-INFINITY), T(0)}; }
+    // one exp per term, taken before the (predicated) case split so that lanes whose terms fall
+    // on different sides of the running maximum do not serialise two exp sequences
     template <typename T> __device__ __forceinline__ static void accum(Acc<T>& a, T v) {
-        if (v > a.m) {
-            a.s = a.s * exp(a.m - v) + T(1);
+        const T d = v - a.m;                    // NaN only when both are -inf: nothing to add
+        const T e = exp(-fabs(d));              // in [0, 1]
+        if (d > T(0)) {                         // new maximum (d = +inf when the accumulator is empty: e = 0)
+            a.s = a.s * e + T(1);
             a.m = v;
-        } else if (v > T(-INFINITY)) {
-            a.s += exp(v - a.m);
+        } else if (d <= T(0)) {                 // v = -inf gives e = 0
+            a.s += e;
         }
     }
     template <typename T> __device__ __forceinline__ static void merge(Acc<T>& a, const Acc<T>& b) {
-        if (b.m > a.m) {
-            a.s = a.s * exp(a.m - b.m) + b.s;
+        const T d = b.m - a.m;
+        const T e = exp(-fabs(d));
+        if (d > T(0)) {
+            a.s = a.s * e + b.s;
             a.m = b.m;
-        } else if (b.m > T(-INFINITY)) {
-            a.s += b.s * exp(b.m - a.m);
+        } else if (d <= T(0)) {
+            a.s += b.s * e;
         }
     }
     template <typename T> __device__ __forceinline__ static T finish(const Acc<T>& a) {

@@ -61,6 +61,20 @@ SIGNATURES = {
                                    ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                    ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
                                    ctypes.c_void_p]),
+    # host compile phase (jt_compile.cpp; no CUDA)
+    "jt_ibuf_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "jt_ibuf_size": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int]),
+    "jt_ibuf_data": (_i32p, [ctypes.c_void_p, ctypes.c_int]),
+    "jt_ibuf_destroy": (None, [ctypes.c_void_p]),
+    "jt_free": (None, [ctypes.c_void_p]),
+    "jt_triangulate": (ctypes.c_int, [ctypes.c_int32, _i64p, ctypes.c_int32, _i32p, _i32p, _i32p, ctypes.c_int32,
+                                      _c_void_pp]),
+    "jt_junction_tree": (ctypes.c_int, [ctypes.c_int32, _i64p, ctypes.c_int32, _i32p, _i32p, ctypes.c_int32,
+                                        _c_void_pp]),
+    "jt_plan_build": (ctypes.c_int, [ctypes.c_int32, _i64p, _i64p, ctypes.c_int32, ctypes.c_int32, _i32p, _i32p,
+                                     ctypes.c_int32, _i32p, _i32p, _i32p, ctypes.c_int32, _i32p, _i32p, _i32p,
+                                     ctypes.c_int32, _i32p, ctypes.c_int32, _i32p, _i32p, _c_void_pp,
+                                     ctypes.POINTER(ctypes.c_size_t)]),
 }
 
 
@@ -209,3 +223,97 @@ def ratio(new_ptr, old_ptr, out_ptr, n, dtype, stream):
 def copy_rows(dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, rows, to_host, stream):
     """``jt_copy_rows``: strided row copy device <-> pinned host on ``stream``."""
     check(lib().jt_copy_rows(dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, rows, int(to_host), stream))
+
+
+# ---------------------------------------------------------------------------------------------
+# host compile phase (jt_compile.cpp): CSR helpers and the three calls
+
+
+def _csr(lists):
+    """(ptr, data) int32 arrays of a list of int lists."""
+    ptr = np.zeros(len(lists) + 1, np.int32)
+    if lists:
+        np.cumsum([len(x) for x in lists], out=ptr[1:])
+    data = np.fromiter((v for x in lists for v in x), np.int32, count=int(ptr[-1]))
+    return ptr, data
+
+
+def _p32(arr):
+    return arr.ctypes.data_as(_i32p) if arr is not None else None
+
+
+def _p64(arr):
+    return arr.ctypes.data_as(_i64p) if arr is not None else None
+
+
+def _take_ibuf(handle):
+    """Copy the int32 arrays of a ``jt_ibuf`` out and destroy it."""
+    try:
+        out = []
+        for k in range(lib().jt_ibuf_count(handle)):
+            n = lib().jt_ibuf_size(handle, k)
+            ptr = lib().jt_ibuf_data(handle, k)
+            out.append(np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n > 0 else np.zeros(0, np.int32))
+        return out
+    finally:
+        lib().jt_ibuf_destroy(handle)
+
+
+def _split(ptr, data):
+    return [data[ptr[i]:ptr[i + 1]].tolist() for i in range(len(ptr) - 1)]
+
+
+def triangulate(var_sizes, factors, order=None):
+    """``jt_triangulate`` on integer variables 0..n-1.  Returns ``(cliques, factor_to_clique,
+    fill_edges, elimination_order)`` as Python lists."""
+    sizes = np.ascontiguousarray(var_sizes, np.int64)
+    fptr, fdata = _csr(factors)
+    order_arr = np.ascontiguousarray(order, np.int32) if order is not None else None
+    handle = ctypes.c_void_p()
+    check(lib().jt_triangulate(len(sizes), _p64(sizes), len(factors), _p32(fptr), _p32(fdata), _p32(order_arr),
+                               len(order_arr) if order_arr is not None else 0, ctypes.byref(handle)))
+    cptr, cvars, f2c, fill, elim = _take_ibuf(handle)
+    return _split(cptr, cvars), f2c.tolist(), fill.reshape(-1, 2).tolist(), elim.tolist()
+
+
+def junction_tree(var_sizes, cliques, root=None):
+    """``jt_junction_tree``.  Returns ``(separators, parent, parent_sep, order)``."""
+    sizes = np.ascontiguousarray(var_sizes, np.int64)
+    cptr, cdata = _csr(cliques)
+    handle = ctypes.c_void_p()
+    check(lib().jt_junction_tree(len(sizes), _p64(sizes), len(cliques), _p32(cptr), _p32(cdata),
+                                 -1 if root is None else int(root), ctypes.byref(handle)))
+    sptr, svars, parent, parent_sep, order = _take_ibuf(handle)
+    return _split(sptr, svars), parent.tolist(), parent_sep.tolist(), order.tolist()
+
+
+def plan_build(sizes, full_sizes, n_cliques, node_vars, tree, factors, factor_to_clique, evidence_vars, outputs):
+    """``jt_plan_build``: the plan blob (bytes) for integer variables.  ``tree`` is ``None`` or
+    ``(order, parent, parent_sep)``; ``factors`` / ``outputs`` may be ``None``."""
+    sizes = np.ascontiguousarray(sizes, np.int64)
+    full = np.ascontiguousarray(full_sizes, np.int64)
+    nptr, ndata = _csr(node_vars)
+    order = parent = parent_sep = None
+    if tree is not None:
+        order, parent, parent_sep = (np.ascontiguousarray(x, np.int32) for x in tree)
+    fptr = fdata = f2c = None
+    n_factors = -1
+    if factors is not None:
+        n_factors = len(factors)
+        fptr, fdata = _csr(factors)
+        f2c = np.ascontiguousarray(factor_to_clique, np.int32)
+    ev = np.ascontiguousarray(evidence_vars, np.int32)
+    optr = odata = None
+    n_out = -1
+    if outputs is not None:
+        n_out = len(outputs)
+        optr, odata = _csr(outputs)
+    blob, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+    check(lib().jt_plan_build(len(sizes), _p64(sizes), _p64(full), n_cliques, len(node_vars) - n_cliques,
+                              _p32(nptr), _p32(ndata), 1 if tree is not None else 0, _p32(order), _p32(parent),
+                              _p32(parent_sep), n_factors, _p32(fptr), _p32(fdata), _p32(f2c), len(ev), _p32(ev),
+                              n_out, _p32(optr), _p32(odata), ctypes.byref(blob), ctypes.byref(nbytes)))
+    try:
+        return ctypes.string_at(blob, nbytes.value)
+    finally:
+        lib().jt_free(blob)

@@ -23,12 +23,26 @@ heap scores, D5 ``raise StopIteration`` in generators).  Here:
   ``PYTHONHASHSEED`` (the reference uses ``tuple(set(..))``, ``construction.py:538``);
 * the tree is rooted at its centre so the level-ordered schedule is as shallow as possible;
 * an explicit elimination ``order`` may be supplied (needed for grid models).
+
+Two implementations of the same algorithms: C++ (``csrc/jt_compile.cpp`` behind
+``jt_triangulate`` / ``jt_junction_tree`` of the C ABI; the default -- 500 variables compile in
+about a millisecond) and the pure-Python ones below (``impl="python"``, or
+``JT_HOST_COMPILE=python`` in the environment), kept as the cross-check: both produce the same
+cliques, the same assignment of factors and the same tree (``tests/test_native_compile.py``).
 """
 
 import heapq
+import os
 from collections import deque
 
 import numpy as np
+
+
+def _use_native(impl):
+    impl = impl or os.environ.get("JT_HOST_COMPILE", "native")
+    if impl not in ("native", "python"):
+        raise ValueError("impl must be 'native' or 'python'")
+    return impl == "native"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -156,17 +170,20 @@ def elimination_clusters(factors, var_sizes, order=None):
     return out_order, clusters, fill_edges
 
 
-def find_triangulation(factors, var_sizes, order=None):
+def find_triangulation(factors, var_sizes, order=None, impl=None):
     """Triangulate the factor graph.
 
     :param factors: list of factors, each a list of variable labels
     :param var_sizes: ``{label: size}``; entries for unused variables are ignored
     :param order: optional elimination order (permutation of the used variables)
+    :param impl: ``"native"`` (C++, default) or ``"python"``
     :return: ``(tri, max_cliques, factor_to_maxclique)`` as the reference
              (``construction.py:176-197``): fill-in edges, maximal cliques (each a list of
              labels sorted by label rank, cf. ``construction.py:347``) and, per factor, the index
              of a maximal clique containing it.
     """
+    if _use_native(impl):
+        return _find_triangulation_native(factors, var_sizes, order)
     variables = _used_variables(factors)
     rank = _label_ranks(variables)
     order_out, clusters, tri = elimination_clusters(factors, var_sizes, order)
@@ -203,6 +220,26 @@ def find_triangulation(factors, var_sizes, order=None):
     return tri, max_cliques, factor_to_maxclique
 
 
+def _find_triangulation_native(factors, var_sizes, order):
+    """``jt_triangulate``: labels are numbered by rank, the C++ side works on the integers."""
+    from . import _native
+    variables = _used_variables(factors)
+    rank = _label_ranks(variables)
+    labels = [None] * len(variables)
+    for v, r in rank.items():
+        labels[r] = v
+    order_ids = None
+    if order is not None:
+        order = list(order)
+        if len(order) != len(variables) or any(v not in rank for v in order) or len(set(order)) != len(order):
+            raise ValueError("order must be a permutation of the variables used by the factors")
+        order_ids = [rank[v] for v in order]
+    cliques, f2c, fill, _ = _native.triangulate([int(var_sizes[v]) for v in labels],
+                                                [[rank[v] for v in f] for f in factors], order_ids)
+    tri = [(labels[a], labels[b]) for a, b in fill]
+    return tri, [[labels[v] for v in c] for c in cliques], f2c
+
+
 # ---------------------------------------------------------------------------------------------
 # junction tree
 
@@ -214,12 +251,13 @@ def _clique_weight(clique, var_sizes):
     return w
 
 
-def construct_junction_tree(cliques, var_sizes, root=None):
+def construct_junction_tree(cliques, var_sizes, root=None, impl=None):
     """Maximum-weight spanning tree over the clique graph, in the reference's nested format.
 
     :param cliques: list of maximal cliques (lists of labels)
     :param var_sizes: ``{label: size}``
     :param root: optional clique index to root the tree at (default: the tree centre)
+    :param impl: ``"native"`` (C++, default) or ``"python"``
     :return: ``(tree, separators)`` -- cf. reference ``construction.py:522-578``.  Separator ``k``
              is node ``len(cliques) + k``.  Empty separators join unconnected components
              (reference ``construction.py:530``).
@@ -227,6 +265,8 @@ def construct_junction_tree(cliques, var_sizes, root=None):
     n = len(cliques)
     if n == 0:
         return [], []
+    if _use_native(impl):
+        return _construct_junction_tree_native(cliques, var_sizes, root)
     all_vars = []
     seen = set()
     for c in cliques:
@@ -331,6 +371,27 @@ def construct_junction_tree(cliques, var_sizes, root=None):
     for u in reversed(order):
         subtree[u] = [u] + [(s_ix, subtree[w]) for s_ix, w in children[u]]
     return subtree[root], separators
+
+
+def _construct_junction_tree_native(cliques, var_sizes, root):
+    """``jt_junction_tree`` and conversion of its arrays to the nested tree format."""
+    from . import _native
+    all_vars = _used_variables(cliques)
+    rank = _label_ranks(all_vars)
+    labels = [None] * len(all_vars)
+    for v, r in rank.items():
+        labels[r] = v
+    n = len(cliques)
+    if root is not None and not 0 <= int(root) < n:
+        raise ValueError("root must be a clique index")
+    seps, parent, parent_sep, order = _native.junction_tree([int(var_sizes[v]) for v in labels],
+                                                            [[rank[v] for v in c] for c in cliques], root)
+    subtree = [None] * n
+    for u in order:
+        subtree[u] = [u]
+    for w in order[1:]:                      # parents precede children: append in order of appearance
+        subtree[parent[w]].append((parent_sep[w], subtree[w]))
+    return subtree[order[0]], [[labels[v] for v in s] for s in seps]
 
 
 # ---------------------------------------------------------------------------------------------

@@ -32,6 +32,8 @@ All device buffers use the batch-innermost layout ``[entry, B]``: the entry offs
 are multiplied by the batch size on the device.
 """
 
+import os
+
 import numpy as np
 
 from . import construction as cons
@@ -178,10 +180,17 @@ class Plan:
     :param full_sizes: ``{var: size}`` of the factor tables as stored (defaults to ``sizes``)
     :param outputs: scopes (variable lists) the marginal stage sums the clique beliefs down to;
                     default: the factor scopes, as ``CliqueGraph.marginalize`` of the reference
+    :param emitter: ``"native"`` (default): tasks and index tables are emitted by the C++ host
+                    compile (``jt_plan_build``, ``csrc/jt_compile.cpp``), tens of times faster on
+                    large trees; ``"python"``: by the ``_build_*`` methods below, the cross-check
+                    (both give byte-identical blobs).  ``JT_PLAN_EMITTER`` overrides the default.
     """
 
     def __init__(self, tree, node_vars, sizes, factors=None, factor_to_clique=None,
-                 evidence_vars=(), full_sizes=None, outputs=None):
+                 evidence_vars=(), full_sizes=None, outputs=None, emitter=None):
+        self.emitter = emitter or os.environ.get("JT_PLAN_EMITTER", "native")
+        if self.emitter not in ("native", "python"):
+            raise ValueError("emitter must be 'native' or 'python'")
         self.tree = tree
         self.node_vars = [list(v) for v in node_vars]
         self.sizes = dict(sizes)
@@ -251,6 +260,17 @@ class Plan:
 
         self._build_factor_tables()
         self._find_uniform_cliques()
+        self.by_depth = {}
+        for c in self.order:
+            self.by_depth.setdefault(self.depth[c], []).append(c)
+        if self.factors is not None:
+            self.clique_factors = [[] for _ in range(self.n_cliques)]
+            for f, home in enumerate(self.factor_to_clique):
+                self.clique_factors[home].append(f)
+        self._blob = None
+        if self.emitter == "native":
+            self._emit_native()
+            return
         self._build_init()
         self._build_collect()
         self._build_distribute()
@@ -260,6 +280,53 @@ class Plan:
         self.tasks_arr = np.asarray(self.tasks, np.int64).reshape(-1, TASK_WORDS)
         self.msgs_arr = np.asarray(self.msgs, np.int64).reshape(-1, MSG_WORDS)
         self.launches_arr = np.asarray(self.launches, np.int64).reshape(-1, LAUNCH_WORDS)
+
+    def _emit_native(self):
+        """Tasks, messages, launches and index tables from ``jt_plan_build`` (C++).  Variables
+        are numbered in order of first appearance; the blob does not depend on the numbering."""
+        from . import _native
+        ids = {}
+
+        def vid(v):
+            if v not in ids:
+                ids[v] = len(ids)
+            return ids[v]
+
+        node_vars = [[vid(v) for v in vs] for vs in self.node_vars]
+        factors = None if self.factors is None else [[vid(v) for v in fv] for fv in self.factors]
+        outputs = None if self.outputs is None else [[vid(v) for v in o] for o in self.outputs]
+        evidence = [vid(v) for v in self.evidence_vars]
+        sizes = [int(self.sizes[v]) for v in ids]
+        full = [int(self.full_sizes.get(v, self.sizes[v])) for v in ids]
+        tree = None
+        if self.tree is not None:
+            tree = (self.order, [self.parent[c] for c in range(self.n_cliques)],
+                    [self.parent_sep[c] for c in range(self.n_cliques)])
+        self._blob = _native.plan_build(sizes, full, self.n_cliques, node_vars, tree, factors,
+                                        self.factor_to_clique, evidence, outputs)
+        words = np.frombuffer(self._blob, np.int64)
+        h = words[:H_WORDS]
+        n_nodes, F, n_out = int(h[H_NCLIQUES] + h[H_NSEPS]), int(h[H_NFACTORS]), int(h[H_NOUT])
+        pos = H_WORDS + 2 * n_nodes + 2 * F + 2 * n_out + int(h[H_NEVID]) + (F + 1 if self.factors is not None else 0) \
+            + 2 * int(h[H_NEVF])
+        # the emitter's own bookkeeping must agree with the metadata computed above
+        expect = (self.n_cliques, self.n_seps, self.clique_entries, self.sep_entries, self.fin_entries,
+                  self.fout_entries, self.uni_entries, self.max_depth)
+        got = tuple(int(h[k]) for k in (H_NCLIQUES, H_NSEPS, H_CLIQUE_ENTRIES, H_SEP_ENTRIES, H_FIN_ENTRIES,
+                                        H_FOUT_ENTRIES, H_UNI_ENTRIES, H_MAXDEPTH))
+        if expect != got:
+            raise RuntimeError("native plan emitter disagrees with the host metadata: %r vs %r" % (got, expect))
+
+        def take(rows, width):
+            nonlocal pos
+            arr = words[pos:pos + rows * width].reshape(rows, width)
+            pos += rows * width
+            return arr
+
+        self.tasks_arr = take(int(h[H_NTASKS]), TASK_WORDS)
+        self.msgs_arr = take(int(h[H_NMSGS]), MSG_WORDS)
+        self.launches_arr = take(int(h[H_NLAUNCHES]), LAUNCH_WORDS)
+        self.tables = np.frombuffer(self._blob, np.int32, count=int(h[H_NTAB]), offset=pos * 8)
 
     # offsets of the three per-separator buffers
     def bel_off(self, sep):
@@ -406,10 +473,7 @@ class Plan:
         per instance (uniform mode)."""
         if self.factors is None:
             return
-        by_clique = [[] for _ in range(self.n_cliques)]
-        for f, home in enumerate(self.factor_to_clique):
-            by_clique[home].append(f)
-        self.clique_factors = by_clique
+        by_clique = self.clique_factors
         begin = len(self.tasks)
         ordered = [c for c in range(self.n_cliques) if self.uniform[c]] + \
                   [c for c in range(self.n_cliques) if not self.uniform[c]]
@@ -442,10 +506,7 @@ class Plan:
 
     def _build_collect(self):
         """E1 + E2: up-messages, deepest level first (uniform subtrees first within a level)."""
-        by_depth = {}
-        for c in self.order:
-            by_depth.setdefault(self.depth[c], []).append(c)
-        self.by_depth = by_depth
+        by_depth = self.by_depth
         for d in range(self.max_depth, 0, -1):
             begin = len(self.tasks)
             ordered = [c for c in by_depth[d] if self.uniform_up[c]] + \
@@ -617,6 +678,8 @@ class Plan:
 
     def to_blob(self):
         """Serialise to the byte blob ``jt_plan_create`` parses (layout: include/jt_b200.h)."""
+        if self._blob is not None:
+            return self._blob
         i64 = lambda xs: np.asarray(xs, np.int64).reshape(-1)
         tables = self.tables
         if tables.size % 2:

@@ -25,9 +25,13 @@
  * Device memory layout: batch-innermost.  A node (clique or separator) with n entries and a
  * batch of B independent propagations is stored as [n][B]; element (entry e, instance b) of the
  * node at entry offset `off` lives at workspace[(off + e) * B + b].  Workspace regions, in
- * entries: [ cliques | separator beliefs | up-messages | down-messages ], i.e. the first
- * (clique_entries + sep_entries) rows are the reference's node order `maxcliques + separators`
- * (junctiontree.py:317-323).  Entry offsets of nodes come from jt_plan_node_range().  After the
+ * entries: [ cliques | separator beliefs | up-messages | down-messages | likelihoods ], i.e. the
+ * first (clique_entries + sep_entries) rows are the reference's node order `maxcliques +
+ * separators` (junctiontree.py:317-323).  The likelihood region (soft evidence; JT_H_LIK_ENTRIES
+ * rows starting at entry clique_entries + 3 * sep_entries, empty for most plans) holds one
+ * [size_v][B] table per soft-evidence variable, in the order given to jt_plan_build; the caller
+ * fills it before jt_init, which multiplies each table into a clique containing the variable --
+ * exactly one more single-variable factor per instance.  Entry offsets of nodes come from jt_plan_node_range().  After the
  * [entries][B] block the workspace holds the per-instance factor offsets (int32 [F][B]), an
  * error counter and the *uniform workspace*: one more copy of the same regions with B = 1
  * (byte offsets: jt_workspace_layout).
@@ -61,7 +65,7 @@
 extern "C" {
 #endif
 
-#define JT_ABI_VERSION 7
+#define JT_ABI_VERSION 8
 
 /* status codes */
 #define JT_OK 0
@@ -104,7 +108,7 @@ enum {
     JT_H_MAGIC, JT_H_VERSION, JT_H_NCLIQUES, JT_H_NSEPS, JT_H_NFACTORS, JT_H_NEVID,
     JT_H_CLIQUE_ENTRIES, JT_H_SEP_ENTRIES, JT_H_FIN_ENTRIES, JT_H_FOUT_ENTRIES, JT_H_NTAB,
     JT_H_NTASKS, JT_H_NMSGS, JT_H_NLAUNCHES, JT_H_MAXDEPTH, JT_H_NEVF, JT_H_ROOT_ENTRIES,
-    JT_H_UNI_ENTRIES, JT_H_NOUT, JT_H_WORDS
+    JT_H_UNI_ENTRIES, JT_H_NOUT, JT_H_LIK_ENTRIES, JT_H_WORDS
 };
 #define JT_TASK_WORDS 24
 enum {
@@ -252,13 +256,16 @@ int jt_junction_tree(int32_t n_vars, const int64_t* var_sizes, int32_t n_cliques
  *   n_factors = -1     : no factors (collect/distribute on given potentials: compute_beliefs)
  *   n_outputs = -1     : marginalise to the factor scopes (CliqueGraph.marginalize); otherwise to
  *                        the listed scopes, each from the smallest clique containing it
+ *   likelihood_vars    : variables with soft evidence (a per-instance likelihood vector in the
+ *                        workspace's likelihood region, see the layout above)
  * Byte-identical to junctiontree/schedule.py Plan.to_blob() of this package for the same input. */
 int jt_plan_build(int32_t n_vars, const int64_t* sizes, const int64_t* full_sizes, int32_t n_cliques,
                   int32_t n_seps, const int32_t* node_ptr, const int32_t* node_vars, int32_t has_tree,
                   const int32_t* order, const int32_t* parent, const int32_t* parent_sep, int32_t n_factors,
                   const int32_t* factor_ptr, const int32_t* factor_vars, const int32_t* factor_to_clique,
                   int32_t n_evidence, const int32_t* evidence_vars, int32_t n_outputs,
-                  const int32_t* output_ptr, const int32_t* output_vars, void** blob, size_t* nbytes);
+                  const int32_t* output_ptr, const int32_t* output_vars, int32_t n_likelihood,
+                  const int32_t* likelihood_vars, void** blob, size_t* nbytes);
 
 #ifdef __cplusplus
 }

@@ -84,13 +84,14 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 size_t dtype_size(int dtype) { return dtype == JT_F64 ? 8 : 4; }
 
 // [ work: entries x B | fbase: F x B int32 | error counter | uniform workspace: entries x 1 ]
+// entries = cliques + 3 x separators (beliefs, up, down) + likelihood tables
 struct WorkspaceLayout {
     size_t work_bytes, fbase_off, err_off, uni_off, total;
 };
 
 WorkspaceLayout workspace_layout(const jt_plan* p, int64_t B, int dtype) {
     WorkspaceLayout w;
-    const int64_t entries = p->hdr[JT_H_CLIQUE_ENTRIES] + 3 * p->hdr[JT_H_SEP_ENTRIES];
+    const int64_t entries = p->hdr[JT_H_CLIQUE_ENTRIES] + 3 * p->hdr[JT_H_SEP_ENTRIES] + p->hdr[JT_H_LIK_ENTRIES];
     w.work_bytes = align_up((size_t)entries * (size_t)B * dtype_size(dtype), 256);
     w.fbase_off = w.work_bytes;
     const size_t fbase = p->hdr[JT_H_NEVID] > 0 ? (size_t)p->hdr[JT_H_NFACTORS] * (size_t)B * 4 : 0;
@@ -238,7 +239,8 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
     take32(p->evf_var, n_evf);
     take32(p->evf_stride, n_evf);
 
-    const int64_t work_entries = w[JT_H_CLIQUE_ENTRIES] + 3 * w[JT_H_SEP_ENTRIES];
+    const int64_t lik_base = w[JT_H_CLIQUE_ENTRIES] + 3 * w[JT_H_SEP_ENTRIES];
+    const int64_t work_entries = lik_base + w[JT_H_LIK_ENTRIES];
     auto bad = [&](const char* what, int64_t i) {
         delete p;
         return fail(JT_ERR_INVALID, "malformed plan: %s (item %lld)", what, (long long)i);
@@ -286,8 +288,10 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
         m.a_hi = (int)q[JT_M_AHI]; m.a_lo = (int)q[JT_M_ALO]; m.b_hi = (int)q[JT_M_BHI]; m.b_lo = (int)q[JT_M_BLO];
         m.fid = (int)q[JT_M_FID]; m.uni = q[JT_M_UNI] ? 1 : 0; m.eoff = 0;
         if (m.off < 0 || m.a_hi < 0 || m.a_lo < 0 || m.b_hi < 0 || m.b_lo < 0 || m.a_hi >= n_tab + 1 ||
-            m.a_lo >= n_tab + 1 || m.b_hi >= n_tab + 1 || m.b_lo >= n_tab + 1 || m.fid >= F)
+            m.a_lo >= n_tab + 1 || m.b_hi >= n_tab + 1 || m.b_lo >= n_tab + 1 || m.fid >= F || m.fid < -2)
             return bad("message descriptor", i);
+        // fid -2: a likelihood table in the workspace (soft evidence operand of an init task)
+        if (m.fid == -2 && (m.off < lik_base || m.off >= work_entries)) return bad("likelihood operand", i);
     }
     p->launches.resize(n_launch);
     for (int64_t i = 0; i < n_launch; ++i, q += JT_LAUNCH_WORDS) {

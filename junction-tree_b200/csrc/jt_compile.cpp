@@ -498,7 +498,9 @@ struct Emitter {
     bool has_tree = false, has_factors = false;
     std::vector<std::vector<int32_t>> node_vars, factors, out_scopes;
     std::vector<int64_t> sizes, full_sizes;
-    std::vector<int32_t> order, parent, parent_sep, depth, f2c, evidence_vars, out_clique;
+    std::vector<int32_t> order, parent, parent_sep, depth, f2c, evidence_vars, out_clique, lik_vars, lik_clique;
+    std::vector<int64_t> lik_off;
+    int64_t lik_base = 0, lik_entries = 0;
     std::vector<std::vector<std::pair<int32_t, int32_t>>> children;   // (sep node, child clique)
     int32_t root = -1, max_depth = 0;
     // derived
@@ -664,6 +666,20 @@ struct Emitter {
         }
         up_base = clique_entries + sep_entries;
         down_base = up_base + sep_entries;
+        // soft evidence: likelihood tables after the down-messages, each multiplied into the
+        // smallest clique containing its variable
+        lik_base = down_base + sep_entries;
+        for (int32_t v : lik_vars) {
+            int32_t best = -1;
+            for (int32_t c = 0; c < n_cliques; ++c)
+                if (std::find(node_vars[c].begin(), node_vars[c].end(), v) != node_vars[c].end() &&
+                    (best < 0 || node_size[c] < node_size[best]))
+                    best = c;
+            if (best < 0) return jt_fail(JT_ERR_INVALID, "host compile: no clique contains a likelihood variable");
+            lik_clique.push_back(best);
+            lik_off.push_back(lik_entries);
+            lik_entries += sizes[v];
+        }
 
         // factor tables, evidence strides, output scopes
         evf_ptr.push_back(0);
@@ -704,6 +720,7 @@ struct Emitter {
             for (size_t f = 0; f < factors.size(); ++f)
                 for (int32_t v : factors[f])
                     if (observed[v]) touched[f2c[f]] = 1;
+            for (int32_t c : lik_clique) touched[c] = 1;      // a likelihood makes the potential per-instance
             if (children[root].empty()) touched[root] = 1;
             for (size_t i = order.size(); i-- > 0;) {
                 const int32_t c = order[i];
@@ -744,6 +761,12 @@ struct Emitter {
                 add_msg(fin_off[f], s_space, nullptr, f, false);
                 clear_strides(factors[f]);
             }
+            for (size_t k = 0; k < lik_vars.size(); ++k)
+                if (lik_clique[k] == c) {                     // fid -2: operand read from the workspace
+                    stride_of[lik_vars[k]] = 1;
+                    add_msg(lik_base + lik_off[k], s_space, nullptr, -2, false);
+                    stride_of[lik_vars[k]] = 0;
+                }
             row[JT_T_SMSG_END] = (int64_t)msgs.size();
             tasks.push_back(std::move(row));
         }
@@ -911,6 +934,7 @@ struct Emitter {
         w[JT_H_ROOT_ENTRIES] = root >= 0 ? node_size[root] : 0;
         w[JT_H_UNI_ENTRIES] = uni_entries;
         w[JT_H_NOUT] = (int64_t)fout_off.size();
+        w[JT_H_LIK_ENTRIES] = lik_entries;
         auto put = [&](const std::vector<int64_t>& v) { w.insert(w.end(), v.begin(), v.end()); };
         put(node_off);
         put(node_size);
@@ -958,7 +982,7 @@ extern "C" int jt_plan_build(int32_t n_vars, const int64_t* sizes, const int64_t
                              int32_t n_factors, const int32_t* factor_ptr, const int32_t* factor_vars,
                              const int32_t* factor_to_clique, int32_t n_evidence, const int32_t* evidence_vars,
                              int32_t n_outputs, const int32_t* output_ptr, const int32_t* output_vars,
-                             void** blob, size_t* nbytes) {
+                             int32_t n_likelihood, const int32_t* likelihood_vars, void** blob, size_t* nbytes) {
     if (!blob || !nbytes) return bad("null output");
     *blob = nullptr;
     *nbytes = 0;
@@ -1040,6 +1064,17 @@ extern "C" int jt_plan_build(int32_t n_vars, const int64_t* sizes, const int64_t
             if (!csr_ok(n_outputs, output_ptr, output_vars, n_vars)) return bad("output scopes");
             read_csr(e.out_scopes, n_outputs, output_ptr, output_vars);
         }
+    }
+    if (n_likelihood < 0 || (n_likelihood > 0 && !likelihood_vars)) return bad("likelihood variables");
+    if (n_likelihood > 0 && (!e.has_factors || !e.has_tree)) return bad("soft evidence needs the factor graph and the tree");
+    for (int32_t i = 0; i < n_likelihood; ++i) {
+        const int32_t v = likelihood_vars[i];
+        if (v < 0 || v >= n_vars) return bad("likelihood variable index");
+        if (std::find(e.evidence_vars.begin(), e.evidence_vars.end(), v) != e.evidence_vars.end())
+            return bad("an observed variable cannot also carry a likelihood");
+        if (std::find(e.lik_vars.begin(), e.lik_vars.end(), v) != e.lik_vars.end())
+            return bad("duplicate likelihood variable");
+        e.lik_vars.push_back(v);
     }
     int rc = e.prepare();
     if (rc != JT_OK) return rc;

@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
         s_lo = s - s_hi * n_slo;
     }
     const T* __restrict__ fin = static_cast<const T*>(a.fin);
+    const T* lik = static_cast<const T*>(a.work);        // likelihood tables (fid -2) live in the workspace
     const int f0 = tk->smsg_begin, nf = tk->smsg_end - f0;
     const bool gather = !a.fin_batched && a.fbase != nullptr;
 
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
     for (int j = 0; j < kInitRegFactors; ++j) {
 #pragma unroll
         for (int u = 0; u < VEC; ++u) fb[j][u] = 0;
-        if (gather && j < nf) {
+        if (gather && j < nf && msgs[f0 + j].fid >= 0) {
             const int* p = a.fbase + (long long)msgs[f0 + j].fid * B + col;
 #pragma unroll
             for (int u = 0; u < VEC; ++u) fb[j][u] = p[u];
@@ -281,7 +282,9 @@ __global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
             if (j < nf) {
                 const DMsg* m = msgs + f0 + j;
                 const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
-                if (a.fin_batched) {
+                if (m->fid < 0) {
+                    mul<SR>(val, ld<T, VEC>(lik + idx * B + col));
+                } else if (a.fin_batched) {
                     mul<SR>(val, ld<T, VEC>(fin + idx * B + col));
                 } else {
 #pragma unroll
@@ -292,7 +295,9 @@ __global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
         for (int j = kInitRegFactors; j < nf; ++j) {   // rare: many factors in one clique
             const DMsg* m = msgs + f0 + j;
             const long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
-            if (a.fin_batched) {
+            if (m->fid < 0) {
+                mul<SR>(val, ld<T, VEC>(lik + idx * B + col));
+            } else if (a.fin_batched) {
                 mul<SR>(val, ld<T, VEC>(fin + idx * B + col));
             } else {
                 const int* p = a.fbase ? a.fbase + (long long)m->fid * B + col : nullptr;

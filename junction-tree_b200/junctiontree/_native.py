@@ -15,7 +15,7 @@ JT_F32, JT_F64 = 0, 1
 JT_SEP_BELIEFS, JT_SKIP_MARGINAL, JT_UNIFORM, JT_NO_UNIFORM, JT_UNIFORM_VALID, JT_NO_BELIEFS = 1, 2, 4, 8, 16, 32
 # semiring bits of the stage flags (include/jt_b200.h JT_SR_*)
 JT_SR_SUM_PRODUCT, JT_SR_MAX_PRODUCT, JT_SR_LOG_SUM_EXP, JT_SR_MAX_SUM, JT_SR_MASK = 0x000, 0x100, 0x200, 0x300, 0x300
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _LIB_NAME = "libjt_b200.so"
 _lib = None
@@ -73,8 +73,8 @@ SIGNATURES = {
                                         _c_void_pp]),
     "jt_plan_build": (ctypes.c_int, [ctypes.c_int32, _i64p, _i64p, ctypes.c_int32, ctypes.c_int32, _i32p, _i32p,
                                      ctypes.c_int32, _i32p, _i32p, _i32p, ctypes.c_int32, _i32p, _i32p, _i32p,
-                                     ctypes.c_int32, _i32p, ctypes.c_int32, _i32p, _i32p, _c_void_pp,
-                                     ctypes.POINTER(ctypes.c_size_t)]),
+                                     ctypes.c_int32, _i32p, ctypes.c_int32, _i32p, _i32p, ctypes.c_int32, _i32p,
+                                     _c_void_pp, ctypes.POINTER(ctypes.c_size_t)]),
 }
 
 
@@ -171,6 +171,7 @@ class DevicePlan:
         out = (ctypes.c_int64 * 4)()
         check(lib().jt_workspace_layout(self._handle, B, dtype_code(dtype), out))
         return {"fbase": out[0], "errors": out[1], "uniform": out[2], "total": out[3]}
+
 
     def upload(self):
         if not self.uploaded:
@@ -287,9 +288,11 @@ def junction_tree(var_sizes, cliques, root=None):
     return _split(sptr, svars), parent.tolist(), parent_sep.tolist(), order.tolist()
 
 
-def plan_build(sizes, full_sizes, n_cliques, node_vars, tree, factors, factor_to_clique, evidence_vars, outputs):
+def plan_build(sizes, full_sizes, n_cliques, node_vars, tree, factors, factor_to_clique, evidence_vars, outputs,
+               likelihood_vars=()):
     """``jt_plan_build``: the plan blob (bytes) for integer variables.  ``tree`` is ``None`` or
     ``(order, parent, parent_sep)``; ``factors`` / ``outputs`` may be ``None``."""
+    lik = np.ascontiguousarray(likelihood_vars, np.int32)
     sizes = np.ascontiguousarray(sizes, np.int64)
     full = np.ascontiguousarray(full_sizes, np.int64)
     nptr, ndata = _csr(node_vars)
@@ -312,7 +315,8 @@ def plan_build(sizes, full_sizes, n_cliques, node_vars, tree, factors, factor_to
     check(lib().jt_plan_build(len(sizes), _p64(sizes), _p64(full), n_cliques, len(node_vars) - n_cliques,
                               _p32(nptr), _p32(ndata), 1 if tree is not None else 0, _p32(order), _p32(parent),
                               _p32(parent_sep), n_factors, _p32(fptr), _p32(fdata), _p32(f2c), len(ev), _p32(ev),
-                              n_out, _p32(optr), _p32(odata), ctypes.byref(blob), ctypes.byref(nbytes)))
+                              n_out, _p32(optr), _p32(odata), len(lik), _p32(lik), ctypes.byref(blob),
+                              ctypes.byref(nbytes)))
     try:
         return ctypes.string_at(blob, nbytes.value)
     finally:

@@ -124,6 +124,34 @@ class Engine:
             host[plan.fin_off[f]:plan.fin_off[f] + plan.fin_size[f]] = a.reshape(-1)
         return t.from_numpy(host).to("cuda"), False
 
+    def likelihoods_host(self, likelihoods, B, dtype, pin=False):
+        """Soft evidence ``{variable: [B, size]}`` as one ``[lik_entries, B]`` host tensor in the
+        layout of the workspace's likelihood region (batch-innermost)."""
+        t = torch()
+        plan = self.plan
+        given = dict(likelihoods or {})
+        if set(given) != set(plan.likelihood_vars):
+            raise ValueError("likelihoods must be given for exactly %r" % (plan.likelihood_vars,))
+        host = np.empty((plan.lik_entries, B), np.dtype(dtype))
+        for k, v in enumerate(plan.likelihood_vars):
+            lam = np.asarray(given[v])
+            if lam.shape != (B, plan.lik_size[k]):
+                raise ValueError("likelihood of %r must have shape [%d, %d], got %s"
+                                 % (v, B, plan.lik_size[k], lam.shape))
+            host[plan.lik_off[k]:plan.lik_off[k] + plan.lik_size[k]] = lam.T
+        out = t.from_numpy(host)
+        return out.pin_memory() if pin else out
+
+    def load_likelihoods(self, ws, B, dtype, likelihoods):
+        """Fill the likelihood region of a workspace (before ``propagate`` / ``jt_init``)."""
+        plan = self.plan
+        if not plan.likelihood_vars:
+            if likelihoods:
+                raise ValueError("this plan was compiled without soft-evidence variables")
+            return
+        host = self.likelihoods_host(likelihoods, B, dtype)
+        self.work_view(ws, B, dtype)[plan.lik_base:plan.lik_base + plan.lik_entries].copy_(host, non_blocking=True)
+
     def evidence_to_device(self, evidence, B):
         t = require_cuda()
         n_ev = len(self.plan.evidence_vars)
@@ -260,13 +288,17 @@ class BatchPipeline:
             for f in range(len(plan.fout_off))
         ]
 
-    def run(self, factor_dev, batched, ev_host, out_host, sync=False):
+    def run(self, factor_dev, batched, ev_host, out_host, sync=False, lik_host=None):
         """Enqueue the whole batch.  ``ev_host``: pinned int32 ``[B, |E|]`` (or None);
-        ``out_host``: tensor from :meth:`host_output`.  The calling stream waits for all chunks."""
+        ``out_host``: tensor from :meth:`host_output`; ``lik_host``: pinned ``[lik_entries, B]``
+        soft evidence (``Engine.likelihoods_host``) when the plan has likelihood variables.  The
+        calling stream waits for all chunks."""
         t = torch()
         plan, dev = self.engine.plan, self.engine.dev
         if batched:
             raise ValueError("per-instance factor tables are not streamed; use Engine.propagate")
+        if (lik_host is None) != (plan.lik_entries == 0):
+            raise ValueError("soft evidence: the plan has %d likelihood entries" % plan.lik_entries)
         cur = t.cuda.current_stream()
         item = self.dtype.itemsize
         for slot in self.slots:
@@ -283,6 +315,10 @@ class BatchPipeline:
                 if self.n_ev:
                     slot["ev"].copy_(ev_host[lo:hi], non_blocking=True)
                     ev_ptr = slot["ev"].data_ptr()
+                if lik_host is not None:          # chunk columns of the likelihood rows -> workspace region
+                    _native.copy_rows(slot["ws"].data_ptr() + plan.lik_base * n * item, n * item,
+                                      lik_host.data_ptr() + lo * item, self.B * item, n * item, plan.lik_entries,
+                                      False, stream.cuda_stream)
                 # host output only: clique beliefs are never read, so they are not written
                 flags = _native.JT_NO_BELIEFS | (_native.JT_UNIFORM_VALID if id(slot) in primed else 0)
                 flags |= self.semiring

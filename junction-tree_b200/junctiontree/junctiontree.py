@@ -124,15 +124,16 @@ class CliqueGraph():
         f2c = self.factor_to_maxclique
         return [f2c[i] for i in range(len(self.factor_graph.factors))]   # list or dict (reference D13)
 
-    def _engine(self, sizes, tree=None, separators=(), evidence_vars=(), full_sizes=None, outputs=None):
+    def _engine(self, sizes, tree=None, separators=(), evidence_vars=(), full_sizes=None, outputs=None,
+                likelihood_vars=()):
         key = (tuple(sizes.get(v) for c in self.maxcliques for v in c), tree is not None,
                tuple(evidence_vars), tuple(tuple(c) for c in self.maxcliques), tuple(self._f2c()),
-               None if outputs is None else tuple(tuple(o) for o in outputs))
+               None if outputs is None else tuple(tuple(o) for o in outputs), tuple(likelihood_vars))
         hit = self._engines.get(key)
         if hit is None:
             node_vars = list(self.maxcliques) + ([list(s) for s in separators] if tree is not None else [])
             plan = sch.Plan(tree, node_vars, sizes, self.factor_graph.factors, self._f2c(),
-                            evidence_vars, full_sizes, outputs)
+                            evidence_vars, full_sizes, outputs, likelihood_vars=likelihood_vars)
             hit = eng.Engine(plan)
             self._engines[key] = hit
         return hit
@@ -192,6 +193,21 @@ class CliqueGraph():
         ]
 
 
+def _likelihood_vars(factor_graph, likelihoods):
+    """Soft-evidence variables in a canonical order (first appearance in the factors)."""
+    if not likelihoods:
+        return []
+    seen = []
+    for fv in factor_graph.factors:
+        for v in fv:
+            if v in likelihoods and v not in seen:
+                seen.append(v)
+    unknown = [v for v in likelihoods if v not in seen]
+    if unknown:
+        raise ValueError("likelihoods on unknown variables %r" % (unknown,))
+    return seen
+
+
 def _semiring(dl):
     """``JT_SR_*`` flag of a distributive law (``None``: sum-product).  Only laws bound to the
     device kernels are accepted here; a law built around a user einsum function goes through
@@ -232,8 +248,9 @@ class JunctionTree():
     # The underlying triangulated clique graph
     clique_tree = attr.ib()
 
-    def _engine(self, sizes, evidence_vars=(), full_sizes=None, outputs=None):
-        return self.clique_tree._engine(sizes, self.tree, self.separators, evidence_vars, full_sizes, outputs)
+    def _engine(self, sizes, evidence_vars=(), full_sizes=None, outputs=None, likelihood_vars=()):
+        return self.clique_tree._engine(sizes, self.tree, self.separators, evidence_vars, full_sizes, outputs,
+                                        likelihood_vars)
 
     def plan(self, evidence_vars=(), sizes=None):
         """The compiled schedule for the current variable sizes (``schedule.Plan``)."""
@@ -273,13 +290,14 @@ class JunctionTree():
         ]
 
     def marginals_batch(self, xs, variables=None, evidence_vars=(), evidence=None, batch=None, dtype=None,
-                        normalize=True, dl=None):
+                        normalize=True, dl=None, likelihoods=None):
         """Posterior marginals of single variables for a batch of evidence (output stage on the
         device: the step after the propagation path).
 
         :param variables: variables to report (default: every unobserved variable)
         :param normalize: divide each marginal by its sum (the default) or return the
                           unnormalised beliefs, as ``propagate`` does
+        :param likelihoods: soft evidence ``{variable: array [B, size]}`` (see ``propagate_batch``)
         :param dl: distributive law; with ``max_product`` / ``max_sum`` the marginals are
                    max-marginals (their argmax is the MAP state when it is unique) and ``log_z`` is
                    the log-probability of the best joint state; ``log_sum_exp`` / ``max_sum`` take
@@ -304,12 +322,14 @@ class JunctionTree():
                         seen.append(v)
             variables = seen
         variables = list(variables)
-        engine = self._engine(eff, evidence_vars, full, outputs=[[v] for v in variables])
+        lik_vars = _likelihood_vars(fg, likelihoods)
+        engine = self._engine(eff, evidence_vars, full, outputs=[[v] for v in variables], likelihood_vars=lik_vars)
         plan = engine.plan
         dtype = np.dtype(dtype) if dtype is not None else _result_dtype(xs)
-        B = int(evidence.shape[0]) if evidence is not None else int(batch) if batch is not None else None
+        B = int(evidence.shape[0]) if evidence is not None else int(batch) if batch is not None else \
+            int(np.shape(likelihoods[lik_vars[0]])[0]) if lik_vars else None
         if B is None:
-            raise ValueError("batch size unknown: give evidence or batch=")
+            raise ValueError("batch size unknown: give evidence, likelihoods or batch=")
         fdev, batched = engine.factors_to_device(xs, dtype)
         ev_host = None
         if plan.evidence_vars:
@@ -321,7 +341,8 @@ class JunctionTree():
         pipe = engine.pipeline(B, dtype, chunk=self._chunk_for(engine, B, dtype), normalize=normalize, log_z=True,
                                semiring=_semiring(dl))
         out_host = pipe.host_output()
-        pipe.run(fdev, False, ev_host, out_host, sync=True)
+        lik_host = engine.likelihoods_host(likelihoods, B, dtype, pin=True) if lik_vars else None
+        pipe.run(fdev, False, ev_host, out_host, sync=True, lik_host=lik_host)
         if ev_host is not None and pipe.evidence_errors():
             raise ValueError("evidence states outside the range of their variable")
         views = pipe.factor_views(out_host)
@@ -337,7 +358,7 @@ class JunctionTree():
         chunk = int(max(1, min(8192, B, (free // 3) // max(per_instance, 1))))
         return max(2, chunk - chunk % 2) if chunk > 1 else 1
 
-    def _propagate_streamed(self, engine, fdev, evidence, B, dtype, semiring=0):
+    def _propagate_streamed(self, engine, fdev, evidence, B, dtype, semiring=0, likelihoods=None):
         """Host-in / host-out propagation of a large batch through ``engine.BatchPipeline``."""
         t = eng.require_cuda()
         plan = engine.plan
@@ -353,15 +374,75 @@ class JunctionTree():
                                  % (B, len(plan.evidence_vars), tuple(ev_host.shape)))
             ev_host = ev_host.pin_memory()
         out_host = pipe.host_output()
-        pipe.run(fdev, False, ev_host, out_host, sync=True)
+        lik_host = engine.likelihoods_host(likelihoods, B, dtype, pin=True) if plan.likelihood_vars else None
+        pipe.run(fdev, False, ev_host, out_host, sync=True, lik_host=lik_host)
         if ev_host is not None:
             bad = pipe.evidence_errors()
             if bad:
                 raise ValueError("%d evidence states are outside the range of their variable" % bad)
         return pipe.factor_views(out_host)
 
+    def propagate_evidence(self, xs, evidence, variables=None, dtype=None, dl=None):
+        """Batched ``apply_evidence`` + ``propagate`` with a different evidence *pattern* per
+        instance (the batched evidence front-end).
+
+        :param xs: factor tables shared by the batch (stored shapes)
+        :param evidence: one ``{variable: state}`` dict per instance -- the argument of the
+                         reference's ``apply_evidence`` (``computation.py:11-34``) -- or, with
+                         ``variables`` given, an int array ``[B, len(variables)]`` in which a
+                         negative entry means "not observed in this instance"
+        :return: a list with one entry per instance: the list of per-factor arrays that
+                 ``tree.propagate([a[0] for a in apply_evidence(xs, factors, evidence[b])])``
+                 returns in the reference (observed axes have length 1)
+
+        Instances are grouped by the set of observed variables; each group is one
+        ``propagate_batch`` call (its own compiled plan, cached per pattern), so the work per
+        instance is that of the sliced network.  The per-instance arrays are views of the
+        group results.
+        """
+        fg = self.clique_tree.factor_graph
+        rank = {}
+        for fv in fg.factors:
+            for v in fv:
+                rank.setdefault(v, len(rank))
+        groups = {}
+        if variables is not None:
+            variables = list(variables)
+            for v in variables:
+                if v not in rank:
+                    raise ValueError("evidence on unknown variable %r" % (v,))
+            table = np.asarray(evidence)
+            if table.ndim != 2 or table.shape[1] != len(variables):
+                raise ValueError("evidence must have shape [B, %d]" % len(variables))
+            B = table.shape[0]
+            masks, inverse = np.unique(table >= 0, axis=0, return_inverse=True)
+            inverse = np.asarray(inverse).reshape(-1)
+            for g, mask in enumerate(masks):
+                rows = np.nonzero(inverse == g)[0]
+                cols = [j for j in np.nonzero(mask)[0].tolist()]
+                cols.sort(key=lambda j: rank[variables[j]])
+                groups[tuple(variables[j] for j in cols)] = (rows, np.ascontiguousarray(table[rows][:, cols], np.int32))
+        else:
+            evidence = list(evidence)
+            B = len(evidence)
+            members = {}
+            for b, ev in enumerate(evidence):
+                for v in ev:
+                    if v not in rank:
+                        raise ValueError("evidence on unknown variable %r" % (v,))
+                members.setdefault(tuple(sorted(ev, key=rank.__getitem__)), []).append(b)
+            for key, rows in members.items():
+                states = np.asarray([[evidence[b][v] for v in key] for b in rows], np.int32).reshape(len(rows), len(key))
+                groups[key] = (np.asarray(rows), states)
+        result = [None] * B
+        for key, (rows, states) in groups.items():
+            outs = self.propagate_batch(xs, list(key), states if key else None, batch=len(rows), dtype=dtype, dl=dl)
+            for j, b in enumerate(rows.tolist()):
+                result[b] = [o[j] for o in outs]
+        return result
+
     def propagate_batch(self, xs, evidence_vars=(), evidence=None, batch=None, dtype=None,
-                        nodes=False, device_output=False, uniform=True, dl=None):
+                        nodes=False, device_output=False, uniform=True, dl=None, likelihoods=None):
         """Many independent propagations over this tree in one pass.
 
         :param xs: factor tables shared by the whole batch (stored shapes, observed axes at full
@@ -377,6 +458,10 @@ class JunctionTree():
         :param uniform: with shared tables, compute potentials and up-messages that no evidence
                         reaches once per batch instead of once per instance (same results)
         :param dl: distributive law (``semirings.py``); default sum-product
+        :param likelihoods: soft evidence ``{variable: array [B, size]}``: a per-instance likelihood
+                            vector multiplied into the model, i.e. one more single-variable factor
+                            per instance (log-likelihoods for the log-domain laws).  A one-hot
+                            vector is hard evidence without slicing the axis.
         :return: list of ``[B, *factor_shape]`` arrays (observed axes have length 1); with
                  ``nodes=True`` a pair ``(factor_outputs, node_beliefs)``
         """
@@ -389,11 +474,14 @@ class JunctionTree():
         eff = dict(full)
         for v in evidence_vars:
             eff[v] = 1
-        engine = self._engine(eff, evidence_vars, full)
+        lik_vars = _likelihood_vars(fg, likelihoods)
+        engine = self._engine(eff, evidence_vars, full, likelihood_vars=lik_vars)
         plan = engine.plan
         dtype = np.dtype(dtype) if dtype is not None else _result_dtype(xs)
         if evidence is not None:
             B = int(evidence.shape[0])
+        elif lik_vars:
+            B = int(np.shape(likelihoods[lik_vars[0]])[0])
         elif per_instance:
             B = int(np.shape(xs[0])[0])
         elif batch is not None:
@@ -404,9 +492,11 @@ class JunctionTree():
         if not nodes and not device_output and not batched and B > _STREAM_THRESHOLD:
             # large batches with host output: stream chunks over two CUDA streams, sized to the
             # free device memory (config 5 needs ~80 MB of workspace per instance)
-            return self._propagate_streamed(engine, fdev, evidence, B, dtype, _semiring(dl))
+            return self._propagate_streamed(engine, fdev, evidence, B, dtype, _semiring(dl), likelihoods)
         edev = engine.evidence_to_device(evidence, B)
-        ws, fout = engine.propagate(fdev, batched, edev, B, dtype, sep_beliefs=nodes, uniform=uniform,
+        ws = engine.workspace(B, dtype)
+        engine.load_likelihoods(ws, B, dtype, likelihoods)
+        ws, fout = engine.propagate(fdev, batched, edev, B, dtype, ws=ws, sep_beliefs=nodes, uniform=uniform,
                                     beliefs=nodes, semiring=_semiring(dl))
         if edev is not None:
             bad = engine.dev.evidence_errors(B, dtype, ws.data_ptr(), engine._stream())

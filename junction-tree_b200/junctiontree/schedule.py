@@ -39,12 +39,12 @@ import numpy as np
 from . import construction as cons
 
 MAGIC = 0x324E4C5042544A  # "JTBPLN2"
-VERSION = 7
+VERSION = 8
 
 # header word indices (int64 words); mirrored in include/jt_b200.h
 H_MAGIC, H_VERSION, H_NCLIQUES, H_NSEPS, H_NFACTORS, H_NEVID, H_CLIQUE_ENTRIES, H_SEP_ENTRIES, \
     H_FIN_ENTRIES, H_FOUT_ENTRIES, H_NTAB, H_NTASKS, H_NMSGS, H_NLAUNCHES, H_MAXDEPTH, \
-    H_NEVF, H_ROOT_ENTRIES, H_UNI_ENTRIES, H_NOUT, H_WORDS = range(20)
+    H_NEVF, H_ROOT_ENTRIES, H_UNI_ENTRIES, H_NOUT, H_LIK_ENTRIES, H_WORDS = range(21)
 
 TASK_WORDS = 24
 (T_KIND, T_SRC, T_OUT, T_BETA, T_BEL, T_OWN, T_NS, T_NR, T_NSLO, T_NRLO, T_SRC_SHI, T_SRC_SLO,
@@ -180,6 +180,12 @@ class Plan:
     :param full_sizes: ``{var: size}`` of the factor tables as stored (defaults to ``sizes``)
     :param outputs: scopes (variable lists) the marginal stage sums the clique beliefs down to;
                     default: the factor scopes, as ``CliqueGraph.marginalize`` of the reference
+    :param likelihood_vars: variables that receive soft evidence: a per-instance likelihood
+                    vector ``lambda_v[x_v]`` multiplied into the potential of a clique containing
+                    ``v`` (the same as one more single-variable factor ``[v]`` per instance).  The
+                    vectors live in the workspace, region ``likelihoods`` ``[lik_entries][B]`` after
+                    the down-messages, slot ``k`` at entry ``lik_base + lik_off[k]``; the caller
+                    fills them before ``jt_init``
     :param emitter: ``"native"`` (default): tasks and index tables are emitted by the C++ host
                     compile (``jt_plan_build``, ``csrc/jt_compile.cpp``), tens of times faster on
                     large trees; ``"python"``: by the ``_build_*`` methods below, the cross-check
@@ -187,7 +193,7 @@ class Plan:
     """
 
     def __init__(self, tree, node_vars, sizes, factors=None, factor_to_clique=None,
-                 evidence_vars=(), full_sizes=None, outputs=None, emitter=None):
+                 evidence_vars=(), full_sizes=None, outputs=None, emitter=None, likelihood_vars=()):
         self.emitter = emitter or os.environ.get("JT_PLAN_EMITTER", "native")
         if self.emitter not in ("native", "python"):
             raise ValueError("emitter must be 'native' or 'python'")
@@ -199,6 +205,14 @@ class Plan:
         self.evidence_vars = list(evidence_vars)
         self.full_sizes = dict(full_sizes) if full_sizes is not None else dict(sizes)
         self.outputs = None if outputs is None else [list(o) for o in outputs]
+        self.likelihood_vars = list(likelihood_vars)
+        if self.likelihood_vars and (self.factors is None or tree is None):
+            raise ValueError("soft evidence needs the factor graph and the tree")
+        if len(set(self.likelihood_vars)) != len(self.likelihood_vars):
+            raise ValueError("duplicate variable in likelihood_vars")
+        for v in self.likelihood_vars:
+            if v in self.evidence_vars:
+                raise ValueError("variable %r is observed: it cannot also carry a likelihood" % (v,))
         for v in self.evidence_vars:
             if int(self.sizes[v]) != 1:
                 raise ValueError("observed variable %r must have effective size 1" % (v,))
@@ -253,7 +267,20 @@ class Plan:
         # workspace regions (entries): [cliques | separator beliefs | up messages | down messages]
         self.up_base = self.clique_entries + self.sep_entries
         self.down_base = self.up_base + self.sep_entries
-        self.work_entries = self.down_base + self.sep_entries
+        # soft evidence: one [size_v][B] likelihood table per variable after the down-messages,
+        # multiplied into the smallest clique containing the variable
+        self.lik_base = self.down_base + self.sep_entries
+        self.lik_off, self.lik_size, self.lik_clique = [], [], []
+        self.lik_entries = 0
+        for v in self.likelihood_vars:
+            holders = [c for c in range(self.n_cliques) if v in self.node_vars[c]]
+            if not holders:
+                raise ValueError("no clique contains the likelihood variable %r" % (v,))
+            self.lik_clique.append(min(holders, key=lambda c: (self.node_size[c], c)))
+            self.lik_off.append(self.lik_entries)
+            self.lik_size.append(int(self.sizes[v]))
+            self.lik_entries += int(self.sizes[v])
+        self.work_entries = self.lik_base + self.lik_entries
 
         self.tab = _TableArena()
         self.tasks, self.msgs, self.launches = [], [], []
@@ -303,7 +330,8 @@ class Plan:
             tree = (self.order, [self.parent[c] for c in range(self.n_cliques)],
                     [self.parent_sep[c] for c in range(self.n_cliques)])
         self._blob = _native.plan_build(sizes, full, self.n_cliques, node_vars, tree, factors,
-                                        self.factor_to_clique, evidence, outputs)
+                                        self.factor_to_clique, evidence, outputs,
+                                        [vid(v) for v in self.likelihood_vars])
         words = np.frombuffer(self._blob, np.int64)
         h = words[:H_WORDS]
         n_nodes, F, n_out = int(h[H_NCLIQUES] + h[H_NSEPS]), int(h[H_NFACTORS]), int(h[H_NOUT])
@@ -311,9 +339,9 @@ class Plan:
             + 2 * int(h[H_NEVF])
         # the emitter's own bookkeeping must agree with the metadata computed above
         expect = (self.n_cliques, self.n_seps, self.clique_entries, self.sep_entries, self.fin_entries,
-                  self.fout_entries, self.uni_entries, self.max_depth)
+                  self.fout_entries, self.uni_entries, self.max_depth, self.lik_entries)
         got = tuple(int(h[k]) for k in (H_NCLIQUES, H_NSEPS, H_CLIQUE_ENTRIES, H_SEP_ENTRIES, H_FIN_ENTRIES,
-                                        H_FOUT_ENTRIES, H_UNI_ENTRIES, H_MAXDEPTH))
+                                        H_FOUT_ENTRIES, H_UNI_ENTRIES, H_MAXDEPTH, H_LIK_ENTRIES))
         if expect != got:
             raise RuntimeError("native plan emitter disagrees with the host metadata: %r vs %r" % (got, expect))
 
@@ -409,6 +437,7 @@ class Plan:
             return
         observed = set(self.evidence_vars)
         touched = set(home for fv, home in zip(self.factors, self.factor_to_clique) if observed & set(fv))
+        touched.update(self.lik_clique)               # a likelihood makes the potential per-instance
         if not self.children[self.root]:
             touched.add(self.root)        # a single clique gets no distribute task: keep it per instance
         for c in reversed(self.order):
@@ -491,6 +520,9 @@ class Plan:
                 for v in self.evidence_vars:
                     st.pop(v, None)
                 self._add_msg(self.fin_off[f], s_space, None, st, fid=f)
+            for k, v in enumerate(self.likelihood_vars):
+                if self.lik_clique[k] == c:           # fid -2: operand read from the workspace
+                    self._add_msg(self.lik_base + self.lik_off[k], s_space, None, {v: 1}, fid=-2)
             row[T_SMSG_END] = len(self.msgs)
             self.tasks.append(row)
         self._launch_split(PHASE_INIT, PHASE_INIT_UNIFORM, PHASE_INIT_INSTANCE, begin, begin + n_uniform, 0)
@@ -674,6 +706,7 @@ class Plan:
         h[H_ROOT_ENTRIES] = self.node_size[self.root] if self.root >= 0 else 0
         h[H_UNI_ENTRIES] = self.uni_entries
         h[H_NOUT] = len(self.fout_off)
+        h[H_LIK_ENTRIES] = self.lik_entries
         return h
 
     def to_blob(self):

@@ -73,6 +73,9 @@ def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np
                 for m in plan.msgs_arr[t[sch.T_SMSG_BEGIN]:t[sch.T_SMSG_END]]:
                     a = _map(tab, m[sch.M_AHI], m[sch.M_ALO], n_s, n_slo)
                     f = int(m[sch.M_FID])
+                    if f == -2:                       # soft evidence: likelihood table in the workspace
+                        val = mul(val, work[m[sch.M_OFF] + a, :])
+                        continue
                     if factor_in.ndim == 2:
                         idx = m[sch.M_OFF] + a
                         val = mul(val, factor_in[idx, :])
@@ -124,6 +127,14 @@ def node_array(plan, work, node, B):
 def factor_array(plan, fout, f, B):
     off, n = plan.fout_off[f], plan.fout_size[f]
     return np.moveaxis(fout[off:off + n].reshape(tuple(plan.fout_shape[f]) + (B,)), -1, 0)
+
+
+def load_likelihoods(plan, work, likelihoods):
+    """Write ``{variable: [B, size]}`` likelihood vectors into the workspace's likelihood region."""
+    for k, v in enumerate(plan.likelihood_vars):
+        off = plan.lik_base + plan.lik_off[k]
+        work[off:off + plan.lik_size[k]] = np.asarray(likelihoods[v], work.dtype).T
+    return work
 
 
 def flatten_factors(plan, values, dtype=np.float64):

@@ -196,6 +196,18 @@ def slice_evidence(values, factors, evidence):
     return out
 
 
+def with_likelihood_factors(factors, factor_to_maxclique, maxcliques, values, likelihoods, b):
+    """Soft evidence in the reference's own terms: a likelihood vector on variable v is one more
+    factor ``[v]`` of the factor graph (assigned to any clique containing v).  Returns the
+    extended ``(factors, factor_to_maxclique, values)`` for instance ``b``."""
+    factors, f2c, values = list(factors), list(factor_to_maxclique), list(values)
+    for v, lam in likelihoods.items():
+        factors.append([v])
+        f2c.append(next(c for c, cv in enumerate(maxcliques) if v in cv))
+        values.append(np.asarray(lam[b], np.float64))
+    return factors, f2c, values
+
+
 def propagate_batch(tree, separators, maxcliques, factor_to_maxclique, factors, sizes, values,
                     evidence_vars=(), evidence=None, n=None, semiring="sum_product"):
     """Loop of independent propagations, one per evidence row.

@@ -500,3 +500,136 @@ def test_random_networks_fuzz(seed):
         assert_close(nodes[kk][pick], w, rtol, "node %d" % kk)
     for f, w in enumerate(want_f):
         assert_close(outs[f][pick], w, rtol, "factor %d" % f)
+
+
+def test_integration_stub_from_the_docs():
+    """The ctypes stub printed in INTEGRATION.md section 2 (what a maintainer of the reference
+    would add) is executed as is -- only the library path is substituted -- on a junction tree
+    object with the reference's attributes, and reproduces the oracle."""
+    import os
+    import re
+    import junctiontree as jt
+    from junctiontree import _native
+    from oracle import ref_fixed
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# junctiontree/_b200\.py.*?)```", text, flags=re.S).group(1)
+    block = block.replace('"libjt_b200.so"', repr(_native.library_path()))
+    scope = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), scope)
+    for net in (wl.sprinkler(), wl.huang_darwiche(), wl.random_dag(12, 3, 2, 3, 8, 5)):
+        tree = jt.create_junction_tree(net["factors"], net["sizes"])
+        got = scope["propagate"](tree, net["values"])
+        ct = tree.clique_tree
+        want, _ = ref_fixed.propagate(tree.tree, tree.separators, ct.maxcliques, ct.factor_to_maxclique,
+                                      net["factors"], net["sizes"], net["values"])
+        for f, (g, w) in enumerate(zip(got, want)):
+            assert_close(g, w, RTOL_F64, "%s factor %d" % (net["name"], f))
+
+
+def test_propagate_evidence_with_a_different_pattern_per_instance():
+    """Batched apply_evidence front-end: every instance has its own set of observed variables;
+    each result equals a propagation of the sliced network (reference semantics:
+    ``apply_evidence`` slicing ``e:e+1``, ``computation.py:11-34``, then ``propagate``)."""
+    import junctiontree as jt
+    from junctiontree import computation as comp
+    from oracle import ref_fixed
+    net = wl.random_dag(13, 3, 2, 4, 8, 21)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    ct = tree.clique_tree
+    rng = np.random.default_rng(5)
+    labels = sorted(net["sizes"])
+    pool = [labels[i] for i in (1, 4, 7, 11)]
+    B = 41
+    evidence = []
+    for b in range(B):
+        chosen = [v for v in pool if rng.random() < 0.5]
+        evidence.append({v: int(rng.integers(0, net["sizes"][v])) for v in chosen})
+    evidence[3] = {}                                   # nothing observed
+    got = tree.propagate_evidence(net["values"], evidence)
+    assert len(got) == B
+    for b in range(B):
+        sliced = [a[0] for a in comp.apply_evidence(net["values"], net["factors"], evidence[b])]
+        eff = dict(net["sizes"], **{v: 1 for v in evidence[b]})
+        want, _ = ref_fixed.propagate(tree.tree, tree.separators, ct.maxcliques, ct.factor_to_maxclique,
+                                      net["factors"], eff, sliced)
+        for f, (g, w) in enumerate(zip(got[b], want)):
+            assert_close(g, w, RTOL_F64, "instance %d factor %d" % (b, f))
+    # the same evidence as an int table with -1 = not observed
+    table = np.full((B, len(pool)), -1, np.int64)
+    for b, ev in enumerate(evidence):
+        for v, s in ev.items():
+            table[b, pool.index(v)] = s
+    again = tree.propagate_evidence(net["values"], table, variables=pool)
+    for b in range(B):
+        for g, w in zip(again[b], got[b]):
+            assert np.array_equal(g, w)
+    with pytest.raises(ValueError):
+        tree.propagate_evidence(net["values"], [{"nope": 0}])
+
+
+@pytest.mark.parametrize("B", [5, 300])
+@pytest.mark.parametrize("uniform", [True, False], ids=["uniform", "per_instance"])
+def test_soft_evidence_likelihood_vectors(B, uniform):
+    """Soft evidence: per-instance likelihood vectors (the workspace's likelihood region) are one
+    more single-variable factor per instance -- compared with the oracle run on the extended
+    factor graph; combined with hard evidence on other variables."""
+    import junctiontree as jt
+    from oracle import ref_fixed
+    net = wl.random_dag(14, 3, 2, 4, 8, 6)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    ct = tree.clique_tree
+    evars = net["evidence_vars"]
+    ev = wl.draw_evidence(net, B)
+    rng = np.random.default_rng(8)
+    free = [v for v in sorted(net["sizes"]) if v not in evars]
+    lik = {v: rng.random((B, net["sizes"][v])) + 0.05 for v in (free[0], free[3], free[7])}
+    outs, nodes = tree.propagate_batch(net["values"], evars, ev, nodes=True, uniform=uniform, likelihoods=lik)
+    for b in sorted(set([0, B // 2, B - 1])):
+        fx, f2cx, vx = ref_fixed.with_likelihood_factors(net["factors"], ct.factor_to_maxclique, ct.maxcliques,
+                                                         net["values"], lik, b)
+        want_f, want_n = ref_fixed.propagate_batch(tree.tree, tree.separators, ct.maxcliques, f2cx, fx, net["sizes"],
+                                                   vx, evars, ev[b:b + 1], n=1)
+        for k, w in enumerate(want_n):
+            assert_close(nodes[k][b], w[0], RTOL_F64, "node %d instance %d" % (k, b))
+        for f in range(len(net["factors"])):
+            assert_close(outs[f][b], want_f[f][0], RTOL_F64, "factor %d instance %d" % (f, b))
+
+
+def test_soft_evidence_one_hot_equals_slicing_and_streams():
+    """One-hot likelihoods reproduce hard evidence (reference tests/test_computation.py:411-459:
+    slicing == one-hot); the chunked pipeline carries likelihoods; log-domain laws take
+    log-likelihoods; posteriors through marginals_batch."""
+    import junctiontree as jt
+    from junctiontree import semirings as sr
+    net = wl.random_dag(12, 3, 2, 3, 8, 5)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    evars = net["evidence_vars"]
+    B = 4096 + 500                                     # above the streaming threshold
+    ev = wl.draw_evidence(net, B)
+    onehot = {v: np.eye(net["sizes"][v])[ev[:, i]] for i, v in enumerate(evars)}
+    hard = tree.propagate_batch(net["values"], evars, ev)
+    soft = tree.propagate_batch(net["values"], likelihoods=onehot)
+    for f, fv in enumerate(net["factors"]):
+        for b in (0, 4095, 4096, B - 1):
+            ix = tuple(slice(int(ev[b, evars.index(v)]), int(ev[b, evars.index(v)]) + 1) if v in evars else slice(None)
+                       for v in fv)
+            assert_close(soft[f][b][ix], hard[f][b], RTOL_F64, "factor %d instance %d" % (f, b))
+            mask = np.ones(soft[f][b].shape, bool)
+            mask[ix] = False
+            assert np.all(soft[f][b][mask] == 0.0)             # no belief outside the observed state
+    free = [v for v in sorted(net["sizes"]) if v not in evars]
+    post_h, logz_h = tree.marginals_batch(net["values"], free, evars, ev)
+    post_s, logz_s = tree.marginals_batch(net["values"], free, likelihoods=onehot)
+    assert_close(logz_s, logz_h, 1e-11, "log Z")
+    for v in free:
+        assert_close(post_s[v], post_h[v], 1e-11, "posterior %s" % v)
+    with np.errstate(divide="ignore"):
+        logv = [np.log(x) for x in net["values"]]
+        post_l, logz_l = tree.marginals_batch(logv, free, likelihoods={v: np.log(x) for v, x in onehot.items()},
+                                              dl=sr.log_sum_exp)
+    assert_close(logz_l, logz_h, 1e-11, "log Z (log domain)")
+    with pytest.raises(ValueError):
+        tree.propagate_batch(net["values"], evars, ev, likelihoods={evars[0]: onehot[evars[0]]})
+    with pytest.raises(ValueError):
+        tree.propagate_batch(net["values"], likelihoods={"nope": np.ones((B, 2))})

@@ -77,10 +77,14 @@ def test_native_compile_fuzz(seed):
     for v in evars:
         eff[v] = 1
     outputs = [[v] for v in labels if v not in evars][:5] or None
-    for ev, out in (([], None), (evars, None), (evars, outputs)):
+    soft = [v for v in labels if v not in evars][1::3]        # soft evidence on some free variables
+    for ev, out, lik in (([], None, ()), (evars, None, ()), (evars, outputs, ()), (evars, None, soft)):
         e = eff if ev else sizes
-        a = sch.Plan(tree, mc + seps, e, factors, f2c, ev, sizes, out, emitter="python")
-        b = sch.Plan(tree, mc + seps, e, factors, f2c, ev, sizes, out, emitter="native")
+        if lik and (tree is None or mc == [[]]):
+            continue
+        a = sch.Plan(tree, mc + seps, e, factors, f2c, ev, sizes, out, emitter="python", likelihood_vars=lik)
+        b = sch.Plan(tree, mc + seps, e, factors, f2c, ev, sizes, out, emitter="native", likelihood_vars=lik)
+        assert a.lik_entries == sum(e[v] for v in lik) and a.work_entries == a.lik_base + a.lik_entries
         assert a.to_blob() == b.to_blob()
         assert np.array_equal(a.tasks_arr, b.tasks_arr) and np.array_equal(a.tables, b.tables)
         assert np.array_equal(a.msgs_arr, b.msgs_arr) and np.array_equal(a.launches_arr, b.launches_arr)

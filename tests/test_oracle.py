@@ -164,3 +164,44 @@ def test_direct_marginals_without_clique_beliefs(net, uniform):
                                         evars, ev, n=B)
     for f in range(len(net["factors"])):
         assert_close(plan_interp.factor_array(plan, fout, f, B), outs[f], 1e-13, "factor %d" % f)
+
+
+def test_soft_evidence_is_one_more_single_variable_factor():
+    """Soft (likelihood) evidence: the plan multiplies a per-instance vector from the
+    workspace's likelihood region into a clique; the oracle states it in the reference's own
+    terms -- an extra factor [v] per instance -- and one-hot likelihoods reproduce hard evidence
+    (the reference's own test of slicing vs one-hot, tests/test_computation.py:411-459)."""
+    from junctiontree import schedule as sch
+    net = wl.random_dag(12, 3, 2, 3, 8, 5)
+    tree, seps, mc, f2c, eff, evars = compile_net(net)
+    B = 3
+    rng = np.random.default_rng(0)
+    free = [v for v in sorted(net["sizes"]) if v not in evars]
+    soft = [free[1], free[4], free[6]]
+    lik = {v: rng.random((B, net["sizes"][v])) + 0.1 for v in soft}
+    ev = wl.draw_evidence(net, B)
+    for uniform in (False, True):
+        plan = sch.Plan(tree, mc + seps, eff, net["factors"], f2c, evars, net["sizes"], likelihood_vars=soft)
+        work = np.zeros((plan.work_entries, B))
+        plan_interp.load_likelihoods(plan, work, lik)
+        work, fout = plan_interp.run(plan, B, work=work, factor_in=plan_interp.flatten_factors(plan, net["values"]),
+                                     evidence=ev, uniform=uniform)
+        for b in range(B):
+            fx, f2cx, vx = ref_fixed.with_likelihood_factors(net["factors"], f2c, mc, net["values"], lik, b)
+            outs, ys = ref_fixed.propagate_batch(tree, seps, mc, f2cx, fx, net["sizes"], vx, evars, ev[b:b + 1], n=1)
+            for k in range(len(mc) + len(seps)):
+                assert_close(plan_interp.node_array(plan, work, k, B)[b], ys[k][0], 1e-13, "node %d" % k)
+            for f in range(len(net["factors"])):
+                assert_close(plan_interp.factor_array(plan, fout, f, B)[b], outs[f][0], 1e-13, "factor %d" % f)
+    # one-hot likelihoods on the observed variables == slicing them
+    plan = sch.Plan(tree, mc + seps, net["sizes"], net["factors"], f2c, likelihood_vars=evars)
+    onehot = {v: np.eye(net["sizes"][v])[ev[:, i]] for i, v in enumerate(evars)}
+    work = plan_interp.load_likelihoods(plan, np.zeros((plan.work_entries, B)), onehot)
+    work, fout = plan_interp.run(plan, B, work=work, factor_in=plan_interp.flatten_factors(plan, net["values"]))
+    outs, _ = ref_fixed.propagate_batch(tree, seps, mc, f2c, net["factors"], net["sizes"], net["values"], evars, ev, n=B)
+    for f, fv in enumerate(net["factors"]):
+        full = plan_interp.factor_array(plan, fout, f, B)
+        for b in range(B):
+            ix = tuple(slice(int(ev[b, evars.index(v)]), int(ev[b, evars.index(v)]) + 1) if v in evars else slice(None)
+                       for v in fv)
+            assert_close(full[b][ix], outs[f][b], 1e-13, "factor %d instance %d" % (f, b))

@@ -40,8 +40,11 @@
  * factors contain no observed variable, and an up-message of a subtree that contains none, are
  * the same for every instance.  They are computed once into the uniform workspace and the batch
  * kernels broadcast them instead of streaming [n][B] rows; every belief and every down-message
- * is still computed and stored per instance, so the results are identical.  jt_propagate
- * enables it automatically when factors_batched = 0.
+ * is still computed and stored per instance, so the results are identical.  The same holds for
+ * a down-message whose whole source side (clique potential, message from above, up-messages of
+ * the other children) is evidence-free: it is also computed once (JT_PHASE_DIST_UNIFORM) and its
+ * consumers read the uniform copy.  jt_propagate enables uniform mode automatically when
+ * factors_batched = 0.
  *
  * Plan blob (produced by junctiontree/schedule.py, Plan.to_blob): little-endian int64 words
  *   header[JT_H_WORDS], node_off[n_nodes], node_size[n_nodes], fin_off[F], fin_size[F],
@@ -65,7 +68,7 @@
 extern "C" {
 #endif
 
-#define JT_ABI_VERSION 8
+#define JT_ABI_VERSION 9
 
 /* status codes */
 #define JT_OK 0
@@ -128,7 +131,7 @@ enum { JT_KIND_PROJECT = 0, JT_KIND_INIT = 1 };
 enum {
     JT_PHASE_INIT, JT_PHASE_COLLECT, JT_PHASE_DIST_PRE, JT_PHASE_DIST_MAIN, JT_PHASE_MARGINAL,
     JT_PHASE_INIT_UNIFORM, JT_PHASE_INIT_INSTANCE, JT_PHASE_COLLECT_UNIFORM, JT_PHASE_COLLECT_INSTANCE,
-    JT_PHASE_DIST_MAIN_MESSAGES, JT_PHASE_MARGINAL_DIRECT
+    JT_PHASE_DIST_MAIN_MESSAGES, JT_PHASE_MARGINAL_DIRECT, JT_PHASE_DIST_UNIFORM, JT_PHASE_DIST_PRE_INSTANCE
 };
 
 typedef struct jt_plan jt_plan;

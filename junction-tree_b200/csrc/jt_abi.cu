@@ -297,7 +297,7 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
     for (int64_t i = 0; i < n_launch; ++i, q += JT_LAUNCH_WORDS) {
         jt_plan::Launch& L = p->launches[i];
         L.phase = (int)q[JT_L_PHASE]; L.begin = (int)q[JT_L_BEGIN]; L.end = (int)q[JT_L_END]; L.level = (int)q[JT_L_LEVEL];
-        if (L.phase < JT_PHASE_INIT || L.phase > JT_PHASE_MARGINAL_DIRECT || L.begin < 0 || L.begin >= L.end || L.end > n_tasks)
+        if (L.phase < JT_PHASE_INIT || L.phase > JT_PHASE_DIST_PRE_INSTANCE || L.begin < 0 || L.begin >= L.end || L.end > n_tasks)
             return bad("launch descriptor", i);
         for (int t = L.begin; t < L.end; ++t)
             if ((p->tasks[t].kind == JT_KIND_INIT) != (L.phase == JT_PHASE_INIT || L.phase == JT_PHASE_INIT_UNIFORM ||
@@ -507,15 +507,23 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
     const int vec = pick_vec(B, dtype);
     KArgs a = base_args(p, B, workspace, vec);
     a.flags = flags;
+    int pre_phase = JT_PHASE_DIST_PRE;
     if (uniform_mode(p, flags)) {
-        a.uni = uniform_ws(p, B, dtype, workspace);
+        // down-messages with an evidence-free source side: once, top level first (B = 1)
+        void* uni = uniform_ws(p, B, dtype, workspace);
+        if (!(flags & JT_UNIFORM_VALID)) {
+            rc = run_phase_uniform(p, JT_PHASE_DIST_UNIFORM, a, dtype, uni, stream);
+            if (rc != JT_OK) return rc;
+        }
+        a.uni = uni;
         a.uniform = 1;
+        pre_phase = JT_PHASE_DIST_PRE_INSTANCE;
     }
     // per level: the tasks that only read psi_C, then the task that overwrites it with beta_C
     // (JT_NO_BELIEFS: only the message-sending tasks, and the kernels skip the belief stores)
     const int main_phase = (flags & JT_NO_BELIEFS) ? JT_PHASE_DIST_MAIN_MESSAGES : JT_PHASE_DIST_MAIN;
     for (const auto& L : p->launches) {
-        if (L.phase != JT_PHASE_DIST_PRE && L.phase != main_phase) continue;
+        if (L.phase != pre_phase && L.phase != main_phase) continue;
         rc = launchers(flags)->dispatch(p, L, a, dtype, vec, stream);
         if (rc != JT_OK) return rc;
     }

@@ -509,7 +509,7 @@ struct Emitter {
     std::vector<int64_t> ev_card, evf_ptr, evf_var, evf_stride;
     int64_t clique_entries = 0, sep_entries = 0, up_base = 0, down_base = 0, fin_entries = 0, fout_entries = 0,
             uni_entries = 0;
-    std::vector<char> uniform, uniform_up;
+    std::vector<char> uniform, uniform_up, uniform_down;   // uniform_down: per separator (node id - n_cliques)
     std::vector<std::vector<int32_t>> by_depth;
     // outputs
     std::vector<int32_t> tab;
@@ -714,6 +714,7 @@ struct Emitter {
         // uniform cliques / subtrees (schedule.py: _find_uniform_cliques)
         uniform.assign(n_cliques, 0);
         uniform_up.assign(n_cliques, 0);
+        uniform_down.assign(n_seps, 0);
         if (has_factors && has_tree) {
             std::vector<char> observed(n_vars, 0), touched(n_cliques, 0);
             for (int32_t v : evidence_vars) observed[v] = 1;
@@ -731,6 +732,16 @@ struct Emitter {
             }
             for (int32_t c = 0; c < n_cliques; ++c)
                 if (uniform[c]) uni_entries += node_size[c];
+            // a down-message is uniform when everything on its source side is
+            for (int32_t c : order) {
+                const bool above = parent[c] < 0 || uniform_down[parent_sep[c] - n_cliques];
+                for (const auto& kid : children[c]) {
+                    bool u = uniform[c] && above;
+                    for (const auto& other : children[c])
+                        if (other.first != kid.first) u = u && uniform_up[other.second];
+                    uniform_down[kid.first - n_cliques] = u;
+                }
+            }
         }
         by_depth.assign(max_depth + 1, {});
         for (int32_t c : order) by_depth[depth[c]].push_back(c);
@@ -810,13 +821,24 @@ struct Emitter {
         bool sending;      // messages still to be attached (false: a finished belief-only task)
     };
 
+    Incoming down_msg(int32_t c) const {
+        const int32_t psep = parent_sep[c];
+        return {down_off(psep), psep, (bool)uniform_down[psep - n_cliques]};
+    }
+
+    // Uniform mode: a down-message whose source side is evidence-free is computed once in the
+    // uniform workspace (JT_PHASE_DIST_UNIFORM) and read by its consumers as a broadcast scalar;
+    // a non-writer task with such a message shrinks to an elementwise task in the instance
+    // launch.  Task order of the first launch of a level: [full form, uniform down | full form,
+    // others | elementwise forms]; JT_PHASE_DIST_PRE is the first two groups,
+    // JT_PHASE_DIST_PRE_INSTANCE the last two.  (schedule.py: _build_distribute)
     void build_distribute() {
         for (int32_t d = 0; d <= max_depth; ++d) {
-            std::vector<Deferred> pre, main_sending, main_leaves;
+            std::vector<Deferred> pre_ud, pre_other, main_sending, main_leaves, inst, unis;
             for (int32_t c : by_depth[d]) {
                 const auto& kids = children[c];
                 std::vector<Incoming> incoming;
-                if (parent[c] >= 0) incoming.push_back({down_off(parent_sep[c]), parent_sep[c], false});
+                if (parent[c] >= 0) incoming.push_back(down_msg(c));
                 for (const Incoming& m : child_ups(c)) incoming.push_back(m);
                 if (kids.empty()) {
                     if (parent[c] < 0) continue;              // single-clique tree: belief = potential
@@ -832,6 +854,8 @@ struct Emitter {
                 }
                 for (size_t i = 0; i < kids.size(); ++i) {
                     const int32_t sep = kids[i].first, kid = kids[i].second;
+                    const bool ud = uniform_down[sep - n_cliques];
+                    const bool writer = i + 1 == kids.size();
                     Deferred t;
                     t.s_space = make_space(node_vars[sep], sizes);
                     t.r_space = make_space(minus(node_vars[c], node_vars[sep]), sizes);
@@ -843,39 +867,67 @@ struct Emitter {
                     for (const Incoming& m : incoming)
                         if (m.sep != sep) t.others.push_back(m);
                     t.sending = true;
-                    const bool writer = i + 1 == kids.size();
-                    if (writer) {
-                        t.row[JT_T_BETA] = node_off[c];
-                        main_sending.push_back(std::move(t));
-                    } else {
-                        pre.push_back(std::move(t));
-                    }
-                }
-            }
-            // tasks that send a message first, the belief-only ones (leaves) last
-            for (int pass = 0; pass < 2; ++pass) {
-                const size_t begin = tasks.size();
-                size_t n_sending = 0;
-                auto place = [&](std::vector<Deferred>& group) {
-                    for (Deferred& t : group) {
-                        if (t.sending) {
-                            attach_msgs(t.row, t.others, t.s_space, t.r_space);
-                            ++n_sending;
+                    if (writer) t.row[JT_T_BETA] = node_off[c];
+                    Deferred u, e;
+                    if (ud) {
+                        u.s_space = t.s_space;
+                        u.r_space = t.r_space;
+                        u.others = t.others;
+                        u.row = new_task(JT_KIND_PROJECT, u.s_space, &u.r_space, c, c, true);
+                        u.row[JT_T_OUT] = down_off(sep);
+                        u.row[JT_T_FLAGS] |= JT_TF_TASK_UNIFORM;
+                        u.sending = true;
+                        if (!writer) {
+                            e.s_space = t.s_space;
+                            e.r_space = make_space({}, sizes);
+                            e.row = new_task(JT_KIND_PROJECT, e.s_space, &e.r_space, c, sep, false);
+                            e.row[JT_T_SRC] = down_off(sep);
+                            e.row[JT_T_FLAGS] |= JT_TF_SRC_UNIFORM;
+                            e.row[JT_T_OUT] = down_off(sep);
+                            e.row[JT_T_BEL] = bel_off(sep);
+                            e.row[JT_T_OWN] = up_off(sep);
+                            if (uniform_up[kid]) e.row[JT_T_FLAGS] |= JT_TF_OWN_UNIFORM;
+                            e.sending = true;
                         }
-                        tasks.push_back(std::move(t.row));
                     }
-                };
-                if (pass == 0) {
-                    place(pre);
-                    launch(JT_PHASE_DIST_PRE, begin, d);
-                } else {
-                    place(main_sending);
-                    place(main_leaves);
-                    launch(JT_PHASE_DIST_MAIN, begin, d);
-                    if (n_sending)
-                        launches.push_back({JT_PHASE_DIST_MAIN_MESSAGES, (int64_t)begin, (int64_t)(begin + n_sending), d});
+                    if (writer) main_sending.push_back(std::move(t));
+                    else if (ud) pre_ud.push_back(std::move(t));
+                    else pre_other.push_back(std::move(t));
+                    if (ud) {
+                        unis.push_back(std::move(u));
+                        if (!writer) inst.push_back(std::move(e));
+                    }
                 }
             }
+            size_t n_sending = 0;
+            auto place = [&](std::vector<Deferred>& group) {
+                for (Deferred& t : group) {
+                    if (t.sending) {
+                        attach_msgs(t.row, t.others, t.s_space, t.r_space);
+                        ++n_sending;
+                    }
+                    tasks.push_back(std::move(t.row));
+                }
+            };
+            size_t begin = tasks.size();
+            const size_t n_ud = pre_ud.size(), n_full = pre_ud.size() + pre_other.size();
+            place(pre_ud);
+            place(pre_other);
+            place(inst);
+            if (n_full) launches.push_back({JT_PHASE_DIST_PRE, (int64_t)begin, (int64_t)(begin + n_full), d});
+            if (tasks.size() > begin + n_ud)
+                launches.push_back({JT_PHASE_DIST_PRE_INSTANCE, (int64_t)(begin + n_ud), (int64_t)tasks.size(), d});
+            // tasks that send a message first, the belief-only ones (leaves) last
+            begin = tasks.size();
+            n_sending = 0;
+            place(main_sending);
+            place(main_leaves);
+            launch(JT_PHASE_DIST_MAIN, begin, d);
+            if (n_sending)
+                launches.push_back({JT_PHASE_DIST_MAIN_MESSAGES, (int64_t)begin, (int64_t)(begin + n_sending), d});
+            begin = tasks.size();
+            place(unis);
+            launch(JT_PHASE_DIST_UNIFORM, begin, d);
         }
     }
 
@@ -905,7 +957,7 @@ struct Emitter {
             row[JT_T_OUT_SPACE] = 1;
             row[JT_T_AUX] = (int64_t)k;
             std::vector<Incoming> incoming;
-            if (parent[c] >= 0) incoming.push_back({down_off(parent_sep[c]), parent_sep[c], false});
+            if (parent[c] >= 0) incoming.push_back(down_msg(c));
             for (const Incoming& m : child_ups(c)) incoming.push_back(m);
             attach_msgs(row, incoming, s_space, r_space);
             tasks.push_back(std::move(row));

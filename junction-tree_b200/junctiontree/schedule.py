@@ -39,7 +39,7 @@ import numpy as np
 from . import construction as cons
 
 MAGIC = 0x324E4C5042544A  # "JTBPLN2"
-VERSION = 8
+VERSION = 9
 
 # header word indices (int64 words); mirrored in include/jt_b200.h
 H_MAGIC, H_VERSION, H_NCLIQUES, H_NSEPS, H_NFACTORS, H_NEVID, H_CLIQUE_ENTRIES, H_SEP_ENTRIES, \
@@ -65,7 +65,7 @@ L_PHASE, L_BEGIN, L_END, L_LEVEL = range(4)
 KIND_PROJECT, KIND_INIT = 0, 1
 (PHASE_INIT, PHASE_COLLECT, PHASE_DIST_PRE, PHASE_DIST_MAIN, PHASE_MARGINAL,
  PHASE_INIT_UNIFORM, PHASE_INIT_INSTANCE, PHASE_COLLECT_UNIFORM, PHASE_COLLECT_INSTANCE,
- PHASE_DIST_MAIN_MESSAGES, PHASE_MARGINAL_DIRECT) = range(11)
+ PHASE_DIST_MAIN_MESSAGES, PHASE_MARGINAL_DIRECT, PHASE_DIST_UNIFORM, PHASE_DIST_PRE_INSTANCE) = range(13)
 SPACE_WORK, SPACE_FOUT = 0, 1
 
 #: trailing-axes table is grown while its length stays within this bound
@@ -432,7 +432,10 @@ class Plan:
         """
         self.uniform = [False] * self.n_cliques
         self.uniform_up = [False] * self.n_cliques
+        self.uniform_down = {}                     # separator node -> its down-message is uniform
         self.uni_entries = 0
+        if self.tree is not None:
+            self.uniform_down = {s: False for c in self.order for s, _ in self.children[c]}
         if self.factors is None or self.tree is None:
             return
         observed = set(self.evidence_vars)
@@ -444,6 +447,13 @@ class Plan:
             self.uniform[c] = c not in touched
             self.uniform_up[c] = self.uniform[c] and all(self.uniform_up[k] for _, k in self.children[c])
         self.uni_entries = sum(self.node_size[c] for c in range(self.n_cliques) if self.uniform[c])
+        # a down-message is uniform when everything on its source side is: the clique's
+        # potential, the message from above and the up-messages of the other children
+        for c in self.order:
+            above = self.parent[c] < 0 or self.uniform_down[self.parent_sep[c]]
+            for s, _ in self.children[c]:
+                self.uniform_down[s] = self.uniform[c] and above and all(
+                    self.uniform_up[k2] for s2, k2 in self.children[c] if s2 != s)
 
     def _add_msg(self, off, s_space, r_space, stride_of, fid=-1, uniform=False):
         a_hi, a_lo = s_space.tables(stride_of)
@@ -559,6 +569,11 @@ class Plan:
             self._launch_split(PHASE_COLLECT, PHASE_COLLECT_UNIFORM, PHASE_COLLECT_INSTANCE,
                                begin, begin + n_uniform, d)
 
+    def _down_msg(self, c):
+        """The message clique c receives from its parent, as an incoming-message triple."""
+        psep = self.parent_sep[c]
+        return (self.down_off(psep), psep, self.uniform_down[psep])
+
     def _build_distribute(self):
         """E3 + E4 + M1 + E5 with a division-free exclude-one product, top level first.
 
@@ -567,14 +582,24 @@ class Plan:
         after the others of its level have read psi_C.  A non-root leaf gets one elementwise
         task.  psi_C is read max(k, 1) times and written once (the reference reads it k+2
         times, ``computation.py:169-224``).
+
+        Uniform mode: a down-message whose whole source side is evidence-free is the same for
+        every instance.  It is computed once, in the uniform workspace (``PHASE_DIST_UNIFORM``
+        tasks, one per such separator), and every consumer reads that copy as a broadcast
+        scalar instead of streaming an [n][B] row per item.  A non-writer task whose message
+        is uniform shrinks to an elementwise task in the instance launch (separator belief =
+        uniform down x up, plus the per-instance copy of the down-message); task order of the
+        first launch of a level: ``[full form, uniform down | full form, others | elementwise
+        forms]`` -- ``PHASE_DIST_PRE`` is the first two groups, ``PHASE_DIST_PRE_INSTANCE``
+        the last two.
         """
         for d in range(0, self.max_depth + 1):
-            pre, main = [], []
+            pre_ud, pre_other, main, inst, unis = [], [], [], [], []
             for c in self.by_depth.get(d, []):
                 kids = self.children[c]
                 incoming = []
                 if self.parent[c] >= 0:
-                    incoming.append((self.down_off(self.parent_sep[c]), self.parent_sep[c], False))
+                    incoming.append(self._down_msg(c))
                 incoming += [(self.up_off(s), s, self.uniform_up[k]) for s, k in kids]
                 if not kids:
                     if self.parent[c] < 0:
@@ -601,24 +626,54 @@ class Plan:
                     if writer:
                         row[T_BETA] = self.node_off[c]
                     # messages are appended when the task is placed (keeps ranges contiguous)
-                    (main if writer else pre).append((row, others, s_space, r_space))
+                    item = (row, others, s_space, r_space)
+                    (main if writer else pre_ud if self.uniform_down[sep] else pre_other).append(item)
+                    if self.uniform_down[sep]:
+                        u_row = self._new_task(KIND_PROJECT, s_space, r_space, c, src_node=c, src_is_psi=True)
+                        u_row[T_OUT] = self.down_off(sep)
+                        u_row[T_FLAGS] |= TF_TASK_UNIFORM
+                        unis.append((u_row, others, s_space, r_space))
+                        if not writer:
+                            none = _Space([], self.sizes)
+                            i_row = self._new_task(KIND_PROJECT, s_space, none, c, src_node=sep)
+                            i_row[T_SRC] = self.down_off(sep)
+                            i_row[T_FLAGS] |= TF_SRC_UNIFORM
+                            i_row[T_OUT] = self.down_off(sep)
+                            i_row[T_BEL] = self.bel_off(sep)
+                            i_row[T_OWN] = self.up_off(sep)
+                            if self.uniform_up[kid]:
+                                i_row[T_FLAGS] |= TF_OWN_UNIFORM
+                            inst.append((i_row, [], s_space, none))
             # tasks that send a message first, the belief-only ones (leaves) last: when clique
             # beliefs are not wanted the launch stops before them
             main.sort(key=lambda item: 0 if isinstance(item, tuple) else 1)
-            for phase, group in ((PHASE_DIST_PRE, pre), (PHASE_DIST_MAIN, main)):
-                begin = len(self.tasks)
-                n_sending = 0
-                for item in group:
-                    if isinstance(item, tuple):
-                        row, others, s_space, r_space = item
-                        self._attach_msgs(row, others, s_space, r_space)
-                        self.tasks.append(row)
-                        n_sending += 1
-                    else:
-                        self.tasks.append(item)
-                self._launch(phase, begin, d)
-                if phase == PHASE_DIST_MAIN and n_sending:
-                    self.launches.append([PHASE_DIST_MAIN_MESSAGES, begin, begin + n_sending, d])
+            begin = len(self.tasks)
+            for row, others, s_space, r_space in pre_ud + pre_other + inst:
+                self._attach_msgs(row, others, s_space, r_space)
+                self.tasks.append(row)
+            n_ud, n_full = len(pre_ud), len(pre_ud) + len(pre_other)
+            if n_full:
+                self.launches.append([PHASE_DIST_PRE, begin, begin + n_full, d])
+            if len(self.tasks) > begin + n_ud:
+                self.launches.append([PHASE_DIST_PRE_INSTANCE, begin + n_ud, len(self.tasks), d])
+            begin = len(self.tasks)
+            n_sending = 0
+            for item in main:
+                if isinstance(item, tuple):
+                    row, others, s_space, r_space = item
+                    self._attach_msgs(row, others, s_space, r_space)
+                    self.tasks.append(row)
+                    n_sending += 1
+                else:
+                    self.tasks.append(item)
+            self._launch(PHASE_DIST_MAIN, begin, d)
+            if n_sending:
+                self.launches.append([PHASE_DIST_MAIN_MESSAGES, begin, begin + n_sending, d])
+            begin = len(self.tasks)
+            for row, others, s_space, r_space in unis:
+                self._attach_msgs(row, others, s_space, r_space)
+                self.tasks.append(row)
+            self._launch(PHASE_DIST_UNIFORM, begin, d)
 
     def _build_marginal(self):
         """E6: per output scope (by default per factor) = clique belief summed down to the scope.
@@ -653,7 +708,7 @@ class Plan:
             row[T_AUX] = k
             incoming = []
             if self.parent[c] >= 0:
-                incoming.append((self.down_off(self.parent_sep[c]), self.parent_sep[c], False))
+                incoming.append(self._down_msg(c))
             incoming += [(self.up_off(sp), sp, self.uniform_up[kid]) for sp, kid in self.children[c]]
             self._attach_msgs(row, incoming, s_space, r_space)
             self.tasks.append(row)
@@ -671,8 +726,10 @@ class Plan:
         """Entries per instance this schedule reads + writes in HBM for init + collect +
         distribute, every buffer counted once per consumer (the accounting of SURVEY.md 8d
         applied to the schedule as built).  In uniform mode the potential of a uniform clique is
-        neither written nor read per instance (only its belief is written) and a uniform
-        up-message is not written or read per instance (only down-message and belief are)."""
+        neither written nor read per instance (only its belief is written), a uniform
+        up-message is not written or read per instance (only down-message and belief are), and a
+        uniform down-message is written per instance (for callers that read it) while the child
+        reads the uniform copy."""
         total = 0
         for c in self.order:
             n = self.node_size[c]
@@ -684,11 +741,12 @@ class Plan:
                 total += n * (1 + reads) + (n if (kids or c != self.root) else 0)
             for s, k in kids:
                 ns = self.node_size[s]
+                down_read = 0 if (uniform and self.uniform_down[s]) else 1
                 if uniform and self.uniform_up[k]:
-                    total += ns * (2 + (1 if sep_beliefs else 0))       # down write + read, belief write
+                    total += ns * (1 + down_read + (1 if sep_beliefs else 0))   # down write (+ read), belief write
                 else:
                     # up: write + parent's collect read + parent's distribute reads + own read
-                    total += ns * (5 + (1 if sep_beliefs else 0))
+                    total += ns * (4 + down_read + (1 if sep_beliefs else 0))
         return total
 
     def header(self):

@@ -40,7 +40,9 @@ def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np
     uni = np.zeros((plan.work_entries, 1), dtype)       # the uniform workspace: same offsets, B = 1
     general = {sch.PHASE_INIT, sch.PHASE_COLLECT}
     split = {sch.PHASE_INIT_UNIFORM, sch.PHASE_INIT_INSTANCE, sch.PHASE_COLLECT_UNIFORM, sch.PHASE_COLLECT_INSTANCE}
-    in_uni_ws = {sch.PHASE_INIT_UNIFORM, sch.PHASE_COLLECT_UNIFORM}
+    in_uni_ws = {sch.PHASE_INIT_UNIFORM, sch.PHASE_COLLECT_UNIFORM, sch.PHASE_DIST_UNIFORM}
+    general |= {sch.PHASE_DIST_PRE}
+    split |= {sch.PHASE_DIST_UNIFORM, sch.PHASE_DIST_PRE_INSTANCE}
     skip = set(general if uniform else split)
     # beliefs=False: messages and outputs only -- no clique belief is written, outputs come
     # straight from psi_C and the incoming messages

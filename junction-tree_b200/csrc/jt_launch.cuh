@@ -113,10 +113,11 @@ struct Launcher {
             return JT_OK;
         }
         if (is_init) {
-            // a thread walks ~32 rows of s so the per-instance factor offsets stay in registers
-            sy_log2 = sy_log2 + 5 > kMaxSyLog2 ? kMaxSyLog2 : sy_log2 + 5;
+            // a thread walks ~32 rows of s (256 when a block spans one row and shares the row
+            // lookups) so the per-instance factor offsets stay in registers
+            sy_log2 = bx_log2 == 8 ? 8 : (sy_log2 + 5 > kMaxSyLog2 ? kMaxSyLog2 : sy_log2 + 5);
             while (sy_log2 > 8 - bx_log2 &&
-                   (L.total_s >> sy_log2) * ((a.Bv + (1LL << bx_log2) - 1) >> bx_log2) < 148 * 4)
+                   (L.total_s >> sy_log2) * ((a.Bv + (1LL << bx_log2) - 1) >> bx_log2) < 148 * 8)
                 --sy_log2;
         }
         a.bx_log2 = bx_log2;
@@ -130,7 +131,9 @@ struct Launcher {
         if (gx > 2147483647LL || gy > 65535)
             return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
         dim3 grid((unsigned)gx, (unsigned)gy, 1);
-        if (is_init)
+        if (is_init && bx_log2 == 8)                     // a block spans one row: shared row lookups
+            jt_init_rows_kernel<SR, T, VEC><<<grid, kThreads, 0, stream>>>(a);
+        else if (is_init)
             jt_init_kernel<SR, T, VEC><<<grid, kThreads, 0, stream>>>(a);
         else
             jt_project_kernel<SR, T, VEC><<<grid, kThreads, 0, stream>>>(a);

@@ -163,6 +163,56 @@ def test_schedule_structure(net):
             assert T[t][sch.T_FLAGS] & sch.TF_TASK_UNIFORM
 
 
+@pytest.mark.parametrize("net", [wl.dag37(), wl.random_dag(30, 3, 2, 3, 30, 4), wl.ising(5)],
+                         ids=lambda n: n["name"])
+def test_uniform_down_messages(net):
+    """Uniform mode's distribute pass: a down-message is uniform iff its whole source side is;
+    it is then computed by a PHASE_DIST_UNIFORM task from uniform operands only, every consumer
+    reads the uniform copy, and the launches uniform mode runs (DIST_PRE_INSTANCE + DIST_MAIN)
+    still write every down-message, separator belief and clique belief exactly once."""
+    plan = _plan(net)
+    T, M = plan.tasks_arr, plan.msgs_arr
+    seps = range(plan.n_cliques, plan.n_cliques + plan.n_seps)
+    child_of = {s: k for c in plan.order for s, k in plan.children[c]}
+    for c in plan.order:
+        above = plan.parent[c] < 0 or plan.uniform_down[plan.parent_sep[c]]
+        for s, _ in plan.children[c]:
+            others = all(plan.uniform_up[k2] for s2, k2 in plan.children[c] if s2 != s)
+            assert plan.uniform_down[s] == (plan.uniform[c] and above and others)
+    if net["name"] in ("dag37", "ising5x5"):
+        assert any(plan.uniform_down.values()) and not all(plan.uniform_down.values())
+    down_of = {plan.down_off(s): s for s in seps}
+    tasks_of = lambda ph: [t for L in plan.launches_arr if L[0] == ph for t in range(L[1], L[2])]
+    uni_tasks = tasks_of(sch.PHASE_DIST_UNIFORM)
+    assert sorted(down_of[int(T[t][sch.T_OUT])] for t in uni_tasks) == sorted(s for s in seps if plan.uniform_down[s])
+    for t in uni_tasks:
+        assert T[t][sch.T_FLAGS] & sch.TF_TASK_UNIFORM and T[t][sch.T_FLAGS] & sch.TF_SRC_UNIFORM
+        assert T[t][sch.T_BETA] < 0 and T[t][sch.T_BEL] < 0
+        assert all(m[sch.M_UNI] for m in M[T[t][sch.T_RMSG_BEGIN]:T[t][sch.T_SMSG_END]])
+    # every reader of a down-message is flagged according to its uniformity
+    for t in range(len(T)):
+        if T[t][sch.T_KIND] != sch.KIND_PROJECT:
+            continue
+        for m in M[T[t][sch.T_RMSG_BEGIN]:T[t][sch.T_SMSG_END]]:
+            if int(m[sch.M_OFF]) in down_of:
+                assert bool(m[sch.M_UNI]) == plan.uniform_down[down_of[int(m[sch.M_OFF])]]
+    # what uniform mode launches per level writes each buffer once
+    inst = tasks_of(sch.PHASE_DIST_PRE_INSTANCE) + tasks_of(sch.PHASE_DIST_MAIN)
+    assert sorted(int(T[t][sch.T_OUT]) for t in inst if T[t][sch.T_OUT] >= 0) == sorted(down_of)
+    assert sorted(int(T[t][sch.T_BEL]) for t in inst if T[t][sch.T_BEL] >= 0) == sorted(plan.bel_off(s) for s in seps)
+    assert sorted(int(T[t][sch.T_BETA]) for t in inst if T[t][sch.T_BETA] >= 0) == \
+        sorted(plan.node_off[c] for c in range(plan.n_cliques))
+    # the elementwise forms: uniform source = the uniform down-message, own = the child's up-message
+    general = set(tasks_of(sch.PHASE_DIST_PRE))
+    for t in tasks_of(sch.PHASE_DIST_PRE_INSTANCE):
+        if t in general:
+            continue
+        s = down_of[int(T[t][sch.T_OUT])]
+        assert plan.uniform_down[s] and T[t][sch.T_NR] == 1 and T[t][sch.T_SRC] == T[t][sch.T_OUT]
+        assert T[t][sch.T_FLAGS] & sch.TF_SRC_UNIFORM and T[t][sch.T_OWN] == plan.up_off(s)
+        assert bool(T[t][sch.T_FLAGS] & sch.TF_OWN_UNIFORM) == plan.uniform_up[child_of[s]]
+
+
 def test_uniform_flags_follow_the_evidence():
     net = wl.dag37()
     plan = _plan(net)

@@ -343,7 +343,10 @@ def run_gpu(args):
     A = w * plan.algorithmic_entries(with_init=True)
     A_msg = w * plan.algorithmic_entries(with_init=False)
     uniform = not args.no_uniform and plan.uni_entries > 0
-    msg_phases = (2, 3, 8) if uniform else (1, 2, 3)     # batch launches of collect + distribute
+    from junctiontree import schedule as sch
+    # batch launches of collect + distribute in the mode that ran
+    msg_phases = (sch.PHASE_COLLECT_INSTANCE, sch.PHASE_DIST_PRE_INSTANCE, sch.PHASE_DIST_MAIN) if uniform \
+        else (sch.PHASE_COLLECT, sch.PHASE_DIST_PRE, sch.PHASE_DIST_MAIN)
     msg_launches = sum(1 for L in plan.launches_arr if L[0] in msg_phases)
     msg_ms_per_launch = msg_ms / args.steps / max(msg_launches, 1)
     achieved = A_msg * B / (msg_ms / args.steps / 1e3) / 1e9

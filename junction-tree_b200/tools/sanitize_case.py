@@ -36,6 +36,28 @@ def main():
             np.testing.assert_allclose(g[:2], w, rtol=rtol)
         print("ok", B, np.dtype(dtype).name, "uniform" if uniform else "per-instance")
     tree.propagate(net["values"])
+    # other semirings (log domain), soft evidence (likelihood region, init_rows kernel at B >= 512),
+    # direct marginals without clique beliefs, output stage
+    from junctiontree import semirings as sr
+    B = 520
+    ev = wl.draw_evidence(net, B)
+    rng = np.random.default_rng(0)
+    free = [v for v in sorted(net["sizes"]) if v not in net["evidence_vars"]]
+    lik = {v: rng.random((B, net["sizes"][v])) + 0.1 for v in free[:2]}
+    for law, name, vals, lk in ((sr.max_product, "max_product", net["values"], lik),
+                                (sr.log_sum_exp, "log_sum_exp", [np.log(v) for v in net["values"]],
+                                 {v: np.log(x) for v, x in lik.items()})):
+        outs, nodes = tree.propagate_batch(vals, net["evidence_vars"], ev, nodes=True, dl=law, likelihoods=lk)
+        b = 3
+        fx, f2cx, vx = ref_fixed.with_likelihood_factors(net["factors"], ct.factor_to_maxclique, ct.maxcliques,
+                                                         vals, lk, b)
+        want_f, want_n = ref_fixed.propagate_batch(tree.tree, tree.separators, ct.maxcliques, f2cx, fx, net["sizes"],
+                                                   vx, net["evidence_vars"], ev[b:b + 1], n=1, semiring=name)
+        for g, w in zip(list(outs) + list(nodes), list(want_f[:len(outs)]) + list(want_n)):
+            np.testing.assert_allclose(g[b], w[0], rtol=1e-11, atol=1e-11)
+        print("ok", name, "with soft evidence")
+    marg, log_z = tree.marginals_batch(net["values"], None, net["evidence_vars"], ev, likelihoods=lik)
+    assert np.all(np.isfinite(log_z))
     print("done")
 
 

@@ -19,8 +19,8 @@ def pytest_sessionstart(session):
     none, so that the ABI tests can load it (nvcc cross-compiles without a GPU)."""
     lib = os.path.join(ROOT, "junction-tree_b200", "junctiontree", "libjt_b200.so")
     if not os.path.exists(lib):
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "junction-tree_b200", "csrc")],
-                              stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-j", str(os.cpu_count() or 4), "-C",
+                               os.path.join(ROOT, "junction-tree_b200", "csrc")], stdout=subprocess.DEVNULL)
 
 
 def pytest_collection_modifyitems(config, items):

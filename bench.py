@@ -97,7 +97,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 break
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def finish(self):
         self._stop_evt.set()

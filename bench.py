@@ -421,13 +421,6 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def pick_vec(B, w):
-    for v in ((2,) if w == 8 else (4, 2)):
-        if B % v == 0:
-            return v
-    return 1
-
-
 def engine_dtype(dtype):
     from junctiontree import engine as eng
     return eng.torch_dtype(dtype)

@@ -35,8 +35,6 @@ import heapq
 import os
 from collections import deque
 
-import numpy as np
-
 
 def _use_native(impl):
     impl = impl or os.environ.get("JT_HOST_COMPILE", "native")

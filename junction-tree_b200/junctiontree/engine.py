@@ -224,11 +224,6 @@ class Engine:
         return fout[off:off + n].view(shape + (B,)).movedim(-1, 0)
 
 
-def make_plan(tree, node_vars, sizes, factors=None, factor_to_clique=None, evidence_vars=(),
-              full_sizes=None):
-    return sch.Plan(tree, node_vars, sizes, factors, factor_to_clique, evidence_vars, full_sizes)
-
-
 class BatchPipeline:
     """End-to-end streaming of a large batch in chunks over several CUDA streams.
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import jt_workloads as wl
-from helpers import RTOL_F32, RTOL_F64, assert_close, compile_net, load_golden, tuplify
+from helpers import RTOL_F32, RTOL_F64, assert_close, load_golden, tuplify
 
 pytestmark = pytest.mark.gpu
 

@@ -8,8 +8,7 @@ import numpy as np
 import pytest
 
 import jt_workloads as wl
-from helpers import (RTOL_F32, RTOL_F64, SEMIRING_NAMES, assert_close, assert_close_semiring, compile_net,
-                     semiring_inputs)
+from helpers import RTOL_F32, RTOL_F64, SEMIRING_NAMES, assert_close, assert_close_semiring, semiring_inputs
 
 pytestmark = pytest.mark.gpu
 

@@ -1,7 +1,6 @@
 """Schedule emitter and the C ABI on a machine without a GPU: the library loads, exports every
 symbol the header declares, parses and validates plan blobs; no compute call is made."""
 
-import ctypes
 import os
 import re
 

@@ -180,6 +180,19 @@ int jt_marginal(jt_plan* plan, int64_t B, int dtype, void* workspace, void* fact
 int jt_propagate(jt_plan* plan, const void* factor_tables, int factors_batched,
                  const int32_t* evidence, int64_t B, int dtype, void* workspace, void* factor_out,
                  int flags, void* stream);
+/* 1 when jt_propagate(plan, ..., B, ..., flags) runs as a single launch of the whole-propagation
+ * kernel (a few instances of a small tree), else 0 */
+int jt_plan_single_launch(const jt_plan* plan, int64_t B, int flags);
+/* JunctionTree.propagate (junctiontree.py:297-331) with HOST buffers in one call: factor tables
+ * (and evidence) host -> device staging buffers, jt_propagate, factor_out device -> host, then
+ * the stream is synchronised -- the results are in host_out on return.  host_* should be pinned;
+ * dev_factors / dev_evidence / workspace / dev_out are caller-owned device buffers of the sizes
+ * jt_propagate needs (dev_evidence and host_evidence may be NULL for plans without evidence
+ * variables).  For small trees this is one kernel between two copies, ~25 us host to host. */
+int jt_propagate_host(jt_plan* plan, const void* host_factors, size_t factor_bytes, const int32_t* host_evidence,
+                      int64_t B, int dtype, void* dev_factors, int32_t* dev_evidence, void* workspace,
+                      void* dev_out, void* host_out, size_t out_bytes, int flags, void* stream);
+
 /* Output stage: divide every output scope of factor_out ([fout_entries][B], as written by
  * jt_marginal) by its sum over the scope, per instance; the sum of scope 0 -- the partition
  * function Z = P(evidence) that the reference computes at the root and discards,

@@ -353,6 +353,21 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
     }
     const int32_t* tabp = reinterpret_cast<const int32_t*>(q);
     p->tab.assign(tabp, tabp + n_tab);
+    // task ranges of the whole-propagation kernel, general mode, in execution order
+    for (int k = 0; k < 2; ++k) {
+        const int main_phase = k ? JT_PHASE_DIST_MAIN_MESSAGES : JT_PHASE_DIST_MAIN;
+        const int marg_phase = k ? JT_PHASE_MARGINAL_DIRECT : JT_PHASE_MARGINAL;
+        auto add = [&](const jt_plan::Launch& L) {
+            p->walk_seq[k].push_back(L.begin);
+            p->walk_seq[k].push_back(L.end);
+            p->walk_items[k] += L.total_items;
+        };
+        for (const auto& L : p->launches) if (L.phase == JT_PHASE_INIT) add(L);
+        for (const auto& L : p->launches) if (L.phase == JT_PHASE_COLLECT) add(L);
+        for (const auto& L : p->launches) if (L.phase == JT_PHASE_DIST_PRE || L.phase == main_phase) add(L);
+        p->walk_marginal[k] = (int)p->walk_seq[k].size() / 2;
+        for (const auto& L : p->launches) if (L.phase == marg_phase) add(L);
+    }
     *out = p;
     return JT_OK;
 }
@@ -366,6 +381,8 @@ void jt_plan_destroy(jt_plan* p) {
         cudaFree(p->d_prefix);
         cudaFree(p->d_ev);
         cudaFree(p->d_out);
+        cudaFree(p->d_walk[0]);
+        cudaFree(p->d_walk[1]);
     }
     delete p;
 }
@@ -435,6 +452,8 @@ int jt_plan_upload(jt_plan* p) {
     std::vector<long long> outs(p->fout_off.begin(), p->fout_off.end());
     outs.insert(outs.end(), p->fout_size.begin(), p->fout_size.end());
     JT_CUDA(up(&p->d_out, outs));
+    JT_CUDA(up(&p->d_walk[0], p->walk_seq[0]));
+    JT_CUDA(up(&p->d_walk[1], p->walk_seq[1]));
     p->device = dev;
     return JT_OK;
 }
@@ -547,8 +566,76 @@ int jt_marginal(jt_plan* p, int64_t B, int dtype, void* workspace, void* factor_
     return run_phase(p, JT_PHASE_MARGINAL_DIRECT, a, dtype, vec, static_cast<cudaStream_t>(stream));
 }
 
+namespace {
+
+// A few instances of a small tree: the level-ordered launches are pure launch latency, so the
+// whole propagation runs as one launch, one CTA per instance (jt_walk_kernel).  JT_DISABLE_WALK=1
+// keeps the per-level launches (A-B timing, and the tests of the per-level kernels at tiny B).
+constexpr int64_t kWalkMaxBatch = 16;
+constexpr long long kWalkMaxItems = 1 << 16;
+
+bool walk_enabled() {
+    static const int on = [] {
+        const char* e = getenv("JT_DISABLE_WALK");
+        return (e && e[0] == '1') ? 0 : 1;
+    }();
+    return on == 1;
+}
+
+}  // namespace
+
+int jt_plan_single_launch(const jt_plan* p, int64_t B, int flags) {
+    if (!p || B <= 0 || B > kWalkMaxBatch || !walk_enabled() || p->hdr[JT_H_NFACTORS] <= 0) return 0;
+    const int k = (flags & JT_NO_BELIEFS) ? 1 : 0;
+    return !p->walk_seq[k].empty() && p->walk_items[k] <= kWalkMaxItems ? 1 : 0;
+}
+
 int jt_propagate(jt_plan* p, const void* factor_tables, int factors_batched, const int32_t* evidence, int64_t B,
                  int dtype, void* workspace, void* factor_out, int flags, void* stream) {
+    if (jt_plan_single_launch(p, B, flags)) {
+        const int k = (flags & JT_NO_BELIEFS) ? 1 : 0;
+        {
+            int rc = check_common(p, B, dtype, workspace);
+            if (rc != JT_OK) return rc;
+            if (!factor_tables) return fail(JT_ERR_INVALID, "factor_tables is null");
+            const bool marginal = !(flags & JT_SKIP_MARGINAL);
+            if (marginal && !factor_out) return fail(JT_ERR_INVALID, "factor_out is null");
+            const int n_evid = (int)p->hdr[JT_H_NEVID];
+            if (n_evid > 0 && !evidence)
+                return fail(JT_ERR_INVALID, "plan has %d evidence variables but evidence is null", n_evid);
+            if (n_evid > 0 && factors_batched)
+                return fail(JT_ERR_INVALID, "per-instance factor tables cannot be combined with evidence indices");
+            const WorkspaceLayout wl = workspace_layout(p, B, dtype);
+            KArgs a = base_args(p, B, workspace, 1);
+            a.tasks = p->d_tasks;
+            a.fin = factor_tables;
+            a.fin_batched = factors_batched ? 1 : 0;
+            a.fout = factor_out;
+            a.flags = flags;
+            jt_walk_args w;
+            memset(&w, 0, sizeof(w));
+            w.seq = p->d_walk[k];
+            w.lik_base = p->hdr[JT_H_CLIQUE_ENTRIES] + 3 * p->hdr[JT_H_SEP_ENTRIES];
+            w.lik_entries = p->hdr[JT_H_LIK_ENTRIES];
+            w.work_entries = w.lik_base + w.lik_entries;
+            w.n_tasks = (int)p->tasks.size();
+            w.n_msgs = (int)p->msgs.size();
+            w.n_tab = (int)p->tab.size();
+            w.n_seq = marginal ? (int)p->walk_seq[k].size() / 2 : p->walk_marginal[k];
+            if (n_evid > 0) {
+                a.fbase = reinterpret_cast<int*>(static_cast<char*>(workspace) + wl.fbase_off);
+                w.evidence = evidence;
+                w.n_evid = n_evid;
+                w.ev_card = p->d_ev;
+                w.evf_ptr = w.ev_card + p->ev_card.size();
+                w.evf_var = w.evf_ptr + p->evf_ptr.size();
+                w.evf_stride = w.evf_var + p->evf_var.size();
+                w.n_factors = (int)p->hdr[JT_H_NFACTORS];
+                w.errors = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + wl.err_off);
+            }
+            return launchers(flags)->walk(a, w, dtype, static_cast<cudaStream_t>(stream));
+        }
+    }
     // shared factor tables: potentials and messages no evidence reaches are computed once
     if (factors_batched) flags &= ~JT_UNIFORM;
     else if (!(flags & JT_NO_UNIFORM)) flags |= JT_UNIFORM;
@@ -560,6 +647,27 @@ int jt_propagate(jt_plan* p, const void* factor_tables, int factors_batched, con
     if (rc != JT_OK) return rc;
     if (flags & JT_SKIP_MARGINAL) return JT_OK;
     return jt_marginal(p, B, dtype, workspace, factor_out, flags, stream);
+}
+
+int jt_propagate_host(jt_plan* p, const void* host_factors, size_t factor_bytes, const int32_t* host_evidence,
+                      int64_t B, int dtype, void* dev_factors, int32_t* dev_evidence, void* workspace,
+                      void* dev_out, void* host_out, size_t out_bytes, int flags, void* stream_) {
+    if (!p || !host_factors || !dev_factors || !host_out || !dev_out) return fail(JT_ERR_INVALID, "null argument");
+    if (B <= 0) return fail(JT_ERR_INVALID, "batch size must be positive");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t n_evid = (size_t)p->hdr[JT_H_NEVID];
+    if (n_evid > 0 && (!host_evidence || !dev_evidence))
+        return fail(JT_ERR_INVALID, "plan has %zu evidence variables but evidence is null", n_evid);
+    JT_CUDA(cudaMemcpyAsync(dev_factors, host_factors, factor_bytes, cudaMemcpyHostToDevice, stream));
+    if (n_evid > 0)
+        JT_CUDA(cudaMemcpyAsync(dev_evidence, host_evidence, (size_t)B * n_evid * sizeof(int32_t),
+                                cudaMemcpyHostToDevice, stream));
+    int rc = jt_propagate(p, dev_factors, 0, n_evid > 0 ? dev_evidence : nullptr, B, dtype, workspace, dev_out, flags,
+                          stream_);
+    if (rc != JT_OK) return rc;
+    JT_CUDA(cudaMemcpyAsync(host_out, dev_out, out_bytes, cudaMemcpyDeviceToHost, stream));
+    JT_CUDA(cudaStreamSynchronize(stream));
+    return JT_OK;
 }
 
 int jt_normalize(jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, int flags, void* stream) {

@@ -103,6 +103,13 @@ struct jt_plan {
     int* d_prefix = nullptr;
     int* d_ev = nullptr;   // ev_card | evf_ptr | evf_var | evf_stride
     long long* d_out = nullptr;   // fout_off | fout_size
+    // whole-propagation kernel: task ranges in execution order, general mode; [0] with clique
+    // beliefs (INIT, COLLECT, DIST_PRE/DIST_MAIN, MARGINAL), [1] without (.., DIST_MAIN_MESSAGES,
+    // MARGINAL_DIRECT); walk_marginal[k] = number of ranges before the marginal stage
+    std::vector<int> walk_seq[2];
+    int walk_marginal[2] = {0, 0};
+    long long walk_items[2] = {0, 0};     // sum of n_s * n_r over the tasks of each sequence
+    int* d_walk[2] = {nullptr, nullptr};
     // > 48 KB dynamic shared memory opted in per [semiring][f32|f64][VPT-1]
     mutable bool tma_attr_set[kNumSemirings][2][2] = {};
 };
@@ -115,6 +122,23 @@ inline bool jt_is_init_phase(int phase) {
 // Per-semiring launchers: one translation unit per semiring (jt_sr_*.cu) instantiates the
 // kernels of jt_kernels.cuh and exports this table; jt_abi.cu picks one by the JT_SR_* flag.
 
+// arguments of the whole-propagation kernel besides KArgs (device pointers)
+struct jt_walk_args {
+    const int* seq;        // [n_seq][2] task ranges in execution order
+    int n_seq;
+    const int* evidence;   // [B][n_evid] or null
+    int n_evid;
+    const int* ev_card;
+    const int* evf_ptr;
+    const int* evf_var;
+    const int* evf_stride;
+    int n_factors;
+    unsigned long long* errors;
+    long long work_entries;            // entries of the [entries][B] block of the workspace
+    long long lik_base, lik_entries;   // its likelihood region
+    int n_tasks, n_msgs, n_tab;        // sizes of the plan's descriptor arrays
+};
+
 struct jt_sr_launchers {
     // all tasks of one launch of the plan (init or projection), kernel chosen by batch shape
     int (*dispatch)(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec,
@@ -123,6 +147,8 @@ struct jt_sr_launchers {
     int (*contract)(const KArgs& a, long long blocks, long long gy, int dtype, int vec, cudaStream_t stream);
     // output stage
     int (*normalize)(const jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, cudaStream_t stream);
+    // init + collect + distribute (+ marginal) of a few instances of a small tree in one launch
+    int (*walk)(const KArgs& a, const jt_walk_args& w, int dtype, cudaStream_t stream);
 };
 
 const jt_sr_launchers* jt_sr_sum_product();

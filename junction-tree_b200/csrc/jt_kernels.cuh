@@ -1128,6 +1128,183 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     if (wbeta) dispatch_ni(std::true_type{}); else dispatch_ni(std::false_type{});
 }
 
+// ------------------------------------------------------------------------------------------
+// Whole-propagation kernel for tiny workloads (a handful of instances of a small tree: the
+// reference's own use, one `tree.propagate(values)` call on a network like its README example).
+// There the level-ordered launches are pure launch latency (config 1: ~10 launches of a few
+// microseconds each).  One CTA owns one instance and walks the whole schedule -- evidence
+// offsets, init, collect, distribute, marginal -- with a block barrier between the launches of
+// the plan; the task semantics are those of jt_project_kernel (general mode: every operand is
+// read per instance, the uniform flags are ignored).  Workspace values written earlier in the
+// same kernel are read with plain loads (never through the read-only path).
+
+struct WalkArgs {
+    const int* seq;        // [n_seq][2] task ranges, in execution order
+    int n_seq;
+    const int* evidence;   // [B][n_evid] or null
+    int n_evid;
+    const int* ev_card;
+    const int* evf_ptr;
+    const int* evf_var;
+    const int* evf_stride;
+    int n_factors;
+    unsigned long long* errors;
+    long long lik_base, lik_entries;   // likelihood region of the workspace (filled by the caller)
+    long long work_entries;            // entries of the workspace column (shared-memory mirror)
+    int n_tasks, n_msgs, n_tab;        // sizes of the plan's descriptor arrays (staged in shared memory)
+};
+
+// The instance's column of the workspace.  SM: mirrored in shared memory (small trees: every
+// dependent read costs a shared-memory access instead of an L2 round trip); stores go through
+// to the global workspace either way, so it ends up as the per-level kernels leave it.
+template <typename T, bool SM>
+struct WalkMem {
+    T* work;
+    T* sw;
+    long long B, b;
+    __device__ __forceinline__ T get(long long idx) const { return SM ? sw[idx] : work[idx * B + b]; }
+    __device__ __forceinline__ void put(long long idx, T v) const {
+        if (SM) sw[idx] = v;
+        work[idx * B + b] = v;
+    }
+};
+
+template <typename SR, typename T, bool SM>
+__device__ __forceinline__ void walk_init(const KArgs& a, const DTask* tk, const WalkMem<T, SM>& mem, int first,
+                                          int stride) {
+    const int* tab = a.tab;             // global or shared: plain loads
+    const DMsg* msgs = a.msgs;
+    const long long B = a.B, b = mem.b;
+    const T* __restrict__ fin = static_cast<const T*>(a.fin);
+    const int n_s = tk->n_s, n_slo = tk->n_slo;
+    for (int s = first; s < n_s; s += stride) {
+        const int s_hi = s / n_slo, s_lo = s - s_hi * n_slo;
+        T val = SR::template one<T>();
+        for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
+            const DMsg* m = msgs + j;
+            const long long idx = m->off + tab[m->a_hi + s_hi] + tab[m->a_lo + s_lo];
+            if (m->fid < 0) val = SR::mul(val, mem.get(idx));
+            else if (a.fin_batched) val = SR::mul(val, __ldg(fin + idx * B + b));
+            else val = SR::mul(val, __ldg(fin + idx + (a.fbase ? a.fbase[(long long)m->fid * B + b] : 0)));
+        }
+        mem.put(tk->out + s, val);
+    }
+}
+
+template <typename SR, typename T, bool SM>
+__device__ __forceinline__ void walk_project(const KArgs& a, const DTask* tk, const WalkMem<T, SM>& mem, int first,
+                                             int stride) {
+    const int* tab = a.tab;             // global or shared: plain loads
+    const DMsg* msgs = a.msgs;
+    const int n_s = tk->n_s, n_slo = tk->n_slo, n_rlo = tk->n_rlo, n_rhi = tk->n_r / tk->n_rlo;
+    const bool has_src = tk->src >= 0;
+    const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS);
+    const int rm0 = tk->rmsg_begin, nr = tk->rmsg_end - rm0;
+    for (int s = first; s < n_s; s += stride) {
+        const int s_hi = s / n_slo, s_lo = s - s_hi * n_slo;
+        T sm = SR::template one<T>();
+        for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
+            const DMsg* m = msgs + j;
+            sm = SR::mul(sm, mem.get(m->off + tab[m->a_hi + s_hi] + tab[m->a_lo + s_lo]));
+        }
+        T own = SR::template one<T>();
+        if (tk->own >= 0) own = mem.get(tk->own + s);
+        const T scale = SR::mul(sm, own);
+        const long long s_off = tab[tk->src_shi + s_hi] + tab[tk->src_slo + s_lo];
+        typename SR::template Acc<T> acc = SR::template acc_zero<T>();
+        for (int rh = 0; rh < n_rhi; ++rh) {
+            for (int rl = 0; rl < n_rlo; ++rl) {
+                const long long e = s_off + tab[tk->src_rhi + rh] + tab[tk->src_rlo + rl];
+                T v = has_src ? mem.get(tk->src + e) : SR::template one<T>();
+                for (int j = 0; j < nr; ++j) {
+                    const DMsg* m = msgs + rm0 + j;
+                    v = SR::mul(v, mem.get(m->off + tab[m->a_hi + s_hi] + tab[m->a_lo + s_lo] +
+                                           tab[m->b_hi + rh] + tab[m->b_lo + rl]));
+                }
+                SR::accum(acc, v);
+                if (wbeta) mem.put(tk->beta + e, SR::mul(v, scale));
+            }
+        }
+        if (tk->out >= 0) {
+            const T o = SR::mul(SR::finish(acc), sm);
+            if (tk->out_space) static_cast<T*>(a.fout)[(tk->out + s) * mem.B + mem.b] = o;
+            else mem.put(tk->out + s, o);
+            if (tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS)) mem.put(tk->bel + s, SR::mul(o, own));
+        }
+    }
+}
+
+template <typename SR, typename T, bool SM>
+__global__ void __launch_bounds__(kThreads) jt_walk_kernel(const KArgs a, const WalkArgs w) {
+    extern __shared__ __align__(16) unsigned char walk_smem[];
+    const long long b = blockIdx.x, B = a.B;
+    const WalkMem<T, SM> mem = {static_cast<T*>(a.work), reinterpret_cast<T*>(walk_smem), B, b};
+    KArgs la = a;
+    const int* seq = w.seq;
+    if (SM) {
+        // the schedule itself (task and message descriptors, index tables, launch ranges) is
+        // staged too: every task is visited once, so from global memory each level would pay a
+        // chain of first-touch L2 misses (descriptor -> message -> table -> value)
+        unsigned char* p = walk_smem + ((w.work_entries * sizeof(T) + 15) / 16) * 16;
+        DTask* s_tasks = reinterpret_cast<DTask*>(p);
+        DMsg* s_msgs = reinterpret_cast<DMsg*>(s_tasks + w.n_tasks);
+        int* s_tab = reinterpret_cast<int*>(s_msgs + w.n_msgs);
+        int* s_seq = s_tab + w.n_tab;
+        const int* g_tasks = reinterpret_cast<const int*>(a.tasks);
+        for (int i = threadIdx.x; i < w.n_tasks * (int)(sizeof(DTask) / 4); i += blockDim.x)
+            reinterpret_cast<int*>(s_tasks)[i] = __ldg(g_tasks + i);
+        const int* g_msgs = reinterpret_cast<const int*>(a.msgs);
+        for (int i = threadIdx.x; i < w.n_msgs * (int)(sizeof(DMsg) / 4); i += blockDim.x)
+            reinterpret_cast<int*>(s_msgs)[i] = __ldg(g_msgs + i);
+        for (int i = threadIdx.x; i < w.n_tab; i += blockDim.x) s_tab[i] = __ldg(a.tab + i);
+        for (int i = threadIdx.x; i < 2 * w.n_seq; i += blockDim.x) s_seq[i] = __ldg(w.seq + i);
+        la.tasks = s_tasks;
+        la.msgs = s_msgs;
+        la.tab = s_tab;
+        seq = s_seq;
+        for (long long i = threadIdx.x; i < w.lik_entries; i += blockDim.x)   // soft evidence written by the caller
+            mem.sw[w.lik_base + i] = mem.work[(w.lik_base + i) * B + b];
+    }
+    if (w.evidence) {     // V1: evidence slicing of this instance (jt_evidence_kernel)
+        unsigned bad = 0;
+        for (int f = threadIdx.x; f < w.n_factors; f += blockDim.x) {
+            int acc = 0;
+            for (int k = w.evf_ptr[f]; k < w.evf_ptr[f + 1]; ++k) {
+                const int var = w.evf_var[k];
+                int state = w.evidence[b * w.n_evid + var];
+                const int card = w.ev_card[var];
+                if (state < 0 || state >= card) {
+                    ++bad;
+                    state = state < 0 ? 0 : card - 1;
+                }
+                acc += state * w.evf_stride[k];
+            }
+            const_cast<int*>(a.fbase)[(long long)f * B + b] = acc;
+        }
+        if (bad) atomicAdd(w.errors, (unsigned long long)bad);
+    }
+    __syncthreads();
+    // the tasks of one range are independent: small ones go to one warp each (task-level
+    // parallelism; a tiny tree has a few outputs per task and a block-wide loop would leave one
+    // warp walking the dependent descriptor -> table -> value loads of every task in turn)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (int q = 0; q < w.n_seq; ++q) {
+        int n_small = 0;
+        for (int t = seq[2 * q]; t < seq[2 * q + 1]; ++t) {
+            const DTask* tk = la.tasks + t;
+            int first = threadIdx.x, stride = blockDim.x;
+            if (tk->n_s <= 64) {
+                if (n_small++ % n_warps != warp) continue;
+                first = lane;
+                stride = 32;
+            }
+            if (tk->kind == JT_KIND_INIT) walk_init<SR, T, SM>(la, tk, mem, first, stride);
+            else walk_project<SR, T, SM>(la, tk, mem, first, stride);
+        }
+        __syncthreads();
+    }
+}
+
 // Output stage: normalise every output scope per instance; log Z from scope 0.
 template <typename SR, typename T>
 __global__ void __launch_bounds__(kThreads)

@@ -173,6 +173,36 @@ struct Launcher {
         return JT_OK;
     }
 
+    // the whole propagation of a few instances of a small tree in one launch (jt_walk_kernel)
+    static int walk(const KArgs& a, const jt_walk_args& w, int dtype, cudaStream_t stream) {
+        WalkArgs d;
+        d.seq = w.seq; d.n_seq = w.n_seq; d.evidence = w.evidence; d.n_evid = w.n_evid; d.ev_card = w.ev_card;
+        d.evf_ptr = w.evf_ptr; d.evf_var = w.evf_var; d.evf_stride = w.evf_stride; d.n_factors = w.n_factors;
+        d.errors = w.errors;
+        d.lik_base = w.lik_base;
+        d.lik_entries = w.lik_entries;
+        d.work_entries = w.work_entries;
+        d.n_tasks = w.n_tasks;
+        d.n_msgs = w.n_msgs;
+        d.n_tab = w.n_tab;
+        // the instance's column of the workspace and the schedule fit the default 48 KB of shared
+        // memory: mirror the column, stage the schedule
+        const size_t smem = ((size_t)w.work_entries * (dtype == JT_F64 ? 8 : 4) + 15) / 16 * 16 +
+                            (size_t)w.n_tasks * sizeof(DTask) + (size_t)w.n_msgs * sizeof(DMsg) +
+                            (size_t)w.n_tab * 4 + (size_t)w.n_seq * 8;
+        const bool sm = smem <= 48 * 1024;
+        if (dtype == JT_F64) {
+            if (sm) jt_walk_kernel<SR, double, true><<<(unsigned)a.B, kThreads, smem, stream>>>(a, d);
+            else jt_walk_kernel<SR, double, false><<<(unsigned)a.B, kThreads, 0, stream>>>(a, d);
+        } else {
+            if (sm) jt_walk_kernel<SR, float, true><<<(unsigned)a.B, kThreads, smem, stream>>>(a, d);
+            else jt_walk_kernel<SR, float, false><<<(unsigned)a.B, kThreads, 0, stream>>>(a, d);
+        }
+        jt_g_launches.fetch_add(1, std::memory_order_relaxed);
+        JT_CUDA(cudaGetLastError());
+        return JT_OK;
+    }
+
     static int normalize(const jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, cudaStream_t stream) {
         const int n_out = (int)p->fout_off.size();
         dim3 grid((unsigned)((B + kThreads - 1) / kThreads), (unsigned)n_out, 1);
@@ -193,6 +223,6 @@ struct Launcher {
 #define JT_DEFINE_SEMIRING(SR, ID, NAME)                                                       \
     const jt_sr_launchers* NAME() {                                                            \
         static const jt_sr_launchers table = {&Launcher<SR, ID>::dispatch, &Launcher<SR, ID>::contract, \
-                                              &Launcher<SR, ID>::normalize};                   \
+                                              &Launcher<SR, ID>::normalize, &Launcher<SR, ID>::walk}; \
         return &table;                                                                         \
     }

@@ -49,6 +49,11 @@ SIGNATURES = {
     "jt_propagate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                     ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_int, ctypes.c_void_p]),
+    "jt_plan_single_launch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    "jt_propagate_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                         ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                         ctypes.c_int, ctypes.c_void_p]),
     "jt_normalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "jt_evidence_errors": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
@@ -195,6 +200,16 @@ class DevicePlan:
     def propagate(self, factors_ptr, batched, evidence_ptr, B, dtype, ws_ptr, out_ptr, flags, stream):
         check(lib().jt_propagate(self._handle, factors_ptr, int(batched), evidence_ptr, B,
                                  dtype_code(dtype), ws_ptr, out_ptr, flags, stream))
+
+    def single_launch(self, B, flags):
+        """True when ``propagate`` of ``B`` instances is one launch of the whole-propagation kernel."""
+        return bool(lib().jt_plan_single_launch(self._handle, B, flags))
+
+    def propagate_host(self, host_factors_ptr, factor_bytes, host_evidence_ptr, B, dtype, dev_factors_ptr,
+                       dev_evidence_ptr, ws_ptr, dev_out_ptr, host_out_ptr, out_bytes, flags, stream):
+        check(lib().jt_propagate_host(self._handle, host_factors_ptr, factor_bytes, host_evidence_ptr, B,
+                                      dtype_code(dtype), dev_factors_ptr, dev_evidence_ptr, ws_ptr, dev_out_ptr,
+                                      host_out_ptr, out_bytes, flags, stream))
 
     def normalize(self, B, dtype, out_ptr, logz_ptr, stream, flags=0):
         check(lib().jt_normalize(self._handle, B, dtype_code(dtype), out_ptr, logz_ptr, flags, stream))

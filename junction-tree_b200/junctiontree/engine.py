@@ -428,6 +428,75 @@ class GraphedPropagation:
             host[plan.fin_off[f]:plan.fin_off[f] + plan.fin_size[f]] = a.reshape(-1)
 
 
+class HostPropagation:
+    """Host-to-host propagation of a few instances of a small tree in ONE library call
+    (``jt_propagate_host``): tables host -> device, the whole-propagation kernel, outputs device
+    -> host, stream synchronised.  For such trees a propagation is launch latency end to end
+    (config 1: one kernel of a few microseconds), so the call path matters more than the
+    kernel: no CUDA graph, no per-call torch stream handling, one ``ctypes`` call.  Same
+    staging buffers and ``set_factors`` interface as :class:`GraphedPropagation`."""
+
+    def __init__(self, engine, B, dtype, semiring=0):
+        t = require_cuda()
+        plan = engine.plan
+        engine.dev.upload()
+        self.engine, self.B, self.dtype = engine, int(B), np.dtype(dtype)
+        tdt = torch_dtype(dtype)
+        n_ev = len(plan.evidence_vars)
+        self.host_factors = t.zeros(max(plan.fin_entries, 1), dtype=tdt).pin_memory()
+        self.host_evidence = t.zeros((self.B, max(n_ev, 1)), dtype=t.int32).pin_memory()
+        self.host_out = t.zeros((max(plan.fout_entries, 1), self.B), dtype=tdt).pin_memory()
+        self.factors = t.zeros_like(self.host_factors, device="cuda")
+        self.evidence = t.zeros_like(self.host_evidence, device="cuda")
+        self.fout = t.zeros_like(self.host_out, device="cuda")
+        self.ws = engine.new_workspace(self.B, dtype)
+        self.stream = t.cuda.Stream()
+        self.flags = _native.JT_NO_BELIEFS | int(semiring)
+        t.cuda.synchronize()                            # staging buffers are zero-filled on the default stream
+        item = self.dtype.itemsize
+        self._call = (self.host_factors.data_ptr(), plan.fin_entries * item,
+                      self.host_evidence.data_ptr() if n_ev else None, self.B, self.dtype,
+                      self.factors.data_ptr(), self.evidence.data_ptr() if n_ev else None, self.ws.data_ptr(),
+                      self.fout.data_ptr(), self.host_out.data_ptr(), plan.fout_entries * self.B * item, self.flags,
+                      self.stream.cuda_stream)
+        self._host_factors_np = self.host_factors.numpy()
+        self._host_out_np = self.host_out.numpy()
+        self._slots = [(plan.fin_off[f], plan.fin_off[f] + plan.fin_size[f], tuple(plan.fin_shape[f]))
+                       for f in range(len(plan.fin_off))]
+
+    def set_factors(self, values):
+        """Copy the factor tables (plan order, stored shapes) into the pinned staging buffer."""
+        host = self._host_factors_np
+        for (lo, hi, shape), v in zip(self._slots, values):
+            a = v if isinstance(v, np.ndarray) else np.asarray(v)
+            if a.shape != shape:
+                raise ValueError("factor table: expected shape %s, got %s" % (list(shape), list(a.shape)))
+            host[lo:hi] = a.reshape(-1)
+
+    def run(self):
+        """Propagate and wait; the result is in ``host_out`` (``[fout_entries, B]``)."""
+        self.engine.dev.propagate_host(*self._call)
+        return self.host_out
+
+
+def _host_runner(self, B, dtype, semiring=0):
+    """Runner for host-in / host-out propagation of ``B`` instances: one library call when the
+    plan runs as a single launch, a CUDA-graph replay otherwise."""
+    flags = _native.JT_NO_BELIEFS | int(semiring)
+    self.dev.upload()
+    if self.dev.single_launch(int(B), flags):
+        key = ("host", int(B), np.dtype(dtype).str, int(semiring))
+        hit = self._workspaces.get(key)
+        if hit is None:
+            hit = HostPropagation(self, B, dtype, semiring)
+            self._workspaces[key] = hit
+        return hit
+    return self.graphed(B, dtype, semiring=semiring)
+
+
+Engine.host_runner = _host_runner
+
+
 def _graphed(self, B, dtype, sep_beliefs=False, uniform=True, semiring=0):
     key = ("graph", int(B), np.dtype(dtype).str, bool(sep_beliefs), bool(uniform), int(semiring))
     hit = self._workspaces.get(key)

@@ -107,6 +107,8 @@ class CliqueGraph():
     factor_graph = attr.ib()
 
     _engines = attr.ib(factory=dict, init=False, repr=False, eq=False)
+    # (shapes, dtypes, semiring) of a single propagate() call -> (runner, output slots)
+    _single = attr.ib(factory=dict, init=False, repr=False, eq=False)
 
     def create_junction_tree(self):
         """Create a Junction tree from a triangulated clique tree."""
@@ -273,21 +275,30 @@ class JunctionTree():
                  clique belief summed down to the factor's variables (reference
                  ``junctiontree.py:297-331``)
         """
-        fg = self.clique_tree.factor_graph
-        sizes = dict(fg.sizes)
-        sizes.update(_effective_sizes(fg.factors, xs))
-        engine = self._engine(sizes)
-        dtype = np.dtype(dtype) if dtype is not None else _result_dtype(xs)
-        plan = engine.plan
-        # single instance: launch-bound, so the whole call (tables in, propagate, beliefs out)
-        # is one CUDA-graph replay over static buffers
-        graphed = engine.graphed(1, dtype, semiring=_semiring(dl))
-        graphed.set_factors(xs)
-        flat = graphed.run().numpy()[:, 0]
-        return [
-            flat[plan.fout_off[f]:plan.fout_off[f] + plan.fout_size[f]].reshape(tuple(plan.fout_shape[f])).copy()
-            for f in range(len(plan.fout_off))
-        ]
+        ct = self.clique_tree
+        xs = [x if isinstance(x, np.ndarray) else np.asarray(x) for x in xs]
+        key = (tuple(x.shape for x in xs), tuple(x.dtype.char for x in xs), dtype, id(dl))
+        hit = ct._single.get(key)
+        if hit is None:
+            fg = ct.factor_graph
+            sizes = dict(fg.sizes)
+            sizes.update(_effective_sizes(fg.factors, xs))
+            engine = self._engine(sizes)
+            plan = engine.plan
+            # single instance: latency-bound.  Small trees: one library call (tables in, one
+            # kernel, beliefs out); larger ones: one CUDA-graph replay over static buffers
+            runner = engine.host_runner(1, np.dtype(dtype) if dtype is not None else _result_dtype(xs),
+                                        semiring=_semiring(dl))
+            slots = [(plan.fout_off[f], plan.fout_off[f] + plan.fout_size[f], tuple(plan.fout_shape[f]))
+                     for f in range(len(plan.fout_off))]
+            hit = (runner, slots, dl)                    # dl is kept alive so that its id stays unique
+            if len(ct._single) >= 16:
+                ct._single.pop(next(iter(ct._single)))
+            ct._single[key] = hit
+        runner, slots, _ = hit
+        runner.set_factors(xs)
+        flat = runner.run().numpy()[:, 0].copy()         # one fresh array; the outputs are views of it
+        return [flat[lo:hi].reshape(shape) for lo, hi, shape in slots]
 
     def marginals_batch(self, xs, variables=None, evidence_vars=(), evidence=None, batch=None, dtype=None,
                         normalize=True, dl=None, likelihoods=None):

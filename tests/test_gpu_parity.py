@@ -633,3 +633,60 @@ def test_soft_evidence_one_hot_equals_slicing_and_streams():
         tree.propagate_batch(net["values"], evars, ev, likelihoods={evars[0]: onehot[evars[0]]})
     with pytest.raises(ValueError):
         tree.propagate_batch(net["values"], likelihoods={"nope": np.ones((B, 2))})
+
+
+def test_small_propagations_run_as_one_launch():
+    """A few instances of a small tree: init + collect + distribute + marginal are one launch of
+    the whole-propagation kernel (one CTA per instance), with and without clique beliefs, with
+    evidence, in every semiring -- and give the oracle's numbers."""
+    import junctiontree as jt
+    from junctiontree import _native, semirings as sr
+    from oracle import ref_fixed
+    net = wl.random_dag(12, 3, 2, 3, 8, 5)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    ct = tree.clique_tree
+    evars = net["evidence_vars"]
+    for B in (1, 5, 16):
+        ev = wl.draw_evidence(net, B)
+        for nodes in (False, True):
+            before = _native.launch_count()
+            res = tree.propagate_batch(net["values"], evars, ev, nodes=nodes)
+            assert _native.launch_count() - before == 1
+            outs, got_nodes = res if nodes else (res, None)
+            want_f, want_n = ref_fixed.propagate_batch(tree.tree, tree.separators, ct.maxcliques, ct.factor_to_maxclique,
+                                                       net["factors"], net["sizes"], net["values"], evars, ev, n=B)
+            for f, (g, w) in enumerate(zip(outs, want_f)):
+                assert_close(g, w, RTOL_F64, "factor %d" % f)
+            if nodes:
+                for k, (g, w) in enumerate(zip(got_nodes, want_n)):
+                    assert_close(g, w, RTOL_F64, "node %d" % k)
+    before = _native.launch_count()
+    tree.propagate_batch(net["values"], evars, wl.draw_evidence(net, 17))
+    assert _native.launch_count() - before > 1                   # larger batches: per-level launches
+    ev = wl.draw_evidence(net, 4)
+    ev[2, 0] = 99
+    with pytest.raises(ValueError):
+        tree.propagate_batch(net["values"], evars, ev)           # out-of-range evidence is still reported
+    before = _native.launch_count()
+    got = tree.propagate_batch(net["values"], evars, wl.draw_evidence(net, 3), dl=sr.max_product)
+    assert _native.launch_count() - before == 1
+    want_f, _ = ref_fixed.propagate_batch(tree.tree, tree.separators, ct.maxcliques, ct.factor_to_maxclique,
+                                          net["factors"], net["sizes"], net["values"], evars,
+                                          wl.draw_evidence(net, 3), n=3, semiring="max_product")
+    for f, (g, w) in enumerate(zip(got, want_f)):
+        assert_close(g, w, RTOL_F64, "max-product factor %d" % f)
+
+
+def test_per_level_kernels_at_tiny_batches_without_the_whole_propagation_kernel():
+    """JT_DISABLE_WALK=1 keeps the per-level launches for tiny batches: the LDG and split-r
+    kernels at B = 1..8 stay covered (the variable is read once per process, hence a subprocess)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, JT_DISABLE_WALK="1")
+    sel = "test_batched_propagation_f64 or test_batched_propagation_f32 or test_golden or test_split_r or test_soft_evidence"
+    run = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider",
+                          os.path.join(root, "tests", "test_gpu_parity.py")], env=env, cwd=root,
+                         capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout[-3000:] + run.stderr[-2000:]

@@ -12,7 +12,12 @@
  *                  (remove_message :99-136 is replaced by a division-free exclude-one product)
  *   jt_marginal    CliqueGraph.marginalize             junctiontree/junctiontree.py:229-274
  *   jt_propagate   JunctionTree.propagate              junctiontree/junctiontree.py:297-331
+ *   jt_propagate_host  the same with host buffers (copies, propagate, synchronise in one call)
  *   jt_contract    SumProduct.einsum                   junctiontree/sum_product.py:14-35
+ *   jt_normalize   the partition function the reference discards  junctiontree/computation.py:90-96
+ *   jt_triangulate / jt_junction_tree   find_triangulation / construct_junction_tree
+ *                                                      junctiontree/construction.py:176-353, 522-601
+ *   jt_plan_build  the per-call Python bookkeeping of the passes above, compiled once
  *
  * Conventions: plain C types only; every function returns JT_OK or an error code and never
  * throws; jt_last_error_string() describes the last error of the calling thread.  The caller

@@ -13,6 +13,7 @@
  *   jt_marginal    CliqueGraph.marginalize             junctiontree/junctiontree.py:229-274
  *   jt_propagate   JunctionTree.propagate              junctiontree/junctiontree.py:297-331
  *   jt_propagate_host  the same with host buffers (copies, propagate, synchronise in one call)
+ *   jt_beliefs_host    compute_beliefs with host buffers  junctiontree/computation.py:37-246
  *   jt_contract    SumProduct.einsum                   junctiontree/sum_product.py:14-35
  *   jt_normalize   the partition function the reference discards  junctiontree/computation.py:90-96
  *   jt_triangulate / jt_junction_tree   find_triangulation / construct_junction_tree
@@ -197,6 +198,14 @@ int jt_plan_single_launch(const jt_plan* plan, int64_t B, int flags);
 int jt_propagate_host(jt_plan* plan, const void* host_factors, size_t factor_bytes, const int32_t* host_evidence,
                       int64_t B, int dtype, void* dev_factors, int32_t* dev_evidence, void* workspace,
                       void* dev_out, void* host_out, size_t out_bytes, int flags, void* stream);
+
+/* compute_beliefs (junctiontree/computation.py:37-246) of ONE instance with host buffers in one
+ * call: clique potentials (clique_entries values, node order) host -> the clique rows of the
+ * workspace, jt_collect + jt_distribute with separator beliefs (a single launch for small
+ * trees), the clique and separator beliefs (clique_entries + sep_entries values, the reference's
+ * node order) device -> host, stream synchronised. */
+int jt_beliefs_host(jt_plan* plan, const void* host_potentials, int dtype, void* workspace, void* host_beliefs,
+                    int flags, void* stream);
 
 /* Output stage: divide every output scope of factor_out ([fout_entries][B], as written by
  * jt_marginal) by its sum over the scope, per instance; the sum of scope 0 -- the partition

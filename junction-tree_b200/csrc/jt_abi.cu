@@ -354,19 +354,21 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
     const int32_t* tabp = reinterpret_cast<const int32_t*>(q);
     p->tab.assign(tabp, tabp + n_tab);
     // task ranges of the whole-propagation kernel, general mode, in execution order
-    for (int k = 0; k < 2; ++k) {
-        const int main_phase = k ? JT_PHASE_DIST_MAIN_MESSAGES : JT_PHASE_DIST_MAIN;
-        const int marg_phase = k ? JT_PHASE_MARGINAL_DIRECT : JT_PHASE_MARGINAL;
+    for (int k = 0; k < 3; ++k) {       // 2: collect + distribute on given potentials (compute_beliefs)
+        const int main_phase = k == 1 ? JT_PHASE_DIST_MAIN_MESSAGES : JT_PHASE_DIST_MAIN;
+        const int marg_phase = k == 1 ? JT_PHASE_MARGINAL_DIRECT : JT_PHASE_MARGINAL;
         auto add = [&](const jt_plan::Launch& L) {
             p->walk_seq[k].push_back(L.begin);
             p->walk_seq[k].push_back(L.end);
             p->walk_items[k] += L.total_items;
         };
-        for (const auto& L : p->launches) if (L.phase == JT_PHASE_INIT) add(L);
+        if (k < 2)
+            for (const auto& L : p->launches) if (L.phase == JT_PHASE_INIT) add(L);
         for (const auto& L : p->launches) if (L.phase == JT_PHASE_COLLECT) add(L);
         for (const auto& L : p->launches) if (L.phase == JT_PHASE_DIST_PRE || L.phase == main_phase) add(L);
         p->walk_marginal[k] = (int)p->walk_seq[k].size() / 2;
-        for (const auto& L : p->launches) if (L.phase == marg_phase) add(L);
+        if (k < 2)
+            for (const auto& L : p->launches) if (L.phase == marg_phase) add(L);
     }
     *out = p;
     return JT_OK;
@@ -381,8 +383,7 @@ void jt_plan_destroy(jt_plan* p) {
         cudaFree(p->d_prefix);
         cudaFree(p->d_ev);
         cudaFree(p->d_out);
-        cudaFree(p->d_walk[0]);
-        cudaFree(p->d_walk[1]);
+        for (int k = 0; k < 3; ++k) cudaFree(p->d_walk[k]);
     }
     delete p;
 }
@@ -452,8 +453,7 @@ int jt_plan_upload(jt_plan* p) {
     std::vector<long long> outs(p->fout_off.begin(), p->fout_off.end());
     outs.insert(outs.end(), p->fout_size.begin(), p->fout_size.end());
     JT_CUDA(up(&p->d_out, outs));
-    JT_CUDA(up(&p->d_walk[0], p->walk_seq[0]));
-    JT_CUDA(up(&p->d_walk[1], p->walk_seq[1]));
+    for (int k = 0; k < 3; ++k) JT_CUDA(up(&p->d_walk[k], p->walk_seq[k]));
     p->device = dev;
     return JT_OK;
 }
@@ -666,6 +666,42 @@ int jt_propagate_host(jt_plan* p, const void* host_factors, size_t factor_bytes,
                           stream_);
     if (rc != JT_OK) return rc;
     JT_CUDA(cudaMemcpyAsync(host_out, dev_out, out_bytes, cudaMemcpyDeviceToHost, stream));
+    JT_CUDA(cudaStreamSynchronize(stream));
+    return JT_OK;
+}
+
+int jt_beliefs_host(jt_plan* p, const void* host_potentials, int dtype, void* workspace, void* host_beliefs,
+                    int flags, void* stream_) {
+    int rc = check_common(p, 1, dtype, workspace);
+    if (rc != JT_OK) return rc;
+    if (!host_potentials || !host_beliefs) return fail(JT_ERR_INVALID, "null argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const size_t w = dtype_size(dtype);
+    const size_t n_c = (size_t)p->hdr[JT_H_CLIQUE_ENTRIES], n_s = (size_t)p->hdr[JT_H_SEP_ENTRIES];
+    flags = (flags & JT_SR_MASK) | JT_SEP_BELIEFS;
+    // B = 1: the [entries][1] block is a plain vector, cliques first, then separator beliefs
+    JT_CUDA(cudaMemcpyAsync(workspace, host_potentials, n_c * w, cudaMemcpyHostToDevice, stream));
+    if (walk_enabled() && !p->walk_seq[2].empty() && p->walk_items[2] <= kWalkMaxItems) {
+        KArgs a = base_args(p, 1, workspace, 1);
+        a.tasks = p->d_tasks;
+        a.flags = flags;
+        jt_walk_args wa;
+        memset(&wa, 0, sizeof(wa));
+        wa.seq = p->d_walk[2];
+        wa.n_seq = (int)p->walk_seq[2].size() / 2;
+        wa.lik_base = p->hdr[JT_H_CLIQUE_ENTRIES] + 3 * p->hdr[JT_H_SEP_ENTRIES];
+        wa.work_entries = wa.lik_base + p->hdr[JT_H_LIK_ENTRIES];
+        wa.n_tasks = (int)p->tasks.size();
+        wa.n_msgs = (int)p->msgs.size();
+        wa.n_tab = (int)p->tab.size();
+        wa.preload = (long long)n_c;           // the potentials just copied in
+        rc = launchers(flags)->walk(a, wa, dtype, stream);
+    } else {
+        rc = jt_collect(p, 1, dtype, workspace, flags, stream_);
+        if (rc == JT_OK) rc = jt_distribute(p, 1, dtype, workspace, flags, stream_);
+    }
+    if (rc != JT_OK) return rc;
+    JT_CUDA(cudaMemcpyAsync(host_beliefs, workspace, (n_c + n_s) * w, cudaMemcpyDeviceToHost, stream));
     JT_CUDA(cudaStreamSynchronize(stream));
     return JT_OK;
 }

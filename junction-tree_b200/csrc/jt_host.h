@@ -106,10 +106,11 @@ struct jt_plan {
     // whole-propagation kernel: task ranges in execution order, general mode; [0] with clique
     // beliefs (INIT, COLLECT, DIST_PRE/DIST_MAIN, MARGINAL), [1] without (.., DIST_MAIN_MESSAGES,
     // MARGINAL_DIRECT); walk_marginal[k] = number of ranges before the marginal stage
-    std::vector<int> walk_seq[2];
-    int walk_marginal[2] = {0, 0};
-    long long walk_items[2] = {0, 0};     // sum of n_s * n_r over the tasks of each sequence
-    int* d_walk[2] = {nullptr, nullptr};
+    // [2] = COLLECT, DIST_PRE/DIST_MAIN only (collect + distribute on given potentials)
+    std::vector<int> walk_seq[3];
+    int walk_marginal[3] = {0, 0, 0};
+    long long walk_items[3] = {0, 0, 0};  // sum of n_s * n_r over the tasks of each sequence
+    int* d_walk[3] = {nullptr, nullptr, nullptr};
     // > 48 KB dynamic shared memory opted in per [semiring][f32|f64][VPT-1]
     mutable bool tma_attr_set[kNumSemirings][2][2] = {};
 };
@@ -137,6 +138,7 @@ struct jt_walk_args {
     long long work_entries;            // entries of the [entries][B] block of the workspace
     long long lik_base, lik_entries;   // its likelihood region
     int n_tasks, n_msgs, n_tab;        // sizes of the plan's descriptor arrays
+    long long preload;                 // leading entries of the column that already hold inputs (compute_beliefs)
 };
 
 struct jt_sr_launchers {

@@ -1152,6 +1152,7 @@ struct WalkArgs {
     long long lik_base, lik_entries;   // likelihood region of the workspace (filled by the caller)
     long long work_entries;            // entries of the workspace column (shared-memory mirror)
     int n_tasks, n_msgs, n_tab;        // sizes of the plan's descriptor arrays (staged in shared memory)
+    long long preload;                 // leading entries of the column that hold inputs written by the caller
 };
 
 // The instance's column of the workspace.  SM: mirrored in shared memory (small trees: every
@@ -1264,6 +1265,8 @@ __global__ void __launch_bounds__(kThreads) jt_walk_kernel(const KArgs a, const 
         seq = s_seq;
         for (long long i = threadIdx.x; i < w.lik_entries; i += blockDim.x)   // soft evidence written by the caller
             mem.sw[w.lik_base + i] = mem.work[(w.lik_base + i) * B + b];
+        for (long long i = threadIdx.x; i < w.preload; i += blockDim.x)       // potentials given by the caller
+            mem.sw[i] = mem.work[i * B + b];
     }
     if (w.evidence) {     // V1: evidence slicing of this instance (jt_evidence_kernel)
         unsigned bad = 0;

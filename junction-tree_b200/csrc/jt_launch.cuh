@@ -181,6 +181,7 @@ struct Launcher {
         d.errors = w.errors;
         d.lik_base = w.lik_base;
         d.lik_entries = w.lik_entries;
+        d.preload = w.preload;
         d.work_entries = w.work_entries;
         d.n_tasks = w.n_tasks;
         d.n_msgs = w.n_msgs;

@@ -54,6 +54,8 @@ SIGNATURES = {
                                          ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                          ctypes.c_int, ctypes.c_void_p]),
+    "jt_beliefs_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "jt_normalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "jt_evidence_errors": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
@@ -210,6 +212,10 @@ class DevicePlan:
         check(lib().jt_propagate_host(self._handle, host_factors_ptr, factor_bytes, host_evidence_ptr, B,
                                       dtype_code(dtype), dev_factors_ptr, dev_evidence_ptr, ws_ptr, dev_out_ptr,
                                       host_out_ptr, out_bytes, flags, stream))
+
+    def beliefs_host(self, host_potentials_ptr, dtype, ws_ptr, host_beliefs_ptr, flags, stream):
+        check(lib().jt_beliefs_host(self._handle, host_potentials_ptr, dtype_code(dtype), ws_ptr, host_beliefs_ptr,
+                                    flags, stream))
 
     def normalize(self, B, dtype, out_ptr, logz_ptr, stream, flags=0):
         check(lib().jt_normalize(self._handle, B, dtype_code(dtype), out_ptr, logz_ptr, flags, stream))

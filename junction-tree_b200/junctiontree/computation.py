@@ -101,20 +101,28 @@ def _compute_beliefs_device(tree, potentials, clique_vars, semiring=0):
     dtype = np.dtype(np.float32) if all(a.dtype == np.float32 for a in arrays) else np.dtype(np.float64)
     engine, sizes = _engine_for(tree, clique_vars, [a.shape for a in arrays])
     plan = engine.plan
-    ws = engine.workspace(1, dtype)
-    work = engine.work_view(ws, 1, dtype)
-    # clique potentials -> workspace (separator inputs are overwritten by the collect pass, as
-    # in the reference: computation.py:92)
-    host = np.empty(plan.clique_entries, dtype)
+    # one library call (jt_beliefs_host): potentials -> the clique rows of the workspace, collect +
+    # distribute (a single launch for small trees), clique and separator beliefs -> host.
+    # Separator inputs are overwritten by the collect pass, as in the reference (computation.py:92)
+    key = ("beliefs", np.dtype(dtype).str)
+    stage = engine._workspaces.get(key)
+    if stage is None:
+        engine.dev.upload()
+        tdt = eng.torch_dtype(dtype)
+        n_nodes = plan.clique_entries + plan.sep_entries
+        host_in = t.zeros(max(plan.clique_entries, 1), dtype=tdt).pin_memory()
+        host_out = t.zeros(max(n_nodes, 1), dtype=tdt).pin_memory()
+        stage = (host_in, host_out, host_in.numpy(), host_out.numpy(), engine.new_workspace(1, dtype), t.cuda.Stream())
+        t.cuda.synchronize()
+        engine._workspaces[key] = stage
+    host_in, host_out, in_np, out_np, ws, stream = stage
     for c in range(plan.n_cliques):
         full = np.broadcast_to(arrays[c], tuple(plan.node_shape[c]))   # size-1 axes (reference D7)
-        host[plan.node_off[c]:plan.node_off[c] + plan.node_size[c]] = full.reshape(-1)
-    work[:plan.clique_entries, 0].copy_(t.from_numpy(host))
-    engine.beliefs_from_potentials(work, 1, dtype, ws, sep_beliefs=True, semiring=semiring)
-    n_nodes = plan.clique_entries + plan.sep_entries
-    flat = work[:n_nodes, 0].cpu().numpy()
+        in_np[plan.node_off[c]:plan.node_off[c] + plan.node_size[c]] = full.reshape(-1)
+    engine.dev.beliefs_host(host_in.data_ptr(), dtype, ws.data_ptr(), host_out.data_ptr(), semiring, stream.cuda_stream)
+    flat = out_np.copy()
     return [
-        flat[plan.node_off[k]:plan.node_off[k] + plan.node_size[k]].reshape(tuple(plan.node_shape[k])).copy()
+        flat[plan.node_off[k]:plan.node_off[k] + plan.node_size[k]].reshape(tuple(plan.node_shape[k]))
         for k in range(len(clique_vars))
     ]
 

@@ -1,9 +1,10 @@
 """Single-propagate latency of the drop-in API (BASELINE.json configs[0]: README network).
 
-    python junction-tree_b200/tools/latency.py
+    python tests/tools/latency.py
 
 Prints one JSON line per network: microseconds per `tree.propagate(values)` call (host arrays in,
-host arrays out, CUDA-graph replay inside) next to the NumPy oracle on one host core.
+host arrays out; one library call for small trees) and per `compute_beliefs` call, next to the
+NumPy oracle on one host core.  Test infrastructure: it times the oracle, so it lives under tests/.
 """
 
 import json
@@ -15,7 +16,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-for p in (ROOT, os.path.dirname(HERE)):
+for p in (ROOT, os.path.join(ROOT, "junction-tree_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 

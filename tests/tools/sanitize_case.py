@@ -1,8 +1,8 @@
 """Small propagation exercising every kernel (TMA ring, uniform warp, LDG, split-r, init), meant
 to be run under compute-sanitizer:
 
-    compute-sanitizer --tool memcheck  python junction-tree_b200/tools/sanitize_case.py
-    compute-sanitizer --tool racecheck python junction-tree_b200/tools/sanitize_case.py
+    compute-sanitizer --tool memcheck  python tests/tools/sanitize_case.py
+    compute-sanitizer --tool racecheck python tests/tools/sanitize_case.py
 """
 
 import os
@@ -11,7 +11,8 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-for p in (os.path.dirname(os.path.dirname(HERE)), os.path.dirname(HERE)):
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (ROOT, os.path.join(ROOT, "junction-tree_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 

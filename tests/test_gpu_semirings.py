@@ -201,3 +201,54 @@ def test_streamed_pipeline_in_another_semiring():
     want_f, _ = _oracle(tree, net, net["values"], net["evidence_vars"], ev[pick], len(pick), "max_product")
     for f, w in enumerate(want_f):
         assert_close(outs[f][pick], w, RTOL_F64, "factor %d" % f)
+
+
+@pytest.mark.parametrize("semiring", SEMIRING_NAMES)
+def test_semiring_properties_at_scale_config2(semiring):
+    """Config 2 at 16,384 instances under the other laws, size-independent properties on every
+    instance on the device: all cliques and separators agree on the semiring total (max-product:
+    the value of the MAP state; log-sum-exp: log Z, equal to the sum-product log Z), a separator
+    belief is the semiring marginal of its child clique; the first instances against the oracle."""
+    import torch
+    import junctiontree as jt
+    net = wl.dag37()
+    B = 16384
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    evars = net["evidence_vars"]
+    ev = wl.draw_evidence(net, B)
+    vals = semiring_inputs(net["values"], semiring)
+    outs, nodes = tree.propagate_batch(vals, evars, ev, nodes=True, device_output=True, dl=_law(semiring))
+    plan = tree.plan(evars)
+
+    def total(x, dims):
+        if semiring == "log_sum_exp":
+            return torch.logsumexp(x, dim=dims)
+        return torch.amax(x, dim=dims)
+
+    log_domain = semiring in ("log_sum_exp", "max_sum")
+    Z = total(nodes[plan.root].reshape(B, -1), [1])
+    assert bool(torch.isfinite(Z).all())
+    for k, nd in enumerate(nodes):
+        zk = total(nd.reshape(B, -1), [1])
+        err = (zk - Z).abs() if log_domain else (zk - Z).abs() / Z
+        assert float(err.max()) < 1e-11, "node %d" % k
+    for c in plan.order[::3]:
+        for s, k in plan.children[c]:
+            kv, sv = plan.node_vars[k], plan.node_vars[s]
+            axes = [1 + i for i, v in enumerate(kv) if v not in sv]
+            marg = total(nodes[k], axes) if axes else nodes[k]
+            kept = [v for v in kv if v in sv]
+            marg = marg.permute([0] + [1 + kept.index(v) for v in sv])
+            err = (marg - nodes[s]).abs() if log_domain else (marg - nodes[s]).abs() / nodes[s].abs().clamp_min(1e-300)
+            assert float(err.max()) < 1e-10
+    if semiring == "log_sum_exp":
+        _, logz = tree.marginals_batch(net["values"], [sorted(net["sizes"])[0]], evars, ev[:512])
+        assert_close(Z[:512].cpu().numpy(), logz, 1e-11, "log Z against the sum-product output stage")
+    want_f, want_n = _oracle(tree, net, vals, evars, ev[:3], 3, semiring)
+    for f, w in enumerate(want_f):
+        assert_close_semiring(outs[f][:3].cpu().numpy(), w, RTOL_F64, semiring, "factor %d" % f)
+    for k in range(0, len(nodes), 5):
+        assert_close_semiring(nodes[k][:3].cpu().numpy(), want_n[k], RTOL_F64, semiring, "node %d" % k)
+    del outs, nodes
+    tree.clique_tree._engines.clear()
+    torch.cuda.empty_cache()

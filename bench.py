@@ -282,6 +282,17 @@ def run_gpu(args):
     msg_ms = sum(e[1].elapsed_time(e[2]) for e in ev_pairs)
 
     # ---- end to end through the public API: pinned host evidence in, per-factor beliefs out ----
+    # (--e2e-batch: a larger batch for the streaming pipelines than fits the dense, all-beliefs
+    # workspace of the timed region above; their chunks use sparse workspaces)
+    B_value = B
+    if args.e2e_batch and args.e2e_batch != B:
+        del ws, fout
+        engine.release()
+        torch.cuda.empty_cache()
+        B = args.e2e_batch
+        ev_e2e = wl.draw_evidence(net, B * world) if evars else None
+        lo, hi = jdist.shard_bounds(B * world, world, rank)
+        ev_host = torch.from_numpy(ev_e2e[lo:hi].copy()).pin_memory() if evars else None
     pipe = engine.pipeline(B, dtype, chunk=args.chunk, semiring=sr_flag)
     out_host = pipe.host_output()
     for _ in range(2):
@@ -335,6 +346,7 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
+    B_e2e, B = B, B_value
     ms_per_step = total_ms / args.steps
     value = B * world / (ms_per_step / 1e3)
     peak, peak_src = load_peaks()
@@ -364,7 +376,7 @@ def run_gpu(args):
                "sample": "%d instances of the same workload (%d per core, %.1f s) through oracle/ref_fixed.py "
                          "(NumPy restatement of the reference), %d processes" % (n, args.cpu_per_core, dt, cores)}
 
-    e2e_value = B * world / (e2e_ms / e2e_steps / 1e3)
+    e2e_value = B_e2e * world / (e2e_ms / e2e_steps / 1e3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -401,13 +413,13 @@ def run_gpu(args):
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(ev_host.numel() * 4) if evars else 0,
-                "d2h_bytes_per_step": int(plan.fout_entries * B * w),
-                "ms_per_step": e2e_ms / e2e_steps, "chunk": e2e_chunk,
+                "d2h_bytes_per_step": int(plan.fout_entries * B_e2e * w),
+                "ms_per_step": e2e_ms / e2e_steps, "chunk": e2e_chunk, "batch_per_gpu": B_e2e,
                 "what": "tree-level streaming API: pinned int32 evidence -> device, propagate incl. "
                         "marginalisation to factor scopes, per-factor beliefs -> pinned host"},
         "gpu_launches": int(launches),
         "gpu_launches_e2e": int(e2e_launches),
-        "e2e_marginals": {"value": B * world / (marg_ms / e2e_steps / 1e3), "unit": UNIT,
+        "e2e_marginals": {"value": B_e2e * world / (marg_ms / e2e_steps / 1e3), "unit": UNIT,
                           "ms_per_step": marg_ms / e2e_steps,
                           "h2d_bytes_per_step": int(ev_host.numel() * 4) if evars else 0,
                           "d2h_bytes_per_step": marg_d2h,
@@ -436,6 +448,8 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--chunk", type=int, default=8192, help="instances per pipeline chunk (e2e)")
+    ap.add_argument("--e2e-batch", type=int, default=0,
+                    help="instances per GPU for the end-to-end pipelines (default: --batch)")
     ap.add_argument("--no-evidence", action="store_true")
     ap.add_argument("--no-uniform", action="store_true",
                     help="materialise every potential and message per instance (general path)")

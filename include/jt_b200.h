@@ -166,6 +166,24 @@ int jt_workspace_layout(const jt_plan* plan, int64_t B, int dtype, int64_t* out4
 int jt_plan_upload(jt_plan* plan);
 
 /*
+ * ---- sparse workspaces (CUDA virtual memory management) ----
+ * The same address layout as a dense workspace of jt_workspace_bytes(), but only the rows that
+ * the stage calls touch when run with `flags` (e.g. JT_UNIFORM | JT_NO_BELIEFS: the streaming
+ * pipelines) are backed by device memory; with most potentials uniform this is a small fraction
+ * (config 5: 15 of 103 MB per instance), so chunks can be several times larger on the same GPU.
+ * Use the pointer exactly like a dense workspace, with the same plan, B, dtype and a subset of
+ * the behaviour implied by `flags` (a stage that touches other rows faults).  Batches of at most
+ * 16 instances of small trees run as one launch in general mode and need a dense workspace.
+ */
+typedef struct jt_sparse_ws jt_sparse_ws;
+/* bytes that would be backed by memory (2 MB granularity) and the dense size, without allocating */
+int jt_workspace_sparse_bytes(const jt_plan* plan, int64_t B, int dtype, int flags, size_t* mapped, size_t* dense);
+int jt_workspace_sparse_create(const jt_plan* plan, int64_t B, int dtype, int flags, jt_sparse_ws** out);
+void* jt_workspace_sparse_ptr(const jt_sparse_ws* ws);
+size_t jt_workspace_sparse_mapped(const jt_sparse_ws* ws);
+void jt_workspace_sparse_destroy(jt_sparse_ws* ws);
+
+/*
  * ---- stages; all pointers are device pointers, stream is a cudaStream_t ----
  *
  * factor_tables : concatenated factor tables in plan order, fin_entries values of `dtype`

@@ -38,6 +38,13 @@ SIGNATURES = {
                                           ctypes.POINTER(ctypes.c_size_t)]),
     "jt_workspace_layout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, _i64p]),
     "jt_plan_upload": (ctypes.c_int, [ctypes.c_void_p]),
+    "jt_workspace_sparse_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
+    "jt_workspace_sparse_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                                  _c_void_pp]),
+    "jt_workspace_sparse_ptr": (ctypes.c_void_p, [ctypes.c_void_p]),
+    "jt_workspace_sparse_mapped": (ctypes.c_size_t, [ctypes.c_void_p]),
+    "jt_workspace_sparse_destroy": (None, [ctypes.c_void_p]),
     "jt_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "jt_collect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
@@ -180,6 +187,16 @@ class DevicePlan:
         return {"fbase": out[0], "errors": out[1], "uniform": out[2], "total": out[3]}
 
 
+    def sparse_bytes(self, B, dtype, flags):
+        """``(mapped, dense)`` bytes of a sparse workspace for the stages run with ``flags``."""
+        mapped, dense = ctypes.c_size_t(), ctypes.c_size_t()
+        check(lib().jt_workspace_sparse_bytes(self._handle, B, dtype_code(dtype), flags, ctypes.byref(mapped),
+                                              ctypes.byref(dense)))
+        return mapped.value, dense.value
+
+    def sparse_workspace(self, B, dtype, flags):
+        return SparseWorkspace(self, B, dtype, flags)
+
     def upload(self):
         if not self.uploaded:
             check(lib().jt_plan_upload(self._handle))
@@ -224,6 +241,31 @@ class DevicePlan:
         out = ctypes.c_int64()
         check(lib().jt_evidence_errors(self._handle, B, dtype_code(dtype), ws_ptr, stream, ctypes.byref(out)))
         return out.value
+
+
+class SparseWorkspace:
+    """A workspace whose untouched rows have no memory behind them (``jt_workspace_sparse_*``).
+    ``data_ptr()`` is used like the pointer of a dense workspace tensor."""
+
+    def __init__(self, plan, B, dtype, flags):
+        self._handle = ctypes.c_void_p()
+        check(lib().jt_workspace_sparse_create(plan.handle, B, dtype_code(dtype), flags, ctypes.byref(self._handle)))
+        self._ptr = lib().jt_workspace_sparse_ptr(self._handle)
+        self.mapped_bytes = lib().jt_workspace_sparse_mapped(self._handle)
+
+    def data_ptr(self):
+        return self._ptr
+
+    def close(self):
+        if self._handle:
+            lib().jt_workspace_sparse_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def contract(op_ptrs, tables, maps, n_s, n_r, n_slo, n_rlo, B, dtype, out_ptr, stream, flags=0):

@@ -66,6 +66,29 @@ class Engine:
         self.clear_evidence_errors(ws, B, dtype)
         return ws
 
+    #: flags the streaming pipelines run the stages with (which rows a sparse workspace backs)
+    PIPELINE_FLAGS = _native.JT_UNIFORM | _native.JT_NO_BELIEFS
+
+    def pipeline_bytes_per_instance(self, dtype, probe=1024):
+        """Device bytes a pipeline chunk needs per instance: workspace (sparse when that saves
+        memory) plus the output block."""
+        self.dev.upload()
+        mapped, dense = self.dev.sparse_bytes(probe, dtype, self.PIPELINE_FLAGS)
+        return min(mapped, dense) // probe + self.plan.fout_entries * np.dtype(dtype).itemsize
+
+    def new_pipeline_workspace(self, B, dtype):
+        """Workspace for a pipeline chunk of ``B`` instances: a sparse one (only the rows the
+        uniform, no-beliefs stages touch are backed by memory -- ``jt_workspace_sparse_*``) when
+        that saves at least 30 %, else a dense tensor.  Batches of at most 16 instances may run
+        as one general-mode launch that touches every row, so they stay dense."""
+        self.dev.upload()
+        if B > 16:
+            mapped, dense = self.dev.sparse_bytes(B, dtype, self.PIPELINE_FLAGS)
+            if mapped < 0.7 * dense:
+                require_cuda()
+                return self.dev.sparse_workspace(B, dtype, self.PIPELINE_FLAGS)
+        return self.new_workspace(B, dtype)
+
     def clear_evidence_errors(self, ws, B, dtype):
         off = self.dev.workspace_layout(B, dtype)["errors"]
         ws[off:off + 256].zero_()
@@ -250,7 +273,7 @@ class BatchPipeline:
         for _ in range(n_streams):
             slot = {
                 "stream": t.cuda.Stream(),
-                "ws": engine.new_workspace(self.chunk, self.dtype),
+                "ws": engine.new_pipeline_workspace(self.chunk, self.dtype),
                 "fout": t.empty((plan.fout_entries, self.chunk), dtype=torch_dtype(self.dtype), device="cuda"),
                 "ev": t.empty((self.chunk, max(self.n_ev, 1)), dtype=t.int32, device="cuda"),
                 "logz": t.empty(self.chunk, dtype=torch_dtype(self.dtype), device="cuda"),
@@ -262,7 +285,7 @@ class BatchPipeline:
         if last != self.chunk:
             self.tail = {
                 "stream": self.slots[(len(self.bounds) - 1) % n_streams]["stream"],
-                "ws": engine.new_workspace(last, self.dtype),
+                "ws": engine.new_pipeline_workspace(last, self.dtype),
                 "fout": t.empty((plan.fout_entries, last), dtype=torch_dtype(self.dtype), device="cuda"),
                 "ev": t.empty((last, max(self.n_ev, 1)), dtype=t.int32, device="cuda"),
                 "logz": t.empty(last, dtype=torch_dtype(self.dtype), device="cuda"),

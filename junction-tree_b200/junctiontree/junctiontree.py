@@ -363,8 +363,7 @@ class JunctionTree():
     def _chunk_for(engine, B, dtype):
         """Instances per pipeline chunk: at most 8192, and a third of the free device memory."""
         t = eng.torch()
-        per_instance = engine.dev.workspace_bytes(2, dtype) - engine.dev.workspace_bytes(1, dtype)
-        per_instance += engine.plan.fout_entries * np.dtype(dtype).itemsize
+        per_instance = engine.pipeline_bytes_per_instance(dtype)
         free, _ = t.cuda.mem_get_info()
         chunk = int(max(1, min(8192, B, (free // 3) // max(per_instance, 1))))
         return max(2, chunk - chunk % 2) if chunk > 1 else 1

@@ -246,6 +246,7 @@ void jt_workspace_sparse_destroy(jt_sparse_ws* ws) {
     if (!ws) return;
     const Driver& d = driver();
     if (d.ok) {
+        cudaDeviceSynchronize();      // unmapping is not stream-ordered: no kernel may still use the rows
         for (const auto& r : ws->ranges) d.unmap(ws->base + r.first, r.second);
         for (CUmemGenericAllocationHandle h : ws->handles) d.release(h);
         if (ws->base) d.free_va(ws->base, ws->va_size);

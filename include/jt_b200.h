@@ -170,7 +170,7 @@ int jt_plan_upload(jt_plan* plan);
  * The same address layout as a dense workspace of jt_workspace_bytes(), but only the rows that
  * the stage calls touch when run with `flags` (e.g. JT_UNIFORM | JT_NO_BELIEFS: the streaming
  * pipelines) are backed by device memory; with most potentials uniform this is a small fraction
- * (config 5: 15 of 103 MB per instance), so chunks can be several times larger on the same GPU.
+ * (config 5: 11 of 80 MB per instance), so chunks can be several times larger on the same GPU.
  * Use the pointer exactly like a dense workspace, with the same plan, B, dtype and a subset of
  * the behaviour implied by `flags` (a stage that touches other rows faults).  Batches of at most
  * 16 instances of small trees run as one launch in general mode and need a dense workspace.

@@ -4,7 +4,7 @@
 //
 // Why: in uniform mode without clique beliefs (the streaming pipelines: JT_UNIFORM | JT_NO_BELIEFS)
 // the potentials and beliefs of evidence-free cliques are never touched per instance -- on
-// config 5 that is 99.98 % of the clique entries, 88 MB of the 103 MB a dense workspace takes per
+// config 5 that is 99.98 % of the clique entries, 69 MB of the 80 MB a dense workspace takes per
 // instance -- so a dense allocation caps the chunk size at a few hundred instances on a 180 GB
 // GPU and the level launches stay small.  The plan, the kernels and every entry offset are
 // unchanged: untouched rows simply have no memory behind them (a stray access faults instead of

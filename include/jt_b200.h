@@ -176,6 +176,9 @@ int jt_plan_upload(jt_plan* plan);
  * 16 instances of small trees run as one launch in general mode and need a dense workspace.
  */
 typedef struct jt_sparse_ws jt_sparse_ws;
+/* the rows (entries of the [entries][B] block) the stages touch when run with `flags`, as merged
+ * half-open intervals [begin, end): up to `capacity` pairs are written, *count receives their number */
+int jt_workspace_sparse_rows(const jt_plan* plan, int flags, int64_t* intervals, int64_t capacity, int64_t* count);
 /* bytes that would be backed by memory (2 MB granularity) and the dense size, without allocating */
 int jt_workspace_sparse_bytes(const jt_plan* plan, int64_t B, int dtype, int flags, size_t* mapped, size_t* dense);
 int jt_workspace_sparse_create(const jt_plan* plan, int64_t B, int dtype, int flags, jt_sparse_ws** out);

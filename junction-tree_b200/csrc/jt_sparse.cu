@@ -163,6 +163,17 @@ std::vector<std::pair<size_t, size_t>> byte_ranges(const jt_plan* p, int64_t B, 
 
 extern "C" {
 
+int jt_workspace_sparse_rows(const jt_plan* p, int flags, int64_t* intervals, int64_t capacity, int64_t* count) {
+    if (!p || !count || capacity < 0 || (capacity > 0 && !intervals)) return jt_fail(JT_ERR_INVALID, "bad argument");
+    const Intervals iv = touched_entries(p, flags);
+    *count = (int64_t)iv.size();
+    for (int64_t i = 0; i < (int64_t)iv.size() && i < capacity; ++i) {
+        intervals[2 * i] = iv[i].first;
+        intervals[2 * i + 1] = iv[i].second;
+    }
+    return JT_OK;
+}
+
 int jt_workspace_sparse_bytes(const jt_plan* p, int64_t B, int dtype, int flags, size_t* mapped, size_t* dense) {
     if (!p || B <= 0 || (dtype != JT_F32 && dtype != JT_F64) || !mapped) return jt_fail(JT_ERR_INVALID, "bad argument");
     size_t total = 0;

@@ -38,6 +38,7 @@ SIGNATURES = {
                                           ctypes.POINTER(ctypes.c_size_t)]),
     "jt_workspace_layout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, _i64p]),
     "jt_plan_upload": (ctypes.c_int, [ctypes.c_void_p]),
+    "jt_workspace_sparse_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _i64p, ctypes.c_int64, _i64p]),
     "jt_workspace_sparse_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                                  ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
     "jt_workspace_sparse_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
@@ -193,6 +194,14 @@ class DevicePlan:
         check(lib().jt_workspace_sparse_bytes(self._handle, B, dtype_code(dtype), flags, ctypes.byref(mapped),
                                               ctypes.byref(dense)))
         return mapped.value, dense.value
+
+    def sparse_rows(self, flags):
+        """Merged ``[begin, end)`` entry intervals the stages touch per instance with ``flags``."""
+        count = ctypes.c_int64()
+        check(lib().jt_workspace_sparse_rows(self._handle, flags, None, 0, ctypes.byref(count)))
+        buf = (ctypes.c_int64 * (2 * max(count.value, 1)))()
+        check(lib().jt_workspace_sparse_rows(self._handle, flags, buf, count.value, ctypes.byref(count)))
+        return [(buf[2 * i], buf[2 * i + 1]) for i in range(count.value)]
 
     def sparse_workspace(self, B, dtype, flags):
         return SparseWorkspace(self, B, dtype, flags)

@@ -29,12 +29,13 @@ def evidence_offsets(plan, evidence, B):
 
 
 def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np.float64, uniform=False,
-        beliefs=True, semiring="sum_product"):
+        beliefs=True, semiring="sum_product", sep_beliefs=True):
     """Execute the plan.  ``work``: [work_entries, B] (clique potentials preloaded when the init
     phase is skipped); ``factor_in``: flat shared factor tables (fin_entries) or per-instance
     [fin_entries, B].  ``uniform``: keep the potentials of evidence-free cliques once, in the
     uniform region, as the device does for shared factor tables.  ``semiring``: the (+, x) pair
-    of the task (``ref_fixed.SEMIRINGS``).  Returns (work, factor_out)."""
+    of the task (``ref_fixed.SEMIRINGS``).  ``sep_beliefs``: the JT_SEP_BELIEFS flag (separator
+    beliefs up * down are stored).  Returns (work, factor_out)."""
     mul, reduce_, one = semiring_ops(semiring)
     tab = plan.tables
     uni = np.zeros((plan.work_entries, 1), dtype)       # the uniform workspace: same offsets, B = 1
@@ -110,7 +111,7 @@ def run(plan, B, work=None, factor_in=None, evidence=None, phases=None, dtype=np
                     fout[t[sch.T_OUT]:t[sch.T_OUT] + n_s] = out
                 else:
                     work[t[sch.T_OUT]:t[sch.T_OUT] + n_s] = out
-            if t[sch.T_BEL] >= 0:
+            if t[sch.T_BEL] >= 0 and sep_beliefs:
                 work[t[sch.T_BEL]:t[sch.T_BEL] + n_s] = mul(out, own)
             if t[sch.T_BETA] >= 0 and beliefs:
                 beta = mul(term, sm[:, None, :])

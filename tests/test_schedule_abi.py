@@ -245,3 +245,45 @@ def test_identical_tables_are_stored_once():
     # the row sweep repeats the same clique structure: far fewer table entries than task maps
     refs = sum(int(t[sch.T_NS]) // int(t[sch.T_NSLO]) + int(t[sch.T_NSLO]) for t in plan.tasks_arr)
     assert plan.tables.size < refs / 2
+
+
+@pytest.mark.parametrize("beliefs", [False, True], ids=["no_beliefs", "beliefs"])
+@pytest.mark.parametrize("uniform", [True, False], ids=["uniform", "per_instance"])
+@pytest.mark.parametrize("net", [wl.dag37(), wl.random_dag(16, 3, 2, 4, 6, 11), wl.ising(4),
+                                 wl.large_state_tree((4, 6, 8, 4, 6, 8))], ids=lambda n: n["name"])
+def test_sparse_workspace_rows_cover_exactly_what_the_schedule_touches(net, uniform, beliefs):
+    """jt_workspace_sparse_rows (which rows of the workspace get memory) against the NumPy
+    interpreter of the same plan: with every other row poisoned the outputs are unchanged (no
+    row outside the intervals is read), no such row is written, and in uniform mode without
+    clique beliefs a large part of the workspace needs no memory."""
+    from oracle import plan_interp
+    tree, seps, mc, f2c, eff, evars = compile_net(net)
+    soft = [v for v in sorted(net["sizes"]) if v not in evars][:1]
+    plan = sch.Plan(tree, mc + seps, eff, net["factors"], f2c, evars, net["sizes"], likelihood_vars=soft)
+    flags = (_native.JT_UNIFORM if uniform else 0) | (_native.JT_SEP_BELIEFS if beliefs else _native.JT_NO_BELIEFS)
+    rows = _native.DevicePlan(plan.to_blob()).sparse_rows(flags)
+    assert all(0 <= lo < hi <= plan.work_entries for lo, hi in rows)
+    assert all(a[1] < b[0] for a, b in zip(rows, rows[1:]))          # merged and sorted
+    mask = np.zeros(plan.work_entries, bool)
+    for lo, hi in rows:
+        mask[lo:hi] = True
+    B = 2
+    ev = wl.draw_evidence(net, B) if evars else None
+    rng = np.random.default_rng(0)
+    lik = {v: rng.random((B, net["sizes"][v])) + 0.1 for v in soft}
+    fin = plan_interp.flatten_factors(plan, net["values"])
+
+    def run(poison):
+        work = np.full((plan.work_entries, B), np.nan if poison else 0.0)
+        plan_interp.load_likelihoods(plan, work, lik)
+        return plan_interp.run(plan, B, work=work, factor_in=fin, evidence=ev, uniform=uniform, beliefs=beliefs,
+                               sep_beliefs=beliefs)
+
+    work0, fout0 = run(False)
+    work1, fout1 = run(True)
+    assert np.all(np.isfinite(fout1)) and np.array_equal(fout0, fout1)
+    assert np.all(np.isnan(work1[~mask]))                            # nothing outside the intervals was written
+    written = ~np.isnan(work1).any(axis=1)
+    assert written[mask].mean() > 0.9                                # and the intervals are (nearly) tight
+    if uniform and not beliefs and net["name"] in ("dag37", "large_state_tree"):
+        assert mask.mean() < 0.6

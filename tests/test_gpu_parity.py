@@ -65,18 +65,19 @@ def test_batched_propagation_f32(net, B):
         assert_close(g, w, RTOL_F32, "factor %d" % f)
 
 
-def test_per_instance_factor_tables():
-    """Leading batch axis on the factor arrays: every instance has its own tables."""
+@pytest.mark.parametrize("B", [10, 40, 300])
+def test_per_instance_factor_tables(B):
+    """Leading batch axis on the factor arrays: every instance has its own tables (B = 10: the
+    whole-propagation kernel; 40: LDG kernels; 300: init_rows and TMA kernels)."""
     import junctiontree as jt
     from oracle import ref_fixed
     net = wl.random_dag(10, 3, 2, 3, 8, 3)
     tree = jt.create_junction_tree(net["factors"], net["sizes"])
-    B = 10
     rng = np.random.default_rng(7)
     vals = [rng.random((B,) + v.shape) + 0.05 for v in net["values"]]
     outs, nodes = tree.propagate_batch(vals, nodes=True)
     ct = tree.clique_tree
-    for b in range(B):
+    for b in sorted(set(range(0, B, max(1, B // 10))) | {B - 1}):
         fo, ys = ref_fixed.propagate(tree.tree, tree.separators, ct.maxcliques, ct.factor_to_maxclique,
                                      net["factors"], net["sizes"], [v[b] for v in vals])
         for k, y in enumerate(ys):

@@ -359,6 +359,14 @@ class JunctionTree():
         views = pipe.factor_views(out_host)
         return dict(zip(variables, views)), pipe.host_logz.numpy()
 
+    def marginals_session(self, xs, batch, variables=None, evidence_vars=(), dtype=None, normalize=True, dl=None,
+                          likelihood_vars=()):
+        """A reusable :class:`MarginalsSession` for serving: everything ``marginals_batch`` sets up
+        per call -- plan, factor tables on the device, chunk workspaces (sparse when that saves
+        memory), streams, pinned staging buffers -- is built once for batches of ``batch``
+        instances; ``session.run(evidence, likelihoods)`` then only streams the batch."""
+        return MarginalsSession(self, xs, batch, variables, evidence_vars, dtype, normalize, dl, likelihood_vars)
+
     @staticmethod
     def _chunk_for(engine, B, dtype):
         """Instances per pipeline chunk: at most 8192, and a third of the free device memory."""
@@ -522,3 +530,71 @@ class JunctionTree():
             if nodes:
                 node_out = [o.cpu().numpy() for o in node_out]
         return (outs, node_out) if nodes else outs
+
+
+class MarginalsSession:
+    """Posterior marginals for repeated batches of one size over one tree (see
+    ``JunctionTree.marginals_session``).  ``run`` returns fresh arrays; ``close`` (or leaving
+    the ``with`` block) frees the device and pinned memory."""
+
+    def __init__(self, tree, xs, batch, variables=None, evidence_vars=(), dtype=None, normalize=True, dl=None,
+                 likelihood_vars=()):
+        t = eng.require_cuda()
+        fg = tree.clique_tree.factor_graph
+        self.evidence_vars = list(evidence_vars)
+        full = dict(fg.sizes)
+        full.update(_effective_sizes(fg.factors, xs))
+        eff = dict(full)
+        for v in self.evidence_vars:
+            eff[v] = 1
+        if variables is None:
+            variables = []
+            for fv in fg.factors:
+                for v in fv:
+                    if v not in variables and v not in self.evidence_vars:
+                        variables.append(v)
+        self.variables = list(variables)
+        self.likelihood_vars = _likelihood_vars(fg, dict.fromkeys(likelihood_vars)) if likelihood_vars else []
+        self.engine = tree._engine(eff, self.evidence_vars, full, outputs=[[v] for v in self.variables],
+                                   likelihood_vars=self.likelihood_vars)
+        self.B = int(batch)
+        self.dtype = np.dtype(dtype) if dtype is not None else _result_dtype(xs)
+        self.fdev, _ = self.engine.factors_to_device(xs, self.dtype)
+        self.pipe = self.engine.pipeline(self.B, self.dtype, chunk=tree._chunk_for(self.engine, self.B, self.dtype),
+                                         normalize=normalize, log_z=True, semiring=_semiring(dl))
+        self.out_host = self.pipe.host_output()
+        n_ev = len(self.engine.plan.evidence_vars)
+        self.ev_host = t.zeros((self.B, n_ev), dtype=t.int32).pin_memory() if n_ev else None
+        self.lik_host = None
+        if self.likelihood_vars:
+            self.lik_host = t.zeros((self.engine.plan.lik_entries, self.B),
+                                    dtype=eng.torch_dtype(self.dtype)).pin_memory()
+
+    def run(self, evidence=None, likelihoods=None):
+        """``(marginals, log_z)`` as ``JunctionTree.marginals_batch`` returns them."""
+        if self.pipe is None:
+            raise RuntimeError("the session is closed")
+        if self.ev_host is not None:
+            ev = np.asarray(evidence)
+            if ev.shape != tuple(self.ev_host.shape):
+                raise ValueError("evidence must have shape %s" % (tuple(self.ev_host.shape),))
+            self.ev_host.numpy()[...] = ev
+        if self.lik_host is not None:
+            self.lik_host.copy_(self.engine.likelihoods_host(likelihoods, self.B, self.dtype))
+        self.pipe.run(self.fdev, False, self.ev_host, self.out_host, sync=True, lik_host=self.lik_host)
+        if self.ev_host is not None and self.pipe.evidence_errors():
+            self.close()           # the error counters live in the workspaces: start from clean ones next time
+            raise ValueError("evidence states outside the range of their variable")
+        views = self.pipe.factor_views(self.out_host)
+        return {v: np.array(a) for v, a in zip(self.variables, views)}, self.pipe.host_logz.numpy().copy()
+
+    def close(self):
+        self.pipe = self.out_host = self.ev_host = self.lik_host = self.fdev = None
+        eng.torch().cuda.empty_cache()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

@@ -728,3 +728,34 @@ def test_streaming_pipeline_on_sparse_workspaces():
     ev[B - 2, 0] = 77
     with pytest.raises(ValueError):
         tree.propagate_batch(net["values"], evars, ev)                    # the error counter lives in the mapped tail
+
+
+def test_marginals_session_reuses_the_pipeline():
+    """Serving: one session, several batches of the same size -- same numbers as marginals_batch,
+    fresh result arrays per call, soft evidence and out-of-range evidence handled."""
+    import junctiontree as jt
+    net = wl.random_dag(14, 3, 2, 4, 8, 6)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    evars = net["evidence_vars"]
+    B = 4096 + 200
+    free = [v for v in sorted(net["sizes"]) if v not in evars]
+    soft = [free[2]]
+    rng = np.random.default_rng(3)
+    with tree.marginals_session(net["values"], B, free, evars, likelihood_vars=soft) as session:
+        results = []
+        for seed in (11, 12):
+            ev = wl.draw_evidence(net, B, seed=seed)
+            lik = {soft[0]: rng.random((B, net["sizes"][soft[0]])) + 0.1}
+            got, log_z = session.run(ev, lik)
+            want, want_z = tree.marginals_batch(net["values"], free, evars, ev, likelihoods=lik)
+            assert_close(log_z, want_z, 1e-13, "log Z")
+            for v in free:
+                assert_close(got[v], want[v], 1e-13, "posterior %s" % v)
+            results.append(got)
+        assert not np.shares_memory(results[0][free[0]], results[1][free[0]])
+        bad = wl.draw_evidence(net, B)
+        bad[7, 0] = -3
+        with pytest.raises(ValueError):
+            session.run(bad, lik)
+    with pytest.raises(RuntimeError):
+        session.run(ev, lik)

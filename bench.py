@@ -370,7 +370,7 @@ def run_gpu(args):
     scheduled = S_msg * B / (msg_ms / args.steps / 1e3) / 1e9
 
     cpu = None
-    if not args.skip_cpu:
+    if not args.skip_cpu and world == 1:          # the CPU baseline is reported by the single-GPU run only
         v, cores, n, dt = cpu_throughput(args.config, args.cpu_per_core, semiring=args.semiring)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d instances of the same workload (%d per core, %.1f s) through oracle/ref_fixed.py "

@@ -287,3 +287,29 @@ def test_sparse_workspace_rows_cover_exactly_what_the_schedule_touches(net, unif
     assert written[mask].mean() > 0.9                                # and the intervals are (nearly) tight
     if uniform and not beliefs and net["name"] in ("dag37", "large_state_tree"):
         assert mask.mean() < 0.6
+
+
+def test_host_entry_points_validate_their_arguments_without_a_device():
+    """The host-buffer entry points and the sparse-workspace queries reject bad arguments before
+    touching CUDA (status code + message, no exception, no crash)."""
+    lib = _native.lib()
+    plan = _plan(wl.huang_darwiche())
+    dp = _native.DevicePlan(plan.to_blob())
+    assert lib.jt_propagate_host(dp.handle, None, 0, None, 1, _native.JT_F64, None, None, None, None, None, 0, 0, None) \
+        == 1 and b"null argument" in lib.jt_last_error_string()
+    assert lib.jt_beliefs_host(None, None, _native.JT_F64, None, None, 0, None) == 1
+    assert b"plan is null" in lib.jt_last_error_string()
+    assert lib.jt_plan_single_launch(dp.handle, 1, 0) == 1                 # small tree, one instance
+    assert lib.jt_plan_single_launch(dp.handle, 17, 0) == 0                # beyond 16 instances: per-level launches
+    assert lib.jt_plan_single_launch(None, 1, 0) == 0
+    big = _native.DevicePlan(_plan(wl.dag37()).to_blob())
+    assert lib.jt_plan_single_launch(big.handle, 1, 0) == 0                # too many (s, r) items for one CTA
+    mapped, dense = dp.sparse_bytes(64, np.float64, _native.JT_UNIFORM | _native.JT_NO_BELIEFS)
+    assert 0 < mapped and dense > 0
+    with pytest.raises(_native.NativeError):
+        dp.sparse_bytes(0, np.float64, 0)
+    # creating a sparse workspace needs a device: a clean error, not a crash
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(_native.NativeError):
+            _native.SparseWorkspace(dp, 64, np.float64, 0)

@@ -759,3 +759,23 @@ def test_marginals_session_reuses_the_pipeline():
             session.run(bad, lik)
     with pytest.raises(RuntimeError):
         session.run(ev, lik)
+
+
+def test_readme_usage_snippet_runs():
+    """The usage block of README.md, executed as printed on the README network of the reference."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "README.md")).read()
+    block = re.search(r"```python\n(import junctiontree as jt.*?)```", text, flags=re.S).group(1)
+    net = wl.sprinkler()
+    B = 65536
+    rng = np.random.default_rng(0)
+    scope = {"factors": net["factors"], "var_sizes": net["sizes"], "values": net["values"],
+             "states": rng.integers(0, 2, size=(B, 1)).astype(np.int32), "lam": rng.random((B, 2)) + 0.1}
+    exec(compile(block, "README.md", "exec"), scope)
+    assert len(scope["out"]) == 4 and scope["outs"][0].shape == (B, 2)
+    assert np.allclose(scope["post"]["rain"].sum(axis=1), 1.0) and scope["log_z"].shape == (B,)
+    assert np.allclose(scope["best"]["rain"].max(axis=1), 1.0)
+    assert len(scope["per_instance"]) == 3 and scope["per_instance"][1][2].shape == (1, 1)
+    assert scope["soft"][3].shape == (B, 2, 2, 2)

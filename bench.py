@@ -293,43 +293,41 @@ def run_gpu(args):
         ev_e2e = wl.draw_evidence(net, B * world) if evars else None
         lo, hi = jdist.shard_bounds(B * world, world, rank)
         ev_host = torch.from_numpy(ev_e2e[lo:hi].copy()).pin_memory() if evars else None
-    pipe = engine.pipeline(B, dtype, chunk=args.chunk, semiring=sr_flag)
-    out_host = pipe.host_output()
+    # the public serving call: tree.propagate_session(...).run(evidence) -- host evidence in,
+    # per-factor beliefs in host memory out (views of the session's pinned buffer)
+    law = {"sum_product": None, "max_product": jt.semirings.max_product, "log_sum_exp": jt.semirings.log_sum_exp,
+           "max_sum": jt.semirings.max_sum}[args.semiring]
+    ev_np = ev_host.numpy() if evars else None
+    session = tree.propagate_session(net["values"], B, evars, dtype=dtype, dl=law, chunk=args.chunk)
     for _ in range(2):
-        pipe.run(fdev, batched, ev_host, out_host)
+        session.run(ev_np, copy=False)
     barrier()
     e2e_steps = max(2, min(args.steps, 5))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l_e2e0 = _native.launch_count()
-    e0.record()
+    t_e2e = time.perf_counter()
     for _ in range(e2e_steps):
-        pipe.run(fdev, batched, ev_host, out_host)
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+        beliefs = session.run(ev_np, copy=False)          # synchronous: the results are on the host on return
+    e2e_ms = (time.perf_counter() - t_e2e) * 1e3
+    assert len(beliefs) == len(net["factors"]) and beliefs[0].shape[0] == B
     e2e_launches = _native.launch_count() - l_e2e0
-    e2e_chunk = pipe.chunk
-    del pipe, out_host
+    e2e_chunk = session.pipe.chunk
+    session.close()
+    del session, beliefs
 
     # ---- the same end to end with the device output stage: normalised single-variable
     # posteriors of the unobserved variables + log P(evidence) instead of raw factor beliefs ----
     free_vars = [v for v in sorted(net["sizes"]) if v not in evars]
-    m_engine = tree._engine(plan.sizes, evars, plan.full_sizes, outputs=[[v] for v in free_vars])
-    m_pipe = m_engine.pipeline(B, dtype, chunk=args.chunk, normalize=True, log_z=True, semiring=sr_flag)
-    m_out = m_pipe.host_output()
-    m_fdev, _ = m_engine.factors_to_device(net["values"], dtype)
+    m_session = tree.marginals_session(net["values"], B, free_vars, evars, dtype=dtype, dl=law, chunk=args.chunk)
     for _ in range(2):
-        m_pipe.run(m_fdev, False, ev_host, m_out)
+        m_session.run(ev_np, copy=False)
     barrier()
-    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    m0.record()
+    t_marg = time.perf_counter()
     for _ in range(e2e_steps):
-        m_pipe.run(m_fdev, False, ev_host, m_out)
-    m1.record()
-    barrier()
-    marg_ms = m0.elapsed_time(m1)
-    marg_d2h = int((m_engine.plan.fout_entries + 1) * B * w)
-    del m_pipe, m_out
+        m_session.run(ev_np, copy=False)
+    marg_ms = (time.perf_counter() - t_marg) * 1e3
+    marg_d2h = int((m_session.engine.plan.fout_entries + 1) * B * w)
+    m_session.close()
+    del m_session
 
     def max_over_ranks(x):
         if world == 1:
@@ -415,16 +413,17 @@ def run_gpu(args):
                 "h2d_bytes_per_step": int(ev_host.numel() * 4) if evars else 0,
                 "d2h_bytes_per_step": int(plan.fout_entries * B_e2e * w),
                 "ms_per_step": e2e_ms / e2e_steps, "chunk": e2e_chunk, "batch_per_gpu": B_e2e,
-                "what": "tree-level streaming API: pinned int32 evidence -> device, propagate incl. "
-                        "marginalisation to factor scopes, per-factor beliefs -> pinned host"},
+                "what": "tree.propagate_session(values, batch, evidence_vars).run(evidence): host int32 "
+                        "evidence -> device, propagate incl. marginalisation to factor scopes, per-factor "
+                        "beliefs -> host memory; wall clock around the synchronous calls"},
         "gpu_launches": int(launches),
         "gpu_launches_e2e": int(e2e_launches),
         "e2e_marginals": {"value": B_e2e * world / (marg_ms / e2e_steps / 1e3), "unit": UNIT,
                           "ms_per_step": marg_ms / e2e_steps,
                           "h2d_bytes_per_step": int(ev_host.numel() * 4) if evars else 0,
                           "d2h_bytes_per_step": marg_d2h,
-                          "what": "JunctionTree.marginals_batch pipeline: same propagation, device output "
-                                  "stage (normalised single-variable posteriors + log Z) -> pinned host"},
+                          "what": "tree.marginals_session(...).run(evidence): same propagation, device output "
+                                  "stage (normalised single-variable posteriors + log Z) -> host memory"},
         "clocks": clocks,
     }
     print_line(json.dumps(line))

@@ -5,6 +5,7 @@ public names as the reference's ``junctiontree/__init__.py`` (``from .junctiontr
 See DESIGN.md for the architecture and INTEGRATION.md for the C ABI.
 """
 
+from . import semirings  # noqa: F401
 from .junctiontree import *  # noqa: F401,F403
 from .junctiontree import (CliqueGraph, FactorGraph, JunctionTree, create_junction_tree,  # noqa: F401
                            einsum)

@@ -360,12 +360,19 @@ class JunctionTree():
         return dict(zip(variables, views)), pipe.host_logz.numpy()
 
     def marginals_session(self, xs, batch, variables=None, evidence_vars=(), dtype=None, normalize=True, dl=None,
-                          likelihood_vars=()):
+                          likelihood_vars=(), chunk=None):
         """A reusable :class:`MarginalsSession` for serving: everything ``marginals_batch`` sets up
         per call -- plan, factor tables on the device, chunk workspaces (sparse when that saves
         memory), streams, pinned staging buffers -- is built once for batches of ``batch``
         instances; ``session.run(evidence, likelihoods)`` then only streams the batch."""
-        return MarginalsSession(self, xs, batch, variables, evidence_vars, dtype, normalize, dl, likelihood_vars)
+        return MarginalsSession(self, xs, batch, variables, evidence_vars, dtype, normalize, dl, likelihood_vars,
+                                chunk=chunk)
+
+    def propagate_session(self, xs, batch, evidence_vars=(), dtype=None, dl=None, likelihood_vars=(), chunk=None):
+        """The same for ``propagate_batch``: ``session.run(evidence)`` returns the per-factor
+        beliefs ``[B, *factor_shape]`` of a batch (host evidence in, host arrays out)."""
+        return MarginalsSession(self, xs, batch, None, evidence_vars, dtype, False, dl, likelihood_vars,
+                                factor_scopes=True, chunk=chunk)
 
     @staticmethod
     def _chunk_for(engine, B, dtype):
@@ -538,7 +545,7 @@ class MarginalsSession:
     the ``with`` block) frees the device and pinned memory."""
 
     def __init__(self, tree, xs, batch, variables=None, evidence_vars=(), dtype=None, normalize=True, dl=None,
-                 likelihood_vars=()):
+                 likelihood_vars=(), factor_scopes=False, chunk=None):
         t = eng.require_cuda()
         fg = tree.clique_tree.factor_graph
         self.evidence_vars = list(evidence_vars)
@@ -547,21 +554,25 @@ class MarginalsSession:
         eff = dict(full)
         for v in self.evidence_vars:
             eff[v] = 1
-        if variables is None:
+        self.factor_scopes = bool(factor_scopes)       # outputs: the factor scopes (propagate) or single variables
+        if variables is None and not self.factor_scopes:
             variables = []
             for fv in fg.factors:
                 for v in fv:
                     if v not in variables and v not in self.evidence_vars:
                         variables.append(v)
-        self.variables = list(variables)
+        self.variables = None if self.factor_scopes else list(variables)
         self.likelihood_vars = _likelihood_vars(fg, dict.fromkeys(likelihood_vars)) if likelihood_vars else []
-        self.engine = tree._engine(eff, self.evidence_vars, full, outputs=[[v] for v in self.variables],
+        self.engine = tree._engine(eff, self.evidence_vars, full,
+                                   outputs=None if self.factor_scopes else [[v] for v in self.variables],
                                    likelihood_vars=self.likelihood_vars)
         self.B = int(batch)
         self.dtype = np.dtype(dtype) if dtype is not None else _result_dtype(xs)
         self.fdev, _ = self.engine.factors_to_device(xs, self.dtype)
-        self.pipe = self.engine.pipeline(self.B, self.dtype, chunk=tree._chunk_for(self.engine, self.B, self.dtype),
-                                         normalize=normalize, log_z=True, semiring=_semiring(dl))
+        self.pipe = self.engine.pipeline(self.B, self.dtype,
+                                         chunk=chunk or tree._chunk_for(self.engine, self.B, self.dtype),
+                                         normalize=normalize and not self.factor_scopes,
+                                         log_z=not self.factor_scopes, semiring=_semiring(dl))
         self.out_host = self.pipe.host_output()
         n_ev = len(self.engine.plan.evidence_vars)
         self.ev_host = t.zeros((self.B, n_ev), dtype=t.int32).pin_memory() if n_ev else None
@@ -570,8 +581,11 @@ class MarginalsSession:
             self.lik_host = t.zeros((self.engine.plan.lik_entries, self.B),
                                     dtype=eng.torch_dtype(self.dtype)).pin_memory()
 
-    def run(self, evidence=None, likelihoods=None):
-        """``(marginals, log_z)`` as ``JunctionTree.marginals_batch`` returns them."""
+    def run(self, evidence=None, likelihoods=None, copy=True):
+        """``(marginals, log_z)`` as ``JunctionTree.marginals_batch`` returns them, or -- for a
+        ``propagate_session`` -- the list of per-factor beliefs of ``propagate_batch``.
+        ``copy=False`` returns views of the session's pinned result buffer, valid until the next
+        ``run`` (no host copy of the results: the call is then bound by the PCIe transfer)."""
         if self.pipe is None:
             raise RuntimeError("the session is closed")
         if self.ev_host is not None:
@@ -586,7 +600,12 @@ class MarginalsSession:
             self.close()           # the error counters live in the workspaces: start from clean ones next time
             raise ValueError("evidence states outside the range of their variable")
         views = self.pipe.factor_views(self.out_host)
-        return {v: np.array(a) for v, a in zip(self.variables, views)}, self.pipe.host_logz.numpy().copy()
+        if copy:
+            views = [np.array(a) for a in views]
+        if self.factor_scopes:
+            return views
+        log_z = self.pipe.host_logz.numpy()
+        return dict(zip(self.variables, views)), log_z.copy() if copy else log_z
 
     def close(self):
         self.pipe = self.out_host = self.ev_host = self.lik_host = self.fdev = None

@@ -779,3 +779,21 @@ def test_readme_usage_snippet_runs():
     assert np.allclose(scope["best"]["rain"].max(axis=1), 1.0)
     assert len(scope["per_instance"]) == 3 and scope["per_instance"][1][2].shape == (1, 1)
     assert scope["soft"][3].shape == (B, 2, 2, 2)
+
+
+def test_propagate_session_returns_factor_beliefs():
+    """propagate_session: the per-factor beliefs of propagate_batch through a reusable pipeline,
+    as copies or as views of the session's pinned buffer."""
+    import junctiontree as jt
+    net = wl.random_dag(14, 3, 2, 3, 8, 2)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    evars = net["evidence_vars"]
+    B = 4096 + 100
+    ev = wl.draw_evidence(net, B)
+    want = tree.propagate_batch(net["values"], evars, ev)
+    with tree.propagate_session(net["values"], B, evars, chunk=2048) as session:
+        got = session.run(ev)
+        views = session.run(ev, copy=False)
+        for f, (g, v, w) in enumerate(zip(got, views, want)):
+            assert_close(g, w, 1e-13, "factor %d" % f)
+            assert np.array_equal(g, v) and not np.shares_memory(g, v)

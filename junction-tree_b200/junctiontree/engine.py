@@ -265,6 +265,7 @@ class BatchPipeline:
         self.host_logz = t.empty(self.B, dtype=torch_dtype(dtype)).pin_memory() if log_z else None
         plan = engine.plan
         self.chunk = int(min(chunk, B))
+        self._primed = set()             # slots whose uniform workspace holds the current factor tables
         self.bounds = [(lo, min(lo + self.chunk, self.B)) for lo in range(0, self.B, self.chunk)]
         n_streams = max(1, min(n_streams, len(self.bounds)))
         engine.dev.upload()
@@ -306,11 +307,13 @@ class BatchPipeline:
             for f in range(len(plan.fout_off))
         ]
 
-    def run(self, factor_dev, batched, ev_host, out_host, sync=False, lik_host=None):
+    def run(self, factor_dev, batched, ev_host, out_host, sync=False, lik_host=None, same_tables=False):
         """Enqueue the whole batch.  ``ev_host``: pinned int32 ``[B, |E|]`` (or None);
         ``out_host``: tensor from :meth:`host_output`; ``lik_host``: pinned ``[lik_entries, B]``
-        soft evidence (``Engine.likelihoods_host``) when the plan has likelihood variables.  The
-        calling stream waits for all chunks."""
+        soft evidence (``Engine.likelihoods_host``) when the plan has likelihood variables.
+        ``same_tables``: the factor tables are those of the previous ``run`` of this pipeline, so
+        the uniform workspaces are still valid and are not recomputed.  The calling stream waits
+        for all chunks."""
         t = torch()
         plan, dev = self.engine.plan, self.engine.dev
         if batched:
@@ -323,7 +326,8 @@ class BatchPipeline:
             slot["stream"].wait_stream(cur)
         # the factor tables are the same for every chunk of this call: the uniform workspace of
         # a slot is computed by the first chunk that uses the slot and reused by the later ones
-        primed = set()
+        primed = self._primed if same_tables else set()
+        self._primed = primed
         for i, (lo, hi) in enumerate(self.bounds):
             n = hi - lo
             slot = self.tail if (self.tail is not None and n != self.chunk) else self.slots[i % len(self.slots)]

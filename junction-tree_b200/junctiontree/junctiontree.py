@@ -574,6 +574,7 @@ class MarginalsSession:
                                          normalize=normalize and not self.factor_scopes,
                                          log_z=not self.factor_scopes, semiring=_semiring(dl))
         self.out_host = self.pipe.host_output()
+        self._ran = False
         n_ev = len(self.engine.plan.evidence_vars)
         self.ev_host = t.zeros((self.B, n_ev), dtype=t.int32).pin_memory() if n_ev else None
         self.lik_host = None
@@ -595,7 +596,10 @@ class MarginalsSession:
             self.ev_host.numpy()[...] = ev
         if self.lik_host is not None:
             self.lik_host.copy_(self.engine.likelihoods_host(likelihoods, self.B, self.dtype))
-        self.pipe.run(self.fdev, False, self.ev_host, self.out_host, sync=True, lik_host=self.lik_host)
+        # the factor tables of a session never change: the uniform workspaces are computed by the first run
+        self.pipe.run(self.fdev, False, self.ev_host, self.out_host, sync=True, lik_host=self.lik_host,
+                      same_tables=self._ran)
+        self._ran = True
         if self.ev_host is not None and self.pipe.evidence_errors():
             self.close()           # the error counters live in the workspaces: start from clean ones next time
             raise ValueError("evidence states outside the range of their variable")

@@ -797,3 +797,41 @@ def test_propagate_session_returns_factor_beliefs():
         for f, (g, v, w) in enumerate(zip(got, views, want)):
             assert_close(g, w, 1e-13, "factor %d" % f)
             assert np.array_equal(g, v) and not np.shares_memory(g, v)
+
+
+@pytest.mark.parametrize("B", [1, 70, 300])
+def test_edge_cases_disconnected_scalar_single_and_impossible_evidence(B):
+    """Edge cases of the reference's domain against brute force over the joint: unconnected
+    components (empty separators, scalar messages: every output is scaled by the other
+    components' partition sums, reference construction.py:530), a scalar factor, a single-clique
+    net, zeros in the tables, evidence of probability zero (Z = 0: normalised output all zeros,
+    log Z = -inf)."""
+    import junctiontree as jt
+    from oracle import brute
+    rng = np.random.default_rng(B)
+    # three components, one of them a single variable, plus a scalar factor
+    factors = [["x", "y"], ["y", "w"], ["z"], ["u", "v"], []]
+    sizes = dict(x=2, y=3, w=2, z=4, u=3, v=2)
+    values = [rng.random([sizes[v] for v in f]) + 0.1 for f in factors[:-1]] + [np.array(2.5)]
+    values[3][1, :] = 0.0                                    # zeros in a table
+    tree = jt.create_junction_tree(factors, sizes)
+    assert any(len(s) == 0 for s in tree.separators)         # components are joined by empty separators
+    ev = rng.integers(0, 3, size=(B, 1)).astype(np.int32)    # evidence on u; state 1 has probability zero
+    ev[0, 0] = 1
+    outs = tree.propagate_batch(values, ["u"], ev)
+    for b in sorted(set([0, B // 2, B - 1])):
+        truth = brute.factor_graph_marginals(factors, values, factors, {"u": int(ev[b, 0])})
+        for f, (g, w) in enumerate(zip(outs, truth)):
+            assert_close(g[b], w, RTOL_F64, "factor %d instance %d" % (f, b))
+    assert np.all(outs[0][0] == 0.0)                         # impossible evidence: every belief is zero
+    marg, log_z = tree.marginals_batch(values, ["x", "z"], ["u"], ev)
+    assert np.isneginf(log_z[0]) and np.all(marg["x"][0] == 0.0)
+    ok = ev[:, 0] != 1
+    assert np.allclose(marg["z"][ok].sum(axis=1), 1.0) and np.all(np.isfinite(log_z[ok]))
+    if B == 1:
+        # single propagate() calls: a one-clique network and a scalar-only factor graph
+        single = jt.create_junction_tree([["a", "b"]], dict(a=2, b=3))
+        table = rng.random((2, 3))
+        assert_close(single.propagate([table])[0], table, RTOL_F64, "single clique")
+        scalar = jt.create_junction_tree([[]], {})
+        assert_close(scalar.propagate([np.array(3.0)])[0], np.array(3.0), RTOL_F64, "scalar factor graph")

@@ -87,6 +87,38 @@ struct SrMaxSum {
     template <typename T> __device__ __forceinline__ static T log_of(T z) { return z; }
 };
 
+// exp(x) for x <= 0 in double precision, 2 ulp (checked against libm over [-700, 0]): table of
+// 2^(j/32) times a degree-6 polynomial on |r| <= ln2/64, about half the FP64 instructions of the
+// library exp -- the float64 log-sum-exp kernels are bound by the FP64 pipe, not by memory.
+// Below -700 the term is < 1e-304 of the running maximum and is dropped.
+__device__ const double kExp2Over32[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237,
+    1.0905077326652577, 1.1143867425958924, 1.1387886347566916, 1.1637248587775775,
+    1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
+    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
+    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228,
+    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.645755478153965,
+    1.681792830507429, 1.718619298122478, 1.7562521603732995, 1.7947090750031072,
+    1.8340080864093424, 1.8741676341103, 1.9152065613971474, 1.9571441241754002,
+};
+
+__device__ __forceinline__ double exp_nonpos(double x) {
+    if (x < -700.0) return 0.0;
+    const double k = rint(x * 46.16624130844683);                            // 32 / ln 2
+    const double r = fma(-k, 4.06140840434059e-10, fma(-k, 0.02166084898635745, x));   // x - k ln2/32 (hi, lo)
+    double p = 1.0 / 720.0;
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int ki = (int)k;
+    const double t = __ldg(kExp2Over32 + (ki & 31)) * p;                     // in [0.99, 2)
+    return __longlong_as_double(__double_as_longlong(t) + ((long long)(ki >> 5) << 52));   // * 2^(k / 32)
+}
+__device__ __forceinline__ float exp_nonpos(float x) { return expf(x); }
+
 // log-sum-exp: the running reduction keeps (max m, sum s of exp(v - m)), one exp per term
 struct SrLogSumExp {
     template <typename T> struct Acc { T m, s; };
@@ -101,7 +133,7 @@ struct SrLogSumExp {
     // on different sides of the running maximum do not serialise two exp sequences
     template <typename T> __device__ __forceinline__ static void accum(Acc<T>& a, T v) {
         const T d = v - a.m;                    // NaN only when both are -inf: nothing to add
-        const T e = exp(-fabs(d));              // in [0, 1]
+        const T e = exp_nonpos(-fabs(d));       // in [0, 1]
         if (d > T(0)) {                         // new maximum (d = +inf when the accumulator is empty: e = 0)
             a.s = a.s * e + T(1);
             a.m = v;
@@ -111,7 +143,7 @@ struct SrLogSumExp {
     }
     template <typename T> __device__ __forceinline__ static void merge(Acc<T>& a, const Acc<T>& b) {
         const T d = b.m - a.m;
-        const T e = exp(-fabs(d));
+        const T e = exp_nonpos(-fabs(d));
         if (d > T(0)) {
             a.s = a.s * e + b.s;
             a.m = b.m;

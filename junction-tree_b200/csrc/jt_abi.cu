@@ -131,6 +131,10 @@ int check_common(const jt_plan* p, int64_t B, int dtype, const void* workspace) 
     if (dtype != JT_F32 && dtype != JT_F64) return fail(JT_ERR_INVALID, "dtype must be JT_F32 or JT_F64");
     if (!workspace) return fail(JT_ERR_INVALID, "workspace is null");
     if (p->device < 0) return fail(JT_ERR_INVALID, "plan not uploaded: call jt_plan_upload first");
+    int dev = -1;
+    JT_CUDA(cudaGetDevice(&dev));
+    if (dev != p->device)
+        return fail(JT_ERR_INVALID, "plan lives on device %d but the current device is %d", p->device, dev);
     return JT_OK;
 }
 

@@ -207,9 +207,12 @@ class DevicePlan:
         return SparseWorkspace(self, B, dtype, flags)
 
     def upload(self):
-        if not self.uploaded:
-            check(lib().jt_plan_upload(self._handle))
-            self.uploaded = True
+        """Upload the descriptors to the current device.  Always goes through the library: the
+        call returns at once when the plan already lives on the current device and fails cleanly
+        when it lives on another one (a plan belongs to one device; engines are cached per
+        device)."""
+        check(lib().jt_plan_upload(self._handle))
+        self.uploaded = True
 
     # stage calls: raw device pointers (ints) and a cudaStream_t (int)
     def init(self, factors_ptr, batched, evidence_ptr, B, dtype, ws_ptr, flags, stream):

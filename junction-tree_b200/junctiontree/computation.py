@@ -77,7 +77,8 @@ def _engine_for(tree, clique_vars, shapes):
         for var, n in zip(node_vars, shape):
             sizes[var] = max(sizes.get(var, 1), int(n))
     try:
-        key = (_tree_key(tree), tuple(tuple(v) for v in clique_vars), tuple(sorted(sizes.items(), key=repr)))
+        key = (_tree_key(tree), tuple(tuple(v) for v in clique_vars), tuple(sorted(sizes.items(), key=repr)),
+               eng.current_device())
         hash(key)
     except TypeError:
         key = None

@@ -109,6 +109,17 @@ def pack_marginals(outputs, requested=None):
     return torch.cat(cols, dim=1)
 
 
+def _empty_outputs(tree, xs, evidence_vars, dtype):
+    """Per-factor outputs of an empty shard: ``[0, *factor_shape]`` tensors (shapes from the plan)."""
+    import torch
+    plan = tree.plan(list(evidence_vars))
+    if dtype is None:
+        dtype = np.float32 if xs and all(np.asarray(x).dtype == np.float32 for x in xs) else np.float64
+    tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    device = "cuda" if torch.cuda.is_available() else "cpu"
+    return [torch.empty((0,) + tuple(shape), dtype=tdt, device=device) for shape in plan.fout_shape]
+
+
 def propagate_sharded(tree, xs, evidence_vars, evidence, requested=None, gather=True, dtype=None,
                       group=None):
     """Propagate this rank's shard of the batch; optionally all-gather requested marginals.
@@ -124,7 +135,12 @@ def propagate_sharded(tree, xs, evidence_vars, evidence, requested=None, gather=
     rank = dist.get_rank(group) if world > 1 else 0
     B = int(np.shape(evidence)[0])
     lo, hi = shard_bounds(B, world, rank)
-    local = tree.propagate_batch(xs, evidence_vars, evidence[lo:hi], dtype=dtype, device_output=True)
+    if hi > lo:
+        local = tree.propagate_batch(xs, evidence_vars, evidence[lo:hi], dtype=dtype, device_output=True)
+    else:
+        # fewer instances than ranks: nothing to compute here, but the collective below still
+        # needs this rank (its peers would block in all_gather otherwise)
+        local = _empty_outputs(tree, xs, evidence_vars, dtype)
     gathered = None
     if gather:
         gathered = all_gather_rows(pack_marginals(local, requested), B, group)

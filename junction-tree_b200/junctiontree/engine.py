@@ -11,6 +11,7 @@ from . import _native
 from . import schedule as sch
 
 _torch = None
+_have_cuda = False
 
 
 def torch():
@@ -28,6 +29,16 @@ def require_cuda():
         raise _native.NativeError(
             "no CUDA device: junctiontree (B200 build) has no CPU execution path")
     return t
+
+
+def current_device():
+    """Index of the current CUDA device, -1 without one (part of the engine cache keys: plan
+    descriptors and workspaces belong to one device)."""
+    global _have_cuda
+    t = torch()
+    if not _have_cuda:
+        _have_cuda = t.cuda.is_available()         # a device does not go away once seen
+    return t.cuda.current_device() if _have_cuda else -1
 
 
 def torch_dtype(dtype):

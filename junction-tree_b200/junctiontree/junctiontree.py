@@ -9,6 +9,8 @@ compiled schedule (``schedule.py`` -> ``libjt_b200.so``).  ``propagate_batch`` i
 independent propagations over the same tree per launch, with per-instance evidence.
 """
 
+import weakref
+
 import numpy as np
 import attr
 
@@ -90,7 +92,21 @@ def _effective_sizes(factors, xs, batched=False):
     return sizes
 
 
-@attr.s(frozen=False)
+# Compiled state (engines, single-call runners) lives outside the attrs objects, so that
+# ``CliqueGraph`` and ``JunctionTree`` stay frozen value classes as in the reference
+# (``junctiontree.py:120,277``): owner id -> {cache name -> dict}, dropped with the owner.
+_caches = {}
+
+
+def _cache_of(owner, name):
+    slot = _caches.get(id(owner))
+    if slot is None:
+        slot = _caches[id(owner)] = {}
+        weakref.finalize(owner, _caches.pop, id(owner), None)
+    return slot.setdefault(name, {})
+
+
+@attr.s(frozen=True)
 class CliqueGraph():
     """
     Clique graph for an underlying factor graph.
@@ -106,9 +122,11 @@ class CliqueGraph():
     # The underlying factor graph
     factor_graph = attr.ib()
 
-    _engines = attr.ib(factory=dict, init=False, repr=False, eq=False)
-    # (shapes, dtypes, semiring) of a single propagate() call -> (runner, output slots)
-    _single = attr.ib(factory=dict, init=False, repr=False, eq=False)
+    @property
+    def _engines(self):
+        """Compiled engines of this clique graph (one per tree, sizes, evidence set, outputs and
+        device; see ``_engine``)."""
+        return _cache_of(self, "engines")
 
     def create_junction_tree(self):
         """Create a Junction tree from a triangulated clique tree."""
@@ -128,9 +146,16 @@ class CliqueGraph():
 
     def _engine(self, sizes, tree=None, separators=(), evidence_vars=(), full_sizes=None, outputs=None,
                 likelihood_vars=()):
-        key = (tuple(sizes.get(v) for c in self.maxcliques for v in c), tree is not None,
+        # everything the plan is compiled from, and the device its descriptors live on: a second
+        # JunctionTree over this clique graph (re-rooted, other separator axis order) or another
+        # current device gets its own engine
+        key = (tuple(sizes.get(v) for c in self.maxcliques for v in c),
+               None if tree is None else comp._tree_key(tree),
+               None if tree is None else tuple(tuple(sep) for sep in separators),
                tuple(evidence_vars), tuple(tuple(c) for c in self.maxcliques), tuple(self._f2c()),
-               None if outputs is None else tuple(tuple(o) for o in outputs), tuple(likelihood_vars))
+               None if outputs is None else tuple(tuple(o) for o in outputs), tuple(likelihood_vars),
+               None if full_sizes is None else tuple(full_sizes.get(v) for v in evidence_vars),
+               eng.current_device())
         hit = self._engines.get(key)
         if hit is None:
             node_vars = list(self.maxcliques) + ([list(s) for s in separators] if tree is not None else [])
@@ -140,12 +165,14 @@ class CliqueGraph():
             self._engines[key] = hit
         return hit
 
-    def evaluate(self, xs, dl=None):
+    def evaluate(self, xs, dl=None, reference_shapes=True):
         """Compute maximum clique values based on factor values.
 
-        GPU stage ``jt_init``.  Unlike the reference (``junctiontree.py:52-61``) a clique
-        variable that none of the assigned factors covers keeps its full size instead of
-        becoming a size-1 axis; the values are the same under broadcasting."""
+        GPU stage ``jt_init``.  As in the reference (``junctiontree.py:52-61``, pinned by its
+        ``tests/test_junctiontree.py:88-109``) a clique variable that none of the assigned
+        factors covers comes back as a size-1 axis; the device computes the full-size potential
+        (constant along such an axis) and the result is sliced.  ``reference_shapes=False``
+        returns the full-size arrays the propagation stages work on."""
         t = eng.require_cuda()
         sizes = dict(self.factor_graph.sizes)
         sizes.update(_effective_sizes(self.factor_graph.factors, xs))
@@ -157,10 +184,17 @@ class CliqueGraph():
         engine.dev.upload()
         engine.dev.init(fdev.data_ptr(), False, None, 1, dtype, ws.data_ptr(), _semiring(dl), engine._stream())
         flat = engine.work_view(ws, 1, dtype)[:plan.clique_entries, 0].cpu().numpy()
-        return [
+        out = [
             flat[plan.node_off[c]:plan.node_off[c] + plan.node_size[c]].reshape(tuple(plan.node_shape[c])).copy()
             for c in range(plan.n_cliques)
         ]
+        if reference_shapes:
+            covered = [set() for _ in self.maxcliques]
+            for fv, home in zip(self.factor_graph.factors, self._f2c()):
+                covered[home].update(fv)
+            out = [y[tuple(slice(None) if v in covered[c] else slice(0, 1) for v in cv)]
+                   for c, (cv, y) in enumerate(zip(self.maxcliques, out))]
+        return out
 
     def marginalize(self, ys, dl=None):
         """Marginalize results for maxcliques to results for factors
@@ -277,8 +311,11 @@ class JunctionTree():
         """
         ct = self.clique_tree
         xs = [x if isinstance(x, np.ndarray) else np.asarray(x) for x in xs]
-        key = (tuple(x.shape for x in xs), tuple(x.dtype.char for x in xs), dtype, id(dl))
-        hit = ct._single.get(key)
+        # (shapes, dtypes, semiring, device) of a single propagate() call -> (runner, output
+        # slots), per JunctionTree: another tree over the same clique graph compiles its own
+        single = _cache_of(self, "single")
+        key = (tuple(x.shape for x in xs), tuple(x.dtype.char for x in xs), dtype, id(dl), eng.current_device())
+        hit = single.get(key)
         if hit is None:
             fg = ct.factor_graph
             sizes = dict(fg.sizes)
@@ -292,9 +329,9 @@ class JunctionTree():
             slots = [(plan.fout_off[f], plan.fout_off[f] + plan.fout_size[f], tuple(plan.fout_shape[f]))
                      for f in range(len(plan.fout_off))]
             hit = (runner, slots, dl)                    # dl is kept alive so that its id stays unique
-            if len(ct._single) >= 16:
-                ct._single.pop(next(iter(ct._single)))
-            ct._single[key] = hit
+            if len(single) >= 16:
+                single.pop(next(iter(single)))
+            single[key] = hit
         runner, slots, _ = hit
         runner.set_factors(xs)
         flat = runner.run().numpy()[:, 0].copy()         # one fresh array; the outputs are views of it
@@ -532,6 +569,10 @@ class JunctionTree():
         node_out = None
         if nodes:
             node_out = [engine.node_tensor(ws, k, B, dtype) for k in range(len(plan.node_vars))]
+            if device_output:
+                # the views alias the engine's cached (B, dtype) workspace, which the next call
+                # with the same batch size overwrites: hand out copies, like the factor outputs
+                node_out = [o.clone() for o in node_out]
         if not device_output:
             outs = [o.cpu().numpy() for o in outs]
             if nodes:

@@ -41,7 +41,8 @@ def main():
     launches = load(args.csv)
     ids = list(launches)
     marks = [i for i in ids if "jt_evidence_kernel" in launches[i]["name"]]
-    lo, hi = marks[args.step], marks[args.step + 1]
+    lo = marks[args.step]
+    hi = marks[args.step + 1] if args.step + 1 < len(marks) else ids[-1] + 1
     print("| id | kernel | grid | time (us) | dram read (GB) | dram write (GB) | dram GB/s | issue active |")
     print("|---|---|---|---|---|---|---|---|")
     total_t = total_b = 0.0

@@ -15,12 +15,11 @@ def pytest_configure(config):
 
 
 def pytest_sessionstart(session):
-    """The shared library is a build product (git-ignored): build it when a fresh checkout has
-    none, so that the ABI tests can load it (nvcc cross-compiles without a GPU)."""
-    lib = os.path.join(ROOT, "junction-tree_b200", "junctiontree", "libjt_b200.so")
-    if not os.path.exists(lib):
-        subprocess.check_call(["make", "-j", str(os.cpu_count() or 4), "-C",
-                               os.path.join(ROOT, "junction-tree_b200", "csrc")], stdout=subprocess.DEVNULL)
+    """The shared library is a build product (git-ignored).  It is rebuilt whenever the kernel
+    or ABI sources differ from the ones it was built from (content hash, `csrc/.build_hash`), so
+    the suite never runs against a stale binary; nvcc cross-compiles without a GPU."""
+    import __graft_entry__ as entry
+    entry.ensure_built(quiet=True)
 
 
 def pytest_collection_modifyitems(config, items):

@@ -41,29 +41,23 @@ def load_peaks():
 
 
 def load_traffic(args, uniform):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu launch list
-    (profiles/r01_traffic.json), when one exists for this exact configuration."""
+    """DRAM bytes per launch of the message-passing kernels as ncu measured them for this exact
+    configuration (profiles/r02_traffic.json: derived from the committed launch lists by
+    tools/summarize_launches.py --update).  A recorded figure, labelled with its source."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
             table = json.load(fh)
         key = "%s:%d:%s:%s" % (args.config, args.batch, args.dtype, "uniform" if uniform else "per_instance")
-        return table[key]["traffic_per_launch"] if args.semiring == "sum_product" else None
+        if args.semiring != "sum_product" or args.no_evidence or args.no_dense:
+            return None
+        return table[key]
     except Exception:
         return None
 
 
 def make_net(name):
-    if name == "dag37":
-        return wl.dag37()
-    if name == "dag500":
-        return wl.dag500()
-    if name == "ising16":
-        return wl.ising(16)
-    if name == "large_state_tree":
-        return wl.large_state_tree()
-    if name == "sprinkler":
-        return wl.sprinkler()
-    raise SystemExit("unknown --config %s" % name)
+    import jt_bench_lib as bl
+    return bl.make_net(name)
 
 
 class ClockSampler(threading.Thread):
@@ -206,10 +200,64 @@ def workload_name(args):
 # GPU arm
 
 
+#: BASELINE.json's configs at their stated sizes (per GPU; weak scaling), beside the main line's
+#: configs[1] with evidence in uniform mode.  (name, batch, dtype, uniform, evidence, beliefs,
+#: sub_batches): config 3's 256 instances run as 2 x 128 (a 76 GB workspace each time), config 5
+#: once with all beliefs stored (dense workspace, 1,024 instances) and once in the pipelines' mode
+#: on a sparse workspace (4,096 instances: outputs only).
+EXTRA_CONFIGS = [
+    ("dag37", 65536, "f64", True, False, True, 1),
+    ("dag37", 65536, "f64", False, True, True, 1),
+    ("ising16", 256, "f64", True, True, True, 2),
+    ("ising16", 256, "f64", False, True, True, 2),
+    ("large_state_tree", 512, "f64", True, True, True, 1),
+    ("large_state_tree", 512, "f64", False, True, True, 1),
+    ("large_state_tree", 512, "f32", True, True, True, 1),
+    ("large_state_tree", 512, "f32", False, True, True, 1),
+    ("dag500", 1024, "f64", True, True, True, 1),
+    ("dag500", 1024, "f64", False, True, True, 1),
+    ("dag500", 4096, "f64", True, True, False, 1),
+]
+
+
+def config_entry(hp, t, peak, sub_batches=1):
+    A, A_msg, S, S_msg = hp.bytes_per_propagation()
+    ms = t["ms_per_step"] * sub_batches
+    B = hp.B * sub_batches
+    return {
+        "config": hp.config, "batch_per_gpu": B, "sub_batches": sub_batches, "dtype": hp.dtype_name,
+        "mode": "uniform" if hp.uniform else "per_instance", "evidence": bool(hp.evars),
+        "beliefs_stored": hp.beliefs, "sparse_workspace": hp.sparse, "dense_contractions": hp.dense and hp.uniform,
+        "ms_per_step": ms, "value": B / ms * 1e3, "unit": UNIT, "launches_per_step": t["launches_per_step"] * sub_batches,
+        "scheduled_bytes_per_propagation": S, "algorithmic_bytes_per_propagation": A,
+        # bytes the schedule moves / step time / measured peak; the A-based figure can exceed 1 in
+        # uniform mode (potentials no evidence reaches are not streamed per instance)
+        "frac": S * B / ms / 1e6 / peak, "frac_algorithmic": A * B / ms / 1e6 / peak,
+        "cliques": hp.plan.n_cliques, "levels": hp.plan.max_depth,
+    }
+
+
+def single_propagate_latency(jt, net, n=300):
+    """Config 1 (BASELINE configs[0]): one `tree.propagate(values)` call, host arrays in and out."""
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    for _ in range(30):
+        tree.propagate(net["values"])
+    times = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        tree.propagate(net["values"])
+        times.append(time.perf_counter() - t0)
+    return {"config": "sprinkler", "batch_per_gpu": 1, "dtype": "f64", "mode": "single propagate() call, host to host",
+            "us_per_propagate": 1e6 * float(np.median(times)), "us_per_propagate_p90": 1e6 * float(np.percentile(times, 90)),
+            "value": 1.0 / float(np.median(times)), "unit": UNIT, "calls": n,
+            "frac": None, "note": "latency-bound: one kernel launch between two small copies (SURVEY.md 8d)"}
+
+
 def run_gpu(args):
     import torch
     import junctiontree as jt
     from junctiontree import _native, distributed as jdist
+    import jt_bench_lib as bl
 
     rank, world = jdist.init_from_env("nccl")
     if world != args.gpus:
@@ -218,40 +266,7 @@ def run_gpu(args):
     dev = torch.cuda.current_device()
     dtype = np.dtype(np.float64 if args.dtype == "f64" else np.float32)
     w = dtype.itemsize
-
-    net = make_net(args.config)
-    tree = jt.create_junction_tree(net["factors"], net["sizes"], order=net.get("order"))
-    evars = [] if args.no_evidence else list(net.get("evidence_vars", []))
-    plan = tree.plan(evars)
-    engine = tree._engine(plan.sizes, evars, plan.full_sizes)
-    B = args.batch                                   # per GPU (weak scaling)
-    ev_all = wl.draw_evidence(net, B * world) if evars else None
-    lo, hi = jdist.shard_bounds(B * world, world, rank)
-    ev_host = torch.from_numpy(ev_all[lo:hi].copy()).pin_memory() if evars else None
-
-    sr_flag = {"sum_product": _native.JT_SR_SUM_PRODUCT, "max_product": _native.JT_SR_MAX_PRODUCT,
-               "log_sum_exp": _native.JT_SR_LOG_SUM_EXP, "max_sum": _native.JT_SR_MAX_SUM}[args.semiring]
-    if args.semiring in ("log_sum_exp", "max_sum"):          # log-domain laws take log potentials
-        net["values"] = [np.log(v) for v in net["values"]]
-    fdev, batched = engine.factors_to_device(net["values"], dtype)
-    ev_dev = ev_host.to("cuda") if evars else None
-    ws = engine.workspace(B, dtype)
-    engine.dev.upload()
-    fout = torch.empty((plan.fout_entries, B), dtype=engine_dtype(dtype), device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
-    ev_ptr = ev_dev.data_ptr() if evars else None
-    flags = _native.JT_SEP_BELIEFS | (0 if args.no_uniform else _native.JT_UNIFORM) | sr_flag
-
-    def hot_path(events=None):
-        if events is not None:
-            events[0].record()
-        engine.dev.init(fdev.data_ptr(), batched, ev_ptr, B, dtype, ws.data_ptr(), flags, stream)
-        if events is not None:
-            events[1].record()
-        engine.dev.collect(B, dtype, ws.data_ptr(), flags, stream)
-        engine.dev.distribute(B, dtype, ws.data_ptr(), flags, stream)
-        if events is not None:
-            events[2].record()
+    peak, peak_src = load_peaks()
 
     def barrier():
         torch.cuda.synchronize()
@@ -259,122 +274,144 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        hot_path()
-    barrier()
+    def max_over_ranks(xs):
+        if world == 1:
+            return list(xs)
+        tns = torch.tensor(list(xs), dtype=torch.float64, device="cuda")
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return [float(v) for v in tns.tolist()]
+
+    B = args.batch                                   # per GPU (weak scaling)
+    hp = bl.HotPath(args.config, B, args.dtype, uniform=not args.no_uniform, evidence=not args.no_evidence,
+                    dense=not args.no_dense, semiring=args.semiring, ev_offset=rank * B, ev_total=B * world)
+    net, tree, plan, evars = hp.net, hp.tree, hp.plan, hp.evars
 
     # ---- timed region: exactly K steps, device-timed, max over ranks ----
     sampler = ClockSampler(dev)
     sampler.start()
-    launches0 = _native.launch_count()
-    ev_pairs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_start.record()
-    for k in range(args.steps):
-        hot_path(ev_pairs[k])
-    t_end.record()
-    barrier()
-    launches = _native.launch_count() - launches0
+    t_main = hp.time(args.steps, args.warmup, barrier)
     clocks = sampler.finish()
-    total_ms = t_start.elapsed_time(t_end)
-    init_ms = sum(e[0].elapsed_time(e[1]) for e in ev_pairs)
-    msg_ms = sum(e[1].elapsed_time(e[2]) for e in ev_pairs)
+    launches = int(round(t_main["launches_per_step"] * args.steps))
+    working_set_gb = hp.working_set_gb()
+    main_entry = config_entry(hp, t_main, peak)
+    A, A_msg, S_all, S_msg = hp.bytes_per_propagation()
+    uniform = hp.uniform
+    msg_launches = hp.msg_launches()
+    ev_host = hp.ev_host
+    net_values = net["values"]
+    hp.release()
+    del hp
 
     # ---- end to end through the public API: pinned host evidence in, per-factor beliefs out ----
-    # (--e2e-batch: a larger batch for the streaming pipelines than fits the dense, all-beliefs
-    # workspace of the timed region above; their chunks use sparse workspaces)
-    B_value = B
-    if args.e2e_batch and args.e2e_batch != B:
-        del ws, fout
-        engine.release()
-        torch.cuda.empty_cache()
-        B = args.e2e_batch
-        ev_e2e = wl.draw_evidence(net, B * world) if evars else None
-        lo, hi = jdist.shard_bounds(B * world, world, rank)
+    B_e2e = args.e2e_batch or B
+    if B_e2e != B:
+        ev_e2e = wl.draw_evidence(net, B_e2e * world) if evars else None
+        lo, hi = jdist.shard_bounds(B_e2e * world, world, rank)
         ev_host = torch.from_numpy(ev_e2e[lo:hi].copy()).pin_memory() if evars else None
-    # the public serving call: tree.propagate_session(...).run(evidence) -- host evidence in,
-    # per-factor beliefs in host memory out (views of the session's pinned buffer)
     law = {"sum_product": None, "max_product": jt.semirings.max_product, "log_sum_exp": jt.semirings.log_sum_exp,
            "max_sum": jt.semirings.max_sum}[args.semiring]
     ev_np = ev_host.numpy() if evars else None
-    session = tree.propagate_session(net["values"], B, evars, dtype=dtype, dl=law, chunk=args.chunk)
-    for _ in range(2):
-        session.run(ev_np, copy=False)
-    barrier()
     e2e_steps = max(2, min(args.steps, 5))
-    l_e2e0 = _native.launch_count()
-    t_e2e = time.perf_counter()
-    for _ in range(e2e_steps):
-        beliefs = session.run(ev_np, copy=False)          # synchronous: the results are on the host on return
-    e2e_ms = (time.perf_counter() - t_e2e) * 1e3
-    assert len(beliefs) == len(net["factors"]) and beliefs[0].shape[0] == B
-    e2e_launches = _native.launch_count() - l_e2e0
-    e2e_chunk = session.pipe.chunk
-    session.close()
-    del session, beliefs
+    e2e_ms = marg_ms = 0.0
+    e2e_launches = e2e_chunk = marg_d2h = 0
+    d2h = {}
+    if not args.skip_e2e:
+        # the public serving call: tree.propagate_session(...).run(evidence) -- host evidence in,
+        # per-factor beliefs in host memory out (views of the session's pinned buffer)
+        session = tree.propagate_session(net_values, B_e2e, evars, dtype=dtype, dl=law, chunk=args.chunk)
+        for _ in range(2):
+            session.run(ev_np, copy=False)
+        barrier()
+        l_e2e0 = _native.launch_count()
+        t_e2e = time.perf_counter()
+        for _ in range(e2e_steps):
+            beliefs = session.run(ev_np, copy=False)          # synchronous: the results are on the host on return
+        e2e_ms = (time.perf_counter() - t_e2e) * 1e3
+        assert len(beliefs) == len(net["factors"]) and beliefs[0].shape[0] == B_e2e
+        e2e_launches = _native.launch_count() - l_e2e0
+        e2e_chunk = session.pipe.chunk
+        # the host ceiling of that call: the same bytes as one plain device -> pinned host copy,
+        # all ranks at once (the copy engines share the host's memory system)
+        out_host = session.out_host
+        probe = torch.empty(out_host.shape, dtype=out_host.dtype, device="cuda")
+        barrier()
+        t_copy = time.perf_counter()
+        for _ in range(3):
+            out_host.copy_(probe, non_blocking=True)
+        torch.cuda.synchronize()
+        d2h_ms = (time.perf_counter() - t_copy) * 1e3 / 3
+        d2h = {"plain_copy_ms": d2h_ms, "plain_copy_gbs_per_gpu": out_host.numel() * w / d2h_ms / 1e6}
+        del probe, out_host
+        session.close()
+        del session, beliefs
 
-    # ---- the same end to end with the device output stage: normalised single-variable
-    # posteriors of the unobserved variables + log P(evidence) instead of raw factor beliefs ----
-    free_vars = [v for v in sorted(net["sizes"]) if v not in evars]
-    m_session = tree.marginals_session(net["values"], B, free_vars, evars, dtype=dtype, dl=law, chunk=args.chunk)
-    for _ in range(2):
-        m_session.run(ev_np, copy=False)
-    barrier()
-    t_marg = time.perf_counter()
-    for _ in range(e2e_steps):
-        m_session.run(ev_np, copy=False)
-    marg_ms = (time.perf_counter() - t_marg) * 1e3
-    marg_d2h = int((m_session.engine.plan.fout_entries + 1) * B * w)
-    m_session.close()
-    del m_session
+        # ---- the same end to end with the device output stage: normalised single-variable
+        # posteriors of the unobserved variables + log P(evidence) instead of raw factor beliefs ----
+        free_vars = [v for v in sorted(net["sizes"]) if v not in evars]
+        m_session = tree.marginals_session(net_values, B_e2e, free_vars, evars, dtype=dtype, dl=law, chunk=args.chunk)
+        for _ in range(2):
+            m_session.run(ev_np, copy=False)
+        barrier()
+        t_marg = time.perf_counter()
+        for _ in range(e2e_steps):
+            m_session.run(ev_np, copy=False)
+        marg_ms = (time.perf_counter() - t_marg) * 1e3
+        marg_d2h = int((m_session.engine.plan.fout_entries + 1) * B_e2e * w)
+        m_session.close()
+        del m_session
 
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        tns = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
-        return float(tns.item())
+    # ---- N > 1: the one collective of the path, the all-gather of requested marginals ----
+    gather = None
+    if world > 1 and evars and not args.skip_e2e:
+        gather = gather_leg(jt, jdist, tree, net, net_values, evars, ev_host, B_e2e, dtype, rank, world, barrier)
 
-    total_ms, init_ms, msg_ms, e2e_ms, marg_ms = (max_over_ranks(x) for x in
-                                                  (total_ms, init_ms, msg_ms, e2e_ms, marg_ms))
+    # ---- the other BASELINE configs at their stated sizes (same step, same timing) ----
+    extras = []
+    if args.configs == "all" and args.semiring == "sum_product":
+        if rank == 0:
+            extras.append(single_propagate_latency(jt, wl.sprinkler()))
+        for name, batch, dt, uni, evid, bel, sub in EXTRA_CONFIGS:
+            ehp = bl.HotPath(name, batch // sub, dt, uniform=uni, evidence=evid, beliefs=bel, dense=not args.no_dense,
+                             ev_offset=rank * (batch // sub), ev_total=(batch // sub) * world)
+            t = ehp.time(max(3, min(args.steps, 5)), 3, barrier)
+            extras.append((ehp, t, sub))
+            entry = config_entry(ehp, t, peak, sub)
+            ehp.release()
+            extras[-1] = entry
+    times = [t_main["ms_per_step"], t_main["init_ms"], t_main["msg_ms"], e2e_ms, marg_ms] + \
+        [e["ms_per_step"] for e in extras if "ms_per_step" in e]
+    times = max_over_ranks(times)
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
+    ms_per_step, init_ms, msg_ms, e2e_ms, marg_ms = times[:5]
+    k = 5
+    for e in extras:
+        if "ms_per_step" in e:                       # max over ranks; every rank ran the same shape
+            scale = times[k] / e["ms_per_step"]
+            e["ms_per_step"] = times[k]
+            e["value"] = e["value"] / scale * world
+            e["frac"] /= scale
+            e["frac_algorithmic"] /= scale
+            k += 1
 
-    B_e2e, B = B, B_value
-    ms_per_step = total_ms / args.steps
     value = B * world / (ms_per_step / 1e3)
-    peak, peak_src = load_peaks()
-    # algorithmic bytes: A = w(4 sum n_C - n_root + 6 sum n_S) per instance;
-    # the message-passing kernel moves everything but the init write (w * sum n_C)
-    A = w * plan.algorithmic_entries(with_init=True)
-    A_msg = w * plan.algorithmic_entries(with_init=False)
-    uniform = not args.no_uniform and plan.uni_entries > 0
-    from junctiontree import schedule as sch
-    # batch launches of collect + distribute in the mode that ran
-    msg_phases = (sch.PHASE_COLLECT_INSTANCE, sch.PHASE_DIST_PRE_INSTANCE, sch.PHASE_DIST_MAIN) if uniform \
-        else (sch.PHASE_COLLECT, sch.PHASE_DIST_PRE, sch.PHASE_DIST_MAIN)
-    msg_launches = sum(1 for L in plan.launches_arr if L[0] in msg_phases)
-    msg_ms_per_launch = msg_ms / args.steps / max(msg_launches, 1)
-    achieved = A_msg * B / (msg_ms / args.steps / 1e3) / 1e9
-    step_gbs = A * B / (ms_per_step / 1e3) / 1e9
-    # bytes this schedule has to move through HBM (uniform operands are read once, not per instance)
-    S_all = w * plan.scheduled_entries(uniform=uniform)
-    n_init = sum(plan.node_size[c] for c in range(plan.n_cliques) if not (uniform and plan.uniform[c]))
-    S_msg = S_all - w * n_init
-    scheduled = S_msg * B / (msg_ms / args.steps / 1e3) / 1e9
+    msg_ms_per_launch = msg_ms / max(msg_launches, 1)
+    scheduled = S_msg * B / (msg_ms / 1e3) / 1e9            # GB/s this schedule moves in the message-passing launches
+    algorithmic = A_msg * B / (msg_ms / 1e3) / 1e9
+    step_gbs = S_all * B / (ms_per_step / 1e3) / 1e9
 
     cpu = None
     if not args.skip_cpu and world == 1:          # the CPU baseline is reported by the single-GPU run only
         v, cores, n, dt = cpu_throughput(args.config, args.cpu_per_core, semiring=args.semiring)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d instances of the same workload (%d per core, %.1f s) through oracle/ref_fixed.py "
-                         "(NumPy restatement of the reference), %d processes" % (n, args.cpu_per_core, dt, cores)}
+                         "(NumPy restatement of the reference; a Python loop over instances, as the reference "
+                         "itself is), %d processes" % (n, args.cpu_per_core, dt, cores)}
 
-    e2e_value = B_e2e * world / (e2e_ms / e2e_steps / 1e3)
+    traffic = load_traffic(args, uniform)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -386,44 +423,52 @@ def run_gpu(args):
             "levels": plan.max_depth, "algorithmic_bytes_per_propagation": A,
             "scheduled_bytes_per_propagation": S_all, "uniform_mode": bool(uniform),
             "uniform_clique_entries": plan.uni_entries if uniform else 0, "semiring": args.semiring,
+            "dense_contractions": bool(uniform and not args.no_dense),
             "step": "evidence slicing + clique init + collect + distribute (clique and separator beliefs)",
-            "l2": "inputs larger than L2 (working set %.1f GB per GPU)" % (plan.work_entries * B * w / 1e9),
-            "step_gbs_algorithmic": step_gbs, "init_ms_per_step": init_ms / args.steps,
-            "message_passing_ms_per_step": msg_ms / args.steps,
+            "l2": "inputs larger than L2 (working set %.1f GB per GPU)" % working_set_gb,
+            "step_gbs_scheduled": step_gbs, "init_ms_per_step": init_ms,
+            "message_passing_ms_per_step": msg_ms,
         },
         "roofline": {
-            "bound": "hbm", "kernel": "jt_project_tma_kernel<%s, %s>" % (
-                {"sum_product": "SrSumProduct", "max_product": "SrMaxProduct", "log_sum_exp": "SrLogSumExp",
-                 "max_sum": "SrMaxSum"}[args.semiring], "double" if w == 8 else "float"),
-            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_source": peak_src, "traffic": load_traffic(args, uniform),
+            "bound": "hbm", "kernel": "jt_project_tma_kernel<%s, %s> (+ jt_dense_kernel<double> for the dense "
+                                      "contractions of uniform mode)" % (bl.SR_KERNEL[args.semiring],
+                                                                         "double" if w == 8 else "float"),
+            # bytes the schedule moves in the collect + distribute launches / their measured time
+            "achieved": scheduled, "peak": peak, "unit": "GB/s", "frac": scheduled / peak,
+            "achieved_algorithmic": algorithmic, "frac_algorithmic": algorithmic / peak,
+            "peak_source": peak_src, "traffic": traffic["traffic_per_launch"] if traffic else None,
+            "traffic_source": traffic,
             "launches_per_step": msg_launches, "avg_launch_ms": msg_ms_per_launch,
-            "algorithmic_bytes_per_launch": A_msg * B / max(msg_launches, 1),
             "scheduled_bytes_per_launch": S_msg * B / max(msg_launches, 1),
-            "scheduled_gbs": scheduled, "scheduled_frac": scheduled / peak,
-            "note": ("achieved/frac use SURVEY.md 8d's algorithmic bytes A (every potential per instance in HBM); "
-                     "uniform mode keeps potentials and up-messages that no evidence reaches once per batch, so "
-                     "the schedule moves fewer bytes than A and frac can exceed 1 -- scheduled_* count the bytes "
-                     "this schedule must move and are the figure to compare with dram traffic")
-                    if uniform else "per-instance potentials: scheduled bytes = algorithmic bytes + re-reads of "
-                                    "psi_C by cliques with several children",
+            "algorithmic_bytes_per_launch": A_msg * B / max(msg_launches, 1),
+            "note": ("frac = bytes this schedule has to move through HBM in the collect + distribute launches "
+                     "(every buffer once per consuming task; uniform operands once per batch) / their CUDA-event "
+                     "time / peak.  frac_algorithmic divides SURVEY.md 8d's A (every potential per instance in "
+                     "HBM) by the same time: uniform mode does not stream the potentials no evidence reaches, so "
+                     "it can exceed 1.  traffic is the ncu dram__bytes of the same command, recorded under "
+                     "profiles/ (traffic_source), not measured in this run"),
         },
+        "configs": [main_entry] + extras,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT,
+        "e2e": {"value": B_e2e * world / (e2e_ms / e2e_steps / 1e3) if e2e_ms else None, "unit": UNIT,
                 "h2d_bytes_per_step": int(ev_host.numel() * 4) if evars else 0,
                 "d2h_bytes_per_step": int(plan.fout_entries * B_e2e * w),
                 "ms_per_step": e2e_ms / e2e_steps, "chunk": e2e_chunk, "batch_per_gpu": B_e2e,
+                "d2h_gbs_per_gpu": plan.fout_entries * B_e2e * w / (e2e_ms / e2e_steps) / 1e6 if e2e_ms else None,
+                "host_ceiling": d2h,
                 "what": "tree.propagate_session(values, batch, evidence_vars).run(evidence): host int32 "
                         "evidence -> device, propagate incl. marginalisation to factor scopes, per-factor "
-                        "beliefs -> host memory; wall clock around the synchronous calls"},
+                        "beliefs -> host memory; wall clock around the synchronous calls.  host_ceiling: the "
+                        "same bytes as one plain device -> pinned-host copy on every rank at once"},
         "gpu_launches": int(launches),
         "gpu_launches_e2e": int(e2e_launches),
-        "e2e_marginals": {"value": B_e2e * world / (marg_ms / e2e_steps / 1e3), "unit": UNIT,
+        "e2e_marginals": {"value": B_e2e * world / (marg_ms / e2e_steps / 1e3) if marg_ms else None, "unit": UNIT,
                           "ms_per_step": marg_ms / e2e_steps,
                           "h2d_bytes_per_step": int(ev_host.numel() * 4) if evars else 0,
                           "d2h_bytes_per_step": marg_d2h,
                           "what": "tree.marginals_session(...).run(evidence): same propagation, device output "
                                   "stage (normalised single-variable posteriors + log Z) -> host memory"},
+        "all_gather": gather,
         "clocks": clocks,
     }
     print_line(json.dumps(line))
@@ -432,9 +477,69 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def engine_dtype(dtype):
-    from junctiontree import engine as eng
-    return eng.torch_dtype(dtype)
+def gather_leg(jt, jdist, tree, net, values, evars, ev_host, B, dtype, rank, world, barrier):
+    """The path's only collective: NCCL all-gather of the requested marginals.
+    Every rank propagates its shard, normalises the single-variable posteriors on the device and
+    gathers [B/G, M] -> [B, M]; rank 0 checks a sample of gathered rows (one of every rank's shard)
+    against the CPU oracle."""
+    import torch
+    import torch.distributed as dist
+    from junctiontree import engine as eng, _native
+    free_vars = [v for v in sorted(net["sizes"]) if v not in evars]
+    full = dict(net["sizes"])
+    eff = dict(full)
+    for v in evars:
+        eff[v] = 1
+    engine = tree._engine(eff, evars, full, outputs=[[v] for v in free_vars])
+    plan = engine.plan
+    fdev, _ = engine.factors_to_device(values, dtype)
+    ev_dev = ev_host.to("cuda")
+    ws = engine.new_pipeline_workspace(B, dtype)
+    fout = torch.empty((plan.fout_entries, B), dtype=eng.torch_dtype(dtype), device="cuda")
+    logz = torch.empty(B, dtype=eng.torch_dtype(dtype), device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    flags = _native.JT_NO_BELIEFS
+    engine.dev.propagate(fdev.data_ptr(), False, ev_dev.data_ptr(), B, dtype, ws.data_ptr(), fout.data_ptr(), flags, stream)
+    engine.dev.normalize(B, dtype, fout.data_ptr(), logz.data_ptr(), stream)
+    local = fout.t().contiguous()                                   # [B, M] rows per instance
+    for _ in range(2):
+        jdist.all_gather_rows(local, B * world)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    reps = 3
+    for _ in range(reps):
+        gathered = jdist.all_gather_rows(local, B * world)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / reps
+    tns = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+    ms = float(tns.item())
+    checked, max_err = 0, 0.0
+    if rank == 0:
+        from oracle import ref_fixed                                # the checker, never the thing measured
+        ct = tree.clique_tree
+        ev_all = wl.draw_evidence(net, B * world)
+        pick = [r * B + j for r in range(world) for j in (0, B - 1)]
+        outs, _ = ref_fixed.propagate_batch(tree.tree, tree.separators, ct.maxcliques, ct.factor_to_maxclique,
+                                            net["factors"], net["sizes"], values, evars, ev_all[pick], n=len(pick))
+        got = gathered[pick].cpu().numpy()
+        col = 0
+        for v, size in zip(free_vars, plan.fout_size):
+            f = next(i for i, fv in enumerate(net["factors"]) if v in fv)
+            axes = tuple(1 + a for a, u in enumerate(net["factors"][f]) if u != v)
+            want = outs[f].sum(axis=axes)
+            want = want / want.sum(axis=1, keepdims=True)
+            max_err = max(max_err, float(np.max(np.abs(got[:, col:col + size] - want) / want)))
+            col += size
+        checked = len(pick)
+        assert max_err < 1e-10, "all-gathered marginals differ from the oracle: %g" % max_err
+    M = plan.fout_entries
+    return {"collective": "nccl all_gather_into_tensor of normalised single-variable posteriors",
+            "rows_per_rank": B, "row_entries": M, "bytes_received_per_rank": int((world - 1) * B * M * dtype.itemsize),
+            "ms": ms, "gbs_per_rank": (world - 1) * B * M * dtype.itemsize / ms / 1e6,
+            "rows_checked_against_oracle": checked, "max_rel_err": max_err}
 
 
 def main():
@@ -455,6 +560,11 @@ def main():
     ap.add_argument("--semiring", default="sum_product",
                     choices=["sum_product", "max_product", "log_sum_exp", "max_sum"],
                     help="distributive law of the kernels (default: the reference's sum-product)")
+    ap.add_argument("--no-dense", action="store_true",
+                    help="uniform mode: keep the dense contractions on the projection kernels (A-B timing)")
+    ap.add_argument("--configs", default="all", choices=["all", "none"],
+                    help="all: also time the other BASELINE configs at their stated sizes (the `configs` block)")
+    ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-per-core", type=int, default=512, help="CPU baseline: instances per core")
     args = ap.parse_args()

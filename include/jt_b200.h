@@ -94,6 +94,8 @@ extern "C" {
 #define JT_NO_BELIEFS 32    /* distribute/marginal/propagate: only messages and outputs are wanted -- clique
                               beliefs are not written and jt_marginal computes the outputs directly from
                               psi_C and the incoming messages (pass the same value to both stages) */
+#define JT_NO_DENSE 64      /* uniform mode: keep every task on the projection kernels (no dense contractions);
+                              pass the same value to every stage */
 #define JT_UNIFORM_VALID 16 /* uniform mode: the uniform workspace of this workspace already holds the
                               potentials and up-messages of these factor tables (an earlier call with
                               the same tables and the same workspace): skip recomputing them */
@@ -160,8 +162,25 @@ int jt_plan_message_offsets(const jt_plan* plan, int sep_node, int64_t* up, int6
 /* bytes of workspace for a batch of B */
 int jt_workspace_bytes(const jt_plan* plan, int64_t B, int dtype, size_t* out);
 /* byte offsets inside the workspace: out4 = { factor offsets, error counter, uniform workspace,
- * total size }; the [entries][B] block starts at 0 */
+ * total size }; the [entries][B] block starts at 0.  The W region of the dense contractions
+ * (below) follows the uniform workspace and is included in the total. */
 int jt_workspace_layout(const jt_plan* plan, int64_t B, int dtype, int64_t* out4);
+
+/* Dense contractions (uniform mode, sum-product, float64, B >= 128; JT_DISABLE_DENSE=1 switches
+ * them off).  A projection task -- the reference's E2 / E4 einsum, computation.py:84-88, 205-207 --
+ * whose potential is shared by the batch and whose only per-instance input is one message M is a
+ * batch of small dense products
+ *     out[s_of[g][i]][b] = sum_k W[g][i][k] * M[mg[g] + mk[k]][b]
+ * (g: the output axes M depends on, i: the other output axes, k: the summed axes M depends on;
+ * W = potential x uniform messages, summed over the axes M does not see).  The groups are derived
+ * from the task's index tables when the plan is loaded; such tasks then run on the FP64 tensor pipe
+ * (mma.sync.m8n8k4.f64) with every row of M and of out moved once per batch tile, instead of one
+ * row of M per (s, r) item.  These three calls expose the derivation (tests, tools):
+ * out16 = { task, message, n_g, n_i, K, n_q, MT, n_it, n_k4, s_of, mg, mk, r_of, w_off, w_size,
+ * launch }, the offsets s_of / mg / mk / r_of index the int32 table of jt_plan_dense_table. */
+int jt_plan_dense_count(const jt_plan* plan);
+int jt_plan_dense_get(const jt_plan* plan, int index, int64_t* out16);
+const int32_t* jt_plan_dense_table(const jt_plan* plan, int64_t* count);
 /* copy the schedule tables to the current CUDA device (idempotent) */
 int jt_plan_upload(jt_plan* plan);
 

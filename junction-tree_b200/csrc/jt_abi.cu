@@ -83,10 +83,10 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 size_t dtype_size(int dtype) { return dtype == JT_F64 ? 8 : 4; }
 
-// [ work: entries x B | fbase: F x B int32 | error counter | uniform workspace: entries x 1 ]
+// [ work: entries x B | fbase: F x B int32 | error counter | uniform workspace: entries x 1 | W region ]
 // entries = cliques + 3 x separators (beliefs, up, down) + likelihood tables
 struct WorkspaceLayout {
-    size_t work_bytes, fbase_off, err_off, uni_off, total;
+    size_t work_bytes, fbase_off, err_off, uni_off, dense_off, total;
 };
 
 WorkspaceLayout workspace_layout(const jt_plan* p, int64_t B, int dtype) {
@@ -98,7 +98,9 @@ WorkspaceLayout workspace_layout(const jt_plan* p, int64_t B, int dtype) {
     w.err_off = w.fbase_off + align_up(fbase, 256);
     w.uni_off = w.err_off + 256;
     const size_t uni = p->hdr[JT_H_UNI_ENTRIES] > 0 ? (size_t)entries * dtype_size(dtype) : 0;
-    w.total = w.uni_off + align_up(uni, 256);
+    // W region of the dense contractions (jt_dense.cu), rebuilt with the uniform workspace
+    w.dense_off = w.uni_off + align_up(uni, 256);
+    w.total = w.dense_off + align_up((size_t)p->dense_w_entries * dtype_size(dtype), 256);
     return w;
 }
 
@@ -149,11 +151,25 @@ KArgs base_args(const jt_plan* p, int64_t B, void* workspace, int vec) {
     return a;
 }
 
+// One launch of the plan.  With `w_region` set (uniform mode, dense contractions enabled) the
+// tasks that are dense contractions run in jt_dense_kernel and the projection kernel gets the
+// block prefix without them.
+int run_launch(jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec, void* w_region,
+               cudaStream_t stream) {
+    int variant = 0;
+    if (w_region && L.dense_end > L.dense_begin) {
+        int rc = jt_dense_launch(p, L, a.work, a.uni, w_region, a.fout, a.B, dtype, a.flags, stream);
+        if (rc != JT_OK) return rc;
+        variant = 1;
+    }
+    return launchers(a.flags)->dispatch(p, L, a, dtype, vec, variant, stream);
+}
+
 // Launches of one phase, in plan order.
-int run_phase(jt_plan* p, int phase, const KArgs& a, int dtype, int vec, cudaStream_t stream) {
+int run_phase(jt_plan* p, int phase, const KArgs& a, int dtype, int vec, cudaStream_t stream, void* w_region = nullptr) {
     for (const auto& L : p->launches) {
         if (L.phase != phase) continue;
-        int rc = launchers(a.flags)->dispatch(p, L, a, dtype, vec, stream);
+        int rc = run_launch(p, L, a, dtype, vec, w_region, stream);
         if (rc != JT_OK) return rc;
     }
     return JT_OK;
@@ -178,7 +194,40 @@ void* uniform_ws(const jt_plan* p, int64_t B, int dtype, void* workspace) {
     return static_cast<char*>(workspace) + workspace_layout(p, B, dtype).uni_off;
 }
 
+// W region of the workspace when this call runs its dense contractions in jt_dense_kernel, else null
+void* dense_region(const jt_plan* p, int64_t B, int dtype, void* workspace, int flags) {
+    if (!jt_dense_enabled(p, B, dtype, flags)) return nullptr;
+    return static_cast<char*>(workspace) + workspace_layout(p, B, dtype).dense_off;
+}
+
 }  // namespace
+
+// Block prefix of a launch of the TMA projection kernel for every item-count target 2^j: per task a
+// chunk of s sized for ~2^j (s, r) items per CTA; layout per j: [n_tasks + 1] first block of each
+// task, [n_tasks] log2 of the task's chunk.  Tasks flagged in `skip` get no blocks.
+int jt_build_item_prefix(jt_plan* p, const jt_plan::Launch& L, const char* skip, size_t* off_out, long long* blocks_out) {
+    for (int j = 0; j <= kItemLog2Max; ++j) {
+        off_out[j] = p->prefix.size();
+        long long acc = 0;
+        std::vector<int> chunk;
+        for (int t = L.begin; t < L.end; ++t) {
+            const DTask& k = p->tasks[t];
+            int nr_log2 = 0;
+            while ((1LL << nr_log2) < k.n_r) ++nr_log2;
+            int c = j - nr_log2;
+            c = c < 0 ? 0 : (c > 30 ? 30 : c);
+            while (c > 0 && (1LL << c) >= 2LL * k.n_s) --c;      // no larger than the task
+            p->prefix.push_back((int)acc);
+            chunk.push_back(c);
+            if (!(skip && skip[t - L.begin])) acc += ((long long)k.n_s + (1LL << c) - 1) >> c;
+            if (acc > 2147483647LL) return fail(JT_ERR_INVALID, "launch too large");
+        }
+        p->prefix.push_back((int)acc);
+        p->prefix.insert(p->prefix.end(), chunk.begin(), chunk.end());
+        blocks_out[j] = acc;
+    }
+    return JT_OK;
+}
 
 extern "C" {
 
@@ -313,26 +362,7 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
         L.total_s = 0;
         L.total_items = 0;
         for (int t = L.begin; t < L.end; ++t) L.total_items += (long long)p->tasks[t].n_s * p->tasks[t].n_r;
-        for (int j = 0; j <= kItemLog2Max; ++j) {
-            L.item_prefix_off[j] = p->prefix.size();
-            long long acc = 0;
-            std::vector<int> chunk;
-            for (int t = L.begin; t < L.end; ++t) {
-                const DTask& k = p->tasks[t];
-                int nr_log2 = 0;
-                while ((1LL << nr_log2) < k.n_r) ++nr_log2;
-                int c = j - nr_log2;
-                c = c < 0 ? 0 : (c > 30 ? 30 : c);
-                while (c > 0 && (1LL << c) >= 2LL * k.n_s) --c;      // no larger than the task
-                p->prefix.push_back((int)acc);
-                chunk.push_back(c);
-                acc += ((long long)k.n_s + (1LL << c) - 1) >> c;
-                if (acc > 2147483647LL) return bad("launch too large", i);
-            }
-            p->prefix.push_back((int)acc);
-            p->prefix.insert(p->prefix.end(), chunk.begin(), chunk.end());
-            L.item_blocks[j] = acc;
-        }
+        if (jt_build_item_prefix(p, L, nullptr, L.item_prefix_off, L.item_blocks) != JT_OK) return bad("launch too large", i);
         for (int t = L.begin; t < L.end; ++t) {
             const DTask& k = p->tasks[t];
             const int rows = (k.src >= 0 ? 1 : 0) + (k.rmsg_end - k.rmsg_begin) + (k.smsg_end - k.smsg_begin) +
@@ -374,6 +404,10 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
         if (k < 2)
             for (const auto& L : p->launches) if (L.phase == marg_phase) add(L);
     }
+    if (jt_dense_build(p) != JT_OK) {
+        delete p;
+        return JT_ERR_INVALID;
+    }
     *out = p;
     return JT_OK;
 }
@@ -381,6 +415,7 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
 void jt_plan_destroy(jt_plan* p) {
     if (!p) return;
     if (p->device >= 0) {
+        jt_dense_free(p);
         cudaFree(p->d_tasks);
         cudaFree(p->d_msgs);
         cudaFree(p->d_tab);
@@ -414,6 +449,25 @@ int jt_plan_message_offsets(const jt_plan* p, int node, int64_t* up, int64_t* do
     if (up) *up = up_base + rel;
     if (down) *down = up_base + p->hdr[JT_H_SEP_ENTRIES] + rel;
     return JT_OK;
+}
+
+int jt_plan_dense_count(const jt_plan* p) { return p ? (int)p->dense.size() : 0; }
+
+int jt_plan_dense_get(const jt_plan* p, int index, int64_t* out16) {
+    if (!p || !out16 || index < 0 || index >= (int)p->dense.size()) return fail(JT_ERR_INVALID, "bad dense index");
+    const DDense& d = p->dense[index];
+    int launch = -1;
+    for (size_t i = 0; i < p->launches.size(); ++i)
+        if (index >= p->launches[i].dense_begin && index < p->launches[i].dense_end) launch = (int)i;
+    const int64_t v[16] = {d.task, d.msg, d.n_g, d.n_i, d.K, d.n_q, d.MT, d.n_it, d.n_k4, d.s_of, d.mg, d.mk,
+                           d.r_of, d.w_off, d.w_size, launch};
+    memcpy(out16, v, sizeof(v));
+    return JT_OK;
+}
+
+const int32_t* jt_plan_dense_table(const jt_plan* p, int64_t* count) {
+    if (count) *count = p ? (int64_t)p->dtab.size() : 0;
+    return p && !p->dtab.empty() ? p->dtab.data() : nullptr;
 }
 
 int jt_workspace_bytes(const jt_plan* p, int64_t B, int dtype, size_t* out) {
@@ -458,6 +512,7 @@ int jt_plan_upload(jt_plan* p) {
     outs.insert(outs.end(), p->fout_size.begin(), p->fout_size.end());
     JT_CUDA(up(&p->d_out, outs));
     for (int k = 0; k < 3; ++k) JT_CUDA(up(&p->d_walk[k], p->walk_seq[k]));
+    if (jt_dense_upload(p) != JT_OK) return JT_ERR_CUDA;
     p->device = dev;
     return JT_OK;
 }
@@ -514,13 +569,18 @@ int jt_collect(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, voi
     if (!uniform_mode(p, flags)) return run_phase(p, JT_PHASE_COLLECT, a, dtype, vec, stream);
     // uniform mode: evidence-free subtrees are collected once (B = 1), then the rest per instance
     void* uni = uniform_ws(p, B, dtype, workspace);
+    void* w_region = dense_region(p, B, dtype, workspace, flags);
     if (!(flags & JT_UNIFORM_VALID)) {
         rc = run_phase_uniform(p, JT_PHASE_COLLECT_UNIFORM, a, dtype, uni, stream);
         if (rc != JT_OK) return rc;
+        if (w_region) {      // W blocks of the collect contractions: potentials x uniform up-messages
+            rc = jt_dense_prepare(p, 0, dtype, uni, w_region, stream);
+            if (rc != JT_OK) return rc;
+        }
     }
     a.uni = uni;
     a.uniform = 1;
-    return run_phase(p, JT_PHASE_COLLECT_INSTANCE, a, dtype, vec, stream);
+    return run_phase(p, JT_PHASE_COLLECT_INSTANCE, a, dtype, vec, stream, w_region);
 }
 
 int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, void* stream_) {
@@ -531,12 +591,18 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
     KArgs a = base_args(p, B, workspace, vec);
     a.flags = flags;
     int pre_phase = JT_PHASE_DIST_PRE;
+    void* w_region = nullptr;
     if (uniform_mode(p, flags)) {
         // down-messages with an evidence-free source side: once, top level first (B = 1)
         void* uni = uniform_ws(p, B, dtype, workspace);
+        w_region = dense_region(p, B, dtype, workspace, flags);
         if (!(flags & JT_UNIFORM_VALID)) {
             rc = run_phase_uniform(p, JT_PHASE_DIST_UNIFORM, a, dtype, uni, stream);
             if (rc != JT_OK) return rc;
+            if (w_region) {  // W blocks of the distribute and marginal contractions (they also need the uniform down-messages)
+                rc = jt_dense_prepare(p, 1, dtype, uni, w_region, stream);
+                if (rc != JT_OK) return rc;
+            }
         }
         a.uni = uni;
         a.uniform = 1;
@@ -547,7 +613,7 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
     const int main_phase = (flags & JT_NO_BELIEFS) ? JT_PHASE_DIST_MAIN_MESSAGES : JT_PHASE_DIST_MAIN;
     for (const auto& L : p->launches) {
         if (L.phase != pre_phase && L.phase != main_phase) continue;
-        rc = launchers(flags)->dispatch(p, L, a, dtype, vec, stream);
+        rc = run_launch(p, L, a, dtype, vec, w_region, stream);
         if (rc != JT_OK) return rc;
     }
     return JT_OK;
@@ -563,11 +629,13 @@ int jt_marginal(jt_plan* p, int64_t B, int dtype, void* workspace, void* factor_
     a.flags = flags;
     if (!(flags & JT_NO_BELIEFS)) return run_phase(p, JT_PHASE_MARGINAL, a, dtype, vec, static_cast<cudaStream_t>(stream));
     // outputs straight from psi_C and the incoming messages (the beliefs were not written)
+    void* w_region = nullptr;
     if (uniform_mode(p, flags)) {
         a.uni = uniform_ws(p, B, dtype, workspace);
         a.uniform = 1;
+        w_region = dense_region(p, B, dtype, workspace, flags);     // prepared by jt_distribute
     }
-    return run_phase(p, JT_PHASE_MARGINAL_DIRECT, a, dtype, vec, static_cast<cudaStream_t>(stream));
+    return run_phase(p, JT_PHASE_MARGINAL_DIRECT, a, dtype, vec, static_cast<cudaStream_t>(stream), w_region);
 }
 
 namespace {

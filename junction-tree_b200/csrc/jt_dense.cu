@@ -1,0 +1,580 @@
+// Dense contraction path of libjt_b200 (uniform mode, sum-product).
+//
+// The contraction is the reference's E2 / E4 einsum (junctiontree/computation.py:84-88, 205-207):
+// a clique potential times the incoming messages, summed down to a separator.  With factor
+// tables shared by the batch (uniform mode) the potential psi_C and most messages are the same
+// for every instance; a projection task whose only per-instance input is ONE message M is then
+//
+//     out[s][b] = sum_r U(s, r) * M[A(s) + B(r)][b]          U = psi_C x uniform messages (scalars)
+//
+// The projection kernels stream one [B] row of M per (s, r) item, i.e. every row of M is re-read
+// from L2 once per output row that uses it (config 4: 64-128 times, config 5: ~5 times on average).
+// Grouping the output rows by the message rows they touch turns the task into a batch of small
+// dense products
+//
+//     out[s_of[g][i]][b] = sum_k W[g][i][k] * M[mg[g] + mk[k]][b]        W = U summed over the
+//                                                                        axes M does not see
+//
+// g = a value of the output axes M depends on, i = the other output axes, k = the summed axes M
+// depends on: per group a [n_i x K] matrix of shared scalars times K message rows.  Every row of
+// M and of out now moves once per batch tile; the arithmetic (2 n_i K flops per 8 (n_i + K)
+// bytes) goes to the FP64 tensor pipe (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4).
+//
+// Nothing of this is in the plan blob: the groups are recovered from the task's index tables
+// when the plan is loaded (distinct values of A(s) and B(r)), so both plan emitters and the ABI
+// are unchanged.  W lives in the *W region* of the workspace (after the uniform workspace) in
+// MMA-fragment order and is rebuilt whenever the uniform workspace is (jt_dense_prepare).
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "jt_kernels.cuh"
+
+namespace {
+
+constexpr int kDWarps = 4;                         // MMA warps per CTA, 32 batch columns each
+constexpr int kDTB = kDWarps * 32;                 // batch columns per CTA
+constexpr int kDKC = 16;                           // message rows per pipeline stage
+constexpr int kDStages = 4;
+constexpr int kDRowPitch = kDTB * 8 + 32;          // bytes; +32: the 4 rows of a B fragment hit distinct banks
+constexpr int kDWBytes = (kDKC / 4) * 4 * 32 * 8;  // W fragments of a stage: 4 k-steps x <= 4 m-tiles x 256 B
+constexpr int kDStageBytes = kDKC * kDRowPitch + kDWBytes;
+constexpr int kDSmem = kDStages * kDStageBytes + 2 * kDStages * 8;
+
+struct DenseArgs {
+    const DDense* dd;      // descriptors of this launch
+    int n;
+    const int* prefix;     // [n + 1] first block of each task, [n] units per CTA
+    const int* dtab;
+    const DTask* tasks;    // all tasks of the plan
+    const DMsg* msgs;
+    const int* tab;
+    void* work;
+    const void* uni;
+    const void* W;
+    void* fout;
+    long long B;
+    int flags;
+};
+
+struct PrepArgs {
+    const DDense* dd;      // all descriptors of the plan
+    const int* list;       // [n] descriptor ids, [n + 1] block prefix
+    int n;
+    const int* dtab;
+    const DTask* tasks;
+    const DMsg* msgs;
+    const int* tab;
+    const void* uni;
+    void* W;
+};
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// W blocks from the uniform workspace: one thread per element of the padded fragment layout.
+//   element (unit = g * n_it + it, k-step k4, m-tile mt, lane) holds W[g][i][k] with
+//   i = it * 8 MT + 8 mt + lane / 4, k = 4 k4 + lane % 4 (zero outside n_i x K):
+//   exactly what thread `lane` feeds to mma.m8n8k4 as the A operand.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) jt_dense_prep_kernel(const PrepArgs a) {
+    const int bid = blockIdx.x;
+    const int* prefix = a.list + a.n;
+    int lo = 0, hi = a.n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(prefix + mid) <= bid) lo = mid; else hi = mid;
+    }
+    const DDense d = a.dd[__ldg(a.list + lo)];
+    const long long idx = (long long)(bid - __ldg(prefix + lo)) * kThreads + threadIdx.x;
+    if (idx >= d.w_size) return;
+    const int lane = (int)(idx & 31);
+    long long rest = idx >> 5;
+    const int mt = (int)(rest % d.MT);
+    rest /= d.MT;
+    const int k4 = (int)(rest % d.n_k4);
+    const long long unit = rest / d.n_k4;
+    const int g = (int)(unit / d.n_it), it = (int)(unit % d.n_it);
+    const int i = (it * d.MT + mt) * 8 + (lane >> 2);
+    const int k = k4 * 4 + (lane & 3);
+    T* W = static_cast<T*>(a.W) + d.w_off;
+    if (i >= d.n_i || k >= d.K) {
+        W[idx] = T(0);
+        return;
+    }
+    const int* __restrict__ tab = a.tab;
+    const int* __restrict__ dtab = a.dtab;
+    const T* __restrict__ uni = static_cast<const T*>(a.uni);
+    const DTask* tk = a.tasks + d.task;
+    const int s = __ldg(dtab + d.s_of + g * d.n_i + i);
+    const int n_slo = tk->n_slo, n_rlo = tk->n_rlo;
+    const int s_hi = s / n_slo, s_lo = s - s_hi * n_slo;
+    // uniform messages that depend on s only
+    T scale = T(1);
+    for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
+        const DMsg* m = a.msgs + j;
+        if (m->uni) scale *= __ldg(uni + m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo));
+    }
+    const long long s_off = tk->src + __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo);
+    T sum = T(0);
+    for (int q = 0; q < d.n_q; ++q) {                  // r ascending: the order of the projection kernels
+        const int r = __ldg(dtab + d.r_of + k * d.n_q + q);
+        const int rh = r / n_rlo, rl = r - rh * n_rlo;
+        T u = __ldg(uni + s_off + __ldg(tab + tk->src_rhi + rh) + __ldg(tab + tk->src_rlo + rl));
+        for (int j = tk->rmsg_begin; j < tk->rmsg_end; ++j) {
+            const DMsg* m = a.msgs + j;
+            if (m->uni)
+                u *= __ldg(uni + m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo) +
+                           __ldg(tab + m->b_hi + rh) + __ldg(tab + m->b_lo + rl));
+        }
+        sum += u;
+    }
+    W[idx] = sum * scale;
+}
+
+// One CTA = kDWarps MMA warps + one producer warp.  It owns a batch tile of kDTB columns and a
+// run of consecutive units (group g, i-tile it) of one task.  Per unit the producer streams the K
+// message rows of the group (16 per stage, one 1-D bulk copy per row, lane = row) and the
+// matching W fragments (one bulk copy) through a 4-stage shared-memory ring; every MMA warp
+// multiplies the [8 MT x 16] W block into its 32 columns of the rows and keeps an
+// [8 MT x 32] accumulator tile in registers (MT <= 4); the epilogue multiplies the per-instance
+// s-only operands in and stores out / bel rows with 16-byte stores.
+template <typename T>
+__global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const DenseArgs a) {
+    static_assert(sizeof(T) == 8, "the f64 kernel");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bid = blockIdx.x;
+    int lo = 0, hi = a.n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a.prefix + mid) <= bid) lo = mid; else hi = mid;
+    }
+    const DDense d = a.dd[lo];
+    const int upc = __ldg(a.prefix + a.n + 1 + lo);
+    const long long units = (long long)d.n_g * d.n_it;
+    const long long u0 = (long long)(bid - __ldg(a.prefix + lo)) * upc;
+    const long long u1 = u0 + upc < units ? u0 + upc : units;
+    const long long B = a.B;
+    const long long col0 = (long long)blockIdx.y * kDTB;
+    const int ncols = (int)(B - col0 < kDTB ? B - col0 : kDTB);
+    const uint32_t row_bytes = (uint32_t)ncols * 8u;
+
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + kDStages * kDStageBytes);
+    const uint32_t ring_u32 = smem_u32(smem);
+    const uint32_t full_u32 = smem_u32(bars), empty_u32 = smem_u32(bars + kDStages);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDStages; ++i) {
+            mbar_init(full_u32 + 8 * i, 1);
+            mbar_init(empty_u32 + 8 * i, kDWarps);
+        }
+        mbar_fence_init();
+    }
+    // stale shared memory must be finite: rows past K of a last stage and columns past the batch
+    // are multiplied by zero fragments / never stored, and 0 * NaN would poison the accumulators
+    for (int i = threadIdx.x; i < kDStages * kDStageBytes / 16; i += blockDim.x)
+        reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const int* __restrict__ dtab = a.dtab;
+    if (warp == kDWarps) {
+        // ---------------- producer warp ----------------
+        const DMsg* m = a.msgs + d.msg;
+        const T* origin = static_cast<const T*>(a.work) + m->eoff + col0;
+        const T* wbase = static_cast<const T*>(a.W) + d.w_off;
+        const long long unit_w = (long long)d.n_k4 * d.MT * 32;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long u = u0; u < u1; ++u) {
+            const int g = (int)(u / d.n_it);
+            const long long row_g = m->off + __ldg(dtab + d.mg + g);
+            for (int c = 0; c < d.n_chunks; ++c) {
+                const int k0 = c * kDKC;
+                const int rows = d.K - k0 < kDKC ? d.K - k0 : kDKC;
+                const int nk4 = d.n_k4 - c * 4 < 4 ? d.n_k4 - c * 4 : 4;
+                long long row = 0;
+                if (lane < rows) row = row_g + __ldg(dtab + d.mk + k0 + lane);
+                const uint32_t full = full_u32 + 8 * stage;
+                const uint32_t dst = ring_u32 + (uint32_t)stage * kDStageBytes;
+                const uint32_t wbytes = (uint32_t)nk4 * d.MT * 256u;
+                mbar_wait(empty_u32 + 8 * stage, phase ^ 1);
+                if (lane == 0) mbar_expect_tx(full, (uint32_t)rows * row_bytes + wbytes);
+                __syncwarp();
+                if (lane < rows) bulk_g2s(dst + (uint32_t)lane * kDRowPitch, origin + row * B, row_bytes, full);
+                if (lane == kDKC) bulk_g2s(dst + kDKC * kDRowPitch, wbase + u * unit_w + (long long)c * 4 * d.MT * 32, wbytes, full);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full);
+                if (++stage == kDStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- MMA warps: warp w owns columns col0 + 32 w .. + 31 ----------------
+    const DTask* tk = a.tasks + d.task;
+    const int MT = d.MT;
+    T* work = static_cast<T*>(a.work);
+    const T* uni = static_cast<const T*>(a.uni);
+    const int tflags = tk->flags;
+    const bool wbel = tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS);
+    const bool has_own = tk->own >= 0;
+    T* obase = (tk->out_space ? static_cast<T*>(a.fout) : work) + tk->out * B;
+    // does the epilogue have per-instance s-only operands?
+    bool s_rows = false;
+    for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) s_rows = s_rows || !a.msgs[j].uni;
+    const int bcol = warp * 32 + (lane >> 2);                      // B fragment: column inside the tile
+    const long long ccol = col0 + warp * 32 + (lane & 3) * 2;      // C fragment: first of two columns, + 8 nt
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long u = u0; u < u1; ++u) {
+        T acc[4][4][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = T(0);
+        for (int c = 0; c < d.n_chunks; ++c) {
+            const int nk4 = d.n_k4 - c * 4 < 4 ? d.n_k4 - c * 4 : 4;
+            mbar_wait(full_u32 + 8 * stage, phase);
+            const unsigned char* st = smem + stage * kDStageBytes;
+            const T* wt = reinterpret_cast<const T*>(st + kDKC * kDRowPitch) + lane;
+            const unsigned char* rows = st + (lane & 3) * kDRowPitch + bcol * 8;
+            for (int q = 0; q < nk4; ++q) {
+                T bf[4];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    bf[nt] = *reinterpret_cast<const T*>(rows + q * 4 * kDRowPitch + nt * 64);
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    if (mt < MT) {
+                        const T af = wt[(q * MT + mt) * 32];
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], af, bf[nt]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_u32 + 8 * stage);
+            if (++stage == kDStages) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+        // epilogue: rows i = it * 8 MT + 8 mt + lane / 4 of group g
+        const int g = (int)(u / d.n_it), it = (int)(u - (long long)g * d.n_it);
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int i = (it * MT + mt) * 8 + (lane >> 2);
+            if (mt < MT && i < d.n_i) {
+                const int s = __ldg(dtab + d.s_of + g * d.n_i + i);
+                T own_u = T(1);
+                const T* own_row = nullptr;
+                if (wbel && has_own) {
+                    if (tflags & JT_TF_OWN_UNIFORM) own_u = __ldg(uni + tk->own + s);
+                    else own_row = work + (tk->own + s) * B;
+                }
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const long long col = ccol + nt * 8;
+                    if (col < B) {                               // B is even: both columns or none
+                        T v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
+                        if (s_rows) {
+                            const int s_hi = s / tk->n_slo, s_lo = s - s_hi * tk->n_slo;
+                            for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
+                                const DMsg* m = a.msgs + j;
+                                if (m->uni) continue;            // folded into W
+                                const T* r = work + m->eoff +
+                                             (m->off + __ldg(a.tab + m->a_hi + s_hi) + __ldg(a.tab + m->a_lo + s_lo)) * B + col;
+                                const double2 x = *reinterpret_cast<const double2*>(r);
+                                v0 *= x.x;
+                                v1 *= x.y;
+                            }
+                        }
+                        *reinterpret_cast<double2*>(obase + (long long)s * B + col) = make_double2(v0, v1);
+                        if (wbel) {
+                            if (own_row) {
+                                const double2 x = *reinterpret_cast<const double2*>(own_row + col);
+                                v0 *= x.x;
+                                v1 *= x.y;
+                            } else {
+                                v0 *= own_u;
+                                v1 *= own_u;
+                            }
+                            *reinterpret_cast<double2*>(work + (tk->bel + s) * B + col) = make_double2(v0, v1);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+bool dense_env_enabled() {   // JT_DISABLE_DENSE=1 keeps every task on the projection kernels (A-B timing)
+    static const int on = [] {
+        const char* e = getenv("JT_DISABLE_DENSE");
+        return (e && e[0] == '1') ? 0 : 1;
+    }();
+    return on == 1;
+}
+
+int phase_group(int phase) {
+    if (phase == JT_PHASE_COLLECT_INSTANCE) return 0;
+    if (phase == JT_PHASE_DIST_PRE_INSTANCE || phase == JT_PHASE_DIST_MAIN_MESSAGES || phase == JT_PHASE_MARGINAL_DIRECT)
+        return 1;
+    return -1;
+}
+
+// distinct values of a two-level additive table map in order of first appearance
+struct Distinct {
+    std::vector<int> value;        // value of each class
+    std::vector<int> cls;          // class of every index
+    std::vector<int> count;
+};
+
+Distinct classify(const jt_plan* p, int hi_off, int lo_off, int n, int n_lo) {
+    Distinct d;
+    d.cls.resize(n);
+    std::unordered_map<int, int> seen;
+    for (int x = 0; x < n; ++x) {
+        const int v = p->tab[hi_off + x / n_lo] + p->tab[lo_off + x % n_lo];
+        auto it = seen.find(v);
+        if (it == seen.end()) {
+            it = seen.emplace(v, (int)d.value.size()).first;
+            d.value.push_back(v);
+            d.count.push_back(0);
+        }
+        d.cls[x] = it->second;
+        ++d.count[it->second];
+    }
+    return d;
+}
+
+}  // namespace
+
+int jt_dense_build(jt_plan* p) {
+    p->dense.clear();
+    p->dtab.clear();
+    p->dense_w_entries = 0;
+    std::vector<int> prep_ids[2];
+    if (p->hdr[JT_H_UNI_ENTRIES] > 0) {
+        for (auto& L : p->launches) {
+            const int group = phase_group(L.phase);
+            L.dense_begin = L.dense_end = (int)p->dense.size();
+            if (group < 0 || !L.tma_ok) continue;
+            for (int t = L.begin; t < L.end; ++t) {
+                const DTask& k = p->tasks[t];
+                if (k.kind != JT_KIND_PROJECT || k.src < 0 || !(k.flags & JT_TF_SRC_UNIFORM) || k.out < 0) continue;
+                if (k.beta >= 0 && L.phase != JT_PHASE_DIST_MAIN_MESSAGES) continue;   // writes the clique belief
+                int msg = -1, n_rows = 0;
+                for (int j = k.rmsg_begin; j < k.rmsg_end; ++j)
+                    if (!p->msgs[j].uni) {
+                        msg = j;
+                        ++n_rows;
+                    }
+                if (n_rows != 1) continue;
+                const DMsg& m = p->msgs[msg];
+                // cheap bound before classifying: at best n_s * n_r items collapse to n_s + n_r rows
+                if ((long long)k.n_s * k.n_r < 64) continue;
+                Distinct gs = classify(p, m.a_hi, m.a_lo, k.n_s, k.n_slo);
+                Distinct ks = classify(p, m.b_hi, m.b_lo, k.n_r, k.n_rlo);
+                const int n_g = (int)gs.value.size(), K = (int)ks.value.size();
+                const int n_i = k.n_s / n_g, n_q = k.n_r / K;
+                bool regular = (long long)n_g * n_i == k.n_s && (long long)K * n_q == k.n_r;
+                for (int c : gs.count) regular = regular && c == n_i;
+                for (int c : ks.count) regular = regular && c == n_q;
+                if (!regular) continue;
+                DDense d;
+                memset(&d, 0, sizeof(d));
+                d.task = t;
+                d.msg = msg;
+                d.n_g = n_g; d.n_i = n_i; d.K = K; d.n_q = n_q;
+                d.MT = std::min(4, (n_i + 7) / 8);
+                d.n_it = (n_i + 8 * d.MT - 1) / (8 * d.MT);
+                d.n_k4 = (K + 3) / 4;
+                d.n_chunks = (d.n_k4 + 3) / 4;
+                // rows moved: the projection kernel streams one row per (s, r) item; here every
+                // group loads its K rows once per i-tile and every output row is written once
+                const long long items = (long long)k.n_s * k.n_r;
+                const long long moved = (long long)n_g * d.n_it * K + k.n_s;
+                if ((long long)n_i * K < 16 || items < 2 * moved) continue;
+                d.w_size = (long long)n_g * d.n_it * d.n_k4 * d.MT * 32;
+                if (d.w_size > (1LL << 40) || p->dtab.size() + (size_t)k.n_s + n_g + K + k.n_r > 2000000000ULL) continue;
+                d.w_off = p->dense_w_entries;
+                p->dense_w_entries += d.w_size;
+                d.s_of = (int)p->dtab.size();
+                p->dtab.resize(p->dtab.size() + k.n_s);
+                {
+                    std::vector<int> fill(n_g, 0);
+                    for (int s = 0; s < k.n_s; ++s) p->dtab[d.s_of + gs.cls[s] * n_i + fill[gs.cls[s]]++] = s;
+                }
+                d.mg = (int)p->dtab.size();
+                p->dtab.insert(p->dtab.end(), gs.value.begin(), gs.value.end());
+                d.mk = (int)p->dtab.size();
+                p->dtab.insert(p->dtab.end(), ks.value.begin(), ks.value.end());
+                d.r_of = (int)p->dtab.size();
+                p->dtab.resize(p->dtab.size() + k.n_r);
+                {
+                    std::vector<int> fill(K, 0);
+                    for (int r = 0; r < k.n_r; ++r) p->dtab[d.r_of + ks.cls[r] * n_q + fill[ks.cls[r]]++] = r;
+                }
+                prep_ids[group].push_back((int)p->dense.size());
+                p->dense.push_back(d);
+            }
+            L.dense_end = (int)p->dense.size();
+        }
+    }
+    p->dense_group_end[0] = (int)prep_ids[0].size();
+    p->dense_group_end[1] = (int)(prep_ids[0].size() + prep_ids[1].size());
+    // prep launches: [n ids][n + 1 block prefix]
+    for (int g = 0; g < 2; ++g) {
+        std::vector<int>& v = p->dense_prep_prefix[g];
+        v = prep_ids[g];
+        long long acc = 0;
+        for (int id : prep_ids[g]) {
+            v.push_back((int)acc);
+            acc += (p->dense[id].w_size + kThreads - 1) / kThreads;
+            if (acc > 2147483647LL) return jt_fail(JT_ERR_INVALID, "dense contraction tables too large");
+        }
+        v.push_back((int)acc);
+    }
+    // block prefixes of the dense launches and the projection-kernel prefixes without their tasks
+    for (auto& L : p->launches) {
+        const int n = L.dense_end - L.dense_begin;
+        L.dense_stages = 0;
+        L.total_items_nd = L.total_items;
+        for (int j = 0; j <= kDenseJMax; ++j) {
+            L.dense_prefix_off[j] = 0;
+            L.dense_blocks[j] = 0;
+        }
+        for (int j = 0; j <= kItemLog2Max; ++j) {
+            L.item_prefix_off_nd[j] = L.item_prefix_off[j];
+            L.item_blocks_nd[j] = L.item_blocks[j];
+        }
+        if (n == 0) continue;
+        std::vector<char> skip(L.end - L.begin, 0);
+        for (int i = L.dense_begin; i < L.dense_end; ++i) {
+            const DDense& d = p->dense[i];
+            skip[d.task - L.begin] = 1;
+            L.dense_stages += (long long)d.n_g * d.n_it * d.n_chunks;
+            L.total_items_nd -= (long long)p->tasks[d.task].n_s * p->tasks[d.task].n_r;
+        }
+        for (int j = 0; j <= kDenseJMax; ++j) {
+            L.dense_prefix_off[j] = p->prefix.size();
+            long long acc = 0;
+            std::vector<int> upc;
+            for (int i = L.dense_begin; i < L.dense_end; ++i) {
+                const DDense& d = p->dense[i];
+                const long long units = (long long)d.n_g * d.n_it;
+                long long u = (1LL << j) / d.n_chunks;
+                u = u < 1 ? 1 : (u > units ? units : u);
+                p->prefix.push_back((int)acc);
+                upc.push_back((int)u);
+                acc += (units + u - 1) / u;
+                if (acc > 2147483647LL) return jt_fail(JT_ERR_INVALID, "dense launch too large");
+            }
+            p->prefix.push_back((int)acc);
+            p->prefix.insert(p->prefix.end(), upc.begin(), upc.end());
+            L.dense_blocks[j] = acc;
+        }
+        int rc = jt_build_item_prefix(p, L, skip.data(), L.item_prefix_off_nd, L.item_blocks_nd);
+        if (rc != JT_OK) return rc;
+    }
+    return JT_OK;
+}
+
+int jt_dense_upload(jt_plan* p) {
+    if (p->dense.empty()) return JT_OK;
+    auto up = [](auto** dst, const auto& v) -> cudaError_t {
+        const size_t bytes = v.size() * sizeof(v[0]);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), bytes ? bytes : 16);
+        if (e != cudaSuccess || !bytes) return e;
+        return cudaMemcpy(*dst, v.data(), bytes, cudaMemcpyHostToDevice);
+    };
+    JT_CUDA(up(&p->d_dense, p->dense));
+    JT_CUDA(up(&p->d_dtab, p->dtab));
+    for (int g = 0; g < 2; ++g) JT_CUDA(up(&p->d_dense_prep[g], p->dense_prep_prefix[g]));
+    return JT_OK;
+}
+
+void jt_dense_free(jt_plan* p) {
+    cudaFree(p->d_dense);
+    cudaFree(p->d_dtab);
+    for (int g = 0; g < 2; ++g) cudaFree(p->d_dense_prep[g]);
+}
+
+bool jt_dense_enabled(const jt_plan* p, int64_t B, int dtype, int flags) {
+    return !p->dense.empty() && dense_env_enabled() && dtype == JT_F64 && (flags & JT_SR_MASK) == JT_SR_SUM_PRODUCT &&
+           (flags & JT_UNIFORM) && !(flags & JT_NO_DENSE) && B % 2 == 0 && B / 2 >= 64;
+}
+
+int jt_dense_prepare(const jt_plan* p, int which, int dtype, const void* uni_ws, void* w_region, cudaStream_t stream) {
+    if (dtype != JT_F64) return jt_fail(JT_ERR_INVALID, "dense contractions are float64 only");
+    const std::vector<int>& v = p->dense_prep_prefix[which];
+    const int n = (int)(v.size() - 1) / 2;
+    if (n <= 0) return JT_OK;
+    PrepArgs a;
+    a.dd = p->d_dense;
+    a.list = p->d_dense_prep[which];
+    a.n = n;
+    a.dtab = p->d_dtab;
+    a.tasks = p->d_tasks;
+    a.msgs = p->d_msgs;
+    a.tab = p->d_tab;
+    a.uni = uni_ws;
+    a.W = w_region;
+    const int blocks = v.back();
+    if (blocks <= 0) return JT_OK;
+    jt_dense_prep_kernel<double><<<(unsigned)blocks, kThreads, 0, stream>>>(a);
+    jt_g_launches.fetch_add(1, std::memory_order_relaxed);
+    JT_CUDA(cudaGetLastError());
+    return JT_OK;
+}
+
+int jt_dense_launch(const jt_plan* p, const jt_plan::Launch& L, void* work, const void* uni_ws, const void* w_region,
+                    void* fout, int64_t B, int dtype, int flags, cudaStream_t stream) {
+    if (dtype != JT_F64) return jt_fail(JT_ERR_INVALID, "dense contractions are float64 only");
+    const int n = L.dense_end - L.dense_begin;
+    if (n <= 0) return JT_OK;
+    const long long tiles = (B + kDTB - 1) / kDTB;
+    // stages per CTA: at least 8 (pipeline fill), more while the grid still covers the machine
+    // four times over (2 CTAs per SM)
+    int j = 3;
+    while (j < kDenseJMax && (L.dense_stages * tiles) >> (j + 1) >= 148LL * 8) ++j;
+    const long long gx = L.dense_blocks[j];
+    if (gx <= 0) return JT_OK;
+    if (gx > 2147483647LL || tiles > 65535)
+        return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, tiles);
+    if (!p->dense_attr_set) {
+        JT_CUDA(cudaFuncSetAttribute(jt_dense_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
+        p->dense_attr_set = true;
+    }
+    DenseArgs a;
+    a.dd = p->d_dense + L.dense_begin;
+    a.n = n;
+    a.prefix = p->d_prefix + L.dense_prefix_off[j];
+    a.dtab = p->d_dtab;
+    a.tasks = p->d_tasks;
+    a.msgs = p->d_msgs;
+    a.tab = p->d_tab;
+    a.work = work;
+    a.uni = uni_ws;
+    a.W = w_region;
+    a.fout = fout;
+    a.B = B;
+    a.flags = flags;
+    jt_dense_kernel<double><<<dim3((unsigned)gx, (unsigned)tiles, 1), (kDWarps + 1) * 32, kDSmem, stream>>>(a);
+    jt_g_launches.fetch_add(1, std::memory_order_relaxed);
+    JT_CUDA(cudaGetLastError());
+    return JT_OK;
+}

@@ -64,7 +64,26 @@ struct KArgs {
     int uniform;          // honour the uniform-operand flags of tasks and messages
 };
 
+// Dense contraction of a batch-shared potential with one per-instance message (uniform mode,
+// sum-product): derived from a projection task when the plan is loaded (jt_dense.cu).
+//   out[s_of[g][i]][b] = sum_k W[g][i][k] * msg[mg[g] + mk[k]][b]
+// W = the uniform operands (potential, uniform messages) summed over the axes the message does
+// not see; it lives in the W region of the workspace in MMA-fragment order (see jt_dense.cu).
+struct DDense {
+    int task;             // index into the plan's tasks: out / bel / own / flags / s-only messages
+    int msg;              // index of the per-instance r-message (DMsg)
+    int n_g, n_i, K;      // groups (distinct message rows bases), output rows per group, contraction length
+    int MT, n_it, n_k4;   // 8-row m-tiles per i-tile, i-tiles per group, k-steps of 4
+    int n_q;              // clique entries summed into one W entry
+    int s_of, mg, mk;     // offsets into the dense int table: s_of[n_g * n_i], mg[n_g], mk[K]
+    int r_of;             // prep: r_of[K * n_q] = the r values summed into column k, ascending
+    int n_chunks;         // stages per unit: ceil(n_k4 / 4)
+    long long w_off;      // element offset of the task's W block inside the W region
+    long long w_size;     // elements
+};
+
 constexpr int kThreads = 256;
+constexpr int kDenseJMax = 16;    // dense launches: per-task units per CTA for ~2^j stages per CTA
 constexpr int kMaxSyLog2 = 12;    // largest chunk of s per block: 4096
 constexpr int kItemLog2Max = 24;
 constexpr int kTmaMaxRows = 8;    // operands per task supported by the TMA kernel (src + messages + own)
@@ -88,6 +107,16 @@ struct jt_plan {
         size_t item_prefix_off[kItemLog2Max + 1];
         long long item_blocks[kItemLog2Max + 1];
         long long total_items;
+        // the same without the tasks that run as dense contractions (variant 1 of dispatch)
+        size_t item_prefix_off_nd[kItemLog2Max + 1];
+        long long item_blocks_nd[kItemLog2Max + 1];
+        long long total_items_nd;
+        // dense contractions of this launch: range in jt_plan::dense, block prefix per j
+        // (layout per j: [n + 1] first block of each task, [n] units per CTA)
+        int dense_begin = 0, dense_end = 0;
+        size_t dense_prefix_off[kDenseJMax + 1];
+        long long dense_blocks[kDenseJMax + 1];
+        long long dense_stages;   // sum over tasks of units * stages per unit
         bool tma_ok;          // every task fits the TMA kernel's stage (rows per stage <= kTmaMaxRows)
         int min_nr;           // smallest n_r of the launch
         int max_nr;           // largest n_r of the launch
@@ -113,7 +142,33 @@ struct jt_plan {
     int* d_walk[3] = {nullptr, nullptr, nullptr};
     // > 48 KB dynamic shared memory opted in per [semiring][f32|f64][VPT-1]
     mutable bool tma_attr_set[kNumSemirings][2][2] = {};
+    // dense contractions (jt_dense.cu): descriptors sorted by launch, their int tables, the size
+    // of the W region in elements; [0] tasks prepared after the uniform collect, [1] after the
+    // uniform distribute (ranges in `dense`, W element ranges)
+    std::vector<DDense> dense;
+    std::vector<int> dtab;
+    long long dense_w_entries = 0;
+    int dense_group_end[2] = {0, 0};          // dense[0 .. end[0]) collect, [end[0] .. end[1]) distribute + marginal
+    std::vector<int> dense_prep_prefix[2];    // block prefix of the prep launches
+    DDense* d_dense = nullptr;
+    int* d_dtab = nullptr;
+    int* d_dense_prep[2] = {nullptr, nullptr};
+    mutable bool dense_attr_set = false;
 };
+
+// jt_abi.cu: block prefix tables of a TMA projection launch (tasks flagged in `skip` get no blocks)
+int jt_build_item_prefix(jt_plan* p, const jt_plan::Launch& L, const char* skip, size_t* off_out, long long* blocks_out);
+
+// jt_dense.cu
+int jt_dense_build(jt_plan* p);                       // derive the dense contractions (plan load)
+int jt_dense_upload(jt_plan* p);
+void jt_dense_free(jt_plan* p);
+bool jt_dense_enabled(const jt_plan* p, int64_t B, int dtype, int flags);
+// W blocks of group `which` (0 collect, 1 distribute + marginal) from the uniform workspace
+int jt_dense_prepare(const jt_plan* p, int which, int dtype, const void* uni_ws, void* w_region, cudaStream_t stream);
+// all dense contractions of one launch
+int jt_dense_launch(const jt_plan* p, const jt_plan::Launch& L, void* work, const void* uni_ws, const void* w_region,
+                    void* fout, int64_t B, int dtype, int flags, cudaStream_t stream);
 
 inline bool jt_is_init_phase(int phase) {
     return phase == JT_PHASE_INIT || phase == JT_PHASE_INIT_UNIFORM || phase == JT_PHASE_INIT_INSTANCE;
@@ -143,7 +198,8 @@ struct jt_walk_args {
 
 struct jt_sr_launchers {
     // all tasks of one launch of the plan (init or projection), kernel chosen by batch shape
-    int (*dispatch)(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec,
+    // variant 1: without the tasks that run as dense contractions (jt_dense_launch does those)
+    int (*dispatch)(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec, int variant,
                     cudaStream_t stream);
     // one projection task outside a plan (jt_contract), LDG kernel
     int (*contract)(const KArgs& a, long long blocks, long long gy, int dtype, int vec, cudaStream_t stream);

@@ -43,20 +43,23 @@ inline bool use_splitr(const jt_plan::Launch& L, long long B, bool is_init) {
 template <typename SR, int SR_ID>
 struct Launcher {
     template <typename T, int VPT>
-    static int launch_tma_vpt(const jt_plan* p, const jt_plan::Launch& L, KArgs a, int ct, cudaStream_t stream) {
+    static int launch_tma_vpt(const jt_plan* p, const jt_plan::Launch& L, KArgs a, int ct, int variant,
+                              cudaStream_t stream) {
         const int tw = ct * VPT;
         const long long tiles = (a.Bv + tw - 1) / tw;
         // (s, r) items per CTA: aim at ~8 CTAs per SM over the launch, but keep >= 64 items per CTA
         // so the pipeline fill is amortised; every task gets its own chunk of s for that item count
         int j = 6;
         const long long target = 148LL * 8;
-        while (j < kItemLog2Max && (L.total_items * tiles) >> (j + 1) >= target) ++j;
+        const long long total_items = variant ? L.total_items_nd : L.total_items;
+        while (j < kItemLog2Max && (total_items * tiles) >> (j + 1) >= target) ++j;
         a.sy_log2 = 0;
         a.bx_log2 = 0;
         a.tasks = p->d_tasks + L.begin;
         a.n_tasks = L.end - L.begin;
-        a.prefix = p->d_prefix + L.item_prefix_off[j];
-        const long long gx = L.item_blocks[j];
+        // variant 1: the block prefix gives no blocks to the tasks that run as dense contractions
+        a.prefix = p->d_prefix + (variant ? L.item_prefix_off_nd[j] : L.item_prefix_off[j]);
+        const long long gx = variant ? L.item_blocks_nd[j] : L.item_blocks[j];
         if (gx <= 0) return JT_OK;
         if (gx > 2147483647LL || tiles > 65535)
             return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, tiles);
@@ -78,21 +81,22 @@ struct Launcher {
     }
 
     template <typename T>
-    static int launch_tma(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
+    static int launch_tma(const jt_plan* p, const jt_plan::Launch& L, KArgs a, int variant, cudaStream_t stream) {
         const int ct = a.Bv >= 256 ? 256 : (a.Bv >= 128 ? 128 : 64);
         // two vectors per consumer thread once the batch fills 512-vector tiles: halves the control
         // instructions per byte of the consumers
         const int forced = tma_vpt_override();
         const bool two = forced ? forced == 2 : a.Bv >= 512;
-        if (two && ct == 256) return launch_tma_vpt<T, 2>(p, L, a, ct, stream);
-        return launch_tma_vpt<T, 1>(p, L, a, ct, stream);
+        if (two && ct == 256) return launch_tma_vpt<T, 2>(p, L, a, ct, variant, stream);
+        return launch_tma_vpt<T, 1>(p, L, a, ct, variant, stream);
     }
 
     template <typename T, int VEC>
-    static int launch_tasks(const jt_plan* p, const jt_plan::Launch& L, KArgs a, cudaStream_t stream) {
+    static int launch_tasks(const jt_plan* p, const jt_plan::Launch& L, KArgs a, int variant, cudaStream_t stream) {
         const bool is_init = jt_is_init_phase(L.phase);
         if (!is_init && VEC * sizeof(T) == 16 && L.tma_ok && a.Bv >= 64 && tma_enabled())
-            return launch_tma<T>(p, L, a, stream);
+            return launch_tma<T>(p, L, a, variant, stream);
+        if (variant) return jt_fail(JT_ERR_INVALID, "internal: dense variant requested for a launch off the TMA path");
         int bx_log2, sy_log2;
         pick_tile(a.Bv, bx_log2, sy_log2);
         if (VEC == 1 && use_splitr(L, a.B, is_init)) {
@@ -142,7 +146,7 @@ struct Launcher {
         return JT_OK;
     }
 
-    static int dispatch(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a_in, int dtype, int vec,
+    static int dispatch(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a_in, int dtype, int vec, int variant,
                         cudaStream_t stream) {
         KArgs a = a_in;
         if (use_splitr(L, a.B, jt_is_init_phase(L.phase))) {   // split-r kernel: scalar batch lanes
@@ -150,12 +154,12 @@ struct Launcher {
             a.Bv = a.B;
         }
         if (dtype == JT_F64) {
-            if (vec == 2) return launch_tasks<double, 2>(p, L, a, stream);
-            return launch_tasks<double, 1>(p, L, a, stream);
+            if (vec == 2) return launch_tasks<double, 2>(p, L, a, variant, stream);
+            return launch_tasks<double, 1>(p, L, a, variant, stream);
         }
-        if (vec == 4) return launch_tasks<float, 4>(p, L, a, stream);
-        if (vec == 2) return launch_tasks<float, 2>(p, L, a, stream);
-        return launch_tasks<float, 1>(p, L, a, stream);
+        if (vec == 4) return launch_tasks<float, 4>(p, L, a, variant, stream);
+        if (vec == 2) return launch_tasks<float, 2>(p, L, a, variant, stream);
+        return launch_tasks<float, 1>(p, L, a, variant, stream);
     }
 
     static int contract(const KArgs& a, long long blocks, long long gy, int dtype, int vec, cudaStream_t stream) {

@@ -13,6 +13,7 @@ import numpy as np
 JT_OK = 0
 JT_F32, JT_F64 = 0, 1
 JT_SEP_BELIEFS, JT_SKIP_MARGINAL, JT_UNIFORM, JT_NO_UNIFORM, JT_UNIFORM_VALID, JT_NO_BELIEFS = 1, 2, 4, 8, 16, 32
+JT_NO_DENSE = 64
 # semiring bits of the stage flags (include/jt_b200.h JT_SR_*)
 JT_SR_SUM_PRODUCT, JT_SR_MAX_PRODUCT, JT_SR_LOG_SUM_EXP, JT_SR_MAX_SUM, JT_SR_MASK = 0x000, 0x100, 0x200, 0x300, 0x300
 ABI_VERSION = 9
@@ -38,6 +39,9 @@ SIGNATURES = {
                                           ctypes.POINTER(ctypes.c_size_t)]),
     "jt_workspace_layout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, _i64p]),
     "jt_plan_upload": (ctypes.c_int, [ctypes.c_void_p]),
+    "jt_plan_dense_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "jt_plan_dense_get": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _i64p]),
+    "jt_plan_dense_table": (_i32p, [ctypes.c_void_p, _i64p]),
     "jt_workspace_sparse_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _i64p, ctypes.c_int64, _i64p]),
     "jt_workspace_sparse_bytes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                                  ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
@@ -187,6 +191,23 @@ class DevicePlan:
         check(lib().jt_workspace_layout(self._handle, B, dtype_code(dtype), out))
         return {"fbase": out[0], "errors": out[1], "uniform": out[2], "total": out[3]}
 
+
+    DENSE_FIELDS = ("task", "msg", "n_g", "n_i", "K", "n_q", "MT", "n_it", "n_k4", "s_of", "mg", "mk", "r_of",
+                    "w_off", "w_size", "launch")
+
+    def dense_tasks(self):
+        """The dense contractions derived from the plan (``jt_plan_dense_*``): a list of dicts
+        (``DENSE_FIELDS``) and the int32 table their offsets index."""
+        n = lib().jt_plan_dense_count(self._handle)
+        out = []
+        for k in range(n):
+            buf = (ctypes.c_int64 * 16)()
+            check(lib().jt_plan_dense_get(self._handle, k, buf))
+            out.append(dict(zip(self.DENSE_FIELDS, list(buf))))
+        count = ctypes.c_int64()
+        ptr = lib().jt_plan_dense_table(self._handle, ctypes.byref(count))
+        table = np.ctypeslib.as_array(ptr, shape=(count.value,)).copy() if count.value else np.zeros(0, np.int32)
+        return out, table
 
     def sparse_bytes(self, B, dtype, flags):
         """``(mapped, dense)`` bytes of a sparse workspace for the stages run with ``flags``."""

@@ -210,18 +210,20 @@ class Engine:
         return torch().cuda.current_stream().cuda_stream
 
     def propagate(self, factor_dev, batched, evidence_dev, B, dtype, ws=None, sep_beliefs=False,
-                  marginal=True, uniform=True, beliefs=True, semiring=0):
+                  marginal=True, uniform=True, beliefs=True, semiring=0, dense=True):
         """init + collect + distribute (+ marginal).  Returns ``(ws, factor_out)``; ``factor_out``
         is a ``[fout_entries, B]`` tensor (``None`` when ``marginal`` is False).  ``uniform``:
         compute potentials and messages no evidence reaches once per batch (shared tables only;
-        results are identical).  ``semiring``: a ``JT_SR_*`` flag (``semirings.py``)."""
+        results are identical).  ``semiring``: a ``JT_SR_*`` flag (``semirings.py``).  ``dense``:
+        in uniform mode, run tasks with a shared potential and one per-instance message as dense
+        contractions on the FP64 tensor pipe (``jt_dense.cu``; same results to rounding)."""
         t = require_cuda()
         self.dev.upload()
         if ws is None:
             ws = self.workspace(B, dtype)
         fout = None
         flags = (_native.JT_SEP_BELIEFS if sep_beliefs else 0) | (0 if uniform else _native.JT_NO_UNIFORM)
-        flags |= semiring
+        flags |= semiring | (0 if dense else _native.JT_NO_DENSE)
         if not beliefs:       # only the outputs are wanted: no clique belief is written
             flags |= _native.JT_NO_BELIEFS
         if marginal:

@@ -504,7 +504,7 @@ class JunctionTree():
         return result
 
     def propagate_batch(self, xs, evidence_vars=(), evidence=None, batch=None, dtype=None,
-                        nodes=False, device_output=False, uniform=True, dl=None, likelihoods=None):
+                        nodes=False, device_output=False, uniform=True, dl=None, likelihoods=None, dense=True):
         """Many independent propagations over this tree in one pass.
 
         :param xs: factor tables shared by the whole batch (stored shapes, observed axes at full
@@ -519,6 +519,9 @@ class JunctionTree():
                               of NumPy arrays
         :param uniform: with shared tables, compute potentials and up-messages that no evidence
                         reaches once per batch instead of once per instance (same results)
+        :param dense: in uniform mode, contract shared potentials with a single per-instance
+                      message on the FP64 tensor pipe (float64 sum-product, B >= 128; same results
+                      to rounding); ``False`` keeps every task on the projection kernels
         :param dl: distributive law (``semirings.py``); default sum-product
         :param likelihoods: soft evidence ``{variable: array [B, size]}``: a per-instance likelihood
                             vector multiplied into the model, i.e. one more single-variable factor
@@ -559,7 +562,7 @@ class JunctionTree():
         ws = engine.workspace(B, dtype)
         engine.load_likelihoods(ws, B, dtype, likelihoods)
         ws, fout = engine.propagate(fdev, batched, edev, B, dtype, ws=ws, sep_beliefs=nodes, uniform=uniform,
-                                    beliefs=nodes, semiring=_semiring(dl))
+                                    beliefs=nodes, semiring=_semiring(dl), dense=dense)
         if edev is not None:
             bad = engine.dev.evidence_errors(B, dtype, ws.data_ptr(), engine._stream())
             if bad:

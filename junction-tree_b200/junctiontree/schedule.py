@@ -722,31 +722,43 @@ class Plan:
         n_root = self.node_size[self.root] if self.root >= 0 else 0
         return (4 if with_init else 3) * self.clique_entries - n_root + 6 * self.sep_entries
 
-    def scheduled_entries(self, uniform=True, sep_beliefs=True):
+    def scheduled_entries(self, uniform=True, sep_beliefs=True, beliefs=True):
         """Entries per instance this schedule reads + writes in HBM for init + collect +
-        distribute, every buffer counted once per consumer (the accounting of SURVEY.md 8d
+        distribute, every buffer counted once per consuming task (the accounting of SURVEY.md 8d
         applied to the schedule as built).  In uniform mode the potential of a uniform clique is
         neither written nor read per instance (only its belief is written), a uniform
         up-message is not written or read per instance (only down-message and belief are), and a
         uniform down-message is written per instance (for callers that read it) while the child
-        reads the uniform copy."""
+        reads the uniform copy.  ``beliefs=False`` (JT_NO_BELIEFS, the pipelines): no clique or
+        separator belief is written; instead every output scope is projected directly from the
+        potential and the incoming messages of its clique, and the outputs are written."""
         total = 0
+        scopes = [0] * self.n_cliques
+        if not beliefs:
+            for c in self.out_clique:
+                scopes[c] += 1
+            total += self.fout_entries
+            sep_beliefs = False
         for c in self.order:
             n = self.node_size[c]
             kids = self.children[c]
-            reads = (0 if c == self.root else 1) + max(len(kids), 1 if c != self.root else 0)
-            if uniform and self.uniform[c]:
-                total += n if (kids or c != self.root) else 0       # belief write
-            else:
-                total += n * (1 + reads) + (n if (kids or c != self.root) else 0)
+            if beliefs:
+                reads = (0 if c == self.root else 1) + max(len(kids), 1 if c != self.root else 0)
+                if uniform and self.uniform[c]:
+                    total += n if (kids or c != self.root) else 0       # belief write
+                else:
+                    total += n * (1 + reads) + (n if (kids or c != self.root) else 0)
+            elif not (uniform and self.uniform[c]):
+                # init write, collect read, one read per message sent down, one per output scope
+                total += n * (1 + (0 if c == self.root else 1) + len(kids) + scopes[c])
             for s, k in kids:
                 ns = self.node_size[s]
-                down_read = 0 if (uniform and self.uniform_down[s]) else 1
+                down_read = 0 if (uniform and self.uniform_down[s]) else 1 + (0 if beliefs else scopes[k])
                 if uniform and self.uniform_up[k]:
                     total += ns * (1 + down_read + (1 if sep_beliefs else 0))   # down write (+ read), belief write
                 else:
                     # up: write + parent's collect read + parent's distribute reads + own read
-                    total += ns * (4 + down_read + (1 if sep_beliefs else 0))
+                    total += ns * (4 + down_read + (1 if sep_beliefs else 0) + (0 if beliefs else scopes[c]))
         return total
 
     def header(self):

@@ -313,3 +313,68 @@ def test_host_entry_points_validate_their_arguments_without_a_device():
     if not torch.cuda.is_available():
         with pytest.raises(_native.NativeError):
             _native.SparseWorkspace(dp, 64, np.float64, 0)
+
+
+def _dense_check(net, with_evidence=True):
+    """Every dense contraction the library derives from a plan equals the projection task it
+    replaces: random uniform workspace and message rows, W built as jt_dense_prep_kernel builds
+    it, grouped products against the direct (s, r) sum."""
+    plan = _plan(net, with_evidence)
+    dp = _native.DevicePlan(plan.to_blob())
+    tasks, dtab = dp.dense_tasks()
+    rng = np.random.default_rng(7)
+    tab = plan.tables.astype(np.int64)
+    B = 3
+    uni = rng.random(plan.work_entries) + 0.1
+    work = rng.random((plan.work_entries, B)) + 0.1
+
+    def amap(hi, lo, n, n_lo):
+        x = np.arange(n)
+        return tab[hi + x // n_lo] + tab[lo + x % n_lo]
+
+    for d in tasks:
+        t = plan.tasks_arr[d["task"]]
+        n_s, n_r, n_slo, n_rlo = (int(t[k]) for k in (sch.T_NS, sch.T_NR, sch.T_NSLO, sch.T_NRLO))
+        assert t[sch.T_FLAGS] & sch.TF_SRC_UNIFORM and t[sch.T_OUT] >= 0
+        m = plan.msgs_arr[d["msg"]]
+        assert not m[sch.M_UNI] and t[sch.T_RMSG_BEGIN] <= d["msg"] < t[sch.T_RMSG_END]
+        S = amap(t[sch.T_SRC_SHI], t[sch.T_SRC_SLO], n_s, n_slo)
+        R = amap(t[sch.T_SRC_RHI], t[sch.T_SRC_RLO], n_r, n_rlo)
+        U = uni[t[sch.T_SRC] + S[:, None] + R[None, :]]                       # [n_s, n_r]
+        for j in range(t[sch.T_RMSG_BEGIN], t[sch.T_RMSG_END]):
+            mj = plan.msgs_arr[j]
+            if mj[sch.M_UNI]:
+                U = U * uni[mj[sch.M_OFF] + amap(mj[sch.M_AHI], mj[sch.M_ALO], n_s, n_slo)[:, None] +
+                            amap(mj[sch.M_BHI], mj[sch.M_BLO], n_r, n_rlo)[None, :]]
+        for j in range(t[sch.T_SMSG_BEGIN], t[sch.T_SMSG_END]):
+            mj = plan.msgs_arr[j]
+            if mj[sch.M_UNI]:
+                U = U * uni[mj[sch.M_OFF] + amap(mj[sch.M_AHI], mj[sch.M_ALO], n_s, n_slo)][:, None]
+        A = amap(m[sch.M_AHI], m[sch.M_ALO], n_s, n_slo)
+        Bm = amap(m[sch.M_BHI], m[sch.M_BLO], n_r, n_rlo)
+        direct = np.einsum("sr,srb->sb", U, work[m[sch.M_OFF] + A[:, None] + Bm[None, :]])
+        n_g, n_i, K, n_q = d["n_g"], d["n_i"], d["K"], d["n_q"]
+        assert n_g * n_i == n_s and K * n_q == n_r
+        s_of = dtab[d["s_of"]:d["s_of"] + n_s].reshape(n_g, n_i)
+        assert sorted(s_of.reshape(-1).tolist()) == list(range(n_s))
+        r_of = dtab[d["r_of"]:d["r_of"] + n_r].reshape(K, n_q)
+        assert sorted(r_of.reshape(-1).tolist()) == list(range(n_r))
+        mg, mk = dtab[d["mg"]:d["mg"] + n_g], dtab[d["mk"]:d["mk"] + K]
+        W = U[s_of[:, :, None, None], r_of[None, None, :, :]].sum(axis=3)     # [n_g, n_i, K]
+        rows = work[m[sch.M_OFF] + mg[:, None] + mk[None, :]]                 # [n_g, K, B]
+        got = np.empty_like(direct)
+        got[s_of] = np.einsum("gik,gkb->gib", W, rows)
+        np.testing.assert_allclose(got, direct, rtol=1e-13)
+        # fragment layout bookkeeping
+        assert d["MT"] == min(4, -(-n_i // 8)) and d["n_it"] == -(-n_i // (8 * d["MT"])) and d["n_k4"] == -(-K // 4)
+        assert d["w_size"] == n_g * d["n_it"] * d["n_k4"] * d["MT"] * 32 and d["w_off"] % 32 == 0
+        assert plan.launches_arr[d["launch"]][0] in (sch.PHASE_COLLECT_INSTANCE, sch.PHASE_DIST_PRE_INSTANCE,
+                                                      sch.PHASE_DIST_MAIN_MESSAGES, sch.PHASE_MARGINAL_DIRECT)
+    return len(tasks)
+
+
+def test_dense_contractions_equal_the_projection_tasks_they_replace():
+    assert _dense_check(wl.large_state_tree((8, 12, 16, 8, 12, 16))) >= 2
+    assert _dense_check(wl.dag37()) >= 3
+    assert _dense_check(wl.random_dag(60, 3, 2, 5, 8, 3)) >= 1
+    assert _dense_check(wl.dag37(), with_evidence=False) == 0          # everything uniform: nothing per instance

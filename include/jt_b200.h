@@ -96,6 +96,8 @@ extern "C" {
                               psi_C and the incoming messages (pass the same value to both stages) */
 #define JT_NO_DENSE 64      /* uniform mode: keep every task on the projection kernels (no dense contractions);
                               pass the same value to every stage */
+#define JT_LOGZ_ONLY 128    /* jt_normalize: only write log Z (the log of the total of output scope 0); the outputs
+                              stay unnormalised */
 #define JT_UNIFORM_VALID 16 /* uniform mode: the uniform workspace of this workspace already holds the
                               potentials and up-messages of these factor tables (an earlier call with
                               the same tables and the same workspace): skip recomputing them */

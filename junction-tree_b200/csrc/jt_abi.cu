@@ -153,16 +153,28 @@ KArgs base_args(const jt_plan* p, int64_t B, void* workspace, int vec) {
 
 // One launch of the plan.  With `w_region` set (uniform mode, dense contractions enabled) the
 // tasks that are dense contractions run in jt_dense_kernel and the projection kernel gets the
-// block prefix without them.
-int run_launch(jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec, void* w_region,
-               cudaStream_t stream) {
+// block prefix without them.  A DIST_MAIN launch in uniform mode (`split`) leaves the clique
+// beliefs of the uniform cliques to jt_beta_kernel: the projection kernel (and the dense
+// contractions of the matching message-only launch) compute the messages, tasks that only write
+// a belief drop out of it.
+int run_launch(jt_plan* p, const jt_plan::Launch& L, const KArgs& a_in, int dtype, int vec, void* w_region,
+               cudaStream_t stream, bool split = false) {
+    KArgs a = a_in;
+    split = split && L.phase == JT_PHASE_DIST_MAIN && L.beta_n > 0;
+    const bool dense = w_region && L.dense_end > L.dense_begin && (L.phase != JT_PHASE_DIST_MAIN || split);
     int variant = 0;
-    if (w_region && L.dense_end > L.dense_begin) {
-        int rc = jt_dense_launch(p, L, a.work, a.uni, w_region, a.fout, a.B, dtype, a.flags, stream);
-        if (rc != JT_OK) return rc;
+    if (split) {
+        a.flags |= JT_X_BETA_SPLIT;
         variant = 1;
     }
-    return launchers(a.flags)->dispatch(p, L, a, dtype, vec, variant, stream);
+    if (dense) {
+        int rc = jt_dense_launch(p, L, a.work, a.uni, w_region, a.fout, a.B, dtype, a.flags, stream);
+        if (rc != JT_OK) return rc;
+        variant = split ? 2 : 1;
+    }
+    int rc = launchers(a.flags)->dispatch(p, L, a, dtype, vec, variant, stream);
+    if (rc != JT_OK || !split) return rc;
+    return launchers(a.flags)->beta(p, L, a, dtype, vec, stream);
 }
 
 // Launches of one phase, in plan order.
@@ -592,7 +604,9 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
     a.flags = flags;
     int pre_phase = JT_PHASE_DIST_PRE;
     void* w_region = nullptr;
+    bool split = false;
     if (uniform_mode(p, flags)) {
+        split = jt_beta_enabled(p, B, dtype, flags) && vec * dtype_size(dtype) == 16;
         // down-messages with an evidence-free source side: once, top level first (B = 1)
         void* uni = uniform_ws(p, B, dtype, workspace);
         w_region = dense_region(p, B, dtype, workspace, flags);
@@ -613,7 +627,7 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
     const int main_phase = (flags & JT_NO_BELIEFS) ? JT_PHASE_DIST_MAIN_MESSAGES : JT_PHASE_DIST_MAIN;
     for (const auto& L : p->launches) {
         if (L.phase != pre_phase && L.phase != main_phase) continue;
-        rc = run_launch(p, L, a, dtype, vec, w_region, stream);
+        rc = run_launch(p, L, a, dtype, vec, w_region, stream, split);
         if (rc != JT_OK) return rc;
     }
     return JT_OK;
@@ -784,7 +798,9 @@ int jt_normalize(jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz,
     const int n_out = (int)p->fout_off.size();
     if (n_out == 0) return JT_OK;
     if (n_out > 65535) return fail(JT_ERR_INVALID, "too many output scopes for one launch");
-    return launchers(flags)->normalize(p, B, dtype, factor_out, logz, static_cast<cudaStream_t>(stream));
+    if ((flags & JT_LOGZ_ONLY) && !logz) return fail(JT_ERR_INVALID, "JT_LOGZ_ONLY needs a logz buffer");
+    return launchers(flags)->normalize(p, B, dtype, factor_out, logz, (flags & JT_LOGZ_ONLY) ? 0 : 1,
+                                       static_cast<cudaStream_t>(stream));
 }
 
 int jt_evidence_errors(jt_plan* p, int64_t B, int dtype, void* workspace, void* stream, int64_t* out) {

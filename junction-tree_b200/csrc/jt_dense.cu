@@ -193,6 +193,32 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
         const long long unit_w = (long long)d.n_k4 * d.MT * 32;
         int stage = 0;
         uint32_t phase = 0;
+        if (d.ups > 1) {
+            // short contractions: a stage holds `ups` consecutive units, unit j in rows j * 4 n_k4 ...
+            const int kpad = d.n_k4 * 4;
+            const int j = lane / kpad, k = lane - j * kpad;
+            for (long long u = u0; u < u1; u += d.ups) {
+                const int nu = (int)(u1 - u < d.ups ? u1 - u : d.ups);
+                const bool live = j < nu && k < d.K;
+                long long row = 0;
+                if (live) row = m->off + __ldg(dtab + d.mg + (int)((u + j) / d.n_it)) + __ldg(dtab + d.mk + k);
+                const uint32_t full = full_u32 + 8 * stage;
+                const uint32_t dst = ring_u32 + (uint32_t)stage * kDStageBytes;
+                const uint32_t wbytes = (uint32_t)nu * d.n_k4 * d.MT * 256u;
+                mbar_wait(empty_u32 + 8 * stage, phase ^ 1);
+                if (lane == 0) mbar_expect_tx(full, (uint32_t)nu * d.K * row_bytes + wbytes);
+                __syncwarp();
+                if (live) bulk_g2s(dst + (uint32_t)lane * kDRowPitch, origin + row * B, row_bytes, full);
+                if (lane == kDKC) bulk_g2s(dst + kDKC * kDRowPitch, wbase + u * unit_w, wbytes, full);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full);
+                if (++stage == kDStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            return;
+        }
         for (long long u = u0; u < u1; ++u) {
             const int g = (int)(u / d.n_it);
             const long long row_g = m->off + __ldg(dtab + d.mg + g);
@@ -236,42 +262,34 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
     const int bcol = warp * 32 + (lane >> 2);                      // B fragment: column inside the tile
     const long long ccol = col0 + warp * 32 + (lane & 3) * 2;      // C fragment: first of two columns, + 8 nt
 
-    int stage = 0;
-    uint32_t phase = 0;
-    for (long long u = u0; u < u1; ++u) {
-        T acc[4][4][2];
+    // the [8 MT x 32] accumulator tile of one unit
+    struct Acc {
+        T v[4][4][2];
+    };
+    auto zero = [](Acc& c) {
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = T(0);
-        for (int c = 0; c < d.n_chunks; ++c) {
-            const int nk4 = d.n_k4 - c * 4 < 4 ? d.n_k4 - c * 4 : 4;
-            mbar_wait(full_u32 + 8 * stage, phase);
-            const unsigned char* st = smem + stage * kDStageBytes;
-            const T* wt = reinterpret_cast<const T*>(st + kDKC * kDRowPitch) + lane;
-            const unsigned char* rows = st + (lane & 3) * kDRowPitch + bcol * 8;
-            for (int q = 0; q < nk4; ++q) {
-                T bf[4];
+            for (int nt = 0; nt < 4; ++nt) c.v[mt][nt][0] = c.v[mt][nt][1] = T(0);
+    };
+    // nk4 k-steps: rows `rows` (4 per step) times W fragments `wt` (MT per step)
+    auto steps = [&](Acc& c, const unsigned char* rows, const T* wt, int nk4) {
+        for (int q = 0; q < nk4; ++q) {
+            T bf[4];
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
-                    bf[nt] = *reinterpret_cast<const T*>(rows + q * 4 * kDRowPitch + nt * 64);
+            for (int nt = 0; nt < 4; ++nt) bf[nt] = *reinterpret_cast<const T*>(rows + q * 4 * kDRowPitch + nt * 64);
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
-                    if (mt < MT) {
-                        const T af = wt[(q * MT + mt) * 32];
+            for (int mt = 0; mt < 4; ++mt) {
+                if (mt < MT) {
+                    const T af = wt[(q * MT + mt) * 32];
 #pragma unroll
-                        for (int nt = 0; nt < 4; ++nt) dmma(acc[mt][nt][0], acc[mt][nt][1], af, bf[nt]);
-                    }
+                    for (int nt = 0; nt < 4; ++nt) dmma(c.v[mt][nt][0], c.v[mt][nt][1], af, bf[nt]);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_u32 + 8 * stage);
-            if (++stage == kDStages) {
-                stage = 0;
-                phase ^= 1;
-            }
         }
-        // epilogue: rows i = it * 8 MT + 8 mt + lane / 4 of group g
+    };
+    // epilogue of unit u: rows i = it * 8 MT + 8 mt + lane / 4 of group g
+    auto epilogue = [&](const Acc& c, long long u) {
         const int g = (int)(u / d.n_it), it = (int)(u - (long long)g * d.n_it);
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
@@ -288,7 +306,7 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
                 for (int nt = 0; nt < 4; ++nt) {
                     const long long col = ccol + nt * 8;
                     if (col < B) {                               // B is even: both columns or none
-                        T v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
+                        T v0 = c.v[mt][nt][0], v1 = c.v[mt][nt][1];
                         if (s_rows) {
                             const int s_hi = s / tk->n_slo, s_lo = s - s_hi * tk->n_slo;
                             for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
@@ -317,6 +335,48 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
                 }
             }
         }
+    };
+
+    int stage = 0;
+    uint32_t phase = 0;
+    auto release = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_u32 + 8 * stage);
+        if (++stage == kDStages) {
+            stage = 0;
+            phase ^= 1;
+        }
+    };
+    const int frag_off = (lane & 3) * kDRowPitch + bcol * 8;         // B fragment of this thread inside a stage
+    if (d.ups > 1) {
+        // short contractions: `ups` units per stage, one after the other
+        const int kpad = d.n_k4 * 4;
+        for (long long u = u0; u < u1; u += d.ups) {
+            const int nu = (int)(u1 - u < d.ups ? u1 - u : d.ups);
+            mbar_wait(full_u32 + 8 * stage, phase);
+            const unsigned char* st = smem + stage * kDStageBytes;
+            const T* wt = reinterpret_cast<const T*>(st + kDKC * kDRowPitch) + lane;
+            for (int j = 0; j < nu; ++j) {
+                Acc c;
+                zero(c);
+                steps(c, st + j * kpad * kDRowPitch + frag_off, wt + j * d.n_k4 * MT * 32, d.n_k4);
+                if (j == nu - 1) release();                       // the stage is consumed: refill during the epilogue
+                epilogue(c, u + j);
+            }
+        }
+        return;
+    }
+    for (long long u = u0; u < u1; ++u) {
+        Acc c;
+        zero(c);
+        for (int ch = 0; ch < d.n_chunks; ++ch) {
+            const int nk4 = d.n_k4 - ch * 4 < 4 ? d.n_k4 - ch * 4 : 4;
+            mbar_wait(full_u32 + 8 * stage, phase);
+            const unsigned char* st = smem + stage * kDStageBytes;
+            steps(c, st + frag_off, reinterpret_cast<const T*>(st + kDKC * kDRowPitch) + lane, nk4);
+            release();
+        }
+        epilogue(c, u);
     }
 }
 
@@ -403,6 +463,7 @@ int jt_dense_build(jt_plan* p) {
                 d.n_it = (n_i + 8 * d.MT - 1) / (8 * d.MT);
                 d.n_k4 = (K + 3) / 4;
                 d.n_chunks = (d.n_k4 + 3) / 4;
+                d.ups = d.n_chunks == 1 ? std::max(1, (kDKC / 4) / d.n_k4) : 1;
                 // rows moved: the projection kernel streams one row per (s, r) item; here every
                 // group loads its K rows once per i-tile and every output row is written once
                 const long long items = (long long)k.n_s * k.n_r;
@@ -448,26 +509,95 @@ int jt_dense_build(jt_plan* p) {
         }
         v.push_back((int)acc);
     }
-    // block prefixes of the dense launches and the projection-kernel prefixes without their tasks
+    // Clique beliefs of uniform cliques: written by jt_beta_kernel instead of the projection task
+    // that sends the last message (DIST_MAIN launches, uniform mode).  Such a task keeps its message
+    // part (which may be a dense contraction: the descriptors of the matching DIST_MAIN_MESSAGES
+    // launch) and a task that only writes a belief leaves the projection launch altogether.
+    const bool small_offsets = p->hdr[JT_H_CLIQUE_ENTRIES] + 3 * p->hdr[JT_H_SEP_ENTRIES] + p->hdr[JT_H_LIK_ENTRIES] < 2147483647LL;
+    for (auto& L : p->launches) {
+        L.beta_n = 0;
+        L.beta_items = 0;
+        L.beta_off = 0;
+        if (L.phase != JT_PHASE_DIST_MAIN || p->hdr[JT_H_UNI_ENTRIES] <= 0 || !L.tma_ok || !small_offsets) continue;
+        std::vector<int> ids;
+        for (int t = L.begin; t < L.end; ++t) {
+            DTask& k = p->tasks[t];
+            if (k.kind != JT_KIND_PROJECT || k.beta < 0 || k.src < 0 || !(k.flags & JT_TF_SRC_UNIFORM)) continue;
+            int rows = (k.own >= 0 && !(k.flags & JT_TF_OWN_UNIFORM)) ? 1 : 0;
+            for (int j = k.rmsg_begin; j < k.smsg_end; ++j) rows += p->msgs[j].uni ? 0 : 1;
+            if (rows > kBetaRows) continue;
+            k.flags |= JT_TF_BETA_SPLIT;
+            ids.push_back(t);
+            L.beta_items += (long long)k.n_s * k.n_r;
+        }
+        if (ids.empty()) continue;
+        L.beta_n = (int)ids.size();
+        L.beta_off = p->prefix.size();
+        p->prefix.insert(p->prefix.end(), ids.begin(), ids.end());
+        for (int ch = kBetaChMin; ch <= kBetaChMax; ++ch) {
+            long long acc = 0;
+            for (int t : ids) {
+                p->prefix.push_back((int)acc);
+                acc += ((long long)p->tasks[t].n_s * p->tasks[t].n_r + (1LL << ch) - 1) >> ch;
+                if (acc > 2147483647LL) return jt_fail(JT_ERR_INVALID, "belief launch too large");
+            }
+            p->prefix.push_back((int)acc);
+        }
+        // the message parts of these tasks may run as the dense contractions of the matching
+        // DIST_MAIN_MESSAGES launch (same first task), if every one of those is split
+        for (const auto& M : p->launches) {
+            if (M.phase != JT_PHASE_DIST_MAIN_MESSAGES || M.begin != L.begin) continue;
+            bool all_split = true;
+            for (int i = M.dense_begin; i < M.dense_end; ++i)
+                all_split = all_split && (p->tasks[p->dense[i].task].flags & JT_TF_BETA_SPLIT);
+            if (all_split) {
+                L.dense_begin = M.dense_begin;
+                L.dense_end = M.dense_end;
+            }
+        }
+    }
+    // block prefixes of the dense launches and the projection-kernel prefixes of the reduced task sets
     for (auto& L : p->launches) {
         const int n = L.dense_end - L.dense_begin;
         L.dense_stages = 0;
-        L.total_items_nd = L.total_items;
+        for (int v = 0; v < 2; ++v) {
+            L.total_items_v[v] = L.total_items;
+            for (int j = 0; j <= kItemLog2Max; ++j) {
+                L.item_prefix_off_v[v][j] = L.item_prefix_off[j];
+                L.item_blocks_v[v][j] = L.item_blocks[j];
+            }
+        }
         for (int j = 0; j <= kDenseJMax; ++j) {
             L.dense_prefix_off[j] = 0;
             L.dense_blocks[j] = 0;
         }
-        for (int j = 0; j <= kItemLog2Max; ++j) {
-            L.item_prefix_off_nd[j] = L.item_prefix_off[j];
-            L.item_blocks_nd[j] = L.item_blocks[j];
-        }
-        if (n == 0) continue;
         std::vector<char> skip(L.end - L.begin, 0);
+        int v_dense = 0;                       // which reduced set excludes the dense contractions
+        if (L.phase == JT_PHASE_DIST_MAIN && L.beta_n > 0) {
+            // [0]: without the tasks that only write a belief
+            for (int t = L.begin; t < L.end; ++t)
+                if ((p->tasks[t].flags & JT_TF_BETA_SPLIT) && p->tasks[t].out < 0) {
+                    skip[t - L.begin] = 1;
+                    L.total_items_v[0] -= (long long)p->tasks[t].n_s * p->tasks[t].n_r;
+                }
+            int rc = jt_build_item_prefix(p, L, skip.data(), L.item_prefix_off_v[0], L.item_blocks_v[0]);
+            if (rc != JT_OK) return rc;
+            L.total_items_v[1] = L.total_items_v[0];
+            v_dense = 1;
+        }
+        if (n == 0) {
+            if (v_dense == 1)
+                for (int j = 0; j <= kItemLog2Max; ++j) {
+                    L.item_prefix_off_v[1][j] = L.item_prefix_off_v[0][j];
+                    L.item_blocks_v[1][j] = L.item_blocks_v[0][j];
+                }
+            continue;
+        }
         for (int i = L.dense_begin; i < L.dense_end; ++i) {
             const DDense& d = p->dense[i];
             skip[d.task - L.begin] = 1;
-            L.dense_stages += (long long)d.n_g * d.n_it * d.n_chunks;
-            L.total_items_nd -= (long long)p->tasks[d.task].n_s * p->tasks[d.task].n_r;
+            L.dense_stages += ((long long)d.n_g * d.n_it + d.ups - 1) / d.ups * d.n_chunks;
+            L.total_items_v[v_dense] -= (long long)p->tasks[d.task].n_s * p->tasks[d.task].n_r;
         }
         for (int j = 0; j <= kDenseJMax; ++j) {
             L.dense_prefix_off[j] = p->prefix.size();
@@ -476,8 +606,9 @@ int jt_dense_build(jt_plan* p) {
             for (int i = L.dense_begin; i < L.dense_end; ++i) {
                 const DDense& d = p->dense[i];
                 const long long units = (long long)d.n_g * d.n_it;
-                long long u = (1LL << j) / d.n_chunks;
-                u = u < 1 ? 1 : (u > units ? units : u);
+                long long u = (1LL << j) / d.n_chunks * d.ups;           // a multiple of the units per stage
+                u = u < d.ups ? d.ups : u;
+                u = u > units ? units : u;
                 p->prefix.push_back((int)acc);
                 upc.push_back((int)u);
                 acc += (units + u - 1) / u;
@@ -487,7 +618,7 @@ int jt_dense_build(jt_plan* p) {
             p->prefix.insert(p->prefix.end(), upc.begin(), upc.end());
             L.dense_blocks[j] = acc;
         }
-        int rc = jt_build_item_prefix(p, L, skip.data(), L.item_prefix_off_nd, L.item_blocks_nd);
+        int rc = jt_build_item_prefix(p, L, skip.data(), L.item_prefix_off_v[v_dense], L.item_blocks_v[v_dense]);
         if (rc != JT_OK) return rc;
     }
     return JT_OK;
@@ -513,9 +644,29 @@ void jt_dense_free(jt_plan* p) {
     for (int g = 0; g < 2; ++g) cudaFree(p->d_dense_prep[g]);
 }
 
+bool jt_tma_path(int64_t B, int dtype) {
+    static const int tma_on = [] {
+        const char* e = getenv("JT_DISABLE_TMA");
+        return (e && e[0] == '1') ? 0 : 1;
+    }();
+    const int vec = dtype == JT_F64 ? 2 : 4;       // 16-byte batch vectors
+    return tma_on == 1 && B % vec == 0 && B / vec >= 64;
+}
+
 bool jt_dense_enabled(const jt_plan* p, int64_t B, int dtype, int flags) {
     return !p->dense.empty() && dense_env_enabled() && dtype == JT_F64 && (flags & JT_SR_MASK) == JT_SR_SUM_PRODUCT &&
-           (flags & JT_UNIFORM) && !(flags & JT_NO_DENSE) && B % 2 == 0 && B / 2 >= 64;
+           (flags & JT_UNIFORM) && !(flags & JT_NO_DENSE) && jt_tma_path(B, dtype);
+}
+
+// uniform mode, beliefs stored, the projection tasks on the TMA kernel (whose block prefixes have
+// the reduced variants); JT_DISABLE_BETA=1 / JT_NO_DENSE keep the beliefs in the projection tasks
+bool jt_beta_enabled(const jt_plan* p, int64_t B, int dtype, int flags) {
+    static const int on = [] {
+        const char* e = getenv("JT_DISABLE_BETA");
+        return (e && e[0] == '1') ? 0 : 1;
+    }();
+    return on == 1 && p->hdr[JT_H_UNI_ENTRIES] > 0 && (flags & JT_UNIFORM) && !(flags & JT_NO_BELIEFS) &&
+           !(flags & JT_NO_DENSE) && jt_tma_path(B, dtype);
 }
 
 int jt_dense_prepare(const jt_plan* p, int which, int dtype, const void* uni_ws, void* w_region, cudaStream_t stream) {

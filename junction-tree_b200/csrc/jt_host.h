@@ -78,9 +78,16 @@ struct DDense {
     int s_of, mg, mk;     // offsets into the dense int table: s_of[n_g * n_i], mg[n_g], mk[K]
     int r_of;             // prep: r_of[K * n_q] = the r values summed into column k, ascending
     int n_chunks;         // stages per unit: ceil(n_k4 / 4)
+    int ups;              // units per stage (short contractions, K <= 8, share a stage), else 1
     long long w_off;      // element offset of the task's W block inside the W region
     long long w_size;     // elements
 };
+
+// internal bits (never in a plan blob or in the public flags)
+constexpr int JT_TF_BETA_SPLIT = 0x100;   // DTask::flags: in uniform mode the clique belief of this task is written by jt_beta_kernel
+constexpr int JT_X_BETA_SPLIT = 0x10000;  // KArgs::flags: ... and this launch runs that way
+constexpr int kBetaRows = 3;              // per-instance row operands jt_beta_kernel multiplies per entry
+constexpr int kBetaChMin = 8, kBetaChMax = 14;   // log2 of the items per block of a jt_beta_kernel launch
 
 constexpr int kThreads = 256;
 constexpr int kDenseJMax = 16;    // dense launches: per-task units per CTA for ~2^j stages per CTA
@@ -107,10 +114,18 @@ struct jt_plan {
         size_t item_prefix_off[kItemLog2Max + 1];
         long long item_blocks[kItemLog2Max + 1];
         long long total_items;
-        // the same without the tasks that run as dense contractions (variant 1 of dispatch)
-        size_t item_prefix_off_nd[kItemLog2Max + 1];
-        long long item_blocks_nd[kItemLog2Max + 1];
-        long long total_items_nd;
+        // reduced task sets (variants 1 and 2 of dispatch).  Launches other than DIST_MAIN: [0] =
+        // without the tasks that run as dense contractions.  DIST_MAIN (uniform mode, beliefs
+        // written by jt_beta_kernel): [0] = without the tasks that only write a belief, [1] = also
+        // without the dense contractions.
+        size_t item_prefix_off_v[2][kItemLog2Max + 1];
+        long long item_blocks_v[2][kItemLog2Max + 1];
+        long long total_items_v[2];
+        // DIST_MAIN: tasks whose clique belief jt_beta_kernel writes ([n] task ids, then per
+        // chunk size 2^kBetaChMin .. 2^kBetaChMax a block prefix [n + 1]), in jt_plan::prefix
+        size_t beta_off = 0;
+        int beta_n = 0;
+        long long beta_items = 0;
         // dense contractions of this launch: range in jt_plan::dense, block prefix per j
         // (layout per j: [n + 1] first block of each task, [n] units per CTA)
         int dense_begin = 0, dense_end = 0;
@@ -164,6 +179,8 @@ int jt_dense_build(jt_plan* p);                       // derive the dense contra
 int jt_dense_upload(jt_plan* p);
 void jt_dense_free(jt_plan* p);
 bool jt_dense_enabled(const jt_plan* p, int64_t B, int dtype, int flags);
+bool jt_tma_path(int64_t B, int dtype);               // batch shape that runs the projection tasks in jt_project_tma_kernel
+bool jt_beta_enabled(const jt_plan* p, int64_t B, int dtype, int flags);
 // W blocks of group `which` (0 collect, 1 distribute + marginal) from the uniform workspace
 int jt_dense_prepare(const jt_plan* p, int which, int dtype, const void* uni_ws, void* w_region, cudaStream_t stream);
 // all dense contractions of one launch
@@ -198,13 +215,17 @@ struct jt_walk_args {
 
 struct jt_sr_launchers {
     // all tasks of one launch of the plan (init or projection), kernel chosen by batch shape
-    // variant 1: without the tasks that run as dense contractions (jt_dense_launch does those)
+    // variant 1, 2: reduced task sets (jt_plan::Launch::item_prefix_off_v), the rest of the launch
+    // runs in jt_dense_kernel / jt_beta_kernel
     int (*dispatch)(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec, int variant,
                     cudaStream_t stream);
+    // clique beliefs of the launch's JT_TF_BETA_SPLIT tasks (uniform mode): beta = scalars x rows
+    int (*beta)(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec, cudaStream_t stream);
     // one projection task outside a plan (jt_contract), LDG kernel
     int (*contract)(const KArgs& a, long long blocks, long long gy, int dtype, int vec, cudaStream_t stream);
     // output stage
-    int (*normalize)(const jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, cudaStream_t stream);
+    int (*normalize)(const jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, int normalize,
+                     cudaStream_t stream);
     // init + collect + distribute (+ marginal) of a few instances of a small tree in one launch
     int (*walk)(const KArgs& a, const jt_walk_args& w, int dtype, cudaStream_t stream);
 };

@@ -7,6 +7,8 @@
 // arithmetic is table-driven and warp-uniform.
 #pragma once
 
+#include <type_traits>
+
 #include "jt_host.h"
 
 namespace {
@@ -35,6 +37,18 @@ __device__ __forceinline__ Pack<T, VEC> ld(const T* p) {
 template <typename T, int VEC>
 __device__ __forceinline__ void st(T* p, const Pack<T, VEC>& x) {
     *reinterpret_cast<Pack<T, VEC>*>(p) = x;
+}
+
+// streaming store (evict-first): for data written once and not re-read by the same launch
+template <typename T, int VEC>
+__device__ __forceinline__ void st_stream(T* p, const Pack<T, VEC>& x) {
+    if constexpr (sizeof(T) * VEC == 16) {
+        __stcs(reinterpret_cast<float4*>(p), *reinterpret_cast<const float4*>(&x));
+    } else if constexpr (sizeof(T) * VEC == 8) {
+        __stcs(reinterpret_cast<float2*>(p), *reinterpret_cast<const float2*>(&x));
+    } else {
+        __stcs(reinterpret_cast<float*>(p), *reinterpret_cast<const float*>(&x));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -455,6 +469,131 @@ __global__ void __launch_bounds__(kThreads) jt_init_rows_kernel(const KArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Clique beliefs in uniform mode (E5, reference computation.py:216-224, for a potential shared by
+// the batch): beta_C[e][b] = U(e) * prod_j row_j[idx_j(e)][b] -- U = psi_C x the uniform messages
+// (scalars from the uniform workspace), rows = the per-instance messages (at most kBetaRows).
+// Nothing is reduced, so this is a streaming write like the clique initialisation and has the
+// same structure as jt_init_rows_kernel: thread t resolves item base + t of a 256-item sub-chunk
+// (scalar, row indices, destination row) into shared memory, then every thread owns a batch
+// vector and walks the sub-chunk with a few 16-byte loads, products and one 16-byte store per
+// entry.  (The projection kernels did this as a side effect of the message tasks at 3.6-5.5 TB/s
+// -- issue-bound consumers, ncu r02 -- against ~7 TB/s for streaming writes.)
+
+struct BetaArgs {
+    const int* list;       // [n] task ids of this launch
+    const int* prefix;     // [n + 1] first block of each task for 2^ch_log2 items per block
+    int n, ch_log2;
+    const DTask* tasks;    // all tasks of the plan
+    const DMsg* msgs;
+    const int* tab;
+    void* work;
+    const void* uni;
+    long long B, Bv;
+    int bx_log2;
+};
+
+template <typename SR, typename T, int VEC>
+__global__ void __launch_bounds__(kThreads, 3) jt_beta_kernel(const BetaArgs a) {
+    typedef Pack<T, VEC> P;
+    __shared__ T su[kThreads];
+    __shared__ int se[kThreads];
+    __shared__ int srow[kBetaRows][kThreads];
+    int lo = 0, hi = a.n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a.prefix + mid) <= (int)blockIdx.x) lo = mid; else hi = mid;
+    }
+    const DTask* tk = a.tasks + __ldg(a.list + lo);
+    const int n_r = tk->n_r, n_slo = tk->n_slo, n_rlo = tk->n_rlo;
+    const long long n_items = (long long)tk->n_s * n_r;
+    const long long i0 = (long long)((int)blockIdx.x - __ldg(a.prefix + lo)) << a.ch_log2;
+    const long long i1 = i0 + (1LL << a.ch_log2) < n_items ? i0 + (1LL << a.ch_log2) : n_items;
+    const int t = threadIdx.x;
+    const int tx = t & ((1 << a.bx_log2) - 1), ty = t >> a.bx_log2, ry = kThreads >> a.bx_log2;
+    const long long bv = ((long long)blockIdx.y << a.bx_log2) + tx;
+    const bool active = bv < a.Bv;
+    const long long B = a.B, col = (active ? bv : 0) * VEC;
+    const int* __restrict__ tab = a.tab;
+    const DMsg* __restrict__ msgs = a.msgs;
+    const T* __restrict__ uni = static_cast<const T*>(a.uni);
+    T* work = static_cast<T*>(a.work);
+    const int tflags = tk->flags;
+    const bool own_row = tk->own >= 0 && !(tflags & JT_TF_OWN_UNIFORM);
+    int n_rows = own_row ? 1 : 0;
+    for (int j = tk->rmsg_begin; j < tk->smsg_end; ++j) n_rows += msgs[j].uni ? 0 : 1;
+    T* beta = work + tk->beta * B + col;
+
+    // U entries per trip: all row loads first, then the products and stores -- loads and stores go
+    // through the same workspace pointer, so the compiler keeps their order and only loads that
+    // are issued back to back are in flight together (8 x 16 bytes per thread)
+    auto rows = [&](auto n_tag, int n) {
+        constexpr int N = decltype(n_tag)::value;
+        constexpr int U = N <= 1 ? 8 : 4;
+        int i = ty;
+        for (; i + (U - 1) * ry < n; i += ry * U) {          // full trips: no bounds checks
+            P x[U][N > 0 ? N : 1];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < N; ++k) x[u][k] = ld<T, VEC>(work + (long long)srow[k][i + u * ry] * B + col);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                P val = pack_fill<T, VEC>(su[i + u * ry]);
+#pragma unroll
+                for (int k = 0; k < N; ++k) mul<SR>(val, x[u][k]);
+                st_stream<T, VEC>(beta + (long long)se[i + u * ry] * B, val);
+            }
+        }
+        for (; i < n; i += ry) {
+            P val = pack_fill<T, VEC>(su[i]);
+#pragma unroll
+            for (int k = 0; k < N; ++k) mul<SR>(val, ld<T, VEC>(work + (long long)srow[k][i] * B + col));
+            st_stream<T, VEC>(beta + (long long)se[i] * B, val);
+        }
+    };
+
+    for (long long base = i0; base < i1; base += kThreads) {
+        const int n = (int)(i1 - base < kThreads ? i1 - base : kThreads);
+        __syncthreads();                                  // the previous sub-chunk has been consumed
+        if (t < n) {
+            const long long item = base + t;
+            const int s = (int)(item / n_r), r = (int)(item - (long long)s * n_r);
+            int s_hi = 0, s_lo = s;
+            if (n_slo < tk->n_s) {
+                s_hi = s / n_slo;
+                s_lo = s - s_hi * n_slo;
+            }
+            const int rh = r / n_rlo, rl = r - rh * n_rlo;
+            const int e = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo) +
+                          __ldg(tab + tk->src_rhi + rh) + __ldg(tab + tk->src_rlo + rl);
+            T u = __ldg(uni + tk->src + e);
+            int k = 0;
+            for (int j = tk->rmsg_begin; j < tk->smsg_end; ++j) {
+                const DMsg* m = msgs + j;
+                long long idx = m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo);
+                if (j < tk->rmsg_end) idx += __ldg(tab + m->b_hi + rh) + __ldg(tab + m->b_lo + rl);
+                if (m->uni) u = SR::mul(u, __ldg(uni + idx));
+                else srow[k++][t] = (int)idx;
+            }
+            if (tk->own >= 0) {
+                if (own_row) srow[k++][t] = (int)(tk->own + s);
+                else u = SR::mul(u, __ldg(uni + tk->own + s));
+            }
+            su[t] = u;
+            se[t] = e;
+        }
+        __syncthreads();
+        if (!active) continue;
+        switch (n_rows) {
+            case 0: rows(std::integral_constant<int, 0>{}, n); break;
+            case 1: rows(std::integral_constant<int, 1>{}, n); break;
+            case 2: rows(std::integral_constant<int, 2>{}, n); break;
+            default: rows(std::integral_constant<int, 3>{}, n); break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // projection task (collect E1+E2, distribute E3+E4+M1+E5, marginal E6, contract)
 //
 // Uniform operands (KArgs::uniform): an operand flagged uniform (the potential of a clique no
@@ -531,7 +670,8 @@ __global__ void __launch_bounds__(kThreads) jt_project_kernel(const KArgs a) {
     const long long s_off = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo);
     const T* sptr = src_uni ? uni + tk->src + s_off : work + ((has_src ? tk->src : 0) + s_off) * B + col;
     const long long spitch = src_uni ? 1 : B;
-    const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS);
+    const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS) &&
+                       !((tflags & JT_TF_BETA_SPLIT) && (a.flags & JT_X_BETA_SPLIT));   // else jt_beta_kernel writes it
     T* bptr = work + ((wbeta ? tk->beta : 0) + s_off) * B + col;
     P scale = sm;
     mul<SR>(scale, own);
@@ -694,7 +834,8 @@ __global__ void __launch_bounds__(kThreads) jt_project_splitr_kernel(const KArgs
     const T scale = SR::mul(sm, own);
 
     const bool has_src = tk->src >= 0, src_uni = (tflags & JT_TF_SRC_UNIFORM) != 0;
-    const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS);
+    const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS) &&
+                       !((tflags & JT_TF_BETA_SPLIT) && (a.flags & JT_X_BETA_SPLIT));
     const long long s_off = __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo);
     const int rm0 = tk->rmsg_begin, nr = tk->rmsg_end - rm0;
     const int n_r = tk->n_r, n_rlo = tk->n_rlo;
@@ -990,7 +1131,9 @@ __global__ void __launch_bounds__(kThreads + 64, 2) jt_project_tma_kernel(const 
     T* work = static_cast<T*>(a.work);
     const long long col = (col0v + t) * VEC;
     const long long vstep = (long long)ct * VEC;         // elements between the vectors of a thread
-    const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS), wout = tk->out >= 0;
+    const bool wbeta = tk->beta >= 0 && !(a.flags & JT_NO_BELIEFS) &&
+                       !((tflags & JT_TF_BETA_SPLIT) && (a.flags & JT_X_BETA_SPLIT));
+    const bool wout = tk->out >= 0;
     const bool wbel = wout && tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS);
     T* bptr = work + (wbeta ? tk->beta : 0) * B + col;
     T* optr = (tk->out_space ? static_cast<T*>(a.fout) : work) + (wout ? tk->out : 0) * B + col;
@@ -1344,7 +1487,7 @@ __global__ void __launch_bounds__(kThreads) jt_walk_kernel(const KArgs a, const 
 template <typename SR, typename T>
 __global__ void __launch_bounds__(kThreads)
 jt_normalize_kernel(T* __restrict__ fout, const long long* __restrict__ out_off,
-                    const long long* __restrict__ out_size, long long B, T* __restrict__ logz) {
+                    const long long* __restrict__ out_size, long long B, T* __restrict__ logz, int normalize) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int k = blockIdx.y;
@@ -1353,7 +1496,8 @@ jt_normalize_kernel(T* __restrict__ fout, const long long* __restrict__ out_off,
     typename SR::template Acc<T> acc = SR::template acc_zero<T>();
     for (long long e = 0; e < n; ++e) SR::accum(acc, col[e * B]);
     const T z = SR::finish(acc);
-    for (long long e = 0; e < n; ++e) col[e * B] = SR::unit(col[e * B], z);
+    if (normalize)
+        for (long long e = 0; e < n; ++e) col[e * B] = SR::unit(col[e * B], z);
     if (k == 0 && logz) logz[b] = SR::log_of(z);
 }
 

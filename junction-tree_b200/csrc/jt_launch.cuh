@@ -51,15 +51,16 @@ struct Launcher {
         // so the pipeline fill is amortised; every task gets its own chunk of s for that item count
         int j = 6;
         const long long target = 148LL * 8;
-        const long long total_items = variant ? L.total_items_nd : L.total_items;
+        const long long total_items = variant ? L.total_items_v[variant - 1] : L.total_items;
         while (j < kItemLog2Max && (total_items * tiles) >> (j + 1) >= target) ++j;
         a.sy_log2 = 0;
         a.bx_log2 = 0;
         a.tasks = p->d_tasks + L.begin;
         a.n_tasks = L.end - L.begin;
-        // variant 1: the block prefix gives no blocks to the tasks that run as dense contractions
-        a.prefix = p->d_prefix + (variant ? L.item_prefix_off_nd[j] : L.item_prefix_off[j]);
-        const long long gx = variant ? L.item_blocks_nd[j] : L.item_blocks[j];
+        // variants 1, 2: the block prefix gives no blocks to the tasks that run in jt_dense_kernel or
+        // only write a belief (jt_beta_kernel)
+        a.prefix = p->d_prefix + (variant ? L.item_prefix_off_v[variant - 1][j] : L.item_prefix_off[j]);
+        const long long gx = variant ? L.item_blocks_v[variant - 1][j] : L.item_blocks[j];
         if (gx <= 0) return JT_OK;
         if (gx > 2147483647LL || tiles > 65535)
             return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, tiles);
@@ -162,6 +163,49 @@ struct Launcher {
         return launch_tasks<float, 1>(p, L, a, variant, stream);
     }
 
+    template <typename T, int VEC>
+    static int launch_beta(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, cudaStream_t stream) {
+        BetaArgs b;
+        int bx_log2, sy_log2;
+        pick_tile(a.Bv, bx_log2, sy_log2);
+        const long long gy = (a.Bv + (1LL << bx_log2) - 1) >> bx_log2;
+        // items per block: as large as still gives ~8 blocks per SM
+        int ch = kBetaChMax;
+        while (ch > kBetaChMin && ((L.beta_items >> ch) + L.beta_n) * gy < 148LL * 8) --ch;
+        const int* prefix = p->prefix.data() + L.beta_off + L.beta_n + (size_t)(ch - kBetaChMin) * (L.beta_n + 1);
+        const long long gx = prefix[L.beta_n];
+        if (gx <= 0) return JT_OK;
+        if (gx > 2147483647LL || gy > 65535)
+            return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
+        b.list = p->d_prefix + L.beta_off;
+        b.prefix = p->d_prefix + L.beta_off + L.beta_n + (size_t)(ch - kBetaChMin) * (L.beta_n + 1);
+        b.n = L.beta_n;
+        b.ch_log2 = ch;
+        b.tasks = p->d_tasks;
+        b.msgs = p->d_msgs;
+        b.tab = p->d_tab;
+        b.work = a.work;
+        b.uni = a.uni;
+        b.B = a.B;
+        b.Bv = a.Bv;
+        b.bx_log2 = bx_log2;
+        jt_beta_kernel<SR, T, VEC><<<dim3((unsigned)gx, (unsigned)gy, 1), kThreads, 0, stream>>>(b);
+        jt_g_launches.fetch_add(1, std::memory_order_relaxed);
+        JT_CUDA(cudaGetLastError());
+        return JT_OK;
+    }
+
+    static int beta(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec, cudaStream_t stream) {
+        if (L.beta_n <= 0) return JT_OK;
+        if (dtype == JT_F64) {
+            if (vec == 2) return launch_beta<double, 2>(p, L, a, stream);
+            return launch_beta<double, 1>(p, L, a, stream);
+        }
+        if (vec == 4) return launch_beta<float, 4>(p, L, a, stream);
+        if (vec == 2) return launch_beta<float, 2>(p, L, a, stream);
+        return launch_beta<float, 1>(p, L, a, stream);
+    }
+
     static int contract(const KArgs& a, long long blocks, long long gy, int dtype, int vec, cudaStream_t stream) {
         dim3 grid((unsigned)blocks, (unsigned)gy, 1);
         if (dtype == JT_F64) {
@@ -208,15 +252,17 @@ struct Launcher {
         return JT_OK;
     }
 
-    static int normalize(const jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, cudaStream_t stream) {
+    static int normalize(const jt_plan* p, int64_t B, int dtype, void* factor_out, void* logz, int normalize,
+                         cudaStream_t stream) {
         const int n_out = (int)p->fout_off.size();
-        dim3 grid((unsigned)((B + kThreads - 1) / kThreads), (unsigned)n_out, 1);
+        // log Z only: the total of scope 0, the outputs stay as they are
+        dim3 grid((unsigned)((B + kThreads - 1) / kThreads), (unsigned)(normalize ? n_out : 1), 1);
         if (dtype == JT_F64)
             jt_normalize_kernel<SR, double><<<grid, kThreads, 0, stream>>>(
-                static_cast<double*>(factor_out), p->d_out, p->d_out + n_out, B, static_cast<double*>(logz));
+                static_cast<double*>(factor_out), p->d_out, p->d_out + n_out, B, static_cast<double*>(logz), normalize);
         else
             jt_normalize_kernel<SR, float><<<grid, kThreads, 0, stream>>>(
-                static_cast<float*>(factor_out), p->d_out, p->d_out + n_out, B, static_cast<float*>(logz));
+                static_cast<float*>(factor_out), p->d_out, p->d_out + n_out, B, static_cast<float*>(logz), normalize);
         jt_g_launches.fetch_add(1, std::memory_order_relaxed);
         JT_CUDA(cudaGetLastError());
         return JT_OK;
@@ -227,7 +273,8 @@ struct Launcher {
 
 #define JT_DEFINE_SEMIRING(SR, ID, NAME)                                                       \
     const jt_sr_launchers* NAME() {                                                            \
-        static const jt_sr_launchers table = {&Launcher<SR, ID>::dispatch, &Launcher<SR, ID>::contract, \
-                                              &Launcher<SR, ID>::normalize, &Launcher<SR, ID>::walk}; \
+        static const jt_sr_launchers table = {&Launcher<SR, ID>::dispatch, &Launcher<SR, ID>::beta, \
+                                              &Launcher<SR, ID>::contract, &Launcher<SR, ID>::normalize, \
+                                              &Launcher<SR, ID>::walk};                        \
         return &table;                                                                         \
     }

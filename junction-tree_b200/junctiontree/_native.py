@@ -13,7 +13,7 @@ import numpy as np
 JT_OK = 0
 JT_F32, JT_F64 = 0, 1
 JT_SEP_BELIEFS, JT_SKIP_MARGINAL, JT_UNIFORM, JT_NO_UNIFORM, JT_UNIFORM_VALID, JT_NO_BELIEFS = 1, 2, 4, 8, 16, 32
-JT_NO_DENSE = 64
+JT_NO_DENSE, JT_LOGZ_ONLY = 64, 128
 # semiring bits of the stage flags (include/jt_b200.h JT_SR_*)
 JT_SR_SUM_PRODUCT, JT_SR_MAX_PRODUCT, JT_SR_LOG_SUM_EXP, JT_SR_MAX_SUM, JT_SR_MASK = 0x000, 0x100, 0x200, 0x300, 0x300
 ABI_VERSION = 9

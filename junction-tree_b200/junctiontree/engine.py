@@ -362,12 +362,10 @@ class BatchPipeline:
                               slot["fout"].data_ptr(), flags, stream.cuda_stream)
                 if self.normalize or self.log_z:
                     # output stage: per-scope normalisation and log Z = log P(evidence)
-                    if self.normalize:
-                        dev.normalize(n, self.dtype, slot["fout"].data_ptr(),
-                                      slot["logz"].data_ptr() if self.log_z else None, stream.cuda_stream,
-                                      self.semiring)
-                    else:
-                        slot["logz"].copy_(_log_total(t, slot["fout"][:plan.fout_size[0]], self.semiring))
+                    # (log Z alone: the same kernel with JT_LOGZ_ONLY leaves the outputs unnormalised)
+                    dev.normalize(n, self.dtype, slot["fout"].data_ptr(),
+                                  slot["logz"].data_ptr() if self.log_z else None, stream.cuda_stream,
+                                  self.semiring | (0 if self.normalize else _native.JT_LOGZ_ONLY))
                     if self.log_z:
                         self.host_logz[lo:hi].copy_(slot["logz"], non_blocking=True)
                 _native.copy_rows(out_host.data_ptr() + lo * item, self.B * item, slot["fout"].data_ptr(),
@@ -384,18 +382,6 @@ class BatchPipeline:
             total += self.engine.dev.evidence_errors(n, self.dtype, slot["ws"].data_ptr(),
                                                      slot["stream"].cuda_stream)
         return total
-
-
-def _log_total(t, scope, semiring):
-    """log of the semiring total of one output scope ``[n, B]`` (plumbing for un-normalised
-    output with log Z; the normalising path does this inside ``jt_normalize``)."""
-    if semiring == _native.JT_SR_MAX_PRODUCT:
-        return t.log(scope.max(dim=0).values)
-    if semiring == _native.JT_SR_LOG_SUM_EXP:
-        return t.logsumexp(scope, dim=0)
-    if semiring == _native.JT_SR_MAX_SUM:
-        return scope.max(dim=0).values
-    return t.log(scope.sum(dim=0))
 
 
 def _pipeline(self, B, dtype, chunk=8192, n_streams=2, normalize=False, log_z=False, semiring=0):

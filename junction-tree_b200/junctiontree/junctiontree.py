@@ -202,22 +202,39 @@ class CliqueGraph():
         For each factor, take the maxclique it belongs to and sum out the axes that don't belong
         to the factor; axes come out in the factor's own order (reference
         ``junctiontree.py:229-274``).  GPU stage ``jt_marginal``.
+
+        Every clique array is taken with the shape it has -- as in the reference, where each
+        factor is one einsum over its own clique -- so the size-1 axes ``evaluate`` returns for
+        uncovered clique variables are summed as axes of length 1.
         """
         t = eng.require_cuda()
         ys = [np.asarray(y) for y in ys]
-        sizes = dict(self.factor_graph.sizes)
+        if len(ys) != len(self.maxcliques):
+            raise ValueError("expected %d clique arrays, got %d" % (len(self.maxcliques), len(ys)))
         for cv, y in zip(self.maxcliques, ys):
-            for var, n in zip(cv, y.shape):
-                sizes[var] = int(n)
-        engine = self._engine(sizes)
+            if y.ndim != len(cv):
+                raise ValueError("clique %r cannot have an array of shape %s" % (cv, y.shape))
+        cache = _cache_of(self, "marginalize")
+        key = (tuple(y.shape for y in ys), tuple(self._f2c()), eng.current_device())
+        engine = cache.get(key)
+        if engine is None:
+            # cliques are independent here, so each gets its own copy (c, var) of its variables:
+            # a variable may then have length 1 in one clique array and its full size in another
+            f2c = self._f2c()
+            sizes = {(c, v): int(n) for c, (cv, y) in enumerate(zip(self.maxcliques, ys)) for v, n in zip(cv, y.shape)}
+            node_vars = [[(c, v) for v in cv] for c, cv in enumerate(self.maxcliques)]
+            factors = [[(f2c[f], v) for v in fv] for f, fv in enumerate(self.factor_graph.factors)]
+            engine = eng.Engine(sch.Plan(None, node_vars, sizes, factors, f2c))
+            if len(cache) >= 16:
+                cache.pop(next(iter(cache)))
+            cache[key] = engine
         plan = engine.plan
         dtype = _result_dtype(ys)
         ws = engine.workspace(1, dtype)
         work = engine.work_view(ws, 1, dtype)
         host = np.empty(plan.clique_entries, dtype)
         for c, y in enumerate(ys):
-            host[plan.node_off[c]:plan.node_off[c] + plan.node_size[c]] = \
-                np.broadcast_to(y, tuple(plan.node_shape[c])).reshape(-1)
+            host[plan.node_off[c]:plan.node_off[c] + plan.node_size[c]] = y.reshape(-1)
         work[:plan.clique_entries, 0].copy_(t.from_numpy(host))
         fout = t.empty((plan.fout_entries, 1), dtype=eng.torch_dtype(dtype), device="cuda")
         engine.dev.upload()
@@ -559,7 +576,10 @@ class JunctionTree():
             # free device memory (config 5 needs ~80 MB of workspace per instance)
             return self._propagate_streamed(engine, fdev, evidence, B, dtype, _semiring(dl), likelihoods)
         edev = engine.evidence_to_device(evidence, B)
-        ws = engine.workspace(B, dtype)
+        # node beliefs handed out as device tensors are views of the workspace: give such a call
+        # a workspace of its own (kept alive by the views) instead of the engine's cached one,
+        # which the next call with the same batch size overwrites
+        ws = engine.new_workspace(B, dtype) if (nodes and device_output) else engine.workspace(B, dtype)
         engine.load_likelihoods(ws, B, dtype, likelihoods)
         ws, fout = engine.propagate(fdev, batched, edev, B, dtype, ws=ws, sep_beliefs=nodes, uniform=uniform,
                                     beliefs=nodes, semiring=_semiring(dl), dense=dense)
@@ -572,10 +592,6 @@ class JunctionTree():
         node_out = None
         if nodes:
             node_out = [engine.node_tensor(ws, k, B, dtype) for k in range(len(plan.node_vars))]
-            if device_output:
-                # the views alias the engine's cached (B, dtype) workspace, which the next call
-                # with the same batch size overwrites: hand out copies, like the factor outputs
-                node_out = [o.clone() for o in node_out]
         if not device_output:
             outs = [o.cpu().numpy() for o in outs]
             if nodes:

@@ -34,3 +34,17 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Max per-entry relative error of every labelled comparison (helpers.assert_close) ->
+    gpurun_out/parity_report.json, when that scratch directory exists (GPU box runs)."""
+    import json
+    try:
+        import helpers
+    except Exception:
+        return
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if helpers.PARITY_REPORT and os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "parity_report.json"), "w") as fh:
+            json.dump(dict(sorted(helpers.PARITY_REPORT.items())), fh, indent=1)

@@ -26,13 +26,37 @@ def tuplify(tree):
     return [tree[0]] + [(s, tuplify(t)) for s, t in tree[1:]]
 
 
-def assert_close(got, want, rtol, what=""):
+#: max per-entry relative error of every comparison, by label (dumped by conftest at session end
+#: to gpurun_out/parity_report.json when that directory exists)
+PARITY_REPORT = {}
+
+
+def max_rel_err(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    if not want.size:
+        return 0.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.abs(got - want) / np.abs(want)
+    rel = np.where(want == 0, np.where(got == 0, 0.0, np.inf), rel)
+    return float(np.max(rel))
+
+
+def assert_close(got, want, rtol, what="", signed=False):
+    """Relative error <= rtol on EVERY entry (north_star: "relative error <= 1e-12 / 1e-5 on every
+    clique and separator potential"); a zero must come back as an exact zero.  ``signed=True`` is
+    for the tests that feed signed random potentials (the reference's own operator tests do,
+    tests/test_computation.py:51-322): sums then cancel, and an entry that is tiny relative to
+    its array is compared against the array scale instead."""
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     assert got.shape == want.shape, "%s: shape %s vs %s" % (what, got.shape, want.shape)
-    scale = np.max(np.abs(want)) if want.size else 0.0
-    # relative error on every entry; entries that are tiny relative to the array (cancellation
-    # in signed test data) are compared against the array scale
-    np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol * scale * 1e-3, err_msg=what)
+    if signed:
+        scale = np.max(np.abs(want)) if want.size else 0.0
+        np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol * scale * 1e-3, err_msg=what)
+        return
+    err = max_rel_err(got, want)
+    if what:
+        PARITY_REPORT[what] = max(err, PARITY_REPORT.get(what, 0.0))
+    assert err <= rtol, "%s: max per-entry relative error %.3g > %g" % (what, err, rtol)
 
 
 def compile_net(net, with_evidence=True):

@@ -14,6 +14,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler injects its library
+
 #include "jt_host.h"
 
 // ------------------------------------------------------------------------------------------
@@ -79,6 +81,41 @@ jt_ratio_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict_
 
 namespace {
 
+// NVTX range per stage and per schedule level (JT_NVTX=1): what a timeline profiler shows as
+// "collect level 17" etc. around the launches of that level.
+bool nvtx_enabled() {
+    static const int on = [] {
+        const char* e = getenv("JT_NVTX");
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    return on == 1;
+}
+
+struct NvtxRange {
+    bool on;
+    NvtxRange(const char* what, int level = -1) : on(nvtx_enabled()) {
+        if (!on) return;
+        char buf[64];
+        if (level >= 0) snprintf(buf, sizeof(buf), "jt %s level %d", what, level);
+        else snprintf(buf, sizeof(buf), "%s", what);
+        nvtxRangePushA(buf);
+    }
+    ~NvtxRange() {
+        if (on) nvtxRangePop();
+    }
+};
+
+const char* phase_name(int phase) {
+    switch (phase) {
+        case JT_PHASE_INIT: case JT_PHASE_INIT_UNIFORM: case JT_PHASE_INIT_INSTANCE: return "init";
+        case JT_PHASE_COLLECT: case JT_PHASE_COLLECT_INSTANCE: return "collect";
+        case JT_PHASE_COLLECT_UNIFORM: return "collect (uniform)";
+        case JT_PHASE_DIST_UNIFORM: return "distribute (uniform)";
+        case JT_PHASE_MARGINAL: case JT_PHASE_MARGINAL_DIRECT: return "marginal";
+        default: return "distribute";
+    }
+}
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 size_t dtype_size(int dtype) { return dtype == JT_F64 ? 8 : 4; }
@@ -97,7 +134,8 @@ WorkspaceLayout workspace_layout(const jt_plan* p, int64_t B, int dtype) {
     const size_t fbase = p->hdr[JT_H_NEVID] > 0 ? (size_t)p->hdr[JT_H_NFACTORS] * (size_t)B * 4 : 0;
     w.err_off = w.fbase_off + align_up(fbase, 256);
     w.uni_off = w.err_off + 256;
-    const size_t uni = p->hdr[JT_H_UNI_ENTRIES] > 0 ? (size_t)entries * dtype_size(dtype) : 0;
+    // uniform workspace: the same entries with B = 1, then the totals of the scalar tasks (jt_dense.cu)
+    const size_t uni = p->hdr[JT_H_UNI_ENTRIES] > 0 ? (size_t)(entries + p->scalar_entries) * dtype_size(dtype) : 0;
     // W region of the dense contractions (jt_dense.cu), rebuilt with the uniform workspace
     w.dense_off = w.uni_off + align_up(uni, 256);
     w.total = w.dense_off + align_up((size_t)p->dense_w_entries * dtype_size(dtype), 256);
@@ -151,6 +189,63 @@ KArgs base_args(const jt_plan* p, int64_t B, void* workspace, int vec) {
     return a;
 }
 
+// Side stream of the calling thread (per device) and a pool of events for fork / join with it.
+// The clique beliefs of uniform cliques (jt_beta_kernel) are final outputs nobody reads during the
+// distribute pass, so they run beside the level-by-level message chain, which alone leaves most of
+// the machine idle on deep trees.  Thread-local: concurrent calls from several host threads never
+// share a stream or an event; everything is joined back into the caller's stream before the stage
+// call returns, so the "enqueue only, never synchronise" contract (and graph capture) holds.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaStream_t aux[2] = {nullptr, nullptr};    // the independent kernels of one level run side by side
+    int device = -1;
+    std::vector<cudaEvent_t> events;
+    size_t used = 0;
+};
+thread_local SideStream g_side;
+
+bool beta_overlap_enabled() {       // JT_BETA_STREAM=0: beliefs in the caller's stream, level by level (A-B timing)
+    static const int on = [] {
+        const char* e = getenv("JT_BETA_STREAM");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on == 1;
+}
+
+cudaError_t side_acquire(cudaStream_t* out) {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!g_side.stream || g_side.device != dev) {
+        g_side.events.clear();                 // events of another device are left to the driver
+        e = cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&g_side.aux[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return e;
+        g_side.device = dev;
+    }
+    if (out) *out = g_side.stream;
+    return cudaSuccess;
+}
+
+bool level_fork_enabled() {         // JT_LEVEL_STREAMS=0: the kernels of a level one after the other (A-B timing)
+    static const int on = [] {
+        const char* e = getenv("JT_LEVEL_STREAMS");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on == 1;
+}
+
+cudaError_t side_event(cudaEvent_t* out) {
+    if (g_side.used == g_side.events.size()) {
+        cudaEvent_t ev;
+        cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        g_side.events.push_back(ev);
+    }
+    *out = g_side.events[g_side.used++];
+    return cudaSuccess;
+}
+
 // One launch of the plan.  With `w_region` set (uniform mode, dense contractions enabled) the
 // tasks that are dense contractions run in jt_dense_kernel and the projection kernel gets the
 // block prefix without them.  A DIST_MAIN launch in uniform mode (`split`) leaves the clique
@@ -158,23 +253,60 @@ KArgs base_args(const jt_plan* p, int64_t B, void* workspace, int vec) {
 // contractions of the matching message-only launch) compute the messages, tasks that only write
 // a belief drop out of it.
 int run_launch(jt_plan* p, const jt_plan::Launch& L, const KArgs& a_in, int dtype, int vec, void* w_region,
-               cudaStream_t stream, bool split = false) {
+               cudaStream_t stream, bool split = false, cudaStream_t beta_stream = nullptr) {
+    NvtxRange range(phase_name(L.phase), L.level);
     KArgs a = a_in;
     split = split && L.phase == JT_PHASE_DIST_MAIN && L.beta_n > 0;
-    const bool dense = w_region && L.dense_end > L.dense_begin && (L.phase != JT_PHASE_DIST_MAIN || split);
+    // dense contractions and scalar tasks leave the projection launch together (one reduced task set)
+    const bool accel = w_region && (L.dense_end > L.dense_begin || L.scalar_n > 0) &&
+                       (L.phase != JT_PHASE_DIST_MAIN || split);
     int variant = 0;
     if (split) {
         a.flags |= JT_X_BETA_SPLIT;
         variant = 1;
     }
-    if (dense) {
-        int rc = jt_dense_launch(p, L, a.work, a.uni, w_region, a.fout, a.B, dtype, a.flags, stream);
-        if (rc != JT_OK) return rc;
-        variant = split ? 2 : 1;
+    if (accel) variant = split ? 2 : 1;
+    const bool has_dense = accel && L.dense_end > L.dense_begin, has_scalar = accel && L.scalar_n > 0;
+    const bool has_proj = (variant ? L.total_items_v[variant - 1] : L.total_items) > 0;
+    // The dense contractions, the scalar tasks and the projection tasks of a launch are independent
+    // of each other: on deep, narrow trees each of them is a small latency-bound kernel, so they
+    // run side by side (fork after everything enqueued so far, join before the next launch).
+    cudaStream_t s_dense = stream, s_scalar = stream;
+    cudaEvent_t ev;
+    const int n_kernels = (has_dense ? 1 : 0) + (has_scalar ? 1 : 0) + (has_proj ? 1 : 0);
+    const bool fork = n_kernels >= 2 && level_fork_enabled();
+    if (fork) {
+        JT_CUDA(side_acquire(nullptr));
+        JT_CUDA(side_event(&ev));
+        JT_CUDA(cudaEventRecord(ev, stream));
+        if (has_dense && (has_proj || has_scalar)) {
+            s_dense = g_side.aux[0];
+            JT_CUDA(cudaStreamWaitEvent(s_dense, ev, 0));
+        }
+        if (has_scalar && has_proj) {
+            s_scalar = g_side.aux[1];
+            JT_CUDA(cudaStreamWaitEvent(s_scalar, ev, 0));
+        }
     }
-    int rc = launchers(a.flags)->dispatch(p, L, a, dtype, vec, variant, stream);
-    if (rc != JT_OK || !split) return rc;
-    return launchers(a.flags)->beta(p, L, a, dtype, vec, stream);
+    int rc = JT_OK;
+    if (has_dense) rc = jt_dense_launch(p, L, a.work, a.uni, w_region, a.fout, a.B, dtype, a.flags, s_dense);
+    if (rc == JT_OK && has_scalar) rc = launchers(a.flags)->scalar(p, L, a, dtype, vec, s_scalar);
+    if (rc == JT_OK && (has_proj || !accel)) rc = launchers(a.flags)->dispatch(p, L, a, dtype, vec, variant, stream);
+    if (rc != JT_OK) return rc;
+    if (fork) {
+        if (s_dense != stream) {
+            JT_CUDA(side_event(&ev));
+            JT_CUDA(cudaEventRecord(ev, s_dense));
+            JT_CUDA(cudaStreamWaitEvent(stream, ev, 0));
+        }
+        if (s_scalar != stream) {
+            JT_CUDA(side_event(&ev));
+            JT_CUDA(cudaEventRecord(ev, s_scalar));
+            JT_CUDA(cudaStreamWaitEvent(stream, ev, 0));
+        }
+    }
+    if (!split) return JT_OK;
+    return launchers(a.flags)->beta(p, L, a, dtype, vec, beta_stream ? beta_stream : stream);
 }
 
 // Launches of one phase, in plan order.
@@ -237,6 +369,41 @@ int jt_build_item_prefix(jt_plan* p, const jt_plan::Launch& L, const char* skip,
         p->prefix.push_back((int)acc);
         p->prefix.insert(p->prefix.end(), chunk.begin(), chunk.end());
         blocks_out[j] = acc;
+    }
+    return JT_OK;
+}
+
+// Everything a launch needs besides its task range: item totals, block prefixes per tile shape
+// and per item-count target, which kernels it may use.
+int jt_launch_tables(jt_plan* p, jt_plan::Launch& L) {
+    L.tma_ok = true;
+    L.min_nr = 2147483647;
+    L.max_nr = 0;
+    L.total_s = 0;
+    L.total_items = 0;
+    for (int t = L.begin; t < L.end; ++t) L.total_items += (long long)p->tasks[t].n_s * p->tasks[t].n_r;
+    int rc = jt_build_item_prefix(p, L, nullptr, L.item_prefix_off, L.item_blocks);
+    if (rc != JT_OK) return rc;
+    for (int t = L.begin; t < L.end; ++t) {
+        const DTask& k = p->tasks[t];
+        const int rows = (k.src >= 0 ? 1 : 0) + (k.rmsg_end - k.rmsg_begin) + (k.smsg_end - k.smsg_begin) +
+                         (k.own >= 0 ? 1 : 0);
+        if (rows < 1 || rows > kTmaMaxRows || k.rmsg_end != k.smsg_begin) L.tma_ok = false;
+        L.min_nr = k.n_r < L.min_nr ? k.n_r : L.min_nr;
+        L.max_nr = k.n_r > L.max_nr ? k.n_r : L.max_nr;
+        L.total_s += k.n_s;
+    }
+    // block prefix per tile shape: a block covers 2^sy consecutive values of s of one task
+    for (int sy = 0; sy <= kMaxSyLog2; ++sy) {
+        L.prefix_off[sy] = p->prefix.size();
+        long long acc = 0;
+        for (int t = L.begin; t < L.end; ++t) {
+            p->prefix.push_back((int)acc);
+            acc += ((long long)p->tasks[t].n_s + (1 << sy) - 1) >> sy;
+            if (acc > 2147483647LL) return fail(JT_ERR_INVALID, "launch too large");
+        }
+        p->prefix.push_back((int)acc);
+        L.blocks[sy] = acc;
     }
     return JT_OK;
 }
@@ -368,34 +535,7 @@ int jt_plan_create(const void* blob, size_t nbytes, jt_plan** out) {
             if ((p->tasks[t].kind == JT_KIND_INIT) != (L.phase == JT_PHASE_INIT || L.phase == JT_PHASE_INIT_UNIFORM ||
                                                         L.phase == JT_PHASE_INIT_INSTANCE))
                 return bad("task kind vs phase", i);
-        L.tma_ok = true;
-        L.min_nr = 2147483647;
-        L.max_nr = 0;
-        L.total_s = 0;
-        L.total_items = 0;
-        for (int t = L.begin; t < L.end; ++t) L.total_items += (long long)p->tasks[t].n_s * p->tasks[t].n_r;
-        if (jt_build_item_prefix(p, L, nullptr, L.item_prefix_off, L.item_blocks) != JT_OK) return bad("launch too large", i);
-        for (int t = L.begin; t < L.end; ++t) {
-            const DTask& k = p->tasks[t];
-            const int rows = (k.src >= 0 ? 1 : 0) + (k.rmsg_end - k.rmsg_begin) + (k.smsg_end - k.smsg_begin) +
-                             (k.own >= 0 ? 1 : 0);
-            if (rows < 1 || rows > kTmaMaxRows || k.rmsg_end != k.smsg_begin) L.tma_ok = false;
-            L.min_nr = k.n_r < L.min_nr ? k.n_r : L.min_nr;
-            L.max_nr = k.n_r > L.max_nr ? k.n_r : L.max_nr;
-            L.total_s += k.n_s;
-        }
-        // block prefix per tile shape: a block covers 2^sy consecutive values of s of one task
-        for (int sy = 0; sy <= kMaxSyLog2; ++sy) {
-            L.prefix_off[sy] = p->prefix.size();
-            long long acc = 0;
-            for (int t = L.begin; t < L.end; ++t) {
-                p->prefix.push_back((int)acc);
-                acc += ((long long)p->tasks[t].n_s + (1 << sy) - 1) >> sy;
-                if (acc > 2147483647LL) return bad("launch too large", i);
-            }
-            p->prefix.push_back((int)acc);
-            L.blocks[sy] = acc;
-        }
+        if (jt_launch_tables(p, L) != JT_OK) return bad("launch too large", i);
     }
     const int32_t* tabp = reinterpret_cast<const int32_t*>(q);
     p->tab.assign(tabp, tabp + n_tab);
@@ -531,6 +671,7 @@ int jt_plan_upload(jt_plan* p) {
 
 int jt_init(jt_plan* p, const void* factor_tables, int factors_batched, const int32_t* evidence, int64_t B,
             int dtype, void* workspace, int flags, void* stream_) {
+    NvtxRange range("jt_init");
     int rc = check_common(p, B, dtype, workspace);
     if (rc != JT_OK) return rc;
     if ((flags & JT_UNIFORM) && factors_batched)
@@ -572,6 +713,8 @@ int jt_init(jt_plan* p, const void* factor_tables, int factors_batched, const in
 }
 
 int jt_collect(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, void* stream_) {
+    NvtxRange range("jt_collect");
+    g_side.used = 0;                      // the event pool of this thread starts over with every stage call
     int rc = check_common(p, B, dtype, workspace);
     if (rc != JT_OK) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -585,8 +728,9 @@ int jt_collect(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, voi
     if (!(flags & JT_UNIFORM_VALID)) {
         rc = run_phase_uniform(p, JT_PHASE_COLLECT_UNIFORM, a, dtype, uni, stream);
         if (rc != JT_OK) return rc;
-        if (w_region) {      // W blocks of the collect contractions: potentials x uniform up-messages
+        if (w_region) {      // W blocks of the collect contractions, totals of the scalar tasks
             rc = jt_dense_prepare(p, 0, dtype, uni, w_region, stream);
+            if (rc == JT_OK) rc = run_phase_uniform(p, JT_PHASE_X_SCALAR0, a, dtype, uni, stream);
             if (rc != JT_OK) return rc;
         }
     }
@@ -596,6 +740,8 @@ int jt_collect(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, voi
 }
 
 int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, void* stream_) {
+    NvtxRange range("jt_distribute");
+    g_side.used = 0;                      // the event pool of this thread starts over with every stage call
     int rc = check_common(p, B, dtype, workspace);
     if (rc != JT_OK) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -613,8 +759,9 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
         if (!(flags & JT_UNIFORM_VALID)) {
             rc = run_phase_uniform(p, JT_PHASE_DIST_UNIFORM, a, dtype, uni, stream);
             if (rc != JT_OK) return rc;
-            if (w_region) {  // W blocks of the distribute and marginal contractions (they also need the uniform down-messages)
+            if (w_region) {  // W blocks and totals of the distribute and marginal tasks (they also need the uniform down-messages)
                 rc = jt_dense_prepare(p, 1, dtype, uni, w_region, stream);
+                if (rc == JT_OK) rc = run_phase_uniform(p, JT_PHASE_X_SCALAR1, a, dtype, uni, stream);
                 if (rc != JT_OK) return rc;
             }
         }
@@ -625,15 +772,37 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
     // per level: the tasks that only read psi_C, then the task that overwrites it with beta_C
     // (JT_NO_BELIEFS: only the message-sending tasks, and the kernels skip the belief stores)
     const int main_phase = (flags & JT_NO_BELIEFS) ? JT_PHASE_DIST_MAIN_MESSAGES : JT_PHASE_DIST_MAIN;
+    cudaStream_t side = nullptr;
+    bool forked = false;
+    if (split && beta_overlap_enabled()) JT_CUDA(side_acquire(&side));
     for (const auto& L : p->launches) {
         if (L.phase != pre_phase && L.phase != main_phase) continue;
-        rc = run_launch(p, L, a, dtype, vec, w_region, stream, split);
+        cudaStream_t beta_stream = nullptr;
+        if (side && L.phase == JT_PHASE_DIST_MAIN && L.beta_n > 0) {
+            // the beliefs of this level need the messages of the levels above (and the collect
+            // pass): everything enqueued so far
+            cudaEvent_t ev;
+            JT_CUDA(side_event(&ev));
+            JT_CUDA(cudaEventRecord(ev, stream));
+            JT_CUDA(cudaStreamWaitEvent(side, ev, 0));
+            beta_stream = side;
+            forked = true;
+        }
+        rc = run_launch(p, L, a, dtype, vec, w_region, stream, split, beta_stream);
         if (rc != JT_OK) return rc;
+    }
+    if (forked) {                               // join: the stage is complete when the caller's stream is
+        cudaEvent_t ev;
+        JT_CUDA(side_event(&ev));
+        JT_CUDA(cudaEventRecord(ev, side));
+        JT_CUDA(cudaStreamWaitEvent(stream, ev, 0));
     }
     return JT_OK;
 }
 
 int jt_marginal(jt_plan* p, int64_t B, int dtype, void* workspace, void* factor_out, int flags, void* stream) {
+    NvtxRange range("jt_marginal");
+    g_side.used = 0;
     int rc = check_common(p, B, dtype, workspace);
     if (rc != JT_OK) return rc;
     if (!factor_out) return fail(JT_ERR_INVALID, "factor_out is null");

@@ -37,8 +37,9 @@
 
 namespace {
 
-constexpr int kDWarps = 4;                         // MMA warps per CTA, 32 batch columns each
-constexpr int kDTB = kDWarps * 32;                 // batch columns per CTA
+constexpr int kDWarps = 8;                         // MMA warps per CTA
+constexpr int kDNT = 2;                            // 8-column n-tiles per warp: 16 batch columns each
+constexpr int kDTB = kDWarps * kDNT * 8;           // batch columns per CTA
 constexpr int kDKC = 16;                           // message rows per pipeline stage
 constexpr int kDStages = 4;
 constexpr int kDRowPitch = kDTB * 8 + 32;          // bytes; +32: the 4 rows of a B fragment hit distinct banks
@@ -143,8 +144,8 @@ __global__ void __launch_bounds__(kThreads) jt_dense_prep_kernel(const PrepArgs 
 // run of consecutive units (group g, i-tile it) of one task.  Per unit the producer streams the K
 // message rows of the group (16 per stage, one 1-D bulk copy per row, lane = row) and the
 // matching W fragments (one bulk copy) through a 4-stage shared-memory ring; every MMA warp
-// multiplies the [8 MT x 16] W block into its 32 columns of the rows and keeps an
-// [8 MT x 32] accumulator tile in registers (MT <= 4); the epilogue multiplies the per-instance
+// multiplies the [8 MT x 16] W block into its 16 columns of the rows and keeps an
+// [8 MT x 16] accumulator tile in registers (MT <= 4); the epilogue multiplies the per-instance
 // s-only operands in and stores out / bel rows with 16-byte stores.
 template <typename T>
 __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const DenseArgs a) {
@@ -259,43 +260,56 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
     // does the epilogue have per-instance s-only operands?
     bool s_rows = false;
     for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) s_rows = s_rows || !a.msgs[j].uni;
-    const int bcol = warp * 32 + (lane >> 2);                      // B fragment: column inside the tile
-    const long long ccol = col0 + warp * 32 + (lane & 3) * 2;      // C fragment: first of two columns, + 8 nt
+    const int bcol = warp * (kDNT * 8) + (lane >> 2);                      // B fragment: column inside the tile
+    const long long ccol = col0 + warp * (kDNT * 8) + (lane & 3) * 2;      // C fragment: first of two columns, + 8 nt
 
     // the [8 MT x 32] accumulator tile of one unit
     struct Acc {
-        T v[4][4][2];
+        T v[4][kDNT][2];
     };
     auto zero = [](Acc& c) {
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) c.v[mt][nt][0] = c.v[mt][nt][1] = T(0);
+            for (int nt = 0; nt < kDNT; ++nt) c.v[mt][nt][0] = c.v[mt][nt][1] = T(0);
     };
     // nk4 k-steps: rows `rows` (4 per step) times W fragments `wt` (MT per step)
     auto steps = [&](Acc& c, const unsigned char* rows, const T* wt, int nk4) {
         for (int q = 0; q < nk4; ++q) {
-            T bf[4];
+            T bf[kDNT];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) bf[nt] = *reinterpret_cast<const T*>(rows + q * 4 * kDRowPitch + nt * 64);
+            for (int nt = 0; nt < kDNT; ++nt) bf[nt] = *reinterpret_cast<const T*>(rows + q * 4 * kDRowPitch + nt * 64);
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) {
                 if (mt < MT) {
                     const T af = wt[(q * MT + mt) * 32];
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) dmma(c.v[mt][nt][0], c.v[mt][nt][1], af, bf[nt]);
+                    for (int nt = 0; nt < kDNT; ++nt) dmma(c.v[mt][nt][0], c.v[mt][nt][1], af, bf[nt]);
                 }
             }
         }
     };
     // epilogue of unit u: rows i = it * 8 MT + 8 mt + lane / 4 of group g
-    auto epilogue = [&](const Acc& c, long long u) {
+    // output rows of unit u handled by this thread (-1: padding), fetched before the k-steps so the
+    // lookups are off the critical path of the epilogue
+    struct Rows {
+        int s[4];
+    };
+    auto unit_rows = [&](long long u) {
+        Rows r;
         const int g = (int)(u / d.n_it), it = (int)(u - (long long)g * d.n_it);
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
             const int i = (it * MT + mt) * 8 + (lane >> 2);
-            if (mt < MT && i < d.n_i) {
-                const int s = __ldg(dtab + d.s_of + g * d.n_i + i);
+            r.s[mt] = (mt < MT && i < d.n_i) ? __ldg(dtab + d.s_of + g * d.n_i + i) : -1;
+        }
+        return r;
+    };
+    auto epilogue = [&](const Acc& c, const Rows& ur) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            if (ur.s[mt] >= 0) {
+                const int s = ur.s[mt];
                 T own_u = T(1);
                 const T* own_row = nullptr;
                 if (wbel && has_own) {
@@ -303,7 +317,7 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
                     else own_row = work + (tk->own + s) * B;
                 }
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
+                for (int nt = 0; nt < kDNT; ++nt) {
                     const long long col = ccol + nt * 8;
                     if (col < B) {                               // B is even: both columns or none
                         T v0 = c.v[mt][nt][0], v1 = c.v[mt][nt][1];
@@ -359,9 +373,10 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
             for (int j = 0; j < nu; ++j) {
                 Acc c;
                 zero(c);
+                const Rows ur = unit_rows(u + j);
                 steps(c, st + j * kpad * kDRowPitch + frag_off, wt + j * d.n_k4 * MT * 32, d.n_k4);
                 if (j == nu - 1) release();                       // the stage is consumed: refill during the epilogue
-                epilogue(c, u + j);
+                epilogue(c, ur);
             }
         }
         return;
@@ -369,6 +384,7 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
     for (long long u = u0; u < u1; ++u) {
         Acc c;
         zero(c);
+        const Rows ur = unit_rows(u);
         for (int ch = 0; ch < d.n_chunks; ++ch) {
             const int nk4 = d.n_k4 - ch * 4 < 4 ? d.n_k4 - ch * 4 : 4;
             mbar_wait(full_u32 + 8 * stage, phase);
@@ -376,7 +392,7 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
             steps(c, st + frag_off, reinterpret_cast<const T*>(st + kDKC * kDRowPitch) + lane, nk4);
             release();
         }
-        epilogue(c, u);
+        epilogue(c, ur);
     }
 }
 
@@ -514,26 +530,73 @@ int jt_dense_build(jt_plan* p) {
     // part (which may be a dense contraction: the descriptors of the matching DIST_MAIN_MESSAGES
     // launch) and a task that only writes a belief leaves the projection launch altogether.
     const bool small_offsets = p->hdr[JT_H_CLIQUE_ENTRIES] + 3 * p->hdr[JT_H_SEP_ENTRIES] + p->hdr[JT_H_LIK_ENTRIES] < 2147483647LL;
+    std::unordered_map<int, int> dense_tasks;              // task -> descriptor
+    for (size_t i = 0; i < p->dense.size(); ++i) dense_tasks[p->dense[i].task] = (int)i;
+    // every r-dependent input uniform, at most kBetaRows per-instance s-only rows: a scalar task
+    auto scalar_ok = [&](const DTask& k) {
+        if (k.kind != JT_KIND_PROJECT || k.src < 0 || !(k.flags & JT_TF_SRC_UNIFORM) || k.out < 0 || k.n_r < 2) return false;
+        for (int j = k.rmsg_begin; j < k.rmsg_end; ++j)
+            if (!p->msgs[j].uni) return false;
+        int rows = 0;
+        for (int j = k.smsg_begin; j < k.smsg_end; ++j) rows += p->msgs[j].uni ? 0 : 1;
+        return rows <= kBetaRows;
+    };
     for (auto& L : p->launches) {
         L.beta_n = 0;
         L.beta_items = 0;
         L.beta_off = 0;
         if (L.phase != JT_PHASE_DIST_MAIN || p->hdr[JT_H_UNI_ENTRIES] <= 0 || !L.tma_ok || !small_offsets) continue;
-        std::vector<int> ids;
+        std::vector<int> ids, inv_off;
         for (int t = L.begin; t < L.end; ++t) {
             DTask& k = p->tasks[t];
             if (k.kind != JT_KIND_PROJECT || k.beta < 0 || k.src < 0 || !(k.flags & JT_TF_SRC_UNIFORM)) continue;
             int rows = (k.own >= 0 && !(k.flags & JT_TF_OWN_UNIFORM)) ? 1 : 0;
             for (int j = k.rmsg_begin; j < k.smsg_end; ++j) rows += p->msgs[j].uni ? 0 : 1;
             if (rows > kBetaRows) continue;
+            // Only where the rest of the task gets cheap without its belief: a task that sends no
+            // message, or whose message part is a dense contraction or a scalar task.  Otherwise
+            // the projection kernel would walk all (s, r) items a second time just for the message
+            // (measured: Ising 16x16, K = 2 contractions: 22.4 -> 25.8 ms with every writer split).
+            if (k.out >= 0 && !dense_tasks.count(t) && !scalar_ok(k)) continue;
+            // walk order of a task without an r space (a leaf clique): the entries sorted by the
+            // row of their first per-instance operand (stable counting sort), so that consecutive
+            // entries reuse the row; other tasks are walked s-major as they are
+            int perm_off = -1;
+            if (k.n_r == 1 && rows > 0 && k.n_s > 1) {
+                int hi = 0, lo = 0;
+                bool found = false;
+                for (int j = k.rmsg_begin; j < k.smsg_end && !found; ++j)
+                    if (!p->msgs[j].uni) {
+                        hi = p->msgs[j].a_hi;
+                        lo = p->msgs[j].a_lo;
+                        found = true;
+                    }
+                if (found) {                                      // (own has row index s: already sorted)
+                    if (p->dtab.size() + (size_t)k.n_s > 2000000000ULL) continue;
+                    std::vector<int> key(k.n_s);
+                    int kmax = 0;
+                    for (int sx = 0; sx < k.n_s; ++sx) {
+                        key[sx] = p->tab[hi + sx / k.n_slo] + p->tab[lo + sx % k.n_slo];
+                        kmax = std::max(kmax, key[sx]);
+                    }
+                    std::vector<int> start((size_t)kmax + 2, 0);
+                    for (int sx = 0; sx < k.n_s; ++sx) ++start[key[sx] + 1];
+                    for (int v = 0; v <= kmax; ++v) start[v + 1] += start[v];
+                    perm_off = (int)p->dtab.size();
+                    p->dtab.resize(p->dtab.size() + k.n_s);
+                    for (int sx = 0; sx < k.n_s; ++sx) p->dtab[perm_off + start[key[sx]]++] = sx;
+                }
+            }
             k.flags |= JT_TF_BETA_SPLIT;
             ids.push_back(t);
+            inv_off.push_back(perm_off);
             L.beta_items += (long long)k.n_s * k.n_r;
         }
         if (ids.empty()) continue;
         L.beta_n = (int)ids.size();
         L.beta_off = p->prefix.size();
         p->prefix.insert(p->prefix.end(), ids.begin(), ids.end());
+        p->prefix.insert(p->prefix.end(), inv_off.begin(), inv_off.end());
         for (int ch = kBetaChMin; ch <= kBetaChMax; ++ch) {
             long long acc = 0;
             for (int t : ids) {
@@ -556,6 +619,79 @@ int jt_dense_build(jt_plan* p) {
             }
         }
     }
+    // Scalar tasks: every r-dependent input is uniform, so the sum over r is a per-batch total.  The
+    // totals are computed by derived B = 1 projection tasks (copies of the task with its uniform
+    // messages only, output behind the entries of the uniform workspace) in two derived launches:
+    // after the uniform collect (collect tasks) and after the uniform distribute (the others).
+    p->scalar_entries = 0;
+    if (p->hdr[JT_H_UNI_ENTRIES] > 0 && small_offsets) {
+        const long long work_entries = p->hdr[JT_H_CLIQUE_ENTRIES] + 3 * p->hdr[JT_H_SEP_ENTRIES] + p->hdr[JT_H_LIK_ENTRIES];
+        std::unordered_map<int, long long> total_of;        // task -> entry of its totals
+        std::vector<DTask> derived[2];
+        const size_t n_launches = p->launches.size();
+        for (size_t li = 0; li < n_launches; ++li) {
+            jt_plan::Launch& L = p->launches[li];
+            L.scalar_n = 0;
+            L.scalar_off = 0;
+            int group = phase_group(L.phase);
+            if (L.phase == JT_PHASE_DIST_MAIN && L.beta_n > 0) group = 1;
+            if (group < 0 || !L.tma_ok) continue;
+            std::vector<int> ids, totals;
+            for (int t = L.begin; t < L.end; ++t) {
+                const DTask k = p->tasks[t];
+                if (!scalar_ok(k)) continue;
+                if (k.beta >= 0 && L.phase != JT_PHASE_DIST_MAIN_MESSAGES &&
+                    !(L.phase == JT_PHASE_DIST_MAIN && (k.flags & JT_TF_BETA_SPLIT)))
+                    continue;
+                auto it = total_of.find(t);
+                if (it == total_of.end()) {
+                    if (work_entries + p->scalar_entries + k.n_s >= 2147483647LL) continue;
+                    it = total_of.emplace(t, work_entries + p->scalar_entries).first;
+                    p->scalar_entries += k.n_s;
+                    DTask d = k;
+                    d.out = it->second;
+                    d.out_space = 0;
+                    d.beta = d.bel = d.own = -1;
+                    d.flags = 0;
+                    d.rmsg_begin = (int)p->msgs.size();
+                    for (int j = k.rmsg_begin; j < k.rmsg_end; ++j) p->msgs.push_back(p->msgs[j]);
+                    d.rmsg_end = d.smsg_begin = (int)p->msgs.size();
+                    for (int j = k.smsg_begin; j < k.smsg_end; ++j)
+                        if (p->msgs[j].uni) p->msgs.push_back(p->msgs[j]);
+                    d.smsg_end = (int)p->msgs.size();
+                    derived[group].push_back(d);
+                }
+                ids.push_back(t);
+                totals.push_back((int)it->second);
+            }
+            if (ids.empty()) continue;
+            L.scalar_n = (int)ids.size();
+            L.scalar_off = p->prefix.size();
+            p->prefix.insert(p->prefix.end(), ids.begin(), ids.end());
+            p->prefix.insert(p->prefix.end(), totals.begin(), totals.end());
+            long long acc = 0;
+            for (int t : ids) {
+                p->prefix.push_back((int)acc);
+                acc += (p->tasks[t].n_s + kScalarRows - 1) / kScalarRows;
+            }
+            p->prefix.push_back((int)acc);
+        }
+        for (int g = 0; g < 2; ++g) {
+            if (derived[g].empty()) continue;
+            jt_plan::Launch D;
+            memset(&D, 0, sizeof(D));
+            D.phase = g == 0 ? JT_PHASE_X_SCALAR0 : JT_PHASE_X_SCALAR1;
+            D.begin = (int)p->tasks.size();
+            p->tasks.insert(p->tasks.end(), derived[g].begin(), derived[g].end());
+            D.end = (int)p->tasks.size();
+            D.level = 0;
+            int rc = jt_launch_tables(p, D);
+            if (rc != JT_OK) return rc;
+            p->launches.push_back(D);
+        }
+    }
+    p->accel = !p->dense.empty();
+    for (const auto& L : p->launches) p->accel = p->accel || L.beta_n > 0 || L.scalar_n > 0;
     // block prefixes of the dense launches and the projection-kernel prefixes of the reduced task sets
     for (auto& L : p->launches) {
         const int n = L.dense_end - L.dense_begin;
@@ -585,12 +721,22 @@ int jt_dense_build(jt_plan* p) {
             L.total_items_v[1] = L.total_items_v[0];
             v_dense = 1;
         }
+        for (int i = 0; i < L.scalar_n; ++i) {
+            const int t = p->prefix[L.scalar_off + i];
+            if (skip[t - L.begin]) continue;
+            skip[t - L.begin] = 1;
+            L.total_items_v[v_dense] -= (long long)p->tasks[t].n_s * p->tasks[t].n_r;
+        }
         if (n == 0) {
-            if (v_dense == 1)
+            if (L.scalar_n > 0) {
+                int rc = jt_build_item_prefix(p, L, skip.data(), L.item_prefix_off_v[v_dense], L.item_blocks_v[v_dense]);
+                if (rc != JT_OK) return rc;
+            } else if (v_dense == 1) {
                 for (int j = 0; j <= kItemLog2Max; ++j) {
                     L.item_prefix_off_v[1][j] = L.item_prefix_off_v[0][j];
                     L.item_blocks_v[1][j] = L.item_blocks_v[0][j];
                 }
+            }
             continue;
         }
         for (int i = L.dense_begin; i < L.dense_end; ++i) {
@@ -625,7 +771,7 @@ int jt_dense_build(jt_plan* p) {
 }
 
 int jt_dense_upload(jt_plan* p) {
-    if (p->dense.empty()) return JT_OK;
+    if (p->dense.empty() && p->dtab.empty()) return JT_OK;
     auto up = [](auto** dst, const auto& v) -> cudaError_t {
         const size_t bytes = v.size() * sizeof(v[0]);
         cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), bytes ? bytes : 16);
@@ -654,7 +800,7 @@ bool jt_tma_path(int64_t B, int dtype) {
 }
 
 bool jt_dense_enabled(const jt_plan* p, int64_t B, int dtype, int flags) {
-    return !p->dense.empty() && dense_env_enabled() && dtype == JT_F64 && (flags & JT_SR_MASK) == JT_SR_SUM_PRODUCT &&
+    return p->accel && dense_env_enabled() && dtype == JT_F64 && (flags & JT_SR_MASK) == JT_SR_SUM_PRODUCT &&
            (flags & JT_UNIFORM) && !(flags & JT_NO_DENSE) && jt_tma_path(B, dtype);
 }
 
@@ -665,8 +811,9 @@ bool jt_beta_enabled(const jt_plan* p, int64_t B, int dtype, int flags) {
         const char* e = getenv("JT_DISABLE_BETA");
         return (e && e[0] == '1') ? 0 : 1;
     }();
-    return on == 1 && p->hdr[JT_H_UNI_ENTRIES] > 0 && (flags & JT_UNIFORM) && !(flags & JT_NO_BELIEFS) &&
-           !(flags & JT_NO_DENSE) && jt_tma_path(B, dtype);
+    // together with the dense contractions and scalar tasks that take over the message parts of
+    // the writers (alone, the split costs a second pass over the items)
+    return on == 1 && !(flags & JT_NO_BELIEFS) && jt_dense_enabled(p, B, dtype, flags);
 }
 
 int jt_dense_prepare(const jt_plan* p, int which, int dtype, const void* uni_ws, void* w_region, cudaStream_t stream) {

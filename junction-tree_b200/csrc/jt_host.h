@@ -86,7 +86,11 @@ struct DDense {
 // internal bits (never in a plan blob or in the public flags)
 constexpr int JT_TF_BETA_SPLIT = 0x100;   // DTask::flags: in uniform mode the clique belief of this task is written by jt_beta_kernel
 constexpr int JT_X_BETA_SPLIT = 0x10000;  // KArgs::flags: ... and this launch runs that way
-constexpr int kBetaRows = 3;              // per-instance row operands jt_beta_kernel multiplies per entry
+// internal phases (launches derived at plan load, never in a blob): the totals of the scalar tasks,
+// ordinary B = 1 projection launches in the uniform workspace after the uniform collect / distribute
+constexpr int JT_PHASE_X_SCALAR0 = 64, JT_PHASE_X_SCALAR1 = 65;
+constexpr int kBetaRows = 3;
+constexpr int kScalarRows = 32;           // output rows per block of jt_scalar_kernel              // per-instance row operands jt_beta_kernel multiplies per entry
 constexpr int kBetaChMin = 8, kBetaChMax = 14;   // log2 of the items per block of a jt_beta_kernel launch
 
 constexpr int kThreads = 256;
@@ -126,6 +130,10 @@ struct jt_plan {
         size_t beta_off = 0;
         int beta_n = 0;
         long long beta_items = 0;
+        // scalar tasks of this launch (uniform mode): [n] task ids, [n] entry of their totals in the
+        // uniform workspace, [n + 1] block prefix (kScalarRows values of s per block), in jt_plan::prefix
+        size_t scalar_off = 0;
+        int scalar_n = 0;
         // dense contractions of this launch: range in jt_plan::dense, block prefix per j
         // (layout per j: [n + 1] first block of each task, [n] units per CTA)
         int dense_begin = 0, dense_end = 0;
@@ -160,6 +168,8 @@ struct jt_plan {
     // dense contractions (jt_dense.cu): descriptors sorted by launch, their int tables, the size
     // of the W region in elements; [0] tasks prepared after the uniform collect, [1] after the
     // uniform distribute (ranges in `dense`, W element ranges)
+    bool accel = false;                       // the plan has dense contractions, scalar tasks or split beliefs
+    long long scalar_entries = 0;             // totals of the scalar tasks, after the entries of the uniform workspace
     std::vector<DDense> dense;
     std::vector<int> dtab;
     long long dense_w_entries = 0;
@@ -171,6 +181,8 @@ struct jt_plan {
     mutable bool dense_attr_set = false;
 };
 
+// jt_abi.cu: the tables of a launch (prefixes per tile shape, totals, kernel eligibility)
+int jt_launch_tables(jt_plan* p, jt_plan::Launch& L);
 // jt_abi.cu: block prefix tables of a TMA projection launch (tasks flagged in `skip` get no blocks)
 int jt_build_item_prefix(jt_plan* p, const jt_plan::Launch& L, const char* skip, size_t* off_out, long long* blocks_out);
 
@@ -221,6 +233,8 @@ struct jt_sr_launchers {
                     cudaStream_t stream);
     // clique beliefs of the launch's JT_TF_BETA_SPLIT tasks (uniform mode): beta = scalars x rows
     int (*beta)(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec, cudaStream_t stream);
+    // scalar tasks of the launch (uniform mode): out[s] = total[s] x the per-instance s-only rows
+    int (*scalar)(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec, cudaStream_t stream);
     // one projection task outside a plan (jt_contract), LDG kernel
     int (*contract)(const KArgs& a, long long blocks, long long gy, int dtype, int vec, cudaStream_t stream);
     // output stage

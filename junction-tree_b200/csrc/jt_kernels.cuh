@@ -480,7 +480,8 @@ __global__ void __launch_bounds__(kThreads) jt_init_rows_kernel(const KArgs a) {
 // -- issue-bound consumers, ncu r02 -- against ~7 TB/s for streaming writes.)
 
 struct BetaArgs {
-    const int* list;       // [n] task ids of this launch
+    const int* list;       // [n] task ids of this launch, then [n] offsets of their walk-order tables (jt_plan::dtab, -1: none)
+    const int* perm;       // walk order of the tasks that have one: position -> (s, r) item
     const int* prefix;     // [n + 1] first block of each task for 2^ch_log2 items per block
     int n, ch_log2;
     const DTask* tasks;    // all tasks of the plan
@@ -504,6 +505,15 @@ __global__ void __launch_bounds__(kThreads, 3) jt_beta_kernel(const BetaArgs a) 
         if (__ldg(a.prefix + mid) <= (int)blockIdx.x) lo = mid; else hi = mid;
     }
     const DTask* tk = a.tasks + __ldg(a.list + lo);
+    // Walk order.  The items are visited s-major, r-minor by default: the rows that depend on s only
+    // (own message, s-only messages) stay put for n_r consecutive entries and the r-dependent ones
+    // cycle through a handful of rows, so all of them are served by L1 and the launch is bound by
+    // its scattered 16-byte-per-thread row writes (~6 TB/s measured; walking the clique in memory
+    // order instead re-reads a row from L2 per entry and runs at half that).  A task without an r
+    // space (a leaf clique: every entry has its own s) gets a table that visits the entries
+    // sorted by their row operand, for the same effect.
+    const int perm_off = __ldg(a.list + a.n + lo);
+    const int* __restrict__ perm = perm_off >= 0 ? a.perm + perm_off : nullptr;
     const int n_r = tk->n_r, n_slo = tk->n_slo, n_rlo = tk->n_rlo;
     const long long n_items = (long long)tk->n_s * n_r;
     const long long i0 = (long long)((int)blockIdx.x - __ldg(a.prefix + lo)) << a.ch_log2;
@@ -526,6 +536,10 @@ __global__ void __launch_bounds__(kThreads, 3) jt_beta_kernel(const BetaArgs a) 
     // U entries per trip: all row loads first, then the products and stores -- loads and stores go
     // through the same workspace pointer, so the compiler keeps their order and only loads that
     // are issued back to back are in flight together (8 x 16 bytes per thread)
+    // U entries per trip: all row loads first, then the products and stores -- loads and stores go
+    // through the same workspace pointer, so the compiler keeps their order and only loads that
+    // are issued back to back are in flight together (8 x 16 bytes per thread).  Consecutive
+    // entries mostly reuse the same rows (see the walk order below), so the loads hit L1.
     auto rows = [&](auto n_tag, int n) {
         constexpr int N = decltype(n_tag)::value;
         constexpr int U = N <= 1 ? 8 : 4;
@@ -556,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 3) jt_beta_kernel(const BetaArgs a) 
         const int n = (int)(i1 - base < kThreads ? i1 - base : kThreads);
         __syncthreads();                                  // the previous sub-chunk has been consumed
         if (t < n) {
-            const long long item = base + t;
+            const long long item = perm ? (long long)__ldg(perm + base + t) : base + t;
             const int s = (int)(item / n_r), r = (int)(item - (long long)s * n_r);
             int s_hi = 0, s_lo = s;
             if (n_slo < tk->n_s) {
@@ -589,6 +603,92 @@ __global__ void __launch_bounds__(kThreads, 3) jt_beta_kernel(const BetaArgs a) 
             case 1: rows(std::integral_constant<int, 1>{}, n); break;
             case 2: rows(std::integral_constant<int, 2>{}, n); break;
             default: rows(std::integral_constant<int, 3>{}, n); break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Scalar tasks (uniform mode): a projection task all of whose r-dependent inputs are uniform,
+//     out[s][b] = ( sum_r U(s, r) ) * prod_j smsg_j[A_j(s)][b]        bel[s][b] = out * own[s][b]
+// The total over r is the same for every instance: it is computed once, in the uniform workspace
+// (an ordinary B = 1 projection launch derived when the plan is loaded, jt_dense.cu), and the
+// batch launch is left with n_s rows of elementwise work instead of n_s * n_r items of scalar
+// bookkeeping (config 4: 786,432 items per task, 0.41-0.44 ms, for 8,192 output rows).
+
+struct ScalarArgs {
+    const int* list;       // [n] task ids, [n] entry of each task's totals in the uniform workspace, [n + 1] block prefix
+    int n;
+    const DTask* tasks;    // all tasks of the plan
+    const DMsg* msgs;
+    const int* tab;
+    void* work;
+    const void* uni;
+    void* fout;
+    long long B, Bv;
+    int bx_log2, flags;
+};
+
+template <typename SR, typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) jt_scalar_kernel(const ScalarArgs a) {
+    typedef Pack<T, VEC> P;
+    __shared__ T su[kScalarRows];
+    __shared__ T sown[kScalarRows];
+    __shared__ int srow[kBetaRows + 1][kScalarRows];
+    const int* prefix = a.list + 2 * a.n;
+    int lo = 0, hi = a.n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(prefix + mid) <= (int)blockIdx.x) lo = mid; else hi = mid;
+    }
+    const DTask* tk = a.tasks + __ldg(a.list + lo);
+    const long long total0 = __ldg(a.list + a.n + lo);
+    const int s0 = ((int)blockIdx.x - __ldg(prefix + lo)) * kScalarRows;
+    const int n = tk->n_s - s0 < kScalarRows ? tk->n_s - s0 : kScalarRows;
+    const int t = threadIdx.x;
+    const int tx = t & ((1 << a.bx_log2) - 1), ty = t >> a.bx_log2, ry = kThreads >> a.bx_log2;
+    const long long bv = ((long long)blockIdx.y << a.bx_log2) + tx;
+    const long long B = a.B, col = bv * VEC;
+    const int* __restrict__ tab = a.tab;
+    const DMsg* __restrict__ msgs = a.msgs;
+    const T* __restrict__ uni = static_cast<const T*>(a.uni);
+    T* work = static_cast<T*>(a.work);
+    const int tflags = tk->flags;
+    const bool wbel = tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS);
+    const bool own_row = wbel && tk->own >= 0 && !(tflags & JT_TF_OWN_UNIFORM);
+    int n_rows = 0;
+    for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) n_rows += msgs[j].uni ? 0 : 1;
+    if (t < n) {
+        const int s = s0 + t;
+        int s_hi = 0, s_lo = s;
+        if (tk->n_slo < tk->n_s) {
+            s_hi = s / tk->n_slo;
+            s_lo = s - s_hi * tk->n_slo;
+        }
+        su[t] = __ldg(uni + total0 + s);
+        int k = 0;
+        for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
+            const DMsg* m = msgs + j;
+            if (!m->uni) srow[k++][t] = (int)(m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo));
+        }
+        sown[t] = SR::template one<T>();
+        if (wbel && tk->own >= 0) {
+            if (own_row) srow[kBetaRows][t] = (int)(tk->own + s);
+            else sown[t] = __ldg(uni + tk->own + s);
+        }
+    }
+    __syncthreads();
+    if (bv >= a.Bv) return;
+    T* out = (tk->out_space ? static_cast<T*>(a.fout) : work) + (tk->out + s0) * B + col;
+    T* bel = work + ((wbel ? tk->bel : 0) + s0) * B + col;
+#pragma unroll 4
+    for (int i = ty; i < n; i += ry) {
+        P val = pack_fill<T, VEC>(su[i]);
+        for (int k = 0; k < n_rows; ++k) mul<SR>(val, ld<T, VEC>(work + (long long)srow[k][i] * B + col));
+        st<T, VEC>(out + (long long)i * B, val);
+        if (wbel) {
+            if (own_row) mul<SR>(val, ld<T, VEC>(work + (long long)srow[kBetaRows][i] * B + col));
+            else mul<SR>(val, pack_fill<T, VEC>(sown[i]));
+            st<T, VEC>(bel + (long long)i * B, val);
         }
     }
 }

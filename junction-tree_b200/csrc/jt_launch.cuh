@@ -172,13 +172,14 @@ struct Launcher {
         // items per block: as large as still gives ~8 blocks per SM
         int ch = kBetaChMax;
         while (ch > kBetaChMin && ((L.beta_items >> ch) + L.beta_n) * gy < 148LL * 8) --ch;
-        const int* prefix = p->prefix.data() + L.beta_off + L.beta_n + (size_t)(ch - kBetaChMin) * (L.beta_n + 1);
+        const int* prefix = p->prefix.data() + L.beta_off + 2 * L.beta_n + (size_t)(ch - kBetaChMin) * (L.beta_n + 1);
         const long long gx = prefix[L.beta_n];
         if (gx <= 0) return JT_OK;
         if (gx > 2147483647LL || gy > 65535)
             return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
         b.list = p->d_prefix + L.beta_off;
-        b.prefix = p->d_prefix + L.beta_off + L.beta_n + (size_t)(ch - kBetaChMin) * (L.beta_n + 1);
+        b.perm = p->d_dtab;
+        b.prefix = p->d_prefix + L.beta_off + 2 * L.beta_n + (size_t)(ch - kBetaChMin) * (L.beta_n + 1);
         b.n = L.beta_n;
         b.ch_log2 = ch;
         b.tasks = p->d_tasks;
@@ -204,6 +205,45 @@ struct Launcher {
         if (vec == 4) return launch_beta<float, 4>(p, L, a, stream);
         if (vec == 2) return launch_beta<float, 2>(p, L, a, stream);
         return launch_beta<float, 1>(p, L, a, stream);
+    }
+
+    template <typename T, int VEC>
+    static int launch_scalar(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, cudaStream_t stream) {
+        ScalarArgs b;
+        int bx_log2, sy_log2;
+        pick_tile(a.Bv, bx_log2, sy_log2);
+        const long long gy = (a.Bv + (1LL << bx_log2) - 1) >> bx_log2;
+        const long long gx = p->prefix[L.scalar_off + 3 * (size_t)L.scalar_n];
+        if (gx <= 0) return JT_OK;
+        if (gx > 2147483647LL || gy > 65535)
+            return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
+        b.list = p->d_prefix + L.scalar_off;
+        b.n = L.scalar_n;
+        b.tasks = p->d_tasks;
+        b.msgs = p->d_msgs;
+        b.tab = p->d_tab;
+        b.work = a.work;
+        b.uni = a.uni;
+        b.fout = a.fout;
+        b.B = a.B;
+        b.Bv = a.Bv;
+        b.bx_log2 = bx_log2;
+        b.flags = a.flags;
+        jt_scalar_kernel<SR, T, VEC><<<dim3((unsigned)gx, (unsigned)gy, 1), kThreads, 0, stream>>>(b);
+        jt_g_launches.fetch_add(1, std::memory_order_relaxed);
+        JT_CUDA(cudaGetLastError());
+        return JT_OK;
+    }
+
+    static int scalar(const jt_plan* p, const jt_plan::Launch& L, const KArgs& a, int dtype, int vec, cudaStream_t stream) {
+        if (L.scalar_n <= 0) return JT_OK;
+        if (dtype == JT_F64) {
+            if (vec == 2) return launch_scalar<double, 2>(p, L, a, stream);
+            return launch_scalar<double, 1>(p, L, a, stream);
+        }
+        if (vec == 4) return launch_scalar<float, 4>(p, L, a, stream);
+        if (vec == 2) return launch_scalar<float, 2>(p, L, a, stream);
+        return launch_scalar<float, 1>(p, L, a, stream);
     }
 
     static int contract(const KArgs& a, long long blocks, long long gy, int dtype, int vec, cudaStream_t stream) {
@@ -274,6 +314,7 @@ struct Launcher {
 #define JT_DEFINE_SEMIRING(SR, ID, NAME)                                                       \
     const jt_sr_launchers* NAME() {                                                            \
         static const jt_sr_launchers table = {&Launcher<SR, ID>::dispatch, &Launcher<SR, ID>::beta, \
+                                              &Launcher<SR, ID>::scalar,                         \
                                               &Launcher<SR, ID>::contract, &Launcher<SR, ID>::normalize, \
                                               &Launcher<SR, ID>::walk};                        \
         return &table;                                                                         \

@@ -202,20 +202,22 @@ def workload_name(args):
 
 #: BASELINE.json's configs at their stated sizes (per GPU; weak scaling), beside the main line's
 #: configs[1] with evidence in uniform mode.  (name, batch, dtype, uniform, evidence, beliefs,
-#: sub_batches): config 3's 256 instances run as 2 x 128 (a 76 GB workspace each time), config 5
-#: once with all beliefs stored (dense workspace, 1,024 instances) and once in the pipelines' mode
-#: on a sparse workspace (4,096 instances: outputs only).
+#: sub_batches): config 3's 256 instances run in one 142 GB workspace (as 2 x 128 when that does not
+#: fit beside whatever else holds memory on the GPU), config 5 once with all beliefs stored (dense
+#: workspace, 1,024 instances) and once in the pipelines' mode on a sparse workspace (4,096
+#: instances: outputs only).  Config 5 with all beliefs stored takes 80 MB per instance: its chunk is
+#: the largest multiple of 256 up to 2,048 that fits the free memory.
 EXTRA_CONFIGS = [
     ("dag37", 65536, "f64", True, False, True, 1),
     ("dag37", 65536, "f64", False, True, True, 1),
-    ("ising16", 256, "f64", True, True, True, 2),
-    ("ising16", 256, "f64", False, True, True, 2),
+    ("ising16", 256, "f64", True, True, True, 1),
+    ("ising16", 256, "f64", False, True, True, 1),
     ("large_state_tree", 512, "f64", True, True, True, 1),
     ("large_state_tree", 512, "f64", False, True, True, 1),
     ("large_state_tree", 512, "f32", True, True, True, 1),
     ("large_state_tree", 512, "f32", False, True, True, 1),
-    ("dag500", 1024, "f64", True, True, True, 1),
-    ("dag500", 1024, "f64", False, True, True, 1),
+    ("dag500", 2048, "f64", True, True, True, 1),       # the largest chunk (<= 2,048) that fits: 80 MB per instance
+    ("dag500", 2048, "f64", False, True, True, 1),
     ("dag500", 4096, "f64", True, True, False, 1),
 ]
 
@@ -371,6 +373,11 @@ def run_gpu(args):
         if rank == 0:
             extras.append(single_propagate_latency(jt, wl.sprinkler()))
         for name, batch, dt, uni, evid, bel, sub in EXTRA_CONFIGS:
+            if name == "ising16" and sub == 1:
+                free, _ = torch.cuda.mem_get_info()
+                sub = 1 if free > 150e9 else 2
+            if name == "dag500" and bel:
+                batch = bl.largest_batch(name, dt, batch)
             ehp = bl.HotPath(name, batch // sub, dt, uniform=uni, evidence=evid, beliefs=bel, dense=not args.no_dense,
                              ev_offset=rank * (batch // sub), ev_total=(batch // sub) * world)
             t = ehp.time(max(3, min(args.steps, 5)), 3, barrier)

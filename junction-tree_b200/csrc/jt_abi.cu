@@ -197,7 +197,12 @@ KArgs base_args(const jt_plan* p, int64_t B, void* workspace, int vec) {
 // call returns, so the "enqueue only, never synchronise" contract (and graph capture) holds.
 struct SideStream {
     cudaStream_t stream = nullptr;
-    cudaStream_t aux[2] = {nullptr, nullptr};    // the independent kernels of one level run side by side
+    cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};   // the independent kernels of one level run side by side
+    cudaStream_t pre = nullptr;                  // the message-only launch of a distribute level beside its belief-writing one
+    cudaStream_t uni = nullptr;                  // the uniform (B = 1) part of the distribute pass, beside the instance collect
+    // jt_collect has already run the uniform part of the distribute pass for this (plan, workspace)
+    const void* uni_dist_plan = nullptr;
+    const void* uni_dist_ws = nullptr;
     int device = -1;
     std::vector<cudaEvent_t> events;
     size_t used = 0;
@@ -219,12 +224,30 @@ cudaError_t side_acquire(cudaStream_t* out) {
     if (!g_side.stream || g_side.device != dev) {
         g_side.events.clear();                 // events of another device are left to the driver
         e = cudaStreamCreateWithFlags(&g_side.stream, cudaStreamNonBlocking);
-        for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&g_side.aux[i], cudaStreamNonBlocking);
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&g_side.aux[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_side.pre, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_side.uni, cudaStreamNonBlocking);
         if (e != cudaSuccess) return e;
         g_side.device = dev;
     }
     if (out) *out = g_side.stream;
     return cudaSuccess;
+}
+
+bool uniform_overlap_enabled() {    // JT_UNIFORM_OVERLAP=0: the uniform part of the distribute pass inside jt_distribute (A-B timing)
+    static const int on = [] {
+        const char* e = getenv("JT_UNIFORM_OVERLAP");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on == 1;
+}
+
+double beta_min_bytes() {           // JT_BETA_MIN_MB: belief bytes of a launch from which they are split off (default 1024)
+    static const double v = [] {
+        const char* e = getenv("JT_BETA_MIN_MB");
+        return (e && e[0]) ? atof(e) * 1e6 : 1024e6;
+    }();
+    return v;
 }
 
 bool level_fork_enabled() {         // JT_LEVEL_STREAMS=0: the kernels of a level one after the other (A-B timing)
@@ -253,10 +276,17 @@ cudaError_t side_event(cudaEvent_t* out) {
 // contractions of the matching message-only launch) compute the messages, tasks that only write
 // a belief drop out of it.
 int run_launch(jt_plan* p, const jt_plan::Launch& L, const KArgs& a_in, int dtype, int vec, void* w_region,
-               cudaStream_t stream, bool split = false, cudaStream_t beta_stream = nullptr) {
+               cudaStream_t stream, bool split = false, cudaStream_t beta_stream = nullptr, int aux_set = 0) {
     NvtxRange range(phase_name(L.phase), L.level);
     KArgs a = a_in;
-    split = split && L.phase == JT_PHASE_DIST_MAIN && L.beta_n > 0;
+    // Splitting the beliefs off pays for the extra kernels (a second latency-bound launch in the
+    // chain, the rows read once more) only when the launch writes a lot: jt_beta_kernel streams at
+    // ~5.9 TB/s against 3.6-5.4 TB/s for the same rows written from inside the projection tasks, i.e.
+    // some tens of microseconds per GB.  Measured (r02): config 4 (3.2-6.4 GB per launch) 2.75 -> 2.06 ms,
+    // Ising 16x16 at B = 128 (0.13 GB per launch) 22.2 -> 22.9 ms.  With batch rows of 64 KB and more the
+    // projection tasks already write at that rate (two vectors per thread), so nothing is gained.
+    split = split && L.phase == JT_PHASE_DIST_MAIN && L.beta_n > 0 &&
+            (double)L.beta_items * (double)a.B * (dtype == JT_F64 ? 8.0 : 4.0) >= beta_min_bytes() && a.B <= 4096;
     // dense contractions and scalar tasks leave the projection launch together (one reduced task set)
     const bool accel = w_region && (L.dense_end > L.dense_begin || L.scalar_n > 0) &&
                        (L.phase != JT_PHASE_DIST_MAIN || split);
@@ -280,11 +310,11 @@ int run_launch(jt_plan* p, const jt_plan::Launch& L, const KArgs& a_in, int dtyp
         JT_CUDA(side_event(&ev));
         JT_CUDA(cudaEventRecord(ev, stream));
         if (has_dense && (has_proj || has_scalar)) {
-            s_dense = g_side.aux[0];
+            s_dense = g_side.aux[2 * aux_set];
             JT_CUDA(cudaStreamWaitEvent(s_dense, ev, 0));
         }
         if (has_scalar && has_proj) {
-            s_scalar = g_side.aux[1];
+            s_scalar = g_side.aux[2 * aux_set + 1];
             JT_CUDA(cudaStreamWaitEvent(s_scalar, ev, 0));
         }
     }
@@ -342,6 +372,17 @@ void* uniform_ws(const jt_plan* p, int64_t B, int dtype, void* workspace) {
 void* dense_region(const jt_plan* p, int64_t B, int dtype, void* workspace, int flags) {
     if (!jt_dense_enabled(p, B, dtype, flags)) return nullptr;
     return static_cast<char*>(workspace) + workspace_layout(p, B, dtype).dense_off;
+}
+
+// The uniform part of the distribute pass: down-messages with an evidence-free source side, once,
+// top level first (B = 1 launches in the uniform workspace), then the W blocks and totals of the
+// distribute and marginal tasks, which also need those messages.
+int uniform_distribute(jt_plan* p, const KArgs& a, int dtype, void* uni, void* w_region, cudaStream_t stream) {
+    int rc = run_phase_uniform(p, JT_PHASE_DIST_UNIFORM, a, dtype, uni, stream);
+    if (rc != JT_OK || !w_region) return rc;
+    rc = jt_dense_prepare(p, 1, dtype, uni, w_region, stream);
+    if (rc == JT_OK) rc = run_phase_uniform(p, JT_PHASE_X_SCALAR1, a, dtype, uni, stream);
+    return rc;
 }
 
 }  // namespace
@@ -734,9 +775,33 @@ int jt_collect(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, voi
             if (rc != JT_OK) return rc;
         }
     }
+    // The uniform part of the distribute pass depends on the uniform collect only: it runs now, on
+    // a stream of its own beside the instance collect (a chain of one tiny launch per level that
+    // would otherwise sit in front of jt_distribute), and jt_distribute finds it done.
+    cudaEvent_t uni_done = nullptr;
+    g_side.uni_dist_plan = g_side.uni_dist_ws = nullptr;
+    if (!(flags & JT_UNIFORM_VALID) && uniform_overlap_enabled()) {
+        cudaEvent_t ev;
+        JT_CUDA(side_acquire(nullptr));
+        JT_CUDA(side_event(&ev));
+        JT_CUDA(cudaEventRecord(ev, stream));
+        JT_CUDA(cudaStreamWaitEvent(g_side.uni, ev, 0));
+        rc = uniform_distribute(p, a, dtype, uni, w_region, g_side.uni);
+        if (rc != JT_OK) return rc;
+        JT_CUDA(side_event(&uni_done));
+        JT_CUDA(cudaEventRecord(uni_done, g_side.uni));
+    }
     a.uni = uni;
     a.uniform = 1;
-    return run_phase(p, JT_PHASE_COLLECT_INSTANCE, a, dtype, vec, stream, w_region);
+    rc = run_phase(p, JT_PHASE_COLLECT_INSTANCE, a, dtype, vec, stream, w_region);
+    if (uni_done) {                     // join: the stage is complete when the caller's stream is
+        JT_CUDA(cudaStreamWaitEvent(stream, uni_done, 0));
+        if (rc == JT_OK) {
+            g_side.uni_dist_plan = p;
+            g_side.uni_dist_ws = workspace;
+        }
+    }
+    return rc;
 }
 
 int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, void* stream_) {
@@ -756,14 +821,11 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
         // down-messages with an evidence-free source side: once, top level first (B = 1)
         void* uni = uniform_ws(p, B, dtype, workspace);
         w_region = dense_region(p, B, dtype, workspace, flags);
-        if (!(flags & JT_UNIFORM_VALID)) {
-            rc = run_phase_uniform(p, JT_PHASE_DIST_UNIFORM, a, dtype, uni, stream);
+        const bool done_by_collect = g_side.uni_dist_plan == p && g_side.uni_dist_ws == workspace;
+        g_side.uni_dist_plan = g_side.uni_dist_ws = nullptr;
+        if (!(flags & JT_UNIFORM_VALID) && !done_by_collect) {
+            rc = uniform_distribute(p, a, dtype, uni, w_region, stream);
             if (rc != JT_OK) return rc;
-            if (w_region) {  // W blocks and totals of the distribute and marginal tasks (they also need the uniform down-messages)
-                rc = jt_dense_prepare(p, 1, dtype, uni, w_region, stream);
-                if (rc == JT_OK) rc = run_phase_uniform(p, JT_PHASE_X_SCALAR1, a, dtype, uni, stream);
-                if (rc != JT_OK) return rc;
-            }
         }
         a.uni = uni;
         a.uniform = 1;
@@ -775,8 +837,39 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
     cudaStream_t side = nullptr;
     bool forked = false;
     if (split && beta_overlap_enabled()) JT_CUDA(side_acquire(&side));
+    const jt_plan::Launch* pending_pre = nullptr;       // the DIST_PRE launch of the current level, not yet enqueued
+    auto run_pre = [&](const jt_plan::Launch& Q, cudaStream_t on, int aux_set) {
+        return run_launch(p, Q, a, dtype, vec, w_region, on, false, nullptr, aux_set);
+    };
     for (const auto& L : p->launches) {
         if (L.phase != pre_phase && L.phase != main_phase) continue;
+        if (L.phase == pre_phase) {
+            if (pending_pre) {                                    // a level without a main launch
+                rc = run_pre(*pending_pre, stream, 0);
+                if (rc != JT_OK) return rc;
+            }
+            pending_pre = &L;
+            continue;
+        }
+        // the two launches of a level side by side when neither touches what the other reads
+        const bool pair = pending_pre && pending_pre->level == L.level && L.pre_independent && uniform_mode(p, flags) &&
+                          level_fork_enabled();
+        cudaEvent_t pre_done = nullptr;
+        if (pending_pre && !pair) {
+            rc = run_pre(*pending_pre, stream, 0);
+            if (rc != JT_OK) return rc;
+        } else if (pair) {
+            cudaEvent_t ev;
+            JT_CUDA(side_acquire(nullptr));
+            JT_CUDA(side_event(&ev));
+            JT_CUDA(cudaEventRecord(ev, stream));
+            JT_CUDA(cudaStreamWaitEvent(g_side.pre, ev, 0));
+            rc = run_pre(*pending_pre, g_side.pre, 1);
+            if (rc != JT_OK) return rc;
+            JT_CUDA(side_event(&pre_done));
+            JT_CUDA(cudaEventRecord(pre_done, g_side.pre));
+        }
+        pending_pre = nullptr;
         cudaStream_t beta_stream = nullptr;
         if (side && L.phase == JT_PHASE_DIST_MAIN && L.beta_n > 0) {
             // the beliefs of this level need the messages of the levels above (and the collect
@@ -789,6 +882,11 @@ int jt_distribute(jt_plan* p, int64_t B, int dtype, void* workspace, int flags, 
             forked = true;
         }
         rc = run_launch(p, L, a, dtype, vec, w_region, stream, split, beta_stream);
+        if (rc != JT_OK) return rc;
+        if (pre_done) JT_CUDA(cudaStreamWaitEvent(stream, pre_done, 0));
+    }
+    if (pending_pre) {
+        rc = run_pre(*pending_pre, stream, 0);
         if (rc != JT_OK) return rc;
     }
     if (forked) {                               // join: the stage is complete when the caller's stream is

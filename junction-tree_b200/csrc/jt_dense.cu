@@ -305,17 +305,38 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
         }
         return r;
     };
+    // Two m-tiles at a time: first every load of the pair (own rows, per-instance s-only rows), then
+    // the products and stores -- loads and stores share the workspace pointer, so only loads issued
+    // back to back overlap their latencies.
     auto epilogue = [&](const Acc& c, const Rows& ur) {
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-            if (ur.s[mt] >= 0) {
-                const int s = ur.s[mt];
-                T own_u = T(1);
-                const T* own_row = nullptr;
+        for (int m0 = 0; m0 < 4; m0 += 2) {
+            if (m0 >= MT) break;
+            double2 ow[2][kDNT];
+            T own_u[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int mt = m0 + h, s = ur.s[mt];
+                own_u[h] = T(1);
+#pragma unroll
+                for (int nt = 0; nt < kDNT; ++nt) ow[h][nt] = make_double2(1.0, 1.0);
+                if (s < 0) continue;
                 if (wbel && has_own) {
-                    if (tflags & JT_TF_OWN_UNIFORM) own_u = __ldg(uni + tk->own + s);
-                    else own_row = work + (tk->own + s) * B;
+                    if (tflags & JT_TF_OWN_UNIFORM) {
+                        own_u[h] = __ldg(uni + tk->own + s);
+                    } else {
+#pragma unroll
+                        for (int nt = 0; nt < kDNT; ++nt) {
+                            const long long col = ccol + nt * 8;
+                            if (col < B) ow[h][nt] = *reinterpret_cast<const double2*>(work + (tk->own + s) * B + col);
+                        }
+                    }
                 }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int mt = m0 + h, s = ur.s[mt];
+                if (s < 0) continue;
 #pragma unroll
                 for (int nt = 0; nt < kDNT; ++nt) {
                     const long long col = ccol + nt * 8;
@@ -335,14 +356,8 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
                         }
                         *reinterpret_cast<double2*>(obase + (long long)s * B + col) = make_double2(v0, v1);
                         if (wbel) {
-                            if (own_row) {
-                                const double2 x = *reinterpret_cast<const double2*>(own_row + col);
-                                v0 *= x.x;
-                                v1 *= x.y;
-                            } else {
-                                v0 *= own_u;
-                                v1 *= own_u;
-                            }
+                            v0 *= ow[h][nt].x * own_u[h];
+                            v1 *= ow[h][nt].y * own_u[h];
                             *reinterpret_cast<double2*>(work + (tk->bel + s) * B + col) = make_double2(v0, v1);
                         }
                     }
@@ -365,6 +380,7 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
     if (d.ups > 1) {
         // short contractions: `ups` units per stage, one after the other
         const int kpad = d.n_k4 * 4;
+        Rows next = unit_rows(u0);                                // looked up one unit ahead
         for (long long u = u0; u < u1; u += d.ups) {
             const int nu = (int)(u1 - u < d.ups ? u1 - u : d.ups);
             mbar_wait(full_u32 + 8 * stage, phase);
@@ -373,7 +389,8 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
             for (int j = 0; j < nu; ++j) {
                 Acc c;
                 zero(c);
-                const Rows ur = unit_rows(u + j);
+                const Rows ur = next;
+                if (u + j + 1 < u1) next = unit_rows(u + j + 1);
                 steps(c, st + j * kpad * kDRowPitch + frag_off, wt + j * d.n_k4 * MT * 32, d.n_k4);
                 if (j == nu - 1) release();                       // the stage is consumed: refill during the epilogue
                 epilogue(c, ur);
@@ -381,10 +398,12 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
         }
         return;
     }
+    Rows next = unit_rows(u0);
     for (long long u = u0; u < u1; ++u) {
         Acc c;
         zero(c);
-        const Rows ur = unit_rows(u);
+        const Rows ur = next;
+        if (u + 1 < u1) next = unit_rows(u + 1);
         for (int ch = 0; ch < d.n_chunks; ++ch) {
             const int nk4 = d.n_k4 - ch * 4 < 4 ? d.n_k4 - ch * 4 : 4;
             mbar_wait(full_u32 + 8 * stage, phase);
@@ -484,7 +503,7 @@ int jt_dense_build(jt_plan* p) {
                 // group loads its K rows once per i-tile and every output row is written once
                 const long long items = (long long)k.n_s * k.n_r;
                 const long long moved = (long long)n_g * d.n_it * K + k.n_s;
-                if ((long long)n_i * K < 16 || items < 2 * moved) continue;
+                if ((long long)n_i * K < 16 || items < 3 * moved) continue;
                 d.w_size = (long long)n_g * d.n_it * d.n_k4 * d.MT * 32;
                 if (d.w_size > (1LL << 40) || p->dtab.size() + (size_t)k.n_s + n_g + K + k.n_r > 2000000000ULL) continue;
                 d.w_off = p->dense_w_entries;
@@ -690,6 +709,22 @@ int jt_dense_build(jt_plan* p) {
             p->launches.push_back(D);
         }
     }
+    // which levels of the distribute pass may run their two launches side by side
+    for (auto& L : p->launches) {
+        L.pre_independent = false;
+        if (L.phase != JT_PHASE_DIST_MAIN && L.phase != JT_PHASE_DIST_MAIN_MESSAGES) continue;
+        L.pre_independent = true;
+        if (L.phase == JT_PHASE_DIST_MAIN_MESSAGES) continue;            // writes no belief at all
+        for (const auto& Q : p->launches) {
+            if (Q.phase != JT_PHASE_DIST_PRE_INSTANCE || Q.level != L.level) continue;
+            for (int t = L.begin; t < L.end; ++t) {
+                const DTask& w = p->tasks[t];
+                if (w.beta < 0 || (w.flags & JT_TF_SRC_UNIFORM)) continue;   // beliefs of shared cliques touch rows nobody reads
+                for (int q = Q.begin; q < Q.end; ++q)
+                    if (p->tasks[q].src == w.beta && !(p->tasks[q].flags & JT_TF_SRC_UNIFORM)) L.pre_independent = false;
+            }
+        }
+    }
     p->accel = !p->dense.empty();
     for (const auto& L : p->launches) p->accel = p->accel || L.beta_n > 0 || L.scalar_n > 0;
     // block prefixes of the dense launches and the projection-kernel prefixes of the reduced task sets
@@ -845,10 +880,11 @@ int jt_dense_launch(const jt_plan* p, const jt_plan::Launch& L, void* work, cons
     const int n = L.dense_end - L.dense_begin;
     if (n <= 0) return JT_OK;
     const long long tiles = (B + kDTB - 1) / kDTB;
-    // stages per CTA: at least 8 (pipeline fill), more while the grid still covers the machine
-    // four times over (2 CTAs per SM)
-    int j = 3;
-    while (j < kDenseJMax && (L.dense_stages * tiles) >> (j + 1) >= 148LL * 8) ++j;
+    // As many CTAs as stage-tiles until the grid covers the machine a few times over (2 CTAs per SM):
+    // on deep trees most launches are small and latency-bound, so a CTA should own as little
+    // serial work as possible; only large launches amortise the prologue over many stages.
+    int j = 0;
+    while (j < kDenseJMax && ((L.dense_stages * tiles) >> j) > 148LL * 2 * 4) ++j;
     const long long gx = L.dense_blocks[j];
     if (gx <= 0) return JT_OK;
     if (gx > 2147483647LL || tiles > 65535)

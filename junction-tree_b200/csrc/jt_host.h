@@ -134,6 +134,10 @@ struct jt_plan {
         // uniform workspace, [n + 1] block prefix (kScalarRows values of s per block), in jt_plan::prefix
         size_t scalar_off = 0;
         int scalar_n = 0;
+        // DIST_MAIN / DIST_MAIN_MESSAGES: no task of this launch overwrites (in place, with its clique
+        // belief) a per-instance potential that a task of the level's DIST_PRE_INSTANCE launch reads,
+        // so the two launches of the level may run side by side
+        bool pre_independent = false;
         // dense contractions of this launch: range in jt_plan::dense, block prefix per j
         // (layout per j: [n + 1] first block of each task, [n] units per CTA)
         int dense_begin = 0, dense_end = 0;

@@ -680,15 +680,35 @@ __global__ void __launch_bounds__(kThreads) jt_scalar_kernel(const ScalarArgs a)
     if (bv >= a.Bv) return;
     T* out = (tk->out_space ? static_cast<T*>(a.fout) : work) + (tk->out + s0) * B + col;
     T* bel = work + ((wbel ? tk->bel : 0) + s0) * B + col;
-#pragma unroll 4
-    for (int i = ty; i < n; i += ry) {
-        P val = pack_fill<T, VEC>(su[i]);
-        for (int k = 0; k < n_rows; ++k) mul<SR>(val, ld<T, VEC>(work + (long long)srow[k][i] * B + col));
-        st<T, VEC>(out + (long long)i * B, val);
-        if (wbel) {
-            if (own_row) mul<SR>(val, ld<T, VEC>(work + (long long)srow[kBetaRows][i] * B + col));
-            else mul<SR>(val, pack_fill<T, VEC>(sown[i]));
-            st<T, VEC>(bel + (long long)i * B, val);
+    // four rows per trip: every load first (row operands, own), then the products and stores
+    constexpr int U = 4;
+    for (int i0 = ty; i0 < n; i0 += ry * U) {
+        P x[U][kBetaRows], xo[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * ry;
+            if (i < n) {
+#pragma unroll
+                for (int k = 0; k < kBetaRows; ++k)
+                    if (k < n_rows) x[u][k] = ld<T, VEC>(work + (long long)srow[k][i] * B + col);
+                if (own_row) xo[u] = ld<T, VEC>(work + (long long)srow[kBetaRows][i] * B + col);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * ry;
+            if (i < n) {
+                P val = pack_fill<T, VEC>(su[i]);
+#pragma unroll
+                for (int k = 0; k < kBetaRows; ++k)
+                    if (k < n_rows) mul<SR>(val, x[u][k]);
+                st<T, VEC>(out + (long long)i * B, val);
+                if (wbel) {
+                    if (own_row) mul<SR>(val, xo[u]);
+                    else mul<SR>(val, pack_fill<T, VEC>(sown[i]));
+                    st<T, VEC>(bel + (long long)i * B, val);
+                }
+            }
         }
     }
 }

@@ -8,6 +8,8 @@ beliefs written per instance), i.e. what SURVEY.md 8d's algorithmic bytes A coun
 belief stored (sparse workspace when that saves memory).
 """
 
+import os
+
 import numpy as np
 
 import jt_workloads as wl
@@ -19,6 +21,23 @@ def make_net(name):
     if name not in nets:
         raise SystemExit("unknown config %s" % name)
     return nets[name]()
+
+
+def largest_batch(config, dtype, cap, step=256, fraction=0.88):
+    """Largest multiple of ``step`` <= ``cap`` whose dense workspace (all beliefs stored) fits in
+    ``fraction`` of the free device memory -- config 5 takes 80 MB per instance, so the chunk size
+    is whatever the GPU holds."""
+    import torch
+    import junctiontree as jt
+    net = make_net(config)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"], order=net.get("order"))
+    evars = list(net.get("evidence_vars", []))
+    plan = tree.plan(evars)
+    engine = tree._engine(plan.sizes, evars, plan.full_sizes)
+    per = engine.dev.workspace_bytes(step, np.dtype(np.float64 if dtype == "f64" else np.float32)) / step
+    free, _ = torch.cuda.mem_get_info()
+    tree.clique_tree._engines.clear()
+    return int(max(step, min(cap, int(fraction * free / per) // step * step)))
 
 
 SR_KERNEL = {"sum_product": "SrSumProduct", "max_product": "SrMaxProduct", "log_sum_exp": "SrLogSumExp",
@@ -94,7 +113,7 @@ class HotPath:
         per step in total and split into init / message passing, and the launches per step."""
         torch = self.torch
         sync = barrier or torch.cuda.synchronize
-        for _ in range(max(warmup, 3)):
+        for _ in range(warmup if os.environ.get("JT_BENCH_SHORT_WARMUP") else max(warmup, 3)):   # (ncu launch lists)
             self.step()
         sync()
         marks = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]

@@ -30,15 +30,26 @@ def main():
     ap.add_argument("--no-beliefs", action="store_true", help="outputs only (what the pipelines run)")
     ap.add_argument("--no-dense", action="store_true", help="keep dense contractions on the projection kernels")
     ap.add_argument("--peak", type=float, default=6451.2, help="HBM GB/s the fractions are quoted against")
+    ap.add_argument("--compare", action="store_true",
+                    help="also time the same step with JT_NO_DENSE in this process (same box, same clocks)")
     args = ap.parse_args()
     hp = bl.HotPath(args.config, args.batch, args.dtype, uniform=not args.no_uniform, evidence=not args.no_evidence,
                     beliefs=not args.no_beliefs, dense=not args.no_dense)
     t = hp.time(args.steps, args.warmup)
+    base_ms = None
+    if args.compare and hp.dense:
+        from junctiontree import _native
+        hp.flags |= _native.JT_NO_DENSE
+        base_ms = hp.time(args.steps, args.warmup)["ms_per_step"]
+        hp.flags &= ~_native.JT_NO_DENSE
+        t2 = hp.time(args.steps, args.warmup)              # and the default once more (drift check)
+        t["ms_per_step_again"] = t2["ms_per_step"]
     A, A_msg, S, S_msg = hp.bytes_per_propagation()
     ms, B = t["ms_per_step"], hp.B
     print(json.dumps({"config": args.config, "batch": B, "dtype": args.dtype, "uniform": hp.uniform,
                       "beliefs": hp.beliefs, "evidence": bool(hp.evars), "dense": hp.dense, "sparse_workspace": hp.sparse,
-                      "ms_per_step": ms, "init_ms": t["init_ms"], "message_passing_ms": t["msg_ms"],
+                      "ms_per_step": ms, "ms_per_step_no_dense": base_ms, "ms_per_step_again": t.get("ms_per_step_again"),
+                      "init_ms": t["init_ms"], "message_passing_ms": t["msg_ms"],
                       "props_per_s": B / ms * 1e3, "launches_per_step": t["launches_per_step"],
                       "scheduled_gb": S * B / 1e9, "scheduled_frac": S * B / ms / 1e6 / args.peak,
                       "algorithmic_gb": A * B / 1e9, "algorithmic_frac": A * B / ms / 1e6 / args.peak}))

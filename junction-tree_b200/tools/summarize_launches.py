@@ -6,7 +6,8 @@ B200_PROFILING.md over `bench.py --steps 2 --warmup 1 --skip-cpu`) per launch an
 
 A step is delimited by two consecutive launches of jt_evidence_kernel.  `--update` rewrites one
 entry of the traffic table that bench.py reads for `roofline.traffic` (DRAM bytes per launch of
-the projection kernel, averaged over the batch projection launches of that step).
+the message-passing kernels -- jt_project_tma_kernel, jt_dense_kernel, jt_beta_kernel, jt_scalar_kernel --
+averaged over those launches of that step).
 """
 import argparse
 import collections
@@ -57,8 +58,9 @@ def main():
         issue = d.get("smsp__issue_active.avg.pct_of_peak_sustained_active")
         total_t += t
         total_b += rb + wb
-        batch = "(1, 1, 1)" not in d["grid"] and d["grid"].split(",")[1].strip() != "1"
-        if "jt_project" in d["name"] and batch:
+        # the batch launches of collect + distribute (the B = 1 launches of the uniform workspace use
+        # jt_project_kernel / jt_project_splitr_kernel / jt_dense_prep_kernel)
+        if any(k in d["name"] for k in ("jt_project_tma_kernel", "jt_dense_kernel", "jt_beta_kernel", "jt_scalar_kernel")):
             proj_t += t
             proj_b += rb + wb
             proj_n += 1

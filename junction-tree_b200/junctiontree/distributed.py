@@ -105,7 +105,13 @@ def pack_marginals(outputs, requested=None):
     import torch
     if requested is None:
         requested = range(len(outputs))
-    cols = [outputs[f].reshape(outputs[f].shape[0], -1) for f in requested]
+    def width(t):               # explicit: reshape(-1) is ambiguous for the empty shard of a small batch
+        n = 1
+        for d in t.shape[1:]:
+            n *= int(d)
+        return n
+
+    cols = [outputs[f].reshape(outputs[f].shape[0], width(outputs[f])) for f in requested]
     return torch.cat(cols, dim=1)
 
 

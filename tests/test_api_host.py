@@ -149,3 +149,40 @@ def test_shape_validation_errors():
         sch.Plan([0, (2, [1])], [["a", "b"], ["b", "c"], ["a"]], {"a": 2, "b": 2, "c": 2})
     with pytest.raises(ValueError):      # observed variable must have effective size 1
         sch.Plan([0], [["a"]], {"a": 2}, [["a"]], [0], ["a"], {"a": 2})
+
+
+def test_two_trees_over_one_clique_graph_get_their_own_plans():
+    """the engine cache is keyed by the tree (root, shape), the separator axis orders,
+    the sizes and the device -- a second JunctionTree over the same CliqueGraph must not reuse the
+    first one's compiled plan."""
+    import attr
+    sizes = {"a": 2, "b": 3, "c": 4, "d": 2, "e": 3}
+    tree = jt.create_junction_tree([["a", "b", "c"], ["b", "c", "d"], ["d", "e"]], sizes)
+    ct = tree.clique_tree
+    assert any(len(s) == 2 for s in tree.separators)
+    assert attr.fields(type(ct)) and type(ct).__attrs_attrs__[0].name == "maxcliques"
+    with pytest.raises(attr.exceptions.FrozenInstanceError):       # frozen, as in the reference (junctiontree.py:120)
+        ct.maxcliques = []
+    plan_a = tree.plan()
+    # the same clique graph, re-rooted at another clique
+    from junctiontree import construction as cons
+    new_root = next(c for c in range(len(ct.maxcliques)) if c != tree.tree[0])
+    tree_b, seps_b = cons.construct_junction_tree(ct.maxcliques, sizes, root=new_root)
+    assert tree_b[0] == new_root != tree.tree[0]
+    other = jt.JunctionTree(tree=tree_b, separators=seps_b, clique_tree=ct)
+    plan_b = other.plan()
+    assert plan_b is not plan_a and plan_b.root == new_root and plan_a.root == tree.tree[0]
+    # separators listed with reversed axis order: a different plan again (other separator shapes)
+    flipped = [list(reversed(s)) for s in tree.separators]
+    third = jt.JunctionTree(tree=tree.tree, separators=flipped, clique_tree=ct)
+    plan_c = third.plan()
+    assert plan_c is not plan_a
+    assert [list(v) for v in plan_c.node_vars[len(ct.maxcliques):]] == flipped
+    assert tree.plan() is plan_a                                    # and the first tree still gets its own
+    # caches live outside the frozen objects and go away with them
+    import gc
+    key = id(ct)
+    assert key in jt.junctiontree._caches
+    del tree, other, third, ct, plan_a, plan_b, plan_c
+    gc.collect()
+    assert key not in jt.junctiontree._caches

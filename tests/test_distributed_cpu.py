@@ -69,3 +69,46 @@ def test_all_gather_rows_world_size_2_gloo(tmp_path, total):
     for rank in range(world):
         ok, refused = np.load(os.path.join(str(tmp_path), "rank%d.npy" % rank))
         assert ok and refused
+
+
+class _FakeTree:
+    """Stands in for a JunctionTree on a machine without a GPU: ``propagate_batch`` returns CPU
+    tensors whose values encode the global instance index, ``plan`` gives the output shapes."""
+
+    class _Plan:
+        fout_shape = [[2], [2, 3]]
+
+    def plan(self, evidence_vars=()):
+        return self._Plan()
+
+    def propagate_batch(self, xs, evidence_vars, evidence, dtype=None, device_output=True):
+        rows = torch.as_tensor(np.asarray(evidence)[:, 0], dtype=torch.float64)
+        return [rows[:, None].repeat(1, 2), rows[:, None, None].repeat(1, 2, 3)]
+
+
+def _sharded_worker(rank, world, port, total, result_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    jdist.init_from_env("gloo")
+    evidence = np.arange(total, dtype=np.int32).reshape(total, 1)      # instance b carries the value b
+    local, gathered = jdist.propagate_sharded(_FakeTree(), [np.ones(2), np.ones((2, 3))], ["v"], evidence)
+    lo, hi = jdist.shard_bounds(total, world, rank)
+    ok = local[0].shape[0] == hi - lo and tuple(gathered.shape) == (total, 8)
+    ok = ok and torch.equal(gathered[:, 0], torch.arange(total, dtype=torch.float64))
+    np.save(os.path.join(result_dir, "sharded%d.npy" % rank), np.array([ok, hi - lo]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [1, 5])
+def test_propagate_sharded_with_fewer_instances_than_ranks(tmp_path, total):
+    """a rank whose shard is empty skips the compute but still joins the all-gather
+    (its peers would block otherwise); world size 2 over gloo."""
+    world, port = 2, _free_port()
+    mp.spawn(_sharded_worker, args=(world, port, total, str(tmp_path)), nprocs=world, join=True)
+    sizes = []
+    for rank in range(world):
+        ok, n = np.load(os.path.join(str(tmp_path), "sharded%d.npy" % rank))
+        assert ok
+        sizes.append(int(n))
+    assert sum(sizes) == total and (total > 1 or 0 in sizes)

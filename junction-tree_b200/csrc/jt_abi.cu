@@ -138,7 +138,7 @@ WorkspaceLayout workspace_layout(const jt_plan* p, int64_t B, int dtype) {
     const size_t uni = p->hdr[JT_H_UNI_ENTRIES] > 0 ? (size_t)(entries + p->scalar_entries) * dtype_size(dtype) : 0;
     // W region of the dense contractions (jt_dense.cu), rebuilt with the uniform workspace
     w.dense_off = w.uni_off + align_up(uni, 256);
-    w.total = w.dense_off + align_up((size_t)p->dense_w_entries * dtype_size(dtype), 256);
+    w.total = w.dense_off + align_up((size_t)p->dense_w_entries * 8, 256);      // W is float64 for both dtypes
     return w;
 }
 

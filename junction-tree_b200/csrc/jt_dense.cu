@@ -105,9 +105,9 @@ __global__ void __launch_bounds__(kThreads) jt_dense_prep_kernel(const PrepArgs 
     const int g = (int)(unit / d.n_it), it = (int)(unit % d.n_it);
     const int i = (it * d.MT + mt) * 8 + (lane >> 2);
     const int k = k4 * 4 + (lane & 3);
-    T* W = static_cast<T*>(a.W) + d.w_off;
+    double* W = static_cast<double*>(a.W) + d.w_off;       // always float64: it feeds the FP64 tensor pipe
     if (i >= d.n_i || k >= d.K) {
-        W[idx] = T(0);
+        W[idx] = 0.0;
         return;
     }
     const int* __restrict__ tab = a.tab;
@@ -118,22 +118,22 @@ __global__ void __launch_bounds__(kThreads) jt_dense_prep_kernel(const PrepArgs 
     const int n_slo = tk->n_slo, n_rlo = tk->n_rlo;
     const int s_hi = s / n_slo, s_lo = s - s_hi * n_slo;
     // uniform messages that depend on s only
-    T scale = T(1);
+    double scale = 1.0;
     for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
         const DMsg* m = a.msgs + j;
-        if (m->uni) scale *= __ldg(uni + m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo));
+        if (m->uni) scale *= (double)__ldg(uni + m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo));
     }
     const long long s_off = tk->src + __ldg(tab + tk->src_shi + s_hi) + __ldg(tab + tk->src_slo + s_lo);
-    T sum = T(0);
+    double sum = 0.0;
     for (int q = 0; q < d.n_q; ++q) {                  // r ascending: the order of the projection kernels
         const int r = __ldg(dtab + d.r_of + k * d.n_q + q);
         const int rh = r / n_rlo, rl = r - rh * n_rlo;
-        T u = __ldg(uni + s_off + __ldg(tab + tk->src_rhi + rh) + __ldg(tab + tk->src_rlo + rl));
+        double u = (double)__ldg(uni + s_off + __ldg(tab + tk->src_rhi + rh) + __ldg(tab + tk->src_rlo + rl));
         for (int j = tk->rmsg_begin; j < tk->rmsg_end; ++j) {
             const DMsg* m = a.msgs + j;
             if (m->uni)
-                u *= __ldg(uni + m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo) +
-                           __ldg(tab + m->b_hi + rh) + __ldg(tab + m->b_lo + rl));
+                u *= (double)__ldg(uni + m->off + __ldg(tab + m->a_hi + s_hi) + __ldg(tab + m->a_lo + s_lo) +
+                                   __ldg(tab + m->b_hi + rh) + __ldg(tab + m->b_lo + rl));
         }
         sum += u;
     }
@@ -149,7 +149,10 @@ __global__ void __launch_bounds__(kThreads) jt_dense_prep_kernel(const PrepArgs 
 // s-only operands in and stores out / bel rows with 16-byte stores.
 template <typename T>
 __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const DenseArgs a) {
-    static_assert(sizeof(T) == 8, "the f64 kernel");
+    // T is the storage type of the workspace rows (float64 or float32); W, the fragments and the
+    // accumulators are float64 either way: the float32 pipeline converts its rows on the way into
+    // the B fragments and rounds once, at the store
+    typedef Pack<T, 2> P2;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bid = blockIdx.x;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
     const long long B = a.B;
     const long long col0 = (long long)blockIdx.y * kDTB;
     const int ncols = (int)(B - col0 < kDTB ? B - col0 : kDTB);
-    const uint32_t row_bytes = (uint32_t)ncols * 8u;
+    const uint32_t row_bytes = (uint32_t)ncols * (uint32_t)sizeof(T);
 
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + kDStages * kDStageBytes);
     const uint32_t ring_u32 = smem_u32(smem);
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
         // ---------------- producer warp ----------------
         const DMsg* m = a.msgs + d.msg;
         const T* origin = static_cast<const T*>(a.work) + m->eoff + col0;
-        const T* wbase = static_cast<const T*>(a.W) + d.w_off;
+        const double* wbase = static_cast<const double*>(a.W) + d.w_off;
         const long long unit_w = (long long)d.n_k4 * d.MT * 32;
         int stage = 0;
         uint32_t phase = 0;
@@ -265,20 +268,21 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
 
     // the [8 MT x 32] accumulator tile of one unit
     struct Acc {
-        T v[4][kDNT][2];
+        double v[4][kDNT][2];
     };
     auto zero = [](Acc& c) {
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < kDNT; ++nt) c.v[mt][nt][0] = c.v[mt][nt][1] = T(0);
+            for (int nt = 0; nt < kDNT; ++nt) c.v[mt][nt][0] = c.v[mt][nt][1] = 0.0;
     };
     // nk4 k-steps: rows `rows` (4 per step) times W fragments `wt` (MT per step)
-    auto steps = [&](Acc& c, const unsigned char* rows, const T* wt, int nk4) {
+    auto steps = [&](Acc& c, const unsigned char* rows, const double* wt, int nk4) {
         for (int q = 0; q < nk4; ++q) {
-            T bf[kDNT];
+            double bf[kDNT];
 #pragma unroll
-            for (int nt = 0; nt < kDNT; ++nt) bf[nt] = *reinterpret_cast<const T*>(rows + q * 4 * kDRowPitch + nt * 64);
+            for (int nt = 0; nt < kDNT; ++nt)
+                bf[nt] = (double)*reinterpret_cast<const T*>(rows + q * 4 * kDRowPitch + nt * 8 * (int)sizeof(T));
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) {
                 if (mt < MT) {
@@ -312,23 +316,23 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
 #pragma unroll
         for (int m0 = 0; m0 < 4; m0 += 2) {
             if (m0 >= MT) break;
-            double2 ow[2][kDNT];
-            T own_u[2];
+            P2 ow[2][kDNT];
+            double own_u[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int mt = m0 + h, s = ur.s[mt];
-                own_u[h] = T(1);
+                own_u[h] = 1.0;
 #pragma unroll
-                for (int nt = 0; nt < kDNT; ++nt) ow[h][nt] = make_double2(1.0, 1.0);
+                for (int nt = 0; nt < kDNT; ++nt) ow[h][nt].v[0] = ow[h][nt].v[1] = T(1);
                 if (s < 0) continue;
                 if (wbel && has_own) {
                     if (tflags & JT_TF_OWN_UNIFORM) {
-                        own_u[h] = __ldg(uni + tk->own + s);
+                        own_u[h] = (double)__ldg(uni + tk->own + s);
                     } else {
 #pragma unroll
                         for (int nt = 0; nt < kDNT; ++nt) {
                             const long long col = ccol + nt * 8;
-                            if (col < B) ow[h][nt] = *reinterpret_cast<const double2*>(work + (tk->own + s) * B + col);
+                            if (col < B) ow[h][nt] = *reinterpret_cast<const P2*>(work + (tk->own + s) * B + col);
                         }
                     }
                 }
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
                 for (int nt = 0; nt < kDNT; ++nt) {
                     const long long col = ccol + nt * 8;
                     if (col < B) {                               // B is even: both columns or none
-                        T v0 = c.v[mt][nt][0], v1 = c.v[mt][nt][1];
+                        double v0 = c.v[mt][nt][0], v1 = c.v[mt][nt][1];
                         if (s_rows) {
                             const int s_hi = s / tk->n_slo, s_lo = s - s_hi * tk->n_slo;
                             for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
@@ -349,16 +353,20 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
                                 if (m->uni) continue;            // folded into W
                                 const T* r = work + m->eoff +
                                              (m->off + __ldg(a.tab + m->a_hi + s_hi) + __ldg(a.tab + m->a_lo + s_lo)) * B + col;
-                                const double2 x = *reinterpret_cast<const double2*>(r);
-                                v0 *= x.x;
-                                v1 *= x.y;
+                                const P2 x = *reinterpret_cast<const P2*>(r);
+                                v0 *= (double)x.v[0];
+                                v1 *= (double)x.v[1];
                             }
                         }
-                        *reinterpret_cast<double2*>(obase + (long long)s * B + col) = make_double2(v0, v1);
+                        P2 o;
+                        o.v[0] = (T)v0;
+                        o.v[1] = (T)v1;
+                        *reinterpret_cast<P2*>(obase + (long long)s * B + col) = o;
                         if (wbel) {
-                            v0 *= ow[h][nt].x * own_u[h];
-                            v1 *= ow[h][nt].y * own_u[h];
-                            *reinterpret_cast<double2*>(work + (tk->bel + s) * B + col) = make_double2(v0, v1);
+                            // from the stored (rounded) message, as the projection kernels form it
+                            o.v[0] = (T)((double)o.v[0] * (double)ow[h][nt].v[0] * own_u[h]);
+                            o.v[1] = (T)((double)o.v[1] * (double)ow[h][nt].v[1] * own_u[h]);
+                            *reinterpret_cast<P2*>(work + (tk->bel + s) * B + col) = o;
                         }
                     }
                 }
@@ -376,7 +384,7 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
             phase ^= 1;
         }
     };
-    const int frag_off = (lane & 3) * kDRowPitch + bcol * 8;         // B fragment of this thread inside a stage
+    const int frag_off = (lane & 3) * kDRowPitch + bcol * (int)sizeof(T);   // B fragment of this thread inside a stage
     if (d.ups > 1) {
         // short contractions: `ups` units per stage, one after the other
         const int kpad = d.n_k4 * 4;
@@ -385,7 +393,7 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
             const int nu = (int)(u1 - u < d.ups ? u1 - u : d.ups);
             mbar_wait(full_u32 + 8 * stage, phase);
             const unsigned char* st = smem + stage * kDStageBytes;
-            const T* wt = reinterpret_cast<const T*>(st + kDKC * kDRowPitch) + lane;
+            const double* wt = reinterpret_cast<const double*>(st + kDKC * kDRowPitch) + lane;
             for (int j = 0; j < nu; ++j) {
                 Acc c;
                 zero(c);
@@ -408,7 +416,7 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
             const int nk4 = d.n_k4 - ch * 4 < 4 ? d.n_k4 - ch * 4 : 4;
             mbar_wait(full_u32 + 8 * stage, phase);
             const unsigned char* st = smem + stage * kDStageBytes;
-            steps(c, st + frag_off, reinterpret_cast<const T*>(st + kDKC * kDRowPitch) + lane, nk4);
+            steps(c, st + frag_off, reinterpret_cast<const double*>(st + kDKC * kDRowPitch) + lane, nk4);
             release();
         }
         epilogue(c, ur);
@@ -835,7 +843,7 @@ bool jt_tma_path(int64_t B, int dtype) {
 }
 
 bool jt_dense_enabled(const jt_plan* p, int64_t B, int dtype, int flags) {
-    return p->accel && dense_env_enabled() && dtype == JT_F64 && (flags & JT_SR_MASK) == JT_SR_SUM_PRODUCT &&
+    return p->accel && dense_env_enabled() && (flags & JT_SR_MASK) == JT_SR_SUM_PRODUCT &&
            (flags & JT_UNIFORM) && !(flags & JT_NO_DENSE) && jt_tma_path(B, dtype);
 }
 
@@ -852,7 +860,6 @@ bool jt_beta_enabled(const jt_plan* p, int64_t B, int dtype, int flags) {
 }
 
 int jt_dense_prepare(const jt_plan* p, int which, int dtype, const void* uni_ws, void* w_region, cudaStream_t stream) {
-    if (dtype != JT_F64) return jt_fail(JT_ERR_INVALID, "dense contractions are float64 only");
     const std::vector<int>& v = p->dense_prep_prefix[which];
     const int n = (int)(v.size() - 1) / 2;
     if (n <= 0) return JT_OK;
@@ -868,7 +875,8 @@ int jt_dense_prepare(const jt_plan* p, int which, int dtype, const void* uni_ws,
     a.W = w_region;
     const int blocks = v.back();
     if (blocks <= 0) return JT_OK;
-    jt_dense_prep_kernel<double><<<(unsigned)blocks, kThreads, 0, stream>>>(a);
+    if (dtype == JT_F64) jt_dense_prep_kernel<double><<<(unsigned)blocks, kThreads, 0, stream>>>(a);
+    else jt_dense_prep_kernel<float><<<(unsigned)blocks, kThreads, 0, stream>>>(a);
     jt_g_launches.fetch_add(1, std::memory_order_relaxed);
     JT_CUDA(cudaGetLastError());
     return JT_OK;
@@ -876,7 +884,6 @@ int jt_dense_prepare(const jt_plan* p, int which, int dtype, const void* uni_ws,
 
 int jt_dense_launch(const jt_plan* p, const jt_plan::Launch& L, void* work, const void* uni_ws, const void* w_region,
                     void* fout, int64_t B, int dtype, int flags, cudaStream_t stream) {
-    if (dtype != JT_F64) return jt_fail(JT_ERR_INVALID, "dense contractions are float64 only");
     const int n = L.dense_end - L.dense_begin;
     if (n <= 0) return JT_OK;
     const long long tiles = (B + kDTB - 1) / kDTB;
@@ -891,6 +898,7 @@ int jt_dense_launch(const jt_plan* p, const jt_plan::Launch& L, void* work, cons
         return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, tiles);
     if (!p->dense_attr_set) {
         JT_CUDA(cudaFuncSetAttribute(jt_dense_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
+        JT_CUDA(cudaFuncSetAttribute(jt_dense_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
         p->dense_attr_set = true;
     }
     DenseArgs a;
@@ -907,7 +915,10 @@ int jt_dense_launch(const jt_plan* p, const jt_plan::Launch& L, void* work, cons
     a.fout = fout;
     a.B = B;
     a.flags = flags;
-    jt_dense_kernel<double><<<dim3((unsigned)gx, (unsigned)tiles, 1), (kDWarps + 1) * 32, kDSmem, stream>>>(a);
+    if (dtype == JT_F64)
+        jt_dense_kernel<double><<<dim3((unsigned)gx, (unsigned)tiles, 1), (kDWarps + 1) * 32, kDSmem, stream>>>(a);
+    else
+        jt_dense_kernel<float><<<dim3((unsigned)gx, (unsigned)tiles, 1), (kDWarps + 1) * 32, kDSmem, stream>>>(a);
     jt_g_launches.fetch_add(1, std::memory_order_relaxed);
     JT_CUDA(cudaGetLastError());
     return JT_OK;

@@ -1,8 +1,16 @@
-O=gpurun_out/r2o
+O=gpurun_out/r2p
 mkdir -p $O
+(time timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8) > $O/gpu_tests.txt 2>&1
+cat $O/gpu_tests.txt
 P="python junction-tree_b200/tools/prof_step.py"
-JT_NVTX=1 JT_BENCH_SHORT_WARMUP=1 timeout 600 ncu --nvtx --nvtx-include "jt collect level 28/" --set full --clock-control none --import-source on -k regex:jt_dense_kernel -c 2 -f -o $O/dense_dag500_l28 $P --config dag500 --batch 1024 --steps 1 --warmup 1 > $O/ncu1.log 2>&1
-tail -3 $O/ncu1.log
-JT_NVTX=1 JT_BENCH_SHORT_WARMUP=1 timeout 600 ncu --nvtx --nvtx-include "jt collect level 29/" --set full --clock-control none --import-source on -k regex:jt_dense_kernel -c 2 -f -o $O/dense_dag500_l29 $P --config dag500 --batch 1024 --steps 1 --warmup 1 > $O/ncu2.log 2>&1
-tail -3 $O/ncu2.log
-ls -la $O
+timeout 300 $P --config large_state_tree --batch 512 --dtype f32 --compare >> $O/steps.jsonl 2>> $O/steps.err
+timeout 300 $P --config large_state_tree --batch 512 --dtype f64 --compare >> $O/steps.jsonl 2>> $O/steps.err
+timeout 300 $P --config dag37 --batch 65536 --dtype f32 --compare >> $O/steps.jsonl 2>> $O/steps.err
+timeout 300 $P --config dag500 --batch 2048 --dtype f32 --compare >> $O/steps.jsonl 2>> $O/steps.err
+python - <<'PY'
+import json
+for line in open("gpurun_out/r2p/steps.jsonl"):
+    d=json.loads(line)
+    print("  %-18s %s B=%-6d beliefs=%-5s ms=%.3f again=%.3f no_dense=%.3f  frac=%.3f launches=%.0f"%(d["config"],d["dtype"],d["batch"],d["beliefs"],d["ms_per_step"],d["ms_per_step_again"] or 0,d["ms_per_step_no_dense"] or 0,d["scheduled_frac"],d["launches_per_step"]))
+PY
+tail -5 $O/steps.err

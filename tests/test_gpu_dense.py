@@ -118,3 +118,38 @@ def test_config4_dense_full_size():
     del outs_d, nodes_d, outs_p, nodes_p
     tree.clique_tree._engines.clear()
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("B", [256, 520])
+@pytest.mark.parametrize("name,make", NETS, ids=[n for n, _ in NETS])
+def test_dense_float32_storage(name, make, B):
+    """The float32 pipeline: rows are stored in float32, the contractions still run on the FP64
+    tensor pipe (converted on the way into the fragments, rounded once at the store): <= 1e-5
+    against the float64 oracle on float32-rounded inputs, and against the projection kernels."""
+    import junctiontree as jt
+    from helpers import RTOL_F32
+    net = make()
+    vals32 = [np.asarray(v, np.float32) for v in net["values"]]
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    evars = net["evidence_vars"]
+    ev = wl.draw_evidence(net, B)
+    l0 = _native.launch_count()
+    outs_d, nodes_d = tree.propagate_batch(vals32, evars, ev, nodes=True, dense=True)
+    l1 = _native.launch_count()
+    outs_p, nodes_p = tree.propagate_batch(vals32, evars, ev, nodes=True, dense=False)
+    l2 = _native.launch_count()
+    assert l1 - l0 > l2 - l1, "dense launches did not run"
+    assert all(a.dtype == np.float32 for a in outs_d)
+    for k, (a, b) in enumerate(zip(list(outs_d) + list(nodes_d), list(outs_p) + list(nodes_p))):
+        assert_close(a, b, RTOL_F32, "%s f32 entry %d dense vs projection" % (name, k))
+    net64 = dict(net)
+    net64["values"] = [np.asarray(v, np.float64) for v in vals32]
+    want_f, want_n = _oracle(tree, net64, evars, ev[:3], 3)
+    for k, w in enumerate(want_n):
+        assert_close(nodes_d[k][:3], w, RTOL_F32, "f32 node %d" % k)
+    for f, w in enumerate(want_f):
+        assert_close(outs_d[f][:3], w, RTOL_F32, "f32 factor %d" % f)
+    # and the pipelines' mode
+    o_d = tree.propagate_batch(vals32, evars, ev, dense=True)
+    for f, w in enumerate(want_f):
+        assert_close(o_d[f][:3], w, RTOL_F32, "f32 outputs-only factor %d" % f)

@@ -10,6 +10,8 @@ import sys
 
 import numpy as np
 
+os.environ.setdefault("JT_BETA_MIN_MB", "0")      # run jt_beta_kernel on these small launches too
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 for p in (ROOT, os.path.join(ROOT, "junction-tree_b200")):
@@ -59,6 +61,29 @@ def main():
         print("ok", name, "with soft evidence")
     marg, log_z = tree.marginals_batch(net["values"], None, net["evidence_vars"], ev, likelihoods=lik)
     assert np.all(np.isfinite(log_z))
+    # round 2: the accelerated uniform-mode kernels (jt_dense_kernel incl. multi-unit stages and the
+    # float32-storage form, jt_dense_prep_kernel, jt_scalar_kernel, jt_beta_kernel on its side
+    # stream, level fork / join) against the projection kernels and the oracle
+    for make in (lambda: wl.large_state_tree((8, 12, 16, 8, 12, 16)), lambda: wl.random_dag(60, 3, 2, 5, 8, 3)):
+        net2 = make()
+        tree2 = jt.create_junction_tree(net2["factors"], net2["sizes"])
+        ct2 = tree2.clique_tree
+        for B, dtype in ((256, np.float64), (1000, np.float64), (520, np.float32)):
+            ev2 = wl.draw_evidence(net2, B)
+            vals = [np.asarray(v, dtype) for v in net2["values"]]
+            outs, nodes = tree2.propagate_batch(vals, net2["evidence_vars"], ev2, nodes=True, dense=True)
+            outs_p, nodes_p = tree2.propagate_batch(vals, net2["evidence_vars"], ev2, nodes=True, dense=False)
+            rtol = 1e-12 if dtype == np.float64 else 1e-5
+            for g, w in zip(list(outs) + list(nodes), list(outs_p) + list(nodes_p)):
+                np.testing.assert_allclose(g, w, rtol=rtol)
+            want_f, want_n = ref_fixed.propagate_batch(tree2.tree, tree2.separators, ct2.maxcliques,
+                                                       ct2.factor_to_maxclique, net2["factors"], net2["sizes"],
+                                                       [np.asarray(v, np.float64) for v in vals],
+                                                       net2["evidence_vars"], ev2[:2], n=2)
+            for g, w in zip(list(outs) + list(nodes), list(want_f) + list(want_n)):
+                np.testing.assert_allclose(g[:2], w, rtol=rtol)
+            tree2.propagate_batch(vals, net2["evidence_vars"], ev2, dense=True)        # outputs only
+            print("ok accelerated", net2["name"], B, np.dtype(dtype).name)
     print("done")
 
 

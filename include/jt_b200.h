@@ -217,6 +217,15 @@ void jt_workspace_sparse_destroy(jt_sparse_ws* ws);
  *                 per-instance evidence variables.  States outside [0, card) are clamped and
  *                 counted; see jt_evidence_errors.
  * flags         : JT_UNIFORM must be passed consistently to init, collect and distribute.
+ *
+ * Streams: every stage call enqueues on `stream` and returns without synchronising.  In uniform
+ * mode a call may run independent kernels of one schedule level side by side, the uniform (B = 1)
+ * half of the distribute pass beside the instance collect (jt_collect enqueues it; jt_distribute on
+ * the same thread, plan and workspace finds it done, any other caller recomputes it) and the clique
+ * beliefs of shared cliques beside the message chain -- on auxiliary streams that belong to the
+ * calling thread and are joined back into `stream` (event wait) before the call returns.  So a stage
+ * is complete exactly when `stream` has drained, calls from several host threads never share a
+ * stream or an event, and the calls stay capturable into a CUDA graph (fork / join pattern).
  */
 int jt_init(jt_plan* plan, const void* factor_tables, int factors_batched, const int32_t* evidence,
             int64_t B, int dtype, void* workspace, int flags, void* stream);

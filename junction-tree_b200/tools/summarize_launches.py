@@ -42,6 +42,13 @@ def main():
     launches = load(args.csv)
     ids = list(launches)
     marks = [i for i in ids if "jt_evidence_kernel" in launches[i]["name"]]
+    if not marks:       # no evidence variables: a step starts with the first init launch after a non-init one
+        prev_init = False
+        for i in ids:
+            is_init = "jt_init" in launches[i]["name"]
+            if is_init and not prev_init:
+                marks.append(i)
+            prev_init = is_init
     lo = marks[args.step]
     hi = marks[args.step + 1] if args.step + 1 < len(marks) else ids[-1] + 1
     print("| id | kernel | grid | time (us) | dram read (GB) | dram write (GB) | dram GB/s | issue active |")

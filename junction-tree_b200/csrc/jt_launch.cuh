@@ -26,14 +26,6 @@ inline bool tma_enabled() {   // JT_DISABLE_TMA=1 forces the LDG kernel (debuggi
     return enabled == 1;
 }
 
-inline bool tma_small_vpt() {
-    static const int on = [] {
-        const char* e = getenv("JT_TMA_SMALL_VPT");
-        return (e && e[0] == '1') ? 1 : 0;
-    }();
-    return on == 1;
-}
-
 inline int tma_vpt_override() {   // JT_TMA_VPT=1|2 overrides the vectors-per-thread choice (A-B timing)
     static const int vpt = [] {
         const char* e = getenv("JT_TMA_VPT");
@@ -96,10 +88,10 @@ struct Launcher {
         // instructions per byte of the consumers
         const int forced = tma_vpt_override();
         const bool two = forced ? forced == 2 : a.Bv >= 512;
-        if (two && ct == 256 && a.Bv >= 512) return launch_tma_vpt<T, 2>(p, L, a, ct, variant, stream);
-        // narrower batches: the same tile with half the consumer threads, two vectors each
-        // (JT_TMA_SMALL_VPT=1; experiment)
-        if (tma_small_vpt() && a.Bv < 512) return launch_tma_vpt<T, 2>(p, L, a, ct / 2, variant, stream);
+        // (measured and rejected, r02: the same tile with half the consumer threads and two vectors each
+        // for batches below 512 vectors -- Ising 16x16 uniform 38.0 -> 36.9 ms, but per instance 82.4 -> 85.4
+        // and config 4 per instance 7.33 -> 8.00 ms)
+        if (two && ct == 256) return launch_tma_vpt<T, 2>(p, L, a, ct, variant, stream);
         return launch_tma_vpt<T, 1>(p, L, a, ct, variant, stream);
     }
 

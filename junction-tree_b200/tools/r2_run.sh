@@ -1,16 +1,21 @@
-O=gpurun_out/r2p
+O=gpurun_out/r2q
 mkdir -p $O
-(time timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8) > $O/gpu_tests.txt 2>&1
-cat $O/gpu_tests.txt
 P="python junction-tree_b200/tools/prof_step.py"
-timeout 300 $P --config large_state_tree --batch 512 --dtype f32 --compare >> $O/steps.jsonl 2>> $O/steps.err
-timeout 300 $P --config large_state_tree --batch 512 --dtype f64 --compare >> $O/steps.jsonl 2>> $O/steps.err
-timeout 300 $P --config dag37 --batch 65536 --dtype f32 --compare >> $O/steps.jsonl 2>> $O/steps.err
-timeout 300 $P --config dag500 --batch 2048 --dtype f32 --compare >> $O/steps.jsonl 2>> $O/steps.err
+for cfg in "ising16 256 f64 --compare" "ising16 256 f64 --no-uniform" "large_state_tree 512 f64 --no-uniform" "large_state_tree 512 f32 --no-uniform" "large_state_tree 512 f32 --compare" "dag500 1024 f64 --compare"; do
+  set -- $cfg
+  timeout 300 $P --config $1 --batch $2 --dtype $3 $4 >> $O/steps.jsonl 2>> $O/steps.err
+  JT_TMA_SMALL_VPT=1 timeout 300 $P --config $1 --batch $2 --dtype $3 $4 >> $O/steps_vpt.jsonl 2>> $O/steps.err
+done
+for cfg in "dag500 2048" "ising16 256" "large_state_tree 512"; do
+  set -- $cfg
+  timeout 300 $P --config $1 --batch $2 --uniform-valid >> $O/steps_uv.jsonl 2>> $O/steps.err
+done
 python - <<'PY'
 import json
-for line in open("gpurun_out/r2p/steps.jsonl"):
-    d=json.loads(line)
-    print("  %-18s %s B=%-6d beliefs=%-5s ms=%.3f again=%.3f no_dense=%.3f  frac=%.3f launches=%.0f"%(d["config"],d["dtype"],d["batch"],d["beliefs"],d["ms_per_step"],d["ms_per_step_again"] or 0,d["ms_per_step_no_dense"] or 0,d["scheduled_frac"],d["launches_per_step"]))
+for f in ("steps","steps_vpt","steps_uv"):
+    print(f)
+    for line in open("gpurun_out/r2q/%s.jsonl"%f):
+        d=json.loads(line)
+        print("  %-18s %s B=%-6d uniform=%-5s ms=%.3f no_dense=%s uniform_valid=%s frac=%.3f"%(d["config"],d["dtype"],d["batch"],d["uniform"],d["ms_per_step"],d.get("ms_per_step_no_dense"),d.get("ms_uniform_valid"),d["scheduled_frac"]))
 PY
 tail -5 $O/steps.err

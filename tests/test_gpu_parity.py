@@ -491,9 +491,12 @@ def test_marginals_batch_output_stage():
         for v, tr in zip(free, truth):
             assert_close(marg[v][b], tr / tr.sum(), 1e-11, "P(%s | e) instance %d" % (v, b))
             assert_close(log_z[b], np.log(tr.sum()), 1e-11, "log Z instance %d" % b)
-    raw, _ = tree.marginals_batch(net["values"], free[:3], evars, ev, normalize=False)
+    raw, raw_log_z = tree.marginals_batch(net["values"], free[:3], evars, ev, normalize=False)
     for v in free[:3]:
         assert_close(raw[v] / raw[v].sum(axis=1, keepdims=True), marg[v], 1e-12, v)
+    # log Z alone (jt_normalize with JT_LOGZ_ONLY): the outputs stay unnormalised, log Z is the same
+    assert_close(raw_log_z, log_z, 1e-12, "log Z without normalisation")
+    assert_close(np.log(raw[free[0]].sum(axis=1)), log_z, 1e-12, "unnormalised totals")
 
 
 @pytest.mark.parametrize("seed", range(24))

@@ -1,22 +1,19 @@
-O=gpurun_out/r2t
+O=gpurun_out/r02
 mkdir -p $O
-P="python junction-tree_b200/tools/prof_step.py"
-for blk in 8 4 16 32 64; do
-for cfg in "large_state_tree 512 f64" "dag500 2048 f64"; do
-  set -- $cfg
-  JT_BETA_BLOCK=$blk timeout 300 $P --config $1 --batch $2 --dtype $3 >> $O/steps_$blk.jsonl 2>> $O/steps.err
-done
-done
-JT_BETA_MIN_MB=256 timeout 300 $P --config dag500 --batch 2048 >> $O/steps_min256.jsonl 2>> $O/steps.err
-JT_BETA_MIN_MB=256 timeout 300 $P --config ising16 --batch 256 --compare >> $O/steps_min256.jsonl 2>> $O/steps.err
-JT_BETA_MIN_MB=64 timeout 300 $P --config ising16 --batch 256 --compare >> $O/steps_min64.jsonl 2>> $O/steps.err
-JT_BETA_MIN_MB=64 timeout 300 $P --config dag500 --batch 2048 >> $O/steps_min64.jsonl 2>> $O/steps.err
+(time timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) > $O/gpu_tests.txt 2>&1
+cat $O/gpu_tests.txt
+python bench.py --steps 10 --warmup 3 > $O/r02_bench_uniform.json 2> $O/bench_uniform.err
+python bench.py --steps 10 --warmup 3 --no-uniform --configs none > $O/r02_bench_perinstance.json 2> $O/bench_perinstance.err
+tail -2 $O/bench_uniform.err
 python - <<'PY'
-import json,glob
-for f in sorted(glob.glob("gpurun_out/r2t/steps_*.jsonl")):
-    print(f)
-    for line in open(f):
-        d=json.loads(line)
-        print("  %-18s %s B=%-6d ms=%.3f no_dense=%s frac=%.3f"%(d["config"],d["dtype"],d["batch"],d["ms_per_step"],d.get("ms_per_step_no_dense"),d["scheduled_frac"]))
+import json
+d=json.loads(open("gpurun_out/r02/r02_bench_uniform.json").read())
+print("value %.0f ms %.3f frac %.3f traffic %s e2e %.0f e2e_marg %.0f"%(d["value"],d["ms_per_step"],d["roofline"]["frac"],d["roofline"]["traffic"],d["e2e"]["value"],d["e2e_marginals"]["value"]))
+for e in d["configs"]:
+    print("  ", e["config"], e.get("batch_per_gpu"), e.get("dtype"), e.get("mode"), e.get("beliefs_stored"), round(e.get("ms_per_step",0),3), round(e["value"]), e.get("frac") and round(e["frac"],3))
 PY
-tail -5 $O/steps.err
+P="python junction-tree_b200/tools/prof_step.py"
+NCU="ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none --csv"
+JT_BENCH_SHORT_WARMUP=1 timeout 1200 $NCU --log-file $O/r02_launches_dag500_uniform.csv $P --config dag500 --batch 2048 --steps 2 --warmup 1 > /dev/null 2>&1
+JT_BENCH_SHORT_WARMUP=1 timeout 600 $NCU --log-file $O/r02_launches_large_state_tree_f64_uniform.csv $P --config large_state_tree --batch 512 --steps 2 --warmup 1 > /dev/null 2>&1
+ls -la $O | tail -8

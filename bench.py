@@ -405,6 +405,10 @@ def run_gpu(args):
             k += 1
 
     value = B * world / (ms_per_step / 1e3)
+    # the main line's own entry of the `configs` block: max-over-ranks time, whole-job value like the others
+    scale = ms_per_step / main_entry["ms_per_step"]
+    main_entry.update(ms_per_step=ms_per_step, value=value, frac=main_entry["frac"] / scale,
+                      frac_algorithmic=main_entry["frac_algorithmic"] / scale)
     msg_ms_per_launch = msg_ms / max(msg_launches, 1)
     scheduled = S_msg * B / (msg_ms / 1e3) / 1e9            # GB/s this schedule moves in the message-passing launches
     algorithmic = A_msg * B / (msg_ms / 1e3) / 1e9

@@ -1,19 +1,17 @@
-O=gpurun_out/r02
-mkdir -p $O
-(time timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) > $O/gpu_tests.txt 2>&1
-cat $O/gpu_tests.txt
-python bench.py --steps 10 --warmup 3 > $O/r02_bench_uniform.json 2> $O/bench_uniform.err
-python bench.py --steps 10 --warmup 3 --no-uniform --configs none > $O/r02_bench_perinstance.json 2> $O/bench_perinstance.err
-tail -2 $O/bench_uniform.err
+mkdir -p gpurun_out/r2u
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r2u/bench_8gpu.json 2> gpurun_out/r2u/bench_8gpu.err
+tail -3 gpurun_out/r2u/bench_8gpu.err
 python - <<'PY'
 import json
-d=json.loads(open("gpurun_out/r02/r02_bench_uniform.json").read())
-print("value %.0f ms %.3f frac %.3f traffic %s e2e %.0f e2e_marg %.0f"%(d["value"],d["ms_per_step"],d["roofline"]["frac"],d["roofline"]["traffic"],d["e2e"]["value"],d["e2e_marginals"]["value"]))
-for e in d["configs"]:
-    print("  ", e["config"], e.get("batch_per_gpu"), e.get("dtype"), e.get("mode"), e.get("beliefs_stored"), round(e.get("ms_per_step",0),3), round(e["value"]), e.get("frac") and round(e["frac"],3))
+d=json.loads(open("gpurun_out/r2u/bench_8gpu.json").read())
+print(d["value"], d["n_gpus"], d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["d2h_gbs_per_gpu"], d["e2e"]["host_ceiling"], "marg", d["e2e_marginals"]["value"])
+print(d["all_gather"])
+print([(e["config"], e.get("mode"), round(e.get("ms_per_step",0),2), round(e["value"])) for e in d["configs"]])
 PY
-P="python junction-tree_b200/tools/prof_step.py"
-NCU="ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none --csv"
-JT_BENCH_SHORT_WARMUP=1 timeout 1200 $NCU --log-file $O/r02_launches_dag500_uniform.csv $P --config dag500 --batch 2048 --steps 2 --warmup 1 > /dev/null 2>&1
-JT_BENCH_SHORT_WARMUP=1 timeout 600 $NCU --log-file $O/r02_launches_large_state_tree_f64_uniform.csv $P --config large_state_tree --batch 512 --steps 2 --warmup 1 > /dev/null 2>&1
-ls -la $O | tail -8
+nvidia-smi topo -m 2>/dev/null | head -14
+python -c "
+import os; print('cpus', os.cpu_count(), 'affinity', len(os.sched_getaffinity(0)))
+for n in range(4):
+    p='/sys/devices/system/node/node%d/cpulist'%n
+    if os.path.exists(p): print(n, open(p).read().strip())
+"

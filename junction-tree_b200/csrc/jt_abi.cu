@@ -250,6 +250,14 @@ double beta_min_bytes() {           // JT_BETA_MIN_MB: belief bytes of a launch 
     return v;
 }
 
+long long beta_max_batch() {        // JT_BETA_MAX_B: largest batch whose beliefs are split off (default 4096: rows of 32 KB)
+    static const long long v = [] {
+        const char* e = getenv("JT_BETA_MAX_B");
+        return (e && e[0]) ? atoll(e) : 4096LL;
+    }();
+    return v;
+}
+
 bool level_fork_enabled() {         // JT_LEVEL_STREAMS=0: the kernels of a level one after the other (A-B timing)
     static const int on = [] {
         const char* e = getenv("JT_LEVEL_STREAMS");
@@ -286,7 +294,7 @@ int run_launch(jt_plan* p, const jt_plan::Launch& L, const KArgs& a_in, int dtyp
     // Ising 16x16 at B = 128 (0.13 GB per launch) 22.2 -> 22.9 ms.  With batch rows of 64 KB and more the
     // projection tasks already write at that rate (two vectors per thread), so nothing is gained.
     split = split && L.phase == JT_PHASE_DIST_MAIN && L.beta_n > 0 &&
-            (double)L.beta_items * (double)a.B * (dtype == JT_F64 ? 8.0 : 4.0) >= beta_min_bytes() && a.B <= 4096;
+            (double)L.beta_items * (double)a.B * (dtype == JT_F64 ? 8.0 : 4.0) >= beta_min_bytes() && a.B <= beta_max_batch();
     // dense contractions and scalar tasks leave the projection launch together (one reduced task set)
     const bool accel = w_region && (L.dense_end > L.dense_begin || L.scalar_n > 0) &&
                        (L.phase != JT_PHASE_DIST_MAIN || split);

@@ -439,6 +439,15 @@ bool beta_walk_blocks() {   // JT_BETA_WALK=items: the plain s-major walk (A-B t
     return on == 1;
 }
 
+long long dense_min_gain() {   // JT_DENSE_MIN_GAIN: rows saved (items / rows moved) from which a task becomes a contraction (default 3)
+    static const long long v = [] {
+        const char* e = getenv("JT_DENSE_MIN_GAIN");
+        const long long x = e ? atoll(e) : 0;
+        return x >= 1 ? x : 3LL;
+    }();
+    return v;
+}
+
 int beta_block() {          // JT_BETA_BLOCK: consecutive clique entries per block of the walk (default 8)
     static const int n = [] {
         const char* e = getenv("JT_BETA_BLOCK");
@@ -528,7 +537,7 @@ int jt_dense_build(jt_plan* p) {
                 // group loads its K rows once per i-tile and every output row is written once
                 const long long items = (long long)k.n_s * k.n_r;
                 const long long moved = (long long)n_g * d.n_it * K + k.n_s;
-                if ((long long)n_i * K < 16 || items < 3 * moved) continue;
+                if ((long long)n_i * K < 16 || items < dense_min_gain() * moved) continue;
                 d.w_size = (long long)n_g * d.n_it * d.n_k4 * d.MT * 32;
                 if (d.w_size > (1LL << 40) || p->dtab.size() + (size_t)k.n_s + n_g + K + k.n_r > 2000000000ULL) continue;
                 d.w_off = p->dense_w_entries;

@@ -1,17 +1,18 @@
-mkdir -p gpurun_out/r2u
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r2u/bench_8gpu.json 2> gpurun_out/r2u/bench_8gpu.err
-tail -3 gpurun_out/r2u/bench_8gpu.err
+O=gpurun_out/r2v
+mkdir -p $O
+P="python junction-tree_b200/tools/prof_step.py"
+timeout 300 $P --config dag37 --batch 65536 --compare >> $O/steps.jsonl 2>> $O/steps.err
+JT_BETA_MAX_B=1000000 timeout 300 $P --config dag37 --batch 65536 --compare >> $O/steps_maxb.jsonl 2>> $O/steps.err
+JT_DENSE_MIN_GAIN=2 timeout 300 $P --config dag37 --batch 65536 --compare >> $O/steps_gain2.jsonl 2>> $O/steps.err
+JT_BETA_MAX_B=1000000 JT_DENSE_MIN_GAIN=2 timeout 300 $P --config dag37 --batch 65536 --compare >> $O/steps_both.jsonl 2>> $O/steps.err
+JT_DENSE_MIN_GAIN=2 timeout 300 $P --config dag500 --batch 2048 >> $O/steps_gain2.jsonl 2>> $O/steps.err
+JT_DENSE_MIN_GAIN=4 timeout 300 $P --config dag500 --batch 2048 >> $O/steps_gain4.jsonl 2>> $O/steps.err
 python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/r2u/bench_8gpu.json").read())
-print(d["value"], d["n_gpus"], d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["d2h_gbs_per_gpu"], d["e2e"]["host_ceiling"], "marg", d["e2e_marginals"]["value"])
-print(d["all_gather"])
-print([(e["config"], e.get("mode"), round(e.get("ms_per_step",0),2), round(e["value"])) for e in d["configs"]])
+import json,glob
+for f in sorted(glob.glob("gpurun_out/r2v/steps*.jsonl")):
+    print(f)
+    for line in open(f):
+        d=json.loads(line)
+        print("  %-18s %s B=%-6d ms=%.3f no_dense=%s frac=%.3f"%(d["config"],d["dtype"],d["batch"],d["ms_per_step"],d.get("ms_per_step_no_dense"),d["scheduled_frac"]))
 PY
-nvidia-smi topo -m 2>/dev/null | head -14
-python -c "
-import os; print('cpus', os.cpu_count(), 'affinity', len(os.sched_getaffinity(0)))
-for n in range(4):
-    p='/sys/devices/system/node/node%d/cpulist'%n
-    if os.path.exists(p): print(n, open(p).read().strip())
-"
+tail -3 $O/steps.err

@@ -140,6 +140,235 @@ __global__ void __launch_bounds__(kThreads) jt_dense_prep_kernel(const PrepArgs 
     W[idx] = sum * scale;
 }
 
+// One MMA warp of jt_dense_kernel for a compile-time number MT of 8-row m-tiles per unit: warp w
+// owns columns col0 + 16 w .. + 15 of the batch tile and keeps the [8 MT x 16] accumulator tile of
+// the current unit in registers.  Everything per unit is unrolled over MT (short contractions run
+// hundreds of units per CTA with 4-8 DMMAs each: the instructions around the DMMAs are what the
+// kernel is bound by there, so no predicated m-tiles, 32-bit unit counters advanced without
+// divisions, row pointers formed once per output row).
+template <typename T, int MT>
+__device__ __forceinline__ void dense_mma_warp(const DenseArgs& a, const DDense& d, const unsigned char* smem,
+                                               const uint32_t full_u32, const uint32_t empty_u32, const int u0,
+                                               const int u1, const long long col0, const int warp, const int lane) {
+    typedef Pack<T, 2> P2;
+    const long long B = a.B;
+    const int* __restrict__ dtab = a.dtab;
+    const DTask* tk = a.tasks + d.task;
+    T* work = static_cast<T*>(a.work);
+    const T* uni = static_cast<const T*>(a.uni);
+    // the task's fields in registers: re-read after every store otherwise (they could alias the workspace)
+    const long long t_own = tk->own, t_bel = tk->bel;
+    const int t_n_slo = tk->n_slo, smsg_begin = tk->smsg_begin, smsg_end = tk->smsg_end;
+    const bool wbel = t_bel >= 0 && (a.flags & JT_SEP_BELIEFS);
+    const bool own_uni = wbel && t_own >= 0 && (tk->flags & JT_TF_OWN_UNIFORM);
+    const bool own_rows = wbel && t_own >= 0 && !(tk->flags & JT_TF_OWN_UNIFORM);
+    // does the epilogue have per-instance s-only operands?
+    bool s_rows = false;
+    for (int j = smsg_begin; j < smsg_end; ++j) s_rows = s_rows || !a.msgs[j].uni;
+    const int bcol = warp * (kDNT * 8) + (lane >> 2);                      // B fragment: column inside the tile
+    const long long ccol = col0 + warp * (kDNT * 8) + (lane & 3) * 2;      // C fragment: first of two columns, + 8 nt
+    bool ok[kDNT];                                                         // B is even: both columns or none
+#pragma unroll
+    for (int nt = 0; nt < kDNT; ++nt) ok[nt] = ccol + nt * 8 < B;
+    T* const obase = (tk->out_space ? static_cast<T*>(a.fout) : work) + tk->out * B + ccol;
+    T* const wcol = work + ccol;
+    const int n_i = d.n_i, n_it = d.n_it;
+    const int* const s_tab = dtab + d.s_of + (lane >> 2);
+
+    struct Acc {
+        double v[MT][kDNT][2];
+    };
+    struct Rows {
+        int s[MT];
+    };
+    // nk4 k-steps: rows `rows` (4 per step) times W fragments `wt` (MT per step)
+    auto steps = [&](Acc& c, const unsigned char* rows, const double* wt, const int nk4) {
+#pragma unroll
+        for (int q = 0; q < kDKC / 4; ++q) {
+            if (q >= nk4) break;
+            double bf[kDNT];
+#pragma unroll
+            for (int nt = 0; nt < kDNT; ++nt)
+                bf[nt] = (double)*reinterpret_cast<const T*>(rows + q * 4 * kDRowPitch + nt * 8 * (int)sizeof(T));
+            double af[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) af[mt] = wt[(q * MT + mt) * 32];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < kDNT; ++nt) dmma(c.v[mt][nt][0], c.v[mt][nt][1], af[mt], bf[nt]);
+        }
+    };
+    // output rows of unit (g, it) handled by this thread: i = (it MT + mt) 8 + lane / 4 (-1: padding),
+    // fetched one unit ahead so the lookups are off the critical path of the epilogue
+    auto lookup = [&](const int g, const int it) {
+        Rows r;
+        const int* t = s_tab + g * n_i + it * (8 * MT);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+            r.s[mt] = it * (8 * MT) + mt * 8 + (lane >> 2) < n_i ? __ldg(t + mt * 8) : -1;
+        return r;
+    };
+    // Two m-tiles at a time: first every load of the pair (own rows, per-instance s-only rows), then
+    // the products and stores -- loads and stores share the workspace pointer, so only loads issued
+    // back to back overlap their latencies.
+    auto epilogue = [&](const Acc& c, const Rows& ur) {
+        if (!wbel && !s_rows) {                                  // a message and nothing else
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int s = ur.s[mt];
+                if (s < 0) continue;
+                T* o = obase + (long long)s * B;
+#pragma unroll
+                for (int nt = 0; nt < kDNT; ++nt) {
+                    if (!ok[nt]) continue;
+                    P2 x;
+                    x.v[0] = (T)c.v[mt][nt][0];
+                    x.v[1] = (T)c.v[mt][nt][1];
+                    *reinterpret_cast<P2*>(o + nt * 8) = x;
+                }
+            }
+            return;
+        }
+#pragma unroll
+        for (int m0 = 0; m0 < MT; m0 += 2) {
+            P2 ow[2][kDNT];
+            double own_u[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (m0 + h >= MT) continue;
+                const int s = ur.s[m0 + h];
+                own_u[h] = 1.0;
+#pragma unroll
+                for (int nt = 0; nt < kDNT; ++nt) ow[h][nt].v[0] = ow[h][nt].v[1] = T(1);
+                if (s < 0) continue;
+                if (own_uni) {
+                    own_u[h] = (double)__ldg(uni + t_own + s);
+                } else if (own_rows) {
+                    const T* r = wcol + (t_own + s) * B;
+#pragma unroll
+                    for (int nt = 0; nt < kDNT; ++nt)
+                        if (ok[nt]) ow[h][nt] = *reinterpret_cast<const P2*>(r + nt * 8);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (m0 + h >= MT) continue;
+                const int mt = m0 + h, s = ur.s[mt];
+                if (s < 0) continue;
+                double v[kDNT][2];
+#pragma unroll
+                for (int nt = 0; nt < kDNT; ++nt) {
+                    v[nt][0] = c.v[mt][nt][0];
+                    v[nt][1] = c.v[mt][nt][1];
+                }
+                if (s_rows) {
+                    const int s_hi = s / t_n_slo, s_lo = s - s_hi * t_n_slo;
+                    for (int j = smsg_begin; j < smsg_end; ++j) {
+                        const DMsg* m = a.msgs + j;
+                        if (m->uni) continue;                    // folded into W
+                        const T* r = wcol + m->eoff + (m->off + __ldg(a.tab + m->a_hi + s_hi) + __ldg(a.tab + m->a_lo + s_lo)) * B;
+#pragma unroll
+                        for (int nt = 0; nt < kDNT; ++nt) {
+                            if (!ok[nt]) continue;
+                            const P2 x = *reinterpret_cast<const P2*>(r + nt * 8);
+                            v[nt][0] *= (double)x.v[0];
+                            v[nt][1] *= (double)x.v[1];
+                        }
+                    }
+                }
+                T* o = obase + (long long)s * B;
+                T* bel = wcol + (t_bel + s) * B;
+#pragma unroll
+                for (int nt = 0; nt < kDNT; ++nt) {
+                    if (!ok[nt]) continue;
+                    P2 x;
+                    x.v[0] = (T)v[nt][0];
+                    x.v[1] = (T)v[nt][1];
+                    *reinterpret_cast<P2*>(o + nt * 8) = x;
+                    if (wbel) {
+                        // from the stored (rounded) message, as the projection kernels form it
+                        x.v[0] = (T)((double)x.v[0] * (double)ow[h][nt].v[0] * own_u[h]);
+                        x.v[1] = (T)((double)x.v[1] * (double)ow[h][nt].v[1] * own_u[h]);
+                        *reinterpret_cast<P2*>(bel + nt * 8) = x;
+                    }
+                }
+            }
+        }
+    };
+
+    int stage = 0;
+    uint32_t phase = 0;
+    auto release = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_u32 + 8 * stage);
+        if (++stage == kDStages) {
+            stage = 0;
+            phase ^= 1;
+        }
+    };
+    const int frag_off = (lane & 3) * kDRowPitch + bcol * (int)sizeof(T);   // B fragment of this thread inside a stage
+    // (gn, itn): the unit after the one whose rows were looked up last
+    int gn = u0 / n_it, itn = u0 - gn * n_it;
+    Rows next = lookup(gn, itn);
+    auto advance = [&]() {
+        if (++itn == n_it) {
+            itn = 0;
+            ++gn;
+        }
+    };
+    advance();
+    if (d.ups > 1) {
+        // short contractions: `ups` units per stage, one after the other
+        const int kpad = d.n_k4 * 4, nk4 = d.n_k4, ups = d.ups;
+        for (int u = u0; u < u1; u += ups) {
+            const int nu = u1 - u < ups ? u1 - u : ups;
+            mbar_wait(full_u32 + 8 * stage, phase);
+            const unsigned char* st = smem + stage * kDStageBytes;
+            const unsigned char* rows = st + frag_off;
+            const double* wt = reinterpret_cast<const double*>(st + kDKC * kDRowPitch) + lane;
+            for (int j = 0; j < nu; ++j) {
+                Acc c;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < kDNT; ++nt) c.v[mt][nt][0] = c.v[mt][nt][1] = 0.0;
+                const Rows ur = next;
+                if (u + j + 1 < u1) {
+                    next = lookup(gn, itn);
+                    advance();
+                }
+                steps(c, rows, wt, nk4);
+                rows += kpad * kDRowPitch;
+                wt += nk4 * MT * 32;
+                if (j == nu - 1) release();                       // the stage is consumed: refill during the epilogue
+                epilogue(c, ur);
+            }
+        }
+        return;
+    }
+    for (int u = u0; u < u1; ++u) {
+        Acc c;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < kDNT; ++nt) c.v[mt][nt][0] = c.v[mt][nt][1] = 0.0;
+        const Rows ur = next;
+        if (u + 1 < u1) {
+            next = lookup(gn, itn);
+            advance();
+        }
+        for (int ch = 0; ch < d.n_chunks; ++ch) {
+            const int nk4 = d.n_k4 - ch * 4 < 4 ? d.n_k4 - ch * 4 : 4;
+            mbar_wait(full_u32 + 8 * stage, phase);
+            const unsigned char* st = smem + stage * kDStageBytes;
+            steps(c, st + frag_off, reinterpret_cast<const double*>(st + kDKC * kDRowPitch) + lane, nk4);
+            release();
+        }
+        epilogue(c, ur);
+    }
+}
+
 // One CTA = kDWarps MMA warps + one producer warp.  It owns a batch tile of kDTB columns and a
 // run of consecutive units (group g, i-tile it) of one task.  Per unit the producer streams the K
 // message rows of the group (16 per stage, one 1-D bulk copy per row, lane = row) and the
@@ -181,11 +410,14 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
         }
         mbar_fence_init();
     }
-    // stale shared memory must be finite: rows past K of a last stage and columns past the batch
-    // are multiplied by zero fragments / never stored, and 0 * NaN would poison the accumulators
-    for (int i = threadIdx.x; i < kDStages * kDStageBytes / 16; i += blockDim.x)
-        reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // Stale shared memory must be finite where a k-step reads it: the rows past K of the last
+    // k-step are multiplied by zero fragments, and 0 * NaN would poison the accumulators.  (Stale
+    // columns past the batch only reach accumulator columns that are never stored.)
+    if (d.K & 3) {
+        for (int i = threadIdx.x; i < kDStages * kDStageBytes / 16; i += blockDim.x)
+            reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
 
     const int* __restrict__ dtab = a.dtab;
@@ -201,11 +433,11 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
             // short contractions: a stage holds `ups` consecutive units, unit j in rows j * 4 n_k4 ...
             const int kpad = d.n_k4 * 4;
             const int j = lane / kpad, k = lane - j * kpad;
-            for (long long u = u0; u < u1; u += d.ups) {
-                const int nu = (int)(u1 - u < d.ups ? u1 - u : d.ups);
+            for (int u = (int)u0; u < (int)u1; u += d.ups) {
+                const int nu = (int)u1 - u < d.ups ? (int)u1 - u : d.ups;
                 const bool live = j < nu && k < d.K;
                 long long row = 0;
-                if (live) row = m->off + __ldg(dtab + d.mg + (int)((u + j) / d.n_it)) + __ldg(dtab + d.mk + k);
+                if (live) row = m->off + __ldg(dtab + d.mg + (u + j) / d.n_it) + __ldg(dtab + d.mk + k);
                 const uint32_t full = full_u32 + 8 * stage;
                 const uint32_t dst = ring_u32 + (uint32_t)stage * kDStageBytes;
                 const uint32_t wbytes = (uint32_t)nu * d.n_k4 * d.MT * 256u;
@@ -223,8 +455,8 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
             }
             return;
         }
-        for (long long u = u0; u < u1; ++u) {
-            const int g = (int)(u / d.n_it);
+        for (int u = (int)u0; u < (int)u1; ++u) {
+            const int g = u / d.n_it;
             const long long row_g = m->off + __ldg(dtab + d.mg + g);
             for (int c = 0; c < d.n_chunks; ++c) {
                 const int k0 = c * kDKC;
@@ -251,175 +483,13 @@ __global__ void __launch_bounds__((kDWarps + 1) * 32, 2) jt_dense_kernel(const D
         return;
     }
 
-    // ---------------- MMA warps: warp w owns columns col0 + 32 w .. + 31 ----------------
-    const DTask* tk = a.tasks + d.task;
-    const int MT = d.MT;
-    T* work = static_cast<T*>(a.work);
-    const T* uni = static_cast<const T*>(a.uni);
-    const int tflags = tk->flags;
-    const bool wbel = tk->bel >= 0 && (a.flags & JT_SEP_BELIEFS);
-    const bool has_own = tk->own >= 0;
-    T* obase = (tk->out_space ? static_cast<T*>(a.fout) : work) + tk->out * B;
-    // does the epilogue have per-instance s-only operands?
-    bool s_rows = false;
-    for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) s_rows = s_rows || !a.msgs[j].uni;
-    const int bcol = warp * (kDNT * 8) + (lane >> 2);                      // B fragment: column inside the tile
-    const long long ccol = col0 + warp * (kDNT * 8) + (lane & 3) * 2;      // C fragment: first of two columns, + 8 nt
-
-    // the [8 MT x 32] accumulator tile of one unit
-    struct Acc {
-        double v[4][kDNT][2];
-    };
-    auto zero = [](Acc& c) {
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < kDNT; ++nt) c.v[mt][nt][0] = c.v[mt][nt][1] = 0.0;
-    };
-    // nk4 k-steps: rows `rows` (4 per step) times W fragments `wt` (MT per step)
-    auto steps = [&](Acc& c, const unsigned char* rows, const double* wt, int nk4) {
-        for (int q = 0; q < nk4; ++q) {
-            double bf[kDNT];
-#pragma unroll
-            for (int nt = 0; nt < kDNT; ++nt)
-                bf[nt] = (double)*reinterpret_cast<const T*>(rows + q * 4 * kDRowPitch + nt * 8 * (int)sizeof(T));
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) {
-                if (mt < MT) {
-                    const T af = wt[(q * MT + mt) * 32];
-#pragma unroll
-                    for (int nt = 0; nt < kDNT; ++nt) dmma(c.v[mt][nt][0], c.v[mt][nt][1], af, bf[nt]);
-                }
-            }
-        }
-    };
-    // epilogue of unit u: rows i = it * 8 MT + 8 mt + lane / 4 of group g
-    // output rows of unit u handled by this thread (-1: padding), fetched before the k-steps so the
-    // lookups are off the critical path of the epilogue
-    struct Rows {
-        int s[4];
-    };
-    auto unit_rows = [&](long long u) {
-        Rows r;
-        const int g = (int)(u / d.n_it), it = (int)(u - (long long)g * d.n_it);
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) {
-            const int i = (it * MT + mt) * 8 + (lane >> 2);
-            r.s[mt] = (mt < MT && i < d.n_i) ? __ldg(dtab + d.s_of + g * d.n_i + i) : -1;
-        }
-        return r;
-    };
-    // Two m-tiles at a time: first every load of the pair (own rows, per-instance s-only rows), then
-    // the products and stores -- loads and stores share the workspace pointer, so only loads issued
-    // back to back overlap their latencies.
-    auto epilogue = [&](const Acc& c, const Rows& ur) {
-#pragma unroll
-        for (int m0 = 0; m0 < 4; m0 += 2) {
-            if (m0 >= MT) break;
-            P2 ow[2][kDNT];
-            double own_u[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int mt = m0 + h, s = ur.s[mt];
-                own_u[h] = 1.0;
-#pragma unroll
-                for (int nt = 0; nt < kDNT; ++nt) ow[h][nt].v[0] = ow[h][nt].v[1] = T(1);
-                if (s < 0) continue;
-                if (wbel && has_own) {
-                    if (tflags & JT_TF_OWN_UNIFORM) {
-                        own_u[h] = (double)__ldg(uni + tk->own + s);
-                    } else {
-#pragma unroll
-                        for (int nt = 0; nt < kDNT; ++nt) {
-                            const long long col = ccol + nt * 8;
-                            if (col < B) ow[h][nt] = *reinterpret_cast<const P2*>(work + (tk->own + s) * B + col);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int mt = m0 + h, s = ur.s[mt];
-                if (s < 0) continue;
-#pragma unroll
-                for (int nt = 0; nt < kDNT; ++nt) {
-                    const long long col = ccol + nt * 8;
-                    if (col < B) {                               // B is even: both columns or none
-                        double v0 = c.v[mt][nt][0], v1 = c.v[mt][nt][1];
-                        if (s_rows) {
-                            const int s_hi = s / tk->n_slo, s_lo = s - s_hi * tk->n_slo;
-                            for (int j = tk->smsg_begin; j < tk->smsg_end; ++j) {
-                                const DMsg* m = a.msgs + j;
-                                if (m->uni) continue;            // folded into W
-                                const T* r = work + m->eoff +
-                                             (m->off + __ldg(a.tab + m->a_hi + s_hi) + __ldg(a.tab + m->a_lo + s_lo)) * B + col;
-                                const P2 x = *reinterpret_cast<const P2*>(r);
-                                v0 *= (double)x.v[0];
-                                v1 *= (double)x.v[1];
-                            }
-                        }
-                        P2 o;
-                        o.v[0] = (T)v0;
-                        o.v[1] = (T)v1;
-                        *reinterpret_cast<P2*>(obase + (long long)s * B + col) = o;
-                        if (wbel) {
-                            // from the stored (rounded) message, as the projection kernels form it
-                            o.v[0] = (T)((double)o.v[0] * (double)ow[h][nt].v[0] * own_u[h]);
-                            o.v[1] = (T)((double)o.v[1] * (double)ow[h][nt].v[1] * own_u[h]);
-                            *reinterpret_cast<P2*>(work + (tk->bel + s) * B + col) = o;
-                        }
-                    }
-                }
-            }
-        }
-    };
-
-    int stage = 0;
-    uint32_t phase = 0;
-    auto release = [&]() {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_u32 + 8 * stage);
-        if (++stage == kDStages) {
-            stage = 0;
-            phase ^= 1;
-        }
-    };
-    const int frag_off = (lane & 3) * kDRowPitch + bcol * (int)sizeof(T);   // B fragment of this thread inside a stage
-    if (d.ups > 1) {
-        // short contractions: `ups` units per stage, one after the other
-        const int kpad = d.n_k4 * 4;
-        Rows next = unit_rows(u0);                                // looked up one unit ahead
-        for (long long u = u0; u < u1; u += d.ups) {
-            const int nu = (int)(u1 - u < d.ups ? u1 - u : d.ups);
-            mbar_wait(full_u32 + 8 * stage, phase);
-            const unsigned char* st = smem + stage * kDStageBytes;
-            const double* wt = reinterpret_cast<const double*>(st + kDKC * kDRowPitch) + lane;
-            for (int j = 0; j < nu; ++j) {
-                Acc c;
-                zero(c);
-                const Rows ur = next;
-                if (u + j + 1 < u1) next = unit_rows(u + j + 1);
-                steps(c, st + j * kpad * kDRowPitch + frag_off, wt + j * d.n_k4 * MT * 32, d.n_k4);
-                if (j == nu - 1) release();                       // the stage is consumed: refill during the epilogue
-                epilogue(c, ur);
-            }
-        }
-        return;
-    }
-    Rows next = unit_rows(u0);
-    for (long long u = u0; u < u1; ++u) {
-        Acc c;
-        zero(c);
-        const Rows ur = next;
-        if (u + 1 < u1) next = unit_rows(u + 1);
-        for (int ch = 0; ch < d.n_chunks; ++ch) {
-            const int nk4 = d.n_k4 - ch * 4 < 4 ? d.n_k4 - ch * 4 : 4;
-            mbar_wait(full_u32 + 8 * stage, phase);
-            const unsigned char* st = smem + stage * kDStageBytes;
-            steps(c, st + frag_off, reinterpret_cast<const double*>(st + kDKC * kDRowPitch) + lane, nk4);
-            release();
-        }
-        epilogue(c, ur);
+    // ---------------- MMA warps ----------------
+    const int iu0 = (int)u0, iu1 = (int)u1;
+    switch (d.MT) {
+    case 1: dense_mma_warp<T, 1>(a, d, smem, full_u32, empty_u32, iu0, iu1, col0, warp, lane); break;
+    case 2: dense_mma_warp<T, 2>(a, d, smem, full_u32, empty_u32, iu0, iu1, col0, warp, lane); break;
+    case 3: dense_mma_warp<T, 3>(a, d, smem, full_u32, empty_u32, iu0, iu1, col0, warp, lane); break;
+    default: dense_mma_warp<T, 4>(a, d, smem, full_u32, empty_u32, iu0, iu1, col0, warp, lane); break;
     }
 }
 
@@ -439,13 +509,21 @@ bool beta_walk_blocks() {   // JT_BETA_WALK=items: the plain s-major walk (A-B t
     return on == 1;
 }
 
-long long dense_min_gain() {   // JT_DENSE_MIN_GAIN: rows saved (items / rows moved) from which a task becomes a contraction (default 3)
-    static const long long v = [] {
+double dense_min_gain() {   // JT_DENSE_MIN_GAIN: items / rows moved from which a task becomes a contraction (default 2)
+    static const double v = [] {
         const char* e = getenv("JT_DENSE_MIN_GAIN");
-        const long long x = e ? atoll(e) : 0;
-        return x >= 1 ? x : 3LL;
+        const double x = e ? atof(e) : 0.0;
+        return x >= 1.0 ? x : 2.0;
     }();
     return v;
+}
+
+bool dense_balance() {      // JT_DENSE_BALANCE=0: units per CTA as the power of two says (A-B timing)
+    static const int on = [] {
+        const char* e = getenv("JT_DENSE_BALANCE");
+        return !(e && e[0] == '0');
+    }();
+    return on != 0;
 }
 
 int beta_block() {          // JT_BETA_BLOCK: consecutive clique entries per block of the walk (default 8)
@@ -537,7 +615,7 @@ int jt_dense_build(jt_plan* p) {
                 // group loads its K rows once per i-tile and every output row is written once
                 const long long items = (long long)k.n_s * k.n_r;
                 const long long moved = (long long)n_g * d.n_it * K + k.n_s;
-                if ((long long)n_i * K < 16 || items < dense_min_gain() * moved) continue;
+                if ((long long)n_i * K < 16 || (double)items < dense_min_gain() * (double)moved) continue;
                 d.w_size = (long long)n_g * d.n_it * d.n_k4 * d.MT * 32;
                 if (d.w_size > (1LL << 40) || p->dtab.size() + (size_t)k.n_s + n_g + K + k.n_r > 2000000000ULL) continue;
                 d.w_off = p->dense_w_entries;
@@ -876,6 +954,12 @@ int jt_dense_build(jt_plan* p) {
                 long long u = (1LL << j) / d.n_chunks * d.ups;           // a multiple of the units per stage
                 u = u < d.ups ? d.ups : u;
                 u = u > units ? units : u;
+                if (dense_balance()) {
+                    // the same number of CTAs, the units spread evenly over them (36 units at 32 per
+                    // CTA would run as 32 + 4: the launch lasts as long as its longest CTA)
+                    const long long nb = (units + u - 1) / u;
+                    u = ((units + nb - 1) / nb + d.ups - 1) / d.ups * d.ups;
+                }
                 p->prefix.push_back((int)acc);
                 upc.push_back((int)u);
                 acc += (units + u - 1) / u;

@@ -616,6 +616,9 @@ int jt_dense_build(jt_plan* p) {
                 const long long items = (long long)k.n_s * k.n_r;
                 const long long moved = (long long)n_g * d.n_it * K + k.n_s;
                 if ((long long)n_i * K < 16 || (double)items < dense_min_gain() * (double)moved) continue;
+                // a CTA contracts whole units: a long sum into a handful of rows has no parallelism
+                // here (the projection kernels split r over blocks)
+                if (K > 4096 && (long long)n_g * d.n_it < 64) continue;
                 d.w_size = (long long)n_g * d.n_it * d.n_k4 * d.MT * 32;
                 if (d.w_size > (1LL << 40) || p->dtab.size() + (size_t)k.n_s + n_g + K + k.n_r > 2000000000ULL) continue;
                 d.w_off = p->dense_w_entries;

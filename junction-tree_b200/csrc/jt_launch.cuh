@@ -34,6 +34,24 @@ inline int tma_vpt_override() {   // JT_TMA_VPT=1|2 overrides the vectors-per-th
     return vpt;
 }
 
+inline int tma_min_item_log2() {   // JT_TMA_MIN_ITEMS_LOG2: smallest (s, r) chunk per CTA of the TMA kernel (default 5: 32 items)
+    static const int v = [] {
+        const char* e = getenv("JT_TMA_MIN_ITEMS_LOG2");
+        const int x = e ? atoi(e) : 5;
+        return x >= 0 && x <= 12 ? x : 5;
+    }();
+    return v;
+}
+
+inline int tma_ctas_per_sm() {   // JT_TMA_CTAS_PER_SM overrides the CTAs per SM a TMA launch aims at before its chunks grow
+    static const int v = [] {
+        const char* e = getenv("JT_TMA_CTAS_PER_SM");
+        const int x = e ? atoi(e) : 0;
+        return x >= 1 && x <= 1024 ? x : 0;
+    }();
+    return v;
+}
+
 // Few instances and long reductions with too few output indices to fill the machine: split r.
 inline bool use_splitr(const jt_plan::Launch& L, long long B, bool is_init) {
     if (is_init || B > 64 || L.max_nr < 128) return false;
@@ -47,10 +65,15 @@ struct Launcher {
                               cudaStream_t stream) {
         const int tw = ct * VPT;
         const long long tiles = (a.Bv + tw - 1) / tw;
-        // (s, r) items per CTA: aim at ~8 CTAs per SM over the launch, but keep >= 64 items per CTA
+        // (s, r) items per CTA: aim at a number of CTAs per SM over the launch, but keep >= 32 items per CTA
         // so the pipeline fill is amortised; every task gets its own chunk of s for that item count
-        int j = 6;
-        const long long target = 148LL * 8;
+        int j = tma_min_item_log2();
+        // Wide batches (many batch tiles per row) take smaller chunks: the CTAs in flight then write
+        // a compact range of rows (tools/micro/write_pattern.cu: 8 KB pieces of 512 KB rows, 64 rows
+        // per CTA 7.0 TB/s, 1024 rows per CTA 6.1 TB/s); narrow batches keep long chunks (measured
+        // on the Ising grid, one tile: 37.9 ms at 8 CTAs per SM, 39.5 at 64)
+        const int per_sm = tma_ctas_per_sm() ? tma_ctas_per_sm() : (tiles >= 16 ? 64 : 8);
+        const long long target = 148LL * per_sm;
         const long long total_items = variant ? L.total_items_v[variant - 1] : L.total_items;
         while (j < kItemLog2Max && (total_items * tiles) >> (j + 1) >= target) ++j;
         a.sy_log2 = 0;

@@ -378,3 +378,24 @@ def test_dense_contractions_equal_the_projection_tasks_they_replace():
     assert _dense_check(wl.dag37()) >= 3
     assert _dense_check(wl.random_dag(60, 3, 2, 5, 8, 3)) >= 1
     assert _dense_check(wl.dag37(), with_evidence=False) == 0          # everything uniform: nothing per instance
+
+
+def test_gpu_dense_nets_reach_every_variant_of_the_dense_kernel():
+    """jt_dense_kernel is instantiated per m-tile count (1-4) with two stage layouts (several short
+    units per stage / one unit over several stages) and zeroes its ring only when K is not a
+    multiple of 4: the networks tests/test_gpu_dense.py runs on the GPU must reach all of them."""
+    import junctiontree as jt
+    from test_gpu_dense import NETS
+    seen = set()
+    for _, make in NETS:
+        net = make()
+        tree = jt.create_junction_tree(net["factors"], net["sizes"])
+        tasks, _ = _native.DevicePlan(tree.plan(net["evidence_vars"]).to_blob()).dense_tasks()
+        for d in tasks:
+            seen.add(("MT", d["MT"]))
+            seen.add(("several i-tiles", d["n_it"] > 1))
+            seen.add(("K % 4 == 0", d["K"] % 4 == 0))
+            seen.add(("short", d["K"] <= 8))
+    for want in [("MT", 1), ("MT", 2), ("MT", 3), ("MT", 4), ("several i-tiles", True), ("several i-tiles", False),
+                 ("K % 4 == 0", True), ("K % 4 == 0", False), ("short", True), ("short", False)]:
+        assert want in seen, want

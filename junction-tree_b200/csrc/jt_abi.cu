@@ -735,6 +735,11 @@ int jt_init(jt_plan* p, const void* factor_tables, int factors_batched, const in
     a.fin = factor_tables;
     a.fin_batched = factors_batched ? 1 : 0;
     a.flags = flags;
+    if (!factors_batched) {
+        long long fin_end = 0;
+        for (size_t f = 0; f < p->fin_off.size(); ++f) fin_end = std::max<long long>(fin_end, p->fin_off[f] + p->fin_size[f]);
+        if (fin_end < 2147483647LL) a.flags |= JT_X_FIN32;
+    }
     if (n_evid > 0) {
         if (!evidence) return fail(JT_ERR_INVALID, "plan has %d evidence variables but evidence is null", n_evid);
         if (factors_batched) return fail(JT_ERR_INVALID, "per-instance factor tables cannot be combined with evidence indices");

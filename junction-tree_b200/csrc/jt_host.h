@@ -86,6 +86,7 @@ struct DDense {
 // internal bits (never in a plan blob or in the public flags)
 constexpr int JT_TF_BETA_SPLIT = 0x100;   // DTask::flags: in uniform mode the clique belief of this task is written by jt_beta_kernel
 constexpr int JT_X_BETA_SPLIT = 0x10000;  // KArgs::flags: ... and this launch runs that way
+constexpr int JT_X_FIN32 = 0x20000;       // KArgs::flags (init): the shared factor tables hold < 2^31 entries, gathers index them in 32 bits
 // internal phases (launches derived at plan load, never in a blob): the totals of the scalar tasks,
 // ordinary B = 1 projection launches in the uniform workspace after the uniform collect / distribute
 constexpr int JT_PHASE_X_SCALAR0 = 64, JT_PHASE_X_SCALAR1 = 65;

@@ -360,8 +360,8 @@ __global__ void __launch_bounds__(kThreads) jt_init_kernel(const KArgs a) {
     }
 }
 
-// Large batches (a block spans one row of s, 256 batch vectors wide): the table lookups of a row
-// are the same for every thread, so they are done once per block -- thread t resolves row
+// Batches of 64 vectors and more (a block spans 1-4 rows of s, 256-64 batch vectors wide): the
+// table lookups of a row are the same for every thread of it, so they are done once per block -- thread t resolves row
 // base + t of a 256-row sub-chunk into shared memory -- and the row loop is left with one
 // shared-memory read, the gathers, the products and the store (ncu, round 1: the per-thread
 // form was issue-bound at 78 % issue-active and 4.4 TB/s of a 7.4 TB/s write ceiling).
@@ -374,7 +374,9 @@ __global__ void __launch_bounds__(kThreads) jt_init_rows_kernel(const KArgs a) {
     const int n_s = tk->n_s;
     const int s_end = min(n_s, s0 + (1 << a.sy_log2));
     const int t = threadIdx.x;
-    const long long bv = (long long)blockIdx.y * kThreads + t;
+    // 2^bx_log2 batch vectors per row of the block, the remaining thread bits walk rows side by side
+    const int lanes = kThreads >> a.bx_log2, tl = t >> a.bx_log2;
+    const long long bv = ((long long)blockIdx.y << a.bx_log2) + (t & ((1 << a.bx_log2) - 1));
     const bool active = bv < a.Bv;
     const int* __restrict__ tab = a.tab;
     const DMsg* __restrict__ msgs = a.msgs;
@@ -410,6 +412,13 @@ __global__ void __launch_bounds__(kThreads) jt_init_rows_kernel(const KArgs a) {
     }
 
     T* out = static_cast<T*>(a.work) + tk->out * B + col;
+    // every factor of the clique is gathered from small shared tables (the usual case: evidence
+    // slicing, no likelihood rows): a row loop without the row-operand alternative -- the compiler
+    // predicates both forms otherwise and a factor costs ~30 issue slots either way -- and with
+    // 32-bit gather indices (ncu r02: Ising grid, 3 factors per clique, 4.4 of ~7 TB/s)
+    bool gathers_only = (a.flags & JT_X_FIN32) && nf <= kInitRegFactors;
+#pragma unroll
+    for (int j = 0; j < kInitRegFactors; ++j) gathers_only = gathers_only && !(j < nf && row_op[j]);
     for (int base = s0; base < s_end; base += kThreads) {
         const int nrows = min(kThreads, s_end - base);
         __syncthreads();                                  // the previous sub-chunk has been consumed
@@ -427,8 +436,35 @@ __global__ void __launch_bounds__(kThreads) jt_init_rows_kernel(const KArgs a) {
         }
         __syncthreads();
         if (!active) continue;
+        if (gathers_only) {
+            // one instantiation of the row loop per factor count: no predicated-off factors in it
+            auto walk = [&](auto nfc) {
+                constexpr int NF = decltype(nfc)::value;
 #pragma unroll 2
-        for (int i = 0; i < nrows; ++i) {
+                for (int i = tl; i < nrows; i += lanes) {
+                    P val = pack_one<SR, T, VEC>();
+#pragma unroll
+                    for (int j = 0; j < NF; ++j) {
+                        const unsigned idx = (unsigned)sidx[j][i];
+#pragma unroll
+                        for (int u = 0; u < VEC; ++u) val.v[u] = SR::mul(val.v[u], __ldg(fin + (idx + (unsigned)fb[j][u])));
+                    }
+                    st<T, VEC>(out + (long long)(base + i) * B, val);
+                }
+            };
+            switch (nf) {
+            case 0: walk(std::integral_constant<int, 0>()); break;
+            case 1: walk(std::integral_constant<int, 1>()); break;
+            case 2: walk(std::integral_constant<int, 2>()); break;
+            case 3: walk(std::integral_constant<int, 3>()); break;
+            case 4: walk(std::integral_constant<int, 4>()); break;
+            case 5: walk(std::integral_constant<int, 5>()); break;
+            default: walk(std::integral_constant<int, 6>()); break;
+            }
+            continue;
+        }
+#pragma unroll 2
+        for (int i = tl; i < nrows; i += lanes) {
             P val = pack_one<SR, T, VEC>();
 #pragma unroll
             for (int j = 0; j < kInitRegFactors; ++j) {

@@ -12,6 +12,8 @@
 namespace {
 
 // tile shape for a batch of Bv vectors: bx = min(256, pow2ceil(Bv)), sy = 256 / bx
+constexpr int kInitRowsMinLog2 = 6;   // jt_init_rows_kernel from 64 batch vectors per row
+
 inline void pick_tile(long long Bv, int& bx_log2, int& sy_log2) {
     bx_log2 = 0;
     while ((1LL << bx_log2) < Bv && bx_log2 < 8) ++bx_log2;
@@ -146,7 +148,7 @@ struct Launcher {
         if (is_init) {
             // a thread walks ~32 rows of s (256 when a block spans one row and shares the row
             // lookups) so the per-instance factor offsets stay in registers
-            sy_log2 = bx_log2 == 8 ? 8 : (sy_log2 + 5 > kMaxSyLog2 ? kMaxSyLog2 : sy_log2 + 5);
+            sy_log2 = bx_log2 >= kInitRowsMinLog2 ? 8 : (sy_log2 + 5 > kMaxSyLog2 ? kMaxSyLog2 : sy_log2 + 5);
             while (sy_log2 > 8 - bx_log2 &&
                    (L.total_s >> sy_log2) * ((a.Bv + (1LL << bx_log2) - 1) >> bx_log2) < 148 * 8)
                 --sy_log2;
@@ -162,7 +164,7 @@ struct Launcher {
         if (gx > 2147483647LL || gy > 65535)
             return jt_fail(JT_ERR_INVALID, "launch grid %lld x %lld exceeds CUDA limits; split the batch", gx, gy);
         dim3 grid((unsigned)gx, (unsigned)gy, 1);
-        if (is_init && bx_log2 == 8)                     // a block spans one row: shared row lookups
+        if (is_init && bx_log2 >= kInitRowsMinLog2)      // a block spans 1-4 whole rows: shared row lookups
             jt_init_rows_kernel<SR, T, VEC><<<grid, kThreads, 0, stream>>>(a);
         else if (is_init)
             jt_init_kernel<SR, T, VEC><<<grid, kThreads, 0, stream>>>(a);

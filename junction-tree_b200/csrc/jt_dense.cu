@@ -518,6 +518,15 @@ double dense_min_gain() {   // JT_DENSE_MIN_GAIN: items / rows moved from which 
     return v;
 }
 
+int dense_waves() {          // JT_DENSE_WAVES: waves of 2 CTAs per SM a dense launch is cut into before its CTAs grow (default 4)
+    static const int v = [] {
+        const char* e = getenv("JT_DENSE_WAVES");
+        const int x = e ? atoi(e) : 4;
+        return x >= 1 && x <= 64 ? x : 4;
+    }();
+    return v;
+}
+
 bool dense_balance() {      // JT_DENSE_BALANCE=0: units per CTA as the power of two says (A-B timing)
     static const int on = [] {
         const char* e = getenv("JT_DENSE_BALANCE");
@@ -1056,7 +1065,7 @@ int jt_dense_launch(const jt_plan* p, const jt_plan::Launch& L, void* work, cons
     // on deep trees most launches are small and latency-bound, so a CTA should own as little
     // serial work as possible; only large launches amortise the prologue over many stages.
     int j = 0;
-    while (j < kDenseJMax && ((L.dense_stages * tiles) >> j) > 148LL * 2 * 4) ++j;
+    while (j < kDenseJMax && ((L.dense_stages * tiles) >> j) > 148LL * 2 * dense_waves()) ++j;
     const long long gx = L.dense_blocks[j];
     if (gx <= 0) return JT_OK;
     if (gx > 2147483647LL || tiles > 65535)

@@ -44,6 +44,12 @@ if [ "$part" = "2" ]; then
   list dag500_perinstance --config dag500 --batch 1024 --no-uniform
   list dag500_pipeline_mode --config dag500 --batch 4096 --no-beliefs
 fi
+if [ "$part" = "4" ]; then   # lighter lists (time + DRAM bytes, one timed step) of the per-instance deep trees
+  NCU="ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv"
+  list1() { name=$1; shift; timeout 600 $NCU --log-file $O/r02_launches_$name.csv $P "$@" --steps 1 --warmup 1 > /dev/null 2>&1; }
+  list1 ising16_perinstance --config ising16 --batch 256 --no-uniform
+  list1 dag500_perinstance --config dag500 --batch 1024 --no-uniform
+fi
 if [ "$part" = "3" ]; then
   timeout 900 compute-sanitizer --tool memcheck python tests/tools/sanitize_case.py 2>&1 | tail -25 > $O/r02_memcheck.txt
   cat $O/r02_memcheck.txt

@@ -1,18 +1,6 @@
-O=gpurun_out/r2h2
+# Final check of the round on one B200: GPU suite, smoke, the default bench line.
+O=gpurun_out/r2final
 mkdir -p $O
-P="python junction-tree_b200/tools/prof_step.py"
-for w in 4 2 1 8; do
-JT_DENSE_WAVES=$w timeout 300 $P --config dag500 --batch 2048 >> $O/steps_w$w.jsonl 2>> $O/steps.err
-JT_DENSE_WAVES=$w timeout 300 $P --config dag500 --batch 4096 --no-beliefs >> $O/steps_w$w.jsonl 2>> $O/steps.err
-JT_DENSE_WAVES=$w timeout 300 $P --config dag37 --batch 65536 >> $O/steps_w$w.jsonl 2>> $O/steps.err
-JT_DENSE_WAVES=$w timeout 300 $P --config large_state_tree --batch 512 >> $O/steps_w$w.jsonl 2>> $O/steps.err
-done
-python - <<'PY'
-import json,glob
-for f in sorted(glob.glob("gpurun_out/r2h2/steps*.jsonl")):
-    print(f)
-    for line in open(f):
-        d=json.loads(line)
-        print("  %-18s %s B=%-6d bel=%d ms=%.3f frac=%.3f"%(d["config"],d["dtype"],d["batch"],d["beliefs"],d["ms_per_step"],d["scheduled_frac"]))
-PY
-tail -3 $O/steps.err
+timeout 1500 python -m pytest tests -x -q -m gpu > $O/pytest.log 2>&1; tail -3 $O/pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/smoke.log 2>&1; tail -2 $O/smoke.log
+timeout 600 python bench.py > $O/bench.json 2> $O/bench.err; tail -c 600 $O/bench.json; tail -2 $O/bench.err

@@ -859,3 +859,50 @@ def test_edge_cases_disconnected_scalar_single_and_impossible_evidence(B):
         assert_close(single.propagate([table])[0], table, RTOL_F64, "single clique")
         scalar = jt.create_junction_tree([[]], {})
         assert_close(scalar.propagate([np.array(3.0)])[0], np.array(3.0), RTOL_F64, "scalar factor graph")
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("B", [40, 70, 200, 600])
+def test_clique_initialisation_with_one_to_eight_factors_per_clique(B, dtype):
+    """The clique initialisation instantiates its row loop per factor count (1-6 gathered factors;
+    more than six take the generic loop) and for blocks that span 1-4 rows of a narrow batch: seven
+    unconnected triples whose single clique holds k = 1..6 and 8 factors, per-instance mode, evidence
+    on one variable of every triple (so every factor with it is gathered per instance).  Brute force
+    per component: the components only scale each other by their evidence likelihoods."""
+    import junctiontree as jt
+    from oracle import brute
+    rng = np.random.default_rng(100 + B)
+    shapes = [["x", "y", "z"], ["x"], ["y", "z"], ["x", "z"], ["z"], ["x", "y"], ["x", "y", "z"], ["y"]]
+    factors, sizes, comp = [], {}, []
+    for c, k in enumerate([1, 2, 3, 4, 5, 6, 8]):
+        names = {v: "%s%d" % (v, c) for v in "xyz"}
+        sizes.update({names["x"]: 2, names["y"]: 3, names["z"]: 2 + c % 2})
+        for f in shapes[:k]:
+            factors.append([names[v] for v in f])
+            comp.append(c)
+    np_dtype = np.float64 if dtype == "f64" else np.float32
+    values = [(rng.random([sizes[v] for v in f]) + 0.25).astype(np_dtype) for f in factors]
+    tree = jt.create_junction_tree(factors, sizes)
+    counts = sorted(np.bincount(tree.clique_tree.factor_to_maxclique).tolist())
+    assert counts == [1, 2, 3, 4, 5, 6, 8], counts
+    evars = ["z%d" % c for c in range(7)]
+    ev = np.stack([rng.integers(0, sizes[v], size=B) for v in evars], axis=1).astype(np.int32)
+    outs = tree.propagate_batch(values, evars, ev, uniform=False)
+    rtol = RTOL_F64 if dtype == "f64" else 2e-5
+    vals64 = [np.asarray(v, np.float64) for v in values]
+    for b in sorted(set([0, 1, B // 2, B - 1])):
+        evidence = {v: int(ev[b, j]) for j, v in enumerate(evars)}
+        # partition sum of every component under this instance's evidence
+        z = []
+        for c in range(7):
+            idx = [i for i in range(len(factors)) if comp[i] == c]
+            total = brute.factor_graph_marginals([factors[i] for i in idx], [vals64[i] for i in idx], [[]],
+                                                 {"z%d" % c: evidence["z%d" % c]})[0]
+            z.append(float(total))
+        for c in range(7):
+            idx = [i for i in range(len(factors)) if comp[i] == c]
+            truth = brute.factor_graph_marginals([factors[i] for i in idx], [vals64[i] for i in idx],
+                                                 [factors[i] for i in idx], {"z%d" % c: evidence["z%d" % c]})
+            others = float(np.prod([z[o] for o in range(7) if o != c]))
+            for i, w in zip(idx, truth):
+                assert_close(outs[i][b], w * others, rtol, "factor %d (component %d) instance %d" % (i, c, b))

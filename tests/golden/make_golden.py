@@ -3,6 +3,9 @@
 Run in the build container only (the reference does not travel to the GPU box):
 
     python tests/golden/make_golden.py          # writes tests/golden/reference_golden.npz + .json
+    python tests/golden/make_golden.py --extra  # writes tests/golden/reference_golden_extra.npz + .json:
+                                                # more random nets of 6-10 variables, each also conditioned
+                                                # on its last variable (round 2; the first file is unchanged)
 
 It imports ``junctiontree`` from ``/root/reference`` (oracle tier T1) and records,
 for every case, the inputs, the structure the reference built (tree, maxcliques, separators,
@@ -123,8 +126,49 @@ def operator_case(name, tree, potentials, variables):
     print(name, "beliefs valid:", case["beliefs_valid"])
 
 
+EXTRA = "--extra" in sys.argv
 rng = np.random.default_rng(20261017)
 R = lambda *shape: rng.standard_normal(shape)     # signed values, like the reference tests
+
+
+def write(stem):
+    np.savez_compressed(os.path.join(HERE, stem + ".npz"), **arrays)
+    meta["numpy"] = np.__version__
+    meta["hashseed"] = os.environ.get("PYTHONHASHSEED", "random")
+    with open(os.path.join(HERE, stem + ".json"), "w") as fh:
+        json.dump(meta, fh, indent=1)
+    print("wrote %d arrays, %d cases" % (len(arrays), len(meta["cases"])))
+
+
+if EXTRA:
+    # random nets of 6-10 variables, kept only when the unmodified reference runs and agrees with
+    # brute force on every output; each is recorded unconditioned and conditioned on its last
+    # variable (state 1) the way the reference tests condition (sizes mutated, arrays sliced) --
+    # the conditioned outputs carry per-factor validity flags (reference defects D3 / D7)
+    for n, max_par, smax, first_seed in ((6, 2, 3, 300), (8, 3, 3, 400), (9, 2, 4, 500), (10, 3, 3, 600)):
+        kept = 0
+        for seed in range(first_seed, first_seed + 60):
+            net = wl.random_dag(n, max_par, 2, smax, n, seed)
+            try:
+                tree = ref_jt.create_junction_tree(net["factors"], dict(net["sizes"]))
+                outs = tree.propagate(net["values"])
+            except Exception:
+                continue
+            truth = brute(net["values"], net["factors"], net["factors"])
+            if not all(close(o, t) for o, t in zip(outs, truth)):
+                continue
+            name = "dag%d_seed%d" % (n, seed)
+            end_to_end(name, net)
+            last = "v%03d" % (n - 1)
+            try:
+                end_to_end(name + "_cond", net, {last: 1})
+            except Exception as exc:
+                print("  conditioned case failed in the reference:", type(exc).__name__, exc)
+            kept += 1
+            if kept == 3:
+                break
+    write("reference_golden_extra")
+    sys.exit(0)
 
 end_to_end("sprinkler", wl.sprinkler())
 end_to_end("sprinkler_wet", wl.sprinkler(), {"wet_grass": 1})
@@ -167,9 +211,4 @@ for seed in range(40):
     if kept == 4:
         break
 
-np.savez_compressed(os.path.join(HERE, "reference_golden.npz"), **arrays)
-meta["numpy"] = np.__version__
-meta["hashseed"] = os.environ.get("PYTHONHASHSEED", "random")
-with open(os.path.join(HERE, "reference_golden.json"), "w") as fh:
-    json.dump(meta, fh, indent=1)
-print("wrote %d arrays, %d cases" % (len(arrays), len(meta["cases"])))
+write("reference_golden")

@@ -15,10 +15,16 @@ RTOL_F32 = 1e-5
 
 
 def load_golden():
-    with open(GOLDEN_JSON) as fh:
-        meta = json.load(fh)
-    arrays = np.load(GOLDEN_NPZ)
-    return meta["cases"], arrays
+    """The recorded reference runs: the reference's own fixtures (reference_golden.*) and, since
+    round 2, twelve more random nets of 6-10 variables, each also conditioned on its last variable
+    (reference_golden_extra.*, ``make_golden.py --extra``).  Returns (cases, arrays by key)."""
+    cases, arrays = [], {}
+    for stem in ("reference_golden", "reference_golden_extra"):
+        with open(os.path.join(HERE, "golden", stem + ".json")) as fh:
+            cases += json.load(fh)["cases"]
+        with np.load(os.path.join(HERE, "golden", stem + ".npz")) as npz:
+            arrays.update({k: npz[k] for k in npz.files})
+    return cases, arrays
 
 
 def tuplify(tree):

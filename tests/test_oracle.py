@@ -49,7 +49,7 @@ def test_ref_fixed_compute_beliefs_matches_reference_on_its_trees():
             if case["beliefs_valid"][k]:
                 assert_close(got[k], arrays[key], RTOL_F64, "%s node %d" % (case["name"], k), signed=case["kind"] == "operator")
                 checked += 1
-    assert checked >= 90
+    assert checked >= 320
 
 
 def test_ref_fixed_propagate_matches_reference_outputs():
@@ -69,7 +69,7 @@ def test_ref_fixed_propagate_matches_reference_outputs():
             if case["outputs_valid"][f]:
                 assert_close(outs[f], arrays[key], RTOL_F64, "%s factor %d" % (case["name"], f))
                 checked += 1
-    assert checked >= 40
+    assert checked >= 250
 
 
 NETS = [wl.sprinkler(), wl.huang_darwiche(), wl.wisconsin(), wl.random_dag(12, 3, 2, 3, 8, 5),

@@ -28,8 +28,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -561,19 +563,133 @@ struct Distinct {
 Distinct classify(const jt_plan* p, int hi_off, int lo_off, int n, int n_lo) {
     Distinct d;
     d.cls.resize(n);
-    std::unordered_map<int, int> seen;
-    for (int x = 0; x < n; ++x) {
-        const int v = p->tab[hi_off + x / n_lo] + p->tab[lo_off + x % n_lo];
-        auto it = seen.find(v);
-        if (it == seen.end()) {
-            it = seen.emplace(v, (int)d.value.size()).first;
-            d.value.push_back(v);
-            d.count.push_back(0);
+    if (n <= 0) return d;
+    // v(x) = hi[x / n_lo] + lo[x % n_lo]; classes are numbered in the order their value first appears.
+    // The values are row offsets inside one message, so their range is usually a small multiple of
+    // n at most: a direct table then (plans with 2^17-entry cliques classify tens of millions of
+    // entries when they are loaded); a hash map otherwise.
+    const int n_hi = (n + n_lo - 1) / n_lo, lo_used = n < n_lo ? n : n_lo;
+    const int* hi = p->tab.data() + hi_off;
+    const int* lo = p->tab.data() + lo_off;
+    long long vmin = (long long)*std::min_element(hi, hi + n_hi) + *std::min_element(lo, lo + lo_used);
+    long long vmax = (long long)*std::max_element(hi, hi + n_hi) + *std::max_element(lo, lo + lo_used);
+    const long long range = vmax - vmin + 1;
+    auto add = [&](int x, int cls) {
+        d.cls[x] = cls;
+        ++d.count[cls];
+    };
+    if (range <= 4LL * n + 4096) {
+        std::vector<int> slot((size_t)range, -1);
+        int x = 0;
+        for (int xh = 0; xh < n_hi; ++xh) {
+            const int base = hi[xh] - (int)vmin;
+            for (int xl = 0; xl < n_lo && x < n; ++xl, ++x) {
+                int& c = slot[(size_t)(base + lo[xl])];
+                if (c < 0) {
+                    c = (int)d.value.size();
+                    d.value.push_back(hi[xh] + lo[xl]);
+                    d.count.push_back(0);
+                }
+                add(x, c);
+            }
         }
-        d.cls[x] = it->second;
-        ++d.count[it->second];
+        return d;
     }
+    std::unordered_map<int, int> seen;
+    int x = 0;
+    for (int xh = 0; xh < n_hi; ++xh)
+        for (int xl = 0; xl < n_lo && x < n; ++xl, ++x) {
+            const int v = hi[xh] + lo[xl];
+            auto it = seen.find(v);
+            if (it == seen.end()) {
+                it = seen.emplace(v, (int)d.value.size()).first;
+                d.value.push_back(v);
+                d.count.push_back(0);
+            }
+            add(x, it->second);
+        }
     return d;
+}
+
+// Walk order of a belief task (position -> (s, r) item), block form: blocks of `beta_block()`
+// consecutive clique entries -- a contiguous run of destination rows -- with the blocks that read
+// the same row sets next to each other (sorted by a hash of their row indices; a collision only
+// costs reuse).  Empty when the task's entries are not a permutation of 0 .. n-1.  A pure function
+// of the plan's tables: jt_dense_build computes the walks of all tasks side by side.
+std::vector<int> block_walk(const jt_plan* p, const DTask& k) {
+    const long long n = (long long)k.n_s * k.n_r;
+    std::vector<int> item_of((size_t)n, -1);
+    std::vector<unsigned long long> ekey((size_t)n);
+    const int n_shi = k.n_s / k.n_slo, n_rhi = k.n_r / k.n_rlo;
+    long long item = 0;
+    bool once = true;
+    for (int sh = 0; sh < n_shi && once; ++sh)
+        for (int sl = 0; sl < k.n_slo && once; ++sl) {
+            const long long e_s = (long long)p->tab[k.src_shi + sh] + p->tab[k.src_slo + sl];
+            unsigned long long hs = 1469598103934665603ULL;
+            for (int j = k.smsg_begin; j < k.smsg_end; ++j)
+                if (!p->msgs[j].uni)
+                    hs = (hs ^ (unsigned long long)(p->msgs[j].off + p->tab[p->msgs[j].a_hi + sh] + p->tab[p->msgs[j].a_lo + sl])) * 1099511628211ULL;
+            if (k.own >= 0 && !(k.flags & JT_TF_OWN_UNIFORM))
+                hs = (hs ^ (unsigned long long)(k.own + (long long)sh * k.n_slo + sl)) * 1099511628211ULL;
+            for (int rh = 0; rh < n_rhi && once; ++rh)
+                for (int rl = 0; rl < k.n_rlo; ++rl, ++item) {
+                    const long long e = e_s + p->tab[k.src_rhi + rh] + p->tab[k.src_rlo + rl];
+                    if (e < 0 || e >= n || item_of[e] != -1) {
+                        once = false;
+                        break;
+                    }
+                    item_of[e] = (int)item;
+                    unsigned long long h = hs;
+                    for (int j = k.rmsg_begin; j < k.rmsg_end; ++j)
+                        if (!p->msgs[j].uni)
+                            h = (h ^ (unsigned long long)(p->msgs[j].off + p->tab[p->msgs[j].a_hi + sh] + p->tab[p->msgs[j].a_lo + sl] +
+                                                          p->tab[p->msgs[j].b_hi + rh] + p->tab[p->msgs[j].b_lo + rl])) * 1099511628211ULL;
+                    ekey[e] = h;
+                }
+        }
+    std::vector<int> perm;
+    if (!once) return perm;
+    const long long W = beta_block();
+    const long long nb = (n + W - 1) / W;
+    std::vector<std::pair<unsigned long long, int>> blocks((size_t)nb);
+    for (long long b = 0; b < nb; ++b) {
+        unsigned long long h = 1469598103934665603ULL;
+        for (long long e = W * b; e < std::min(n, W * b + W); ++e) h = (h ^ ekey[e]) * 1099511628211ULL;
+        blocks[b] = {h, (int)b};
+    }
+    std::sort(blocks.begin(), blocks.end());
+    perm.reserve((size_t)n);
+    for (const auto& blk : blocks)
+        for (long long e = W * blk.second; e < std::min(n, W * blk.second + W); ++e) perm.push_back(item_of[e]);
+    return perm;
+}
+
+// ... and of a leaf clique (no r space) in the plain item walk: s sorted by its first per-instance
+// row operand (counting sort, stable).  Empty when the task has no such operand.
+std::vector<int> leaf_walk(const jt_plan* p, const DTask& k) {
+    std::vector<int> perm;
+    int hi = 0, lo = 0;
+    bool found = false;
+    for (int j = k.rmsg_begin; j < k.smsg_end && !found; ++j)
+        if (!p->msgs[j].uni) {
+            hi = p->msgs[j].a_hi;
+            lo = p->msgs[j].a_lo;
+            found = true;
+        }
+    if (!found) return perm;                              // (own has row index s: already sorted)
+    std::vector<int> key(k.n_s);
+    int kmax = 0;
+    for (int sx = 0; sx < k.n_s; ++sx) {
+        key[sx] = p->tab[hi + sx / k.n_slo] + p->tab[lo + sx % k.n_slo];
+        kmax = std::max(kmax, key[sx]);
+    }
+    std::vector<int> start((size_t)kmax + 2, 0);
+    for (int sx = 0; sx < k.n_s; ++sx) ++start[key[sx] + 1];
+    for (int v = 0; v <= kmax; ++v) start[v + 1] += start[v];
+    perm.resize(k.n_s);
+    for (int sx = 0; sx < k.n_s; ++sx) perm[start[key[sx]]++] = sx;
+    return perm;
 }
 
 }  // namespace
@@ -684,6 +800,72 @@ int jt_dense_build(jt_plan* p) {
         for (int j = k.smsg_begin; j < k.smsg_end; ++j) rows += p->msgs[j].uni ? 0 : 1;
         return rows <= kBetaRows;
     };
+    // Which belief tasks are split off, and which walk table each gets (1: blocks, 2: leaf sort, 0: none).
+    // Both are functions of the plan alone, so the tables -- tens of millions of entries on plans with
+    // 2^17-entry cliques -- are computed side by side on the host's cores first and appended to the
+    // dense table in task order below.
+    auto beta_rows = [&](const DTask& k) {
+        int rows = (k.own >= 0 && !(k.flags & JT_TF_OWN_UNIFORM)) ? 1 : 0;
+        for (int j = k.rmsg_begin; j < k.smsg_end; ++j) rows += p->msgs[j].uni ? 0 : 1;
+        return rows;
+    };
+    auto beta_candidate = [&](const jt_plan::Launch& L, int t) {
+        if (L.phase != JT_PHASE_DIST_MAIN || p->hdr[JT_H_UNI_ENTRIES] <= 0 || !L.tma_ok || !small_offsets) return false;
+        const DTask& k = p->tasks[t];
+        if (k.kind != JT_KIND_PROJECT || k.beta < 0 || k.src < 0 || !(k.flags & JT_TF_SRC_UNIFORM)) return false;
+        if (beta_rows(k) > kBetaRows) return false;
+        return !(k.out >= 0 && !dense_tasks.count(t) && !scalar_ok(k));
+    };
+    auto walk_kind = [&](const DTask& k, int rows) {
+        if (beta_walk_blocks() && rows > 0 && (long long)k.n_s * k.n_r > 8) return 1;
+        if (k.n_r == 1 && rows > 0 && k.n_s > 1) return 2;
+        return 0;
+    };
+    auto leaf_has_operand = [&](const DTask& k) {
+        for (int j = k.rmsg_begin; j < k.smsg_end; ++j)
+            if (!p->msgs[j].uni) return true;
+        return false;
+    };
+    std::unordered_map<int, std::vector<int>> walks;       // task -> precomputed walk
+    {
+        std::vector<int> jobs;
+        long long total = 0;
+        for (const auto& L : p->launches)
+            for (int t = L.begin; t < L.end; ++t)
+                if (beta_candidate(L, t)) {
+                    const DTask& k = p->tasks[t];
+                    const int w = walk_kind(k, beta_rows(k));
+                    if (w == 0 || (w == 2 && !leaf_has_operand(k))) continue;
+                    jobs.push_back(t);
+                    total += (long long)k.n_s * k.n_r;
+                }
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int n_threads = (int)std::min<size_t>(jobs.size(), std::min(16u, hw ? hw : 1u));
+        if (n_threads > 1 && total <= (1LL << 28)) {       // at most 1 GB of tables in flight
+            std::vector<std::vector<int>> out(jobs.size());
+            std::atomic<size_t> next(0);
+            auto work = [&]() {
+                for (size_t i = next.fetch_add(1); i < jobs.size(); i = next.fetch_add(1)) {
+                    const DTask& k = p->tasks[jobs[i]];
+                    out[i] = walk_kind(k, beta_rows(k)) == 1 ? block_walk(p, k) : leaf_walk(p, k);
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int i = 1; i < n_threads; ++i) pool.emplace_back(work);
+            work();
+            for (auto& th : pool) th.join();
+            for (size_t i = 0; i < jobs.size(); ++i) walks[jobs[i]] = std::move(out[i]);
+        }
+    }
+    auto take_walk = [&](int t, const DTask& k, int kind) {
+        auto it = walks.find(t);
+        if (it != walks.end()) {
+            std::vector<int> w = std::move(it->second);
+            walks.erase(it);
+            return w;
+        }
+        return kind == 1 ? block_walk(p, k) : leaf_walk(p, k);
+    };
     for (auto& L : p->launches) {
         L.beta_n = 0;
         L.beta_items = 0;
@@ -709,77 +891,24 @@ int jt_dense_build(jt_plan* p) {
             // of 16 KB cycling per s) fall out of L1; config 4 unchanged.  JT_BETA_WALK=items: the
             // s-major walk, with a leaf clique (no r space) sorted by its row operand.
             int perm_off = -1;
-            if (beta_walk_blocks() && rows > 0 && (long long)k.n_s * k.n_r > 8) {
+            const int walk = walk_kind(k, rows);
+            if (walk == 1) {
                 const long long n = (long long)k.n_s * k.n_r;
                 if (p->dtab.size() + (size_t)n > 2000000000ULL) continue;
-                std::vector<int> item_of((size_t)n, -1);
-                std::vector<unsigned long long> ekey((size_t)n);
-                const int n_shi = k.n_s / k.n_slo, n_rhi = k.n_r / k.n_rlo;
-                long long item = 0;
-                bool once = true;
-                for (int sh = 0; sh < n_shi && once; ++sh)
-                    for (int sl = 0; sl < k.n_slo && once; ++sl) {
-                        const long long e_s = (long long)p->tab[k.src_shi + sh] + p->tab[k.src_slo + sl];
-                        unsigned long long hs = 1469598103934665603ULL;
-                        for (int j = k.smsg_begin; j < k.smsg_end; ++j)
-                            if (!p->msgs[j].uni)
-                                hs = (hs ^ (unsigned long long)(p->msgs[j].off + p->tab[p->msgs[j].a_hi + sh] + p->tab[p->msgs[j].a_lo + sl])) * 1099511628211ULL;
-                        if (k.own >= 0 && !(k.flags & JT_TF_OWN_UNIFORM))
-                            hs = (hs ^ (unsigned long long)(k.own + (long long)sh * k.n_slo + sl)) * 1099511628211ULL;
-                        for (int rh = 0; rh < n_rhi && once; ++rh)
-                            for (int rl = 0; rl < k.n_rlo; ++rl, ++item) {
-                                const long long e = e_s + p->tab[k.src_rhi + rh] + p->tab[k.src_rlo + rl];
-                                if (e < 0 || e >= n || item_of[e] != -1) {
-                                    once = false;
-                                    break;
-                                }
-                                item_of[e] = (int)item;
-                                unsigned long long h = hs;
-                                for (int j = k.rmsg_begin; j < k.rmsg_end; ++j)
-                                    if (!p->msgs[j].uni)
-                                        h = (h ^ (unsigned long long)(p->msgs[j].off + p->tab[p->msgs[j].a_hi + sh] + p->tab[p->msgs[j].a_lo + sl] +
-                                                                      p->tab[p->msgs[j].b_hi + rh] + p->tab[p->msgs[j].b_lo + rl])) * 1099511628211ULL;
-                                ekey[e] = h;
-                            }
-                    }
-                if (once) {
-                    const long long W = beta_block();
-                    const long long nb = (n + W - 1) / W;
-                    std::vector<std::pair<unsigned long long, int>> blocks((size_t)nb);
-                    for (long long b = 0; b < nb; ++b) {
-                        unsigned long long h = 1469598103934665603ULL;
-                        for (long long e = W * b; e < std::min(n, W * b + W); ++e) h = (h ^ ekey[e]) * 1099511628211ULL;
-                        blocks[b] = {h, (int)b};
-                    }
-                    std::sort(blocks.begin(), blocks.end());
+                std::vector<int> perm = take_walk(t, k, walk);
+                if (!perm.empty()) {
                     perm_off = (int)p->dtab.size();
-                    p->dtab.reserve(p->dtab.size() + (size_t)n);
-                    for (const auto& blk : blocks)
-                        for (long long e = W * blk.second; e < std::min(n, W * blk.second + W); ++e) p->dtab.push_back(item_of[e]);
+                    p->dtab.insert(p->dtab.end(), perm.begin(), perm.end());
                 }
-            } else if (k.n_r == 1 && rows > 0 && k.n_s > 1) {
-                int hi = 0, lo = 0;
-                bool found = false;
-                for (int j = k.rmsg_begin; j < k.smsg_end && !found; ++j)
-                    if (!p->msgs[j].uni) {
-                        hi = p->msgs[j].a_hi;
-                        lo = p->msgs[j].a_lo;
-                        found = true;
-                    }
-                if (found) {                                      // (own has row index s: already sorted)
+            } else if (walk == 2) {
+                // (a leaf clique without a per-instance message operand: own has row index s, already sorted)
+                if (!leaf_has_operand(k)) {
+                    // nothing to sort by
+                } else {
                     if (p->dtab.size() + (size_t)k.n_s > 2000000000ULL) continue;
-                    std::vector<int> key(k.n_s);
-                    int kmax = 0;
-                    for (int sx = 0; sx < k.n_s; ++sx) {
-                        key[sx] = p->tab[hi + sx / k.n_slo] + p->tab[lo + sx % k.n_slo];
-                        kmax = std::max(kmax, key[sx]);
-                    }
-                    std::vector<int> start((size_t)kmax + 2, 0);
-                    for (int sx = 0; sx < k.n_s; ++sx) ++start[key[sx] + 1];
-                    for (int v = 0; v <= kmax; ++v) start[v + 1] += start[v];
+                    std::vector<int> perm = take_walk(t, k, walk);
                     perm_off = (int)p->dtab.size();
-                    p->dtab.resize(p->dtab.size() + k.n_s);
-                    for (int sx = 0; sx < k.n_s; ++sx) p->dtab[perm_off + start[key[sx]]++] = sx;
+                    p->dtab.insert(p->dtab.end(), perm.begin(), perm.end());
                 }
             }
             k.flags |= JT_TF_BETA_SPLIT;

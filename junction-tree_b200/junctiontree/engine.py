@@ -5,6 +5,8 @@ goes through the C ABI of ``libjt_b200.so`` (``_native.py``).  Buffers use the b
 layout ``[entry, B]`` (see ``include/jt_b200.h``).
 """
 
+import os
+
 import numpy as np
 
 from . import _native
@@ -53,6 +55,12 @@ class Engine:
         self.plan = plan
         self.dev = _native.DevicePlan(plan.to_blob())
         self._workspaces = {}
+        #: which binding of the C ABI the stage calls on tensor workspaces go through: "ctypes"
+        #: (``_native.py``) or "torch" (the PyTorch extension, ``torch_ops.py``); same library,
+        #: same plan handle either way
+        self.binding = os.environ.get("JT_BINDING", "ctypes")
+        if self.binding not in ("ctypes", "torch"):
+            raise ValueError("JT_BINDING must be 'ctypes' or 'torch', got %r" % self.binding)
 
     # -----------------------------------------------------------------------------------------
     # memory
@@ -230,6 +238,11 @@ class Engine:
             fout = t.empty((self.plan.fout_entries, B), dtype=torch_dtype(dtype), device="cuda")
         else:
             flags |= _native.JT_SKIP_MARGINAL
+        if self.binding == "torch" and t.is_tensor(ws):
+            from . import torch_ops
+            torch_ops.ops().propagate(torch_ops.handle_of(self.dev), factor_dev, bool(batched), evidence_dev, ws,
+                                      fout, B, flags)
+            return ws, fout
         self.dev.propagate(factor_dev.data_ptr(), batched,
                            evidence_dev.data_ptr() if evidence_dev is not None else None,
                            B, dtype, ws.data_ptr(), fout.data_ptr() if fout is not None else None,
@@ -239,10 +252,16 @@ class Engine:
     def beliefs_from_potentials(self, work, B, dtype, ws, sep_beliefs=True, semiring=0):
         """collect + distribute on clique potentials already stored in the workspace."""
         self.dev.upload()
+        sep = _native.JT_SEP_BELIEFS if sep_beliefs else 0
+        if self.binding == "torch" and torch().is_tensor(ws):
+            from . import torch_ops
+            handle, tdt = torch_ops.handle_of(self.dev), torch_dtype(dtype)
+            torch_ops.ops().collect(handle, ws, B, tdt, semiring)
+            torch_ops.ops().distribute(handle, ws, B, tdt, sep | semiring)
+            return
         stream = self._stream()
         self.dev.collect(B, dtype, ws.data_ptr(), semiring, stream)
-        self.dev.distribute(B, dtype, ws.data_ptr(), (_native.JT_SEP_BELIEFS if sep_beliefs else 0) | semiring,
-                            stream)
+        self.dev.distribute(B, dtype, ws.data_ptr(), sep | semiring, stream)
 
     # -----------------------------------------------------------------------------------------
     # views of results

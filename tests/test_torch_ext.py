@@ -122,3 +122,42 @@ def test_engine_binding_switch(monkeypatch):
     monkeypatch.setenv("JT_BINDING", "numpy")
     with pytest.raises(ValueError, match="JT_BINDING"):
         eng.Engine(plan)
+
+
+def test_both_bindings_release_the_gil_during_a_call():
+    """"the torch binding releases the GIL".  Loading the Ising 16x16 plan takes a few
+    hundred milliseconds inside the library (jt_plan_create derives the dense contractions and the
+    belief walk tables); a Python thread must keep running meanwhile, through either binding."""
+    import threading
+    import jt_bench_lib as bl
+    net = bl.make_net("ising16")
+    tree, seps, mc, f2c, eff, evars = compile_net(net)
+    blob = sch.Plan(tree, mc + seps, eff, net["factors"], f2c, evars, net["sizes"]).to_blob()
+    tensor = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+    ops = torch_ops.ops()
+
+    def through_torch():
+        ops.plan_destroy(ops.plan_create(tensor))
+
+    def through_ctypes():
+        _native.DevicePlan(blob).close()
+
+    for call in (through_torch, through_ctypes):
+        done, failed = [], []
+
+        def work(call=call):
+            try:
+                call()
+            except Exception as exc:          # reported below; the spin loop must still end
+                failed.append(exc)
+            finally:
+                done.append(True)
+
+        worker = threading.Thread(target=work)
+        worker.start()
+        spins = 0
+        while not done:
+            spins += 1
+        worker.join()
+        assert not failed, failed
+        assert spins > 1000, "%s held the GIL for the whole call" % call.__name__

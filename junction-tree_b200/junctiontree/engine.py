@@ -71,11 +71,20 @@ class Engine:
         One workspace per (B, dtype) is cached; callers running several streams allocate their
         own with :meth:`new_workspace`."""
         key = (int(B), np.dtype(dtype).str)
-        ws = self._workspaces.get(key)
+        ws = self._workspaces.pop(key, None)
         if ws is None:
+            # at most MAX_CACHED_WORKSPACES batch sizes stay cached (least recently used first out):
+            # a caller with ever-changing batch sizes -- propagate_evidence groups instances by
+            # evidence pattern -- must not pin one workspace per size it ever used
+            plain = [k for k in self._workspaces if isinstance(k[0], int)]
+            for stale in plain[:max(0, len(plain) - self.MAX_CACHED_WORKSPACES + 1)]:
+                del self._workspaces[stale]
             ws = self.new_workspace(B, dtype)
-            self._workspaces[key] = ws
+        self._workspaces[key] = ws              # (re)inserted last: dicts keep insertion order
         return ws
+
+    #: plain (B, dtype) workspaces kept by :meth:`workspace`
+    MAX_CACHED_WORKSPACES = 4
 
     def new_workspace(self, B, dtype):
         t = require_cuda()

@@ -98,6 +98,10 @@ def _effective_sizes(factors, xs, batched=False):
 _caches = {}
 
 
+#: compiled engines kept per clique graph (see ``CliqueGraph._engine``)
+_MAX_ENGINES = 64
+
+
 def _cache_of(owner, name):
     slot = _caches.get(id(owner))
     if slot is None:
@@ -156,13 +160,19 @@ class CliqueGraph():
                None if outputs is None else tuple(tuple(o) for o in outputs), tuple(likelihood_vars),
                None if full_sizes is None else tuple(full_sizes.get(v) for v in evidence_vars),
                eng.current_device())
-        hit = self._engines.get(key)
+        engines = self._engines
+        hit = engines.pop(key, None)
         if hit is None:
             node_vars = list(self.maxcliques) + ([list(s) for s in separators] if tree is not None else [])
             plan = sch.Plan(tree, node_vars, sizes, self.factor_graph.factors, self._f2c(),
                             evidence_vars, full_sizes, outputs, likelihood_vars=likelihood_vars)
             hit = eng.Engine(plan)
-            self._engines[key] = hit
+            # least recently used first out: every distinct evidence pattern of propagate_evidence
+            # compiles its own plan (descriptors on the device, cached workspaces); an engine still
+            # held by a caller (a session) simply stays alive outside the cache
+            while len(engines) >= _MAX_ENGINES:
+                engines.pop(next(iter(engines)))
+        engines[key] = hit                      # (re)inserted last: dicts keep insertion order
         return hit
 
     def evaluate(self, xs, dl=None, reference_shapes=True):

@@ -186,3 +186,42 @@ def test_two_trees_over_one_clique_graph_get_their_own_plans():
     del tree, other, third, ct, plan_a, plan_b, plan_c
     gc.collect()
     assert key not in jt.junctiontree._caches
+
+
+def test_engine_and_workspace_caches_are_bounded(monkeypatch):
+    """Every distinct evidence pattern (propagate_evidence) compiles its own plan and every batch
+    size gets its own workspace: both caches drop their least recently used entry instead of
+    growing with the number of patterns / sizes ever seen."""
+    from junctiontree import engine as eng
+    import jt_workloads as wl
+    net = wl.random_dag(12, 3, 2, 3, 8, 5)
+    tree = jt.create_junction_tree(net["factors"], net["sizes"])
+    monkeypatch.setattr(jt.junctiontree, "_MAX_ENGINES", 3)
+    labels = sorted(net["sizes"])
+    plans = [tree.plan([v]) for v in labels[:3]]
+    assert len(tree.clique_tree._engines) == 3
+    assert tree.plan([labels[0]]) is plans[0]                 # a hit: now the most recently used
+    fourth = tree.plan([labels[3]])
+    assert len(tree.clique_tree._engines) == 3
+    assert tree.plan([labels[0]]) is plans[0]                 # survived, the oldest (labels[1]) went
+    assert tree.plan([labels[3]]) is fourth
+    assert tree.plan([labels[1]]) is not plans[1]             # recompiled
+    assert len(tree.clique_tree._engines) == 3
+
+    engine = tree._engine(plans[0].sizes, [labels[0]], plans[0].full_sizes)
+    made = []
+    monkeypatch.setattr(eng.Engine, "new_workspace", lambda self, B, dtype: made.append(B) or object())
+    first = engine.workspace(8, np.float64)
+    for B in (16, 32, 64):
+        engine.workspace(B, np.float64)
+    assert engine.workspace(8, np.float64) is first and made == [8, 16, 32, 64]
+    engine.workspace(128, np.float64)                         # fifth size: the least recently used (16) goes
+    assert engine.workspace(8, np.float64) is first
+    assert sum(isinstance(k[0], int) for k in engine._workspaces) == eng.Engine.MAX_CACHED_WORKSPACES
+    engine.workspace(16, np.float64)
+    assert made == [8, 16, 32, 64, 128, 16]
+    engine._workspaces[("graph", 1)] = "runner"               # tagged entries (runners) are not counted or evicted
+    for B in (256, 512, 1024, 2048, 4096):
+        engine.workspace(B, np.float32)
+    assert engine._workspaces[("graph", 1)] == "runner"
+    assert sum(isinstance(k[0], int) for k in engine._workspaces) == eng.Engine.MAX_CACHED_WORKSPACES

@@ -399,3 +399,29 @@ def test_gpu_dense_nets_reach_every_variant_of_the_dense_kernel():
     for want in [("MT", 1), ("MT", 2), ("MT", 3), ("MT", 4), ("several i-tiles", True), ("several i-tiles", False),
                  ("K % 4 == 0", True), ("K % 4 == 0", False), ("short", True), ("short", False)]:
         assert want in seen, want
+
+
+def test_plan_load_derivation_is_pinned():
+    """What jt_plan_create derives from a blob (dense contractions, the table behind them incl. the
+    belief kernel's walk tables) is read by the kernels as is.  Its fingerprints on the five
+    BASELINE configs and the nets of the dense GPU tests are committed
+    (tests/golden/derived_tables.json, make_derived.py): a plan-load change meant as a pure
+    speed-up must not move them, and an intended change has to regenerate the file -- together
+    with a GPU parity run."""
+    import json
+    knobs = [k for k in ("JT_DISABLE_DENSE", "JT_BETA_WALK", "JT_DENSE_MIN_GAIN", "JT_DENSE_WAVES", "JT_DENSE_BALANCE",
+                         "JT_BETA_BLOCK", "JT_DISABLE_BETA", "JT_BETA_MIN_MB", "JT_BETA_MAX_B") if os.environ.get(k)]
+    if knobs:
+        pytest.skip("selection-rule knobs set in the environment: %s" % knobs)
+    sys_path_entry = os.path.join(ROOT, "tests", "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_derived", os.path.join(sys_path_entry, "make_derived.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(mod.OUT) as fh:
+        want = json.load(fh)
+    got = mod.fingerprints()
+    assert set(got) == set(want)
+    for name in sorted(want):
+        assert got[name] == want[name], "derived tables of %s changed (see tests/golden/make_derived.py)" % name
+    assert mod.fingerprints() == got                    # built on all host cores: still deterministic
